@@ -1,0 +1,157 @@
+/*
+ * raocp_b200.h -- C-ABI of the B200-native Chambolle-Pock path of raocp-toolbox.
+ *
+ * The reference (pure Python, /root/reference) has no FFI layer; its boundary for this path is the class API
+ * raocp.core.Cache / Operator / Solver.  Each entry point below cites the reference interface it replaces
+ * (paths relative to /root/reference).  Plain pointers and sizes only; all host buffers are caller-owned, all device
+ * memory is library-owned for the lifetime of the handle.  One handle per host thread.  Every function returns
+ * 0 on success or a negative rb_status; rb_last_error() gives the message.
+ *
+ * COMPACT EXCHANGE LAYOUT (float64, per problem instance; no placeholders -- see DESIGN.md "Data layout"):
+ *   primal (Np doubles) = [ x (n*nx) | u (m*nu) | y (sum_i 2c_i+1; node i: [y_a(c_i); y_b(c_i); y_last]) | tau (n) | s (n) ]
+ *   dual   (Nd doubles) = [ d1 (like y) | d2 (m) | d3 ((n-1)*nx, row j-1 = edge into node j) | d4 ((n-1)*nu) | d5 (n-1)
+ *                           | d6 (n-1) | d7 (m*(nx+nu), iff nonleaf rectangles) | d11 (L*nx) | d12 (L) | d13 (L)
+ *                           | d14 (L*nx, iff leaf rectangles) ],  L = n - m.
+ *   Reference numbering of these segments: raocp/core/cache.py:126-170.  With batch > 1 the instances are
+ *   concatenated (instance-major).
+ */
+#ifndef RAOCP_B200_H
+#define RAOCP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rb_solver rb_solver; /* opaque handle */
+
+typedef enum {
+    RB_OK = 0,
+    RB_ERR_INVALID = -1,      /* bad argument / inconsistent problem description */
+    RB_ERR_CUDA = -2,         /* CUDA runtime error (message has the cudaError string) */
+    RB_ERR_NO_DEVICE = -3,    /* no usable CUDA device: there is NO CPU fallback */
+    RB_ERR_NUMERIC = -4,      /* NaN met in a rectangle projection (reference: ValueError, rectangle.py:58-59)
+                                 or Cholesky breakdown in the offline factorisation */
+    RB_ERR_STATE = -5         /* call order error (e.g. iterate before offline / initial state) */
+} rb_status;
+
+/* Problem description = what the reference's Cache reads through RAOCP accessors (raocp/core/raocp_spec.py:56-75)
+ * and ScenarioTree queries (raocp/core/scenario_tree.py:75-154), flattened once on the host.
+ * Nodes are numbered stage by stage, children of a node contiguous (reference factory order,
+ * scenario_tree.py:273-315); nonleaf nodes are 0..m-1. */
+typedef struct {
+    int32_t n;                 /* nodes                     (tree.num_nodes) */
+    int32_t m;                 /* nonleaf nodes             (tree.num_nonleaf_nodes) */
+    int32_t nx, nu;            /* state / input sizes       (cache.py:19-20) */
+    int32_t num_stages;        /* N+1                       (tree.num_stages) */
+    int32_t batch;             /* independent initial states solved together (>=1; reference: 1) */
+    const int32_t *stage_off;  /* [num_stages+1] first node of every stage (nodes_at_stage, scenario_tree.py:123) */
+    const int32_t *parent;     /* [n]  ancestor_of, -1 at the root */
+    const int32_t *child_first;/* [m]  children_of(i)[0] */
+    const int32_t *child_count;/* [m]  len(children_of(i)) */
+    /* dynamics, indexed by the CHILD node j>=1 through a table (raocp_spec.py:56-60) */
+    int32_t num_dyn;
+    const int32_t *dyn_idx;    /* [n]  table row of node j (entry 0 ignored) */
+    const double *A;           /* [num_dyn][nx][nx] row-major */
+    const double *B;           /* [num_dyn][nx][nu] row-major */
+    /* nonleaf costs, indexed by the CHILD node (operators.py:33-36,84-87): matrix square roots as stored by the
+     * host cost objects (costs.py:21,26) */
+    int32_t num_cost;
+    const int32_t *cost_idx;   /* [n] */
+    const double *sqrtQ;       /* [num_cost][nx][nx] */
+    const double *sqrtR;       /* [num_cost][nu][nu] */
+    /* leaf costs (operators.py:46-47,89) */
+    int32_t num_leafcost;
+    const int32_t *leafcost_idx; /* [L] */
+    const double *sqrtQf;      /* [num_leafcost][nx][nx] */
+    /* rectangles (rectangle.py:24-35): bounds on [x;u] (nonleaf) and x (leaf); 0 tables = constraint inactive */
+    int32_t num_nl_rect;
+    const int32_t *nl_rect_idx;  /* [m] */
+    const double *nl_lo, *nl_hi; /* [num_nl_rect][nx+nu] */
+    int32_t num_leaf_rect;
+    const int32_t *leaf_rect_idx;/* [L] */
+    const double *leaf_lo, *leaf_hi; /* [num_leaf_rect][nx] */
+    /* AVaR risks (risks.py:28-35): alpha per nonleaf node, conditional probability of every node given its parent */
+    const double *risk_alpha;  /* [m] */
+    const double *cond_prob;   /* [n]  (entry 0 ignored) = b_i[0:c_i] of the parent */
+    /* factorisation classes: nodes with the same class share (P, K, R~^-1).  cls[i] in [0, num_cls); classes must be
+     * ordered so that every child's class index is LARGER than its parent's (leaves have class -1 -> P = I).
+     * The trivial choice cls[i] = i (one class per node) reproduces the reference's per-node loop (cache.py:207-233). */
+    int32_t num_cls;
+    const int32_t *cls;        /* [m] */
+    int32_t device;            /* CUDA device ordinal */
+} rb_problem;
+
+/* -- lifetime ---------------------------------------------------------------------------------------------------- */
+/* Cache.__init__ without the offline phase (cache.py:13-47): uploads the problem, allocates zero iterates. */
+int rb_create(const rb_problem *problem, rb_solver **out);
+void rb_destroy(rb_solver *s);
+const char *rb_last_error(const rb_solver *s);       /* s may be NULL: error of the last failed rb_create */
+int rb_set_stream(rb_solver *s, void *cuda_stream);  /* launch on this cudaStream_t (NULL = library's own stream) */
+int rb_sizes(const rb_solver *s, int64_t *np, int64_t *nd); /* compact per-instance sizes Np, Nd */
+int rb_synchronize(rb_solver *s);
+
+/* -- offline ----------------------------------------------------------------------------------------------------- */
+/* Cache._offline (cache.py:200-242): Riccati-like factorisation per class.  The null-space matrices of
+ * offline_projection_kernel (cache.py:235-242) are not needed: the AVaR kernel projector is closed-form. */
+int rb_offline(rb_solver *s);
+/* test hook: per-class P [num_cls][nx][nx], K [num_cls][nu][nx], R~^-1 [num_cls][nu][nu] (any pointer may be NULL) */
+int rb_get_offline(rb_solver *s, double *P, double *K, double *Rinv);
+
+/* -- iterate access (cache.py:59-122) ---------------------------------------------------------------------------- */
+/* which: 0 = current iterate (Cache.__primal / __dual), 1 = old iterate (__old_primal / __old_dual) */
+int rb_set_primal(rb_solver *s, int which, const double *compact); /* Cache.set_primal, cache.py:84-101 */
+int rb_get_primal(rb_solver *s, int which, double *compact);       /* Cache.get_primal, cache.py:59-60 */
+int rb_set_dual(rb_solver *s, int which, const double *compact);   /* Cache.set_dual, cache.py:103-122 */
+int rb_get_dual(rb_solver *s, int which, double *compact);         /* Cache.get_dual, cache.py:65-66 */
+int rb_set_initial_state(rb_solver *s, const double *x0);          /* Cache.cache_initial_state, cache.py:79-82;
+                                                                      x0 is [batch][nx] */
+int rb_update_cache(rb_solver *s);                                 /* Cache.update_cache, cache.py:186-196: old <- current */
+
+/* -- linear operator (operators.py:19-94), host vectors in / out (compact layout, batch instances) ---------------- */
+int rb_apply_L(rb_solver *s, const double *primal_in, double *dual_out);   /* Operator.ell / linop_ell */
+int rb_apply_Lt(rb_solver *s, const double *dual_in, double *primal_out);  /* Operator.ell_transpose / linop_ell_transpose */
+/* lambda_max(L* L) as the maximum over the diagonal blocks of L* L (replaces ARPACK eigs, solver.py:105-118) */
+int rb_lambda_max(rb_solver *s, double *lambda_max);
+
+/* -- the four half steps on the device-resident iterates (solver.py:27-61) ----------------------------------------- */
+int rb_primal_half(rb_solver *s, double alpha);   /* Solver.primal_k_plus_half: current_p = old_p - alpha L*(old_d) */
+int rb_prox_f(rb_solver *s, double alpha);        /* Cache.proximal_of_f, cache.py:248-251 (on current_p) */
+int rb_s0_shift(rb_solver *s, double alpha);      /* Cache.proximal_of_relaxation_s_at_stage_zero, cache.py:253-257 */
+int rb_project_dynamics(rb_solver *s);            /* Cache.project_on_dynamics, cache.py:259-288 */
+int rb_project_kernel(rb_solver *s);              /* Cache.project_on_kernel, cache.py:290-317 */
+int rb_dual_half(rb_solver *s, double alpha);     /* Solver.dual_k_plus_half: current_d = old_d + alpha L(2 cur_p - old_p) */
+int rb_prox_g_conj(rb_solver *s, double alpha);   /* Cache.proximal_of_g_conjugate, cache.py:321-327 (on current_d) */
+int rb_modify_dual(rb_solver *s, double alpha);   /* Cache.modify_dual, cache.py:329-332 */
+int rb_add_halves(rb_solver *s);                  /* Cache.add_halves, cache.py:334-347 */
+int rb_project_nonleaf(rb_solver *s);             /* Cache.project_on_constraints_nonleaf, cache.py:349-371 */
+int rb_project_leaf(rb_solver *s);                /* Cache.project_on_constraints_leaf, cache.py:373-390 */
+int rb_modify_projection(rb_solver *s, double alpha, const double *modified_dual); /* cache.py:392-393 */
+
+/* Solver._calculate_chock_errors + the inf-norms (solver.py:63-95,137-141) between old and current iterates.
+ * norms: [batch][6] = xi0, xi1, xi2, delta0, delta1, delta2.  vectors (optional, may be NULL): six compact host
+ * vectors [xi0 (Np) | xi1 (Np) | xi2 (Nd) | delta0 (Np) | delta1 (Np) | delta2 (Nd)] per instance. */
+int rb_residuals(rb_solver *s, double alpha, double *norms, double *vectors);
+
+/* -- the fused loop: Solver.chock's while-loop (solver.py:124-161) entirely on the device ---------------------------
+ * Runs until iteration index >= max_iters or max(xi0,xi1,xi2) <= tol for every instance (so max_iters+1 iterations
+ * when not converged, like the reference).  Only the six residual norms per iteration leave the device.
+ * xi_hist / delta_hist: [capacity][batch][3] (may be NULL).  Returns the reference's status in *status
+ * (0 converged, 1 not) and the number of iterations executed in *iters. */
+int rb_iterate(rb_solver *s, double alpha, int32_t max_iters, double tol, int32_t check_every,
+               double *xi_hist, double *delta_hist, int32_t hist_capacity, int32_t *iters, int32_t *status);
+/* benchmark hook: exactly `iters` fused iterations, no host synchronisation inside, residual norms of the last
+ * iteration in norms[batch][6]. */
+int rb_iterate_fixed(rb_solver *s, double alpha, int32_t iters, double *norms);
+int rb_launch_count(const rb_solver *s, int64_t *kernels_launched); /* kernels launched by this handle so far */
+
+/* -- stand-alone projections (cones.py:30-132, rectangle.py:29-59): host vector in, host vector out ----------------
+ * cone: 0 Real, 1 Zero, 2 NonnegativeOrthant, 3 SecondOrderCone (last entry is t). */
+int rb_cone_project(int32_t cone, int32_t dim, const double *in, double *out);
+int rb_box_project(int32_t dim, const double *in, const double *lo, const double *hi, double *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAOCP_B200_H */

@@ -1,0 +1,77 @@
+"""Seeded synthetic RAOCP instances for the five BASELINE.json configurations plus the
+reference's own demo problem (reference main.py:11-80).  TEST / BENCH INFRASTRUCTURE.
+
+`spec(name)` returns plain arrays; `build(spec, api)` turns them into a problem with either the reference's classes
+(oracle.ref_loader.RefApi) or raocp_b200.core -- both expose the same builder API -- so that the very same numbers
+reach the reference, the oracles and the CUDA path.
+"""
+import numpy as np
+
+# name: (modes, horizon N, stopping time tau, nx, nu)
+SHAPES = {
+    "cfg1": (2, 4, 4, 2, 1),       # 31 nodes      (BASELINE.json configs[0])
+    "cfg2": (3, 10, 5, 10, 5),     # 1 579 nodes   (configs[1])
+    "cfg3": (4, 20, 6, 20, 10),    # 62 805 nodes  (configs[2])
+    "cfg4": (2, 9, 9, 8, 4),       # 1 023 nodes x 4096 initial states (configs[3])
+    "cfg5": (3, 18, 6, 64, 32),    # 9 841 nodes   (configs[4])
+    # scaled-down siblings used by parity tests so the reference / node oracle finish in seconds
+    "mini2": (3, 5, 3, 4, 2),      # 3 modes, ragged-free, 94-ish nodes
+    "mini3": (4, 7, 3, 6, 3),
+    "mini5": (3, 6, 3, 16, 8),
+}
+
+
+def spec(name, seed=0, batch=1):
+    """Seeded random instance of one of SHAPES (P,v ~ normalised U(0.1,1); A_w ~ N(0,1) scaled to
+    spectral radius 0.9; B_w ~ N(0,1)/sqrt(nx); Q_w,R_w,Qf = diag U(0.5,2); AVaR(0.5); |x|<=5, |u|<=1; x0 ~ U(-1,1))."""
+    modes, horizon, tau, nx, nu = SHAPES[name]
+    rng = np.random.default_rng(seed)
+    p = rng.uniform(0.1, 1.0, size=(modes, modes))
+    p /= p.sum(axis=1, keepdims=True)
+    v = rng.uniform(0.1, 1.0, size=modes)
+    v /= v.sum()
+    a_list, b_list, q_list, r_list = [], [], [], []
+    for _ in range(modes):
+        a = rng.standard_normal((nx, nx))
+        a *= 0.9 / np.max(np.abs(np.linalg.eigvals(a)))
+        a_list.append(a)
+        b_list.append(rng.standard_normal((nx, nu)) / np.sqrt(nx))
+        q_list.append(np.diag(rng.uniform(0.5, 2.0, size=nx)))
+        r_list.append(np.diag(rng.uniform(0.5, 2.0, size=nu)))
+    qf = np.diag(rng.uniform(0.5, 2.0, size=nx))
+    x0 = rng.uniform(-1.0, 1.0, size=(nx, batch))
+    return dict(name=name, seed=seed, p=p, v=v, horizon=horizon, tau=tau, nx=nx, nu=nu,
+                a=a_list, b=b_list, q=q_list, r=r_list, qf=qf, avar=0.5,
+                x_lim=5.0, u_lim=1.0, x0=x0, rectangles=True)
+
+
+def demo_spec():
+    """The reference's demo problem, numbers from reference main.py:11-80 (43 nodes, nx=3, nu=2, AVaR 0.95)."""
+    p = np.array([[0.1, 0.8, 0.1], [0.4, 0.6, 0.0], [0.0, 0.3, 0.7]])
+    v = np.array([0.1, 0.6, 0.3])
+    f = 0.1
+    aw = f * np.array([[1, 2, 1], [1, 1, 2], [2, 1, 1]], dtype=float)
+    bw = f * np.array([[1, 0], [1, 0], [0, 2]], dtype=float)
+    q = 0.2 * f * np.eye(3)
+    r = 0.2 * f * np.eye(2)
+    return dict(name="demo", seed=None, p=p, v=v, horizon=4, tau=3, nx=3, nu=2,
+                a=[0.5 * aw, aw, -0.5 * aw], b=[-0.5 * bw, bw, 0.5 * bw],
+                q=[q, q, q], r=[r, r, r], qf=f * 0.1 * np.eye(3), avar=0.95,
+                x_lim=7.0, u_lim=0.1, x0=np.array([[5.0], [-6.0], [-1.0]]), rectangles=True)
+
+
+def build(s, api):
+    """Problem object (RAOCP) for spec `s` using the classes of `api` (reference or raocp_b200.core)."""
+    tree = api.MarkovChainScenarioTreeFactory(s["p"], s["v"], s["horizon"], s["tau"]).create()
+    nl, lf = api.Nonleaf(), api.Leaf()
+    nx, nu = s["nx"], s["nu"]
+    dyn = [api.Dynamics(a, b) for a, b in zip(s["a"], s["b"])]
+    nl_costs = [api.Quadratic(nl, q, r) for q, r in zip(s["q"], s["r"])]
+    problem = api.RAOCP(tree).with_markovian_dynamics(dyn).with_markovian_nonleaf_costs(nl_costs) \
+        .with_all_leaf_costs(api.Quadratic(lf, s["qf"])).with_all_risks(api.AVaR(s["avar"]))
+    if s.get("rectangles", True):
+        hi_nl = np.vstack((s["x_lim"] * np.ones((nx, 1)), s["u_lim"] * np.ones((nu, 1))))
+        hi_l = s["x_lim"] * np.ones((nx, 1))
+        problem = problem.with_all_nonleaf_constraints(api.Rectangle(nl, -hi_nl, hi_nl)) \
+            .with_all_leaf_constraints(api.Rectangle(lf, -hi_l, hi_l))
+    return problem

@@ -1,0 +1,134 @@
+// common.cuh -- device-side problem view, layout and warp helpers shared by all raocp_b200 kernels (sm_100a, FP64).
+//
+// Layout (DESIGN.md "Data layout in HBM"): one padded primal buffer and one padded dual buffer per iterate copy,
+// segments in the compact order of include/raocp_b200.h, every segment start rounded up to 16 doubles (128 B),
+// instance-major for batch > 1.  Node-major rows: x row i = nx consecutive doubles, so a warp that owns node i reads
+// its rows with consecutive lanes (coalesced).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rb {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kMaxDim = 64;  // max(nx, nu) supported by the per-warp shared-memory scratch rows
+
+struct Layout {
+    int n, m, nleaf, nx, nu, nxu;
+    int num_stages, batch;
+    int has_nl_rect, has_leaf_rect;
+    int ysz;
+    // per-instance strides and segment offsets (doubles)
+    long long np_pad, nd_pad;
+    long long px, pu, py, ptau, ps;
+    long long d1, d2, d3, d4, d5, d6, d7, d11, d12, d13, d14;
+};
+
+struct Topo {
+    const int *parent, *child_first, *child_count, *yoff;
+    const int *dyn_idx, *cost_idx, *leafcost_idx, *nl_rect_idx, *leaf_rect_idx, *cls;
+    const double *cond_prob, *risk_alpha;
+};
+
+// Operator tables.  "T" = stored transposed, so that the matrix-vector product with one output row per lane reads
+// consecutive addresses across lanes (see mv_acc below).
+struct Tabs {
+    const double *A, *AT;      // [num_dyn][nx][nx]
+    const double *B, *BT;      // B: [num_dyn][nx][nu], BT: [num_dyn][nu][nx]
+    const double *sqT, *srT;   // transposes of sqrtQ / sqrtR
+    const double *sqfT;        // transpose of sqrtQf
+    const double *nl_lo, *nl_hi, *leaf_lo, *leaf_hi;
+    const double *K, *KT;      // K: [num_cls][nu][nx], KT: [num_cls][nx][nu]
+    const double *RinvT;       // [num_cls][nu][nu] transpose of R~^-1
+    int sq_diag, sr_diag, sqf_diag;  // 1 if every matrix of the table is diagonal (fast path)
+};
+
+struct Params {
+    Layout L;
+    Topo t;
+    Tabs m;
+};
+
+// ---- warp helpers -------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// out[k] += scale * sum_l MT[l*rows + k] * v[l]   (k = lane, lane+32, ...; v and out are warp-private shared rows).
+// MT is the TRANSPOSE of the rows x cols matrix being applied, so lanes read consecutive addresses for every l.
+__device__ __forceinline__ void mv_acc(const double *__restrict__ MT, const double *v, int rows, int cols,
+                                       double *out, double scale, int lane) {
+    for (int k = lane; k < rows; k += 32) {
+        double acc = 0.0;
+        for (int l = 0; l < cols; ++l) acc = fma(__ldg(MT + (long long)l * rows + k), v[l], acc);
+        out[k] += scale * acc;
+    }
+}
+// out[k] = sum_l MT[l*rows+k] v[l]
+__device__ __forceinline__ void mv_set(const double *__restrict__ MT, const double *v, int rows, int cols,
+                                       double *out, int lane) {
+    for (int k = lane; k < rows; k += 32) {
+        double acc = 0.0;
+        for (int l = 0; l < cols; ++l) acc = fma(__ldg(MT + (long long)l * rows + k), v[l], acc);
+        out[k] = acc;
+    }
+}
+
+// ---- projections (device forms of reference cones.py / rectangle.py) -----------------------------------------------
+// Rectangle._constrain, rectangle.py:50-59.  NaN cannot be constrained: *bad is set and NaN is returned.
+__device__ __forceinline__ double box_clip(double v, double lo, double hi, int *bad) {
+    if (lo <= v && v <= hi) return v;
+    if (v <= lo) return lo;
+    if (v >= hi) return hi;
+    *bad = 1;
+    return v;
+}
+
+// SecondOrderCone.project, cones.py:113-132, on a warp-private shared row w[0..dim-1] whose LAST entry is t.
+// Returns the scaling pair (cz, ct): projection = (cz * w[0..dim-2], ct_is_value ? ct : w[dim-1]) encoded as
+//   mode 0: projection = w (inside the cone);  mode 1: projection = 0 (inside the polar);  mode 2: boundary, with
+//   t_new = (r+t)/2 and first part t_new * (w / r).
+struct SocResult {
+    int mode;
+    double r, t_new;
+};
+__device__ __forceinline__ SocResult soc_classify(const double *w, int dim, int lane) {
+    double ss = 0.0;
+    for (int k = lane; k < dim - 1; k += 32) ss = fma(w[k], w[k], ss);
+    ss = warp_sum(ss);
+    SocResult res;
+    res.r = sqrt(ss);
+    const double t = w[dim - 1];
+    if (res.r <= t) res.mode = 0;
+    else if (res.r <= -t) res.mode = 1;
+    else res.mode = 2;
+    res.t_new = (res.r + t) / 2;
+    return res;
+}
+__device__ __forceinline__ double soc_entry(const SocResult &s, double wk, bool is_last) {
+    if (s.mode == 0) return wk;
+    if (s.mode == 1) return 0.0;
+    return is_last ? s.t_new : s.t_new * (wk / s.r);
+}
+
+// non-negative doubles order like their bit patterns, so an unsigned 64-bit atomicMax is an atomic max; NaN (larger
+// than +inf as a bit pattern) sticks, which is how a non-finite residual reaches the host.
+__device__ __forceinline__ void atomic_max_nonneg(double *addr, double v) {
+    atomicMax(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+__device__ __forceinline__ double absmax_nan(double running, double v) {
+    // fmax drops NaN; keep it instead so that a NaN iterate is reported
+    const double a = fabs(v);
+    return (a != a || running != running) ? __longlong_as_double(0x7ff8000000000000LL) : fmax(running, a);
+}
+
+}  // namespace rb

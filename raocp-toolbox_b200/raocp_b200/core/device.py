@@ -1,0 +1,211 @@
+"""DeviceSolver: thin object wrapper over the C-ABI handle (include/raocp_b200.h) -- no arithmetic here."""
+import ctypes as C
+
+import numpy as np
+
+from .. import _lib
+from .flatten import FlatProblem
+
+
+class DeviceSolver:
+    def __init__(self, flat: FlatProblem):
+        self.flat = flat
+        self._lib = _lib.load()
+        self._keep = []  # host arrays referenced by the rb_problem struct during rb_create
+
+        def ip(arr):
+            arr = np.ascontiguousarray(arr, dtype=np.int32)
+            self._keep.append(arr)
+            return _lib.iptr(arr)
+
+        def dp(arr):
+            arr = np.ascontiguousarray(arr, dtype=np.float64)
+            self._keep.append(arr)
+            return _lib.dptr(arr)
+
+        f = flat
+        pb = _lib.RbProblem()
+        pb.n, pb.m, pb.nx, pb.nu, pb.num_stages, pb.batch = f.n, f.m, f.nx, f.nu, f.num_stages, f.batch
+        pb.stage_off, pb.parent = ip(f.stage_off), ip(f.parent)
+        pb.child_first, pb.child_count = ip(f.child_first), ip(f.child_count)
+        pb.num_dyn, pb.dyn_idx, pb.A, pb.B = f.A.shape[0], ip(f.dyn_idx), dp(f.A), dp(f.B)
+        pb.num_cost, pb.cost_idx, pb.sqrtQ, pb.sqrtR = f.sqrtQ.shape[0], ip(f.cost_idx), dp(f.sqrtQ), dp(f.sqrtR)
+        pb.num_leafcost, pb.leafcost_idx, pb.sqrtQf = f.sqrtQf.shape[0], ip(f.leafcost_idx), dp(f.sqrtQf)
+        if f.nl_rect:
+            pb.num_nl_rect, pb.nl_rect_idx = f.nonleaf_lo.shape[0], ip(f.nonleaf_rect_idx)
+            pb.nl_lo, pb.nl_hi = dp(f.nonleaf_lo), dp(f.nonleaf_hi)
+        else:
+            pb.num_nl_rect = 0
+        if f.leaf_rect:
+            pb.num_leaf_rect, pb.leaf_rect_idx = f.leaf_lo.shape[0], ip(f.leaf_rect_idx)
+            pb.leaf_lo, pb.leaf_hi = dp(f.leaf_lo), dp(f.leaf_hi)
+        else:
+            pb.num_leaf_rect = 0
+        pb.risk_alpha, pb.cond_prob = dp(f.risk_alpha), dp(f.cond_prob)
+        pb.num_cls, pb.cls = f.num_cls, ip(f.cls)
+        pb.device = f.device
+        handle = C.c_void_p()
+        _lib.check(self._lib.rb_create(C.byref(pb), C.byref(handle)))
+        self._h = handle
+        self._keep = []
+        np_, nd_ = C.c_int64(), C.c_int64()
+        self._call("rb_sizes", C.byref(np_), C.byref(nd_))
+        assert (np_.value, nd_.value) == (f.np_, f.nd_), "host / device layout mismatch"
+        self.np_, self.nd_, self.batch = f.np_, f.nd_, f.batch
+
+    def _call(self, name, *args):
+        _lib.check(getattr(self._lib, name)(self._h, *args), self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.rb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing ------------------------------------------------------------------------------------------------
+    def set_stream(self, cuda_stream_ptr):
+        self._call("rb_set_stream", C.c_void_p(cuda_stream_ptr))
+
+    def synchronize(self):
+        self._call("rb_synchronize")
+
+    def launch_count(self):
+        k = C.c_int64()
+        self._call("rb_launch_count", C.byref(k))
+        return k.value
+
+    def offline(self):
+        self._call("rb_offline")
+
+    def get_offline(self):
+        f = self.flat
+        p = np.empty((f.num_cls, f.nx, f.nx))
+        k = np.empty((f.num_cls, f.nu, f.nx))
+        ri = np.empty((f.num_cls, f.nu, f.nu))
+        self._call("rb_get_offline", _lib.dptr(p), _lib.dptr(k), _lib.dptr(ri))
+        return p, k, ri
+
+    def _batched(self, compact, size):
+        arr = np.ascontiguousarray(np.asarray(compact, dtype=np.float64))
+        if arr.size == size and self.batch > 1:
+            arr = np.ascontiguousarray(np.broadcast_to(arr.reshape(1, size), (self.batch, size)))
+        if arr.size != size * self.batch:
+            raise Exception(f"expected {self.batch} x {size} doubles, got {arr.size}")
+        return arr
+
+    def set_primal(self, which, compact):
+        arr = self._batched(compact, self.np_)
+        self._call("rb_set_primal", which, _lib.dptr(arr))
+
+    def get_primal(self, which):
+        out = np.empty((self.batch, self.np_))
+        self._call("rb_get_primal", which, _lib.dptr(out))
+        return out
+
+    def set_dual(self, which, compact):
+        arr = self._batched(compact, self.nd_)
+        self._call("rb_set_dual", which, _lib.dptr(arr))
+
+    def get_dual(self, which):
+        out = np.empty((self.batch, self.nd_))
+        self._call("rb_get_dual", which, _lib.dptr(out))
+        return out
+
+    def set_initial_state(self, x0):
+        """x0: (nx,), (nx,1) or (nx, batch) like the columns of the reference's initial_state"""
+        f = self.flat
+        arr = np.asarray(x0, dtype=np.float64)
+        if arr.size == f.nx:
+            arr = np.broadcast_to(arr.reshape(1, f.nx), (self.batch, f.nx))
+        elif arr.shape == (f.nx, self.batch):
+            arr = arr.T
+        else:
+            raise Exception(f"initial state must have {f.nx} entries (or shape ({f.nx}, {self.batch}))")
+        arr = np.ascontiguousarray(arr)
+        self._call("rb_set_initial_state", _lib.dptr(arr))
+
+    def update_cache(self):
+        self._call("rb_update_cache")
+
+    def apply_L(self, primal_compact):
+        arr = self._batched(primal_compact, self.np_)
+        out = np.empty((self.batch, self.nd_))
+        self._call("rb_apply_L", _lib.dptr(arr), _lib.dptr(out))
+        return out
+
+    def apply_Lt(self, dual_compact):
+        arr = self._batched(dual_compact, self.nd_)
+        out = np.empty((self.batch, self.np_))
+        self._call("rb_apply_Lt", _lib.dptr(arr), _lib.dptr(out))
+        return out
+
+    def lambda_max(self):
+        v = C.c_double()
+        self._call("rb_lambda_max", C.byref(v))
+        return v.value
+
+    # ---- steps ---------------------------------------------------------------------------------------------------
+    def primal_half(self, alpha):
+        self._call("rb_primal_half", float(alpha))
+
+    def prox_f(self, alpha):
+        self._call("rb_prox_f", float(alpha))
+
+    def s0_shift(self, alpha):
+        self._call("rb_s0_shift", float(alpha))
+
+    def project_dynamics(self):
+        self._call("rb_project_dynamics")
+
+    def project_kernel(self):
+        self._call("rb_project_kernel")
+
+    def dual_half(self, alpha):
+        self._call("rb_dual_half", float(alpha))
+
+    def prox_g_conj(self, alpha):
+        self._call("rb_prox_g_conj", float(alpha))
+
+    def modify_dual(self, alpha):
+        self._call("rb_modify_dual", float(alpha))
+
+    def add_halves(self):
+        self._call("rb_add_halves")
+
+    def project_nonleaf(self):
+        self._call("rb_project_nonleaf")
+
+    def project_leaf(self):
+        self._call("rb_project_leaf")
+
+    def modify_projection(self, alpha, modified_dual_compact):
+        arr = self._batched(modified_dual_compact, self.nd_)
+        self._call("rb_modify_projection", float(alpha), _lib.dptr(arr))
+
+    def residuals(self, alpha, vectors=False):
+        norms = np.empty((self.batch, 6))
+        vec = np.empty((self.batch, 4 * self.np_ + 2 * self.nd_)) if vectors else None
+        self._call("rb_residuals", float(alpha), _lib.dptr(norms), _lib.dptr(vec) if vectors else None)
+        return norms, vec
+
+    def iterate(self, alpha, max_iters, tol, history=True):
+        cap = max_iters + 1
+        xi = np.zeros((cap, self.batch, 3)) if history else None
+        delta = np.zeros((cap, self.batch, 3)) if history else None
+        iters, status = C.c_int32(), C.c_int32()
+        self._call("rb_iterate", float(alpha), int(max_iters), float(tol), 1,
+                   _lib.dptr(xi) if history else None, _lib.dptr(delta) if history else None, cap,
+                   C.byref(iters), C.byref(status))
+        if history:
+            xi, delta = xi[: iters.value], delta[: iters.value]
+        return status.value, iters.value, xi, delta
+
+    def iterate_fixed(self, alpha, iters):
+        norms = np.empty((self.batch, 6))
+        self._call("rb_iterate_fixed", float(alpha), int(iters), _lib.dptr(norms))
+        return norms
