@@ -1,0 +1,182 @@
+"""Host-side logic (CPU only): tree factory known answers, builder API, AVaR / Rectangle data, flattening and the
+block-list <-> compact layout maps, and that the C-ABI library loads and exports every declared symbol."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import raocp_b200 as r
+from raocp_b200 import _lib
+from raocp_b200.core.flatten import FlatProblem
+from oracle import problems, ref_loader
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---- scenario tree: known answers of reference tests/test_scenario_tree.py:26-131 -------------------------------------
+def _kat_tree():
+    p = np.array([[0.1, 0.8, 0.1], [0.4, 0.6, 0], [0, 0.3, 0.7]])
+    v = np.array([0.5, 0.5, 0])
+    return r.core.MarkovChainScenarioTreeFactory(p, v, 4, 3).create()
+
+
+def test_tree_known_answers():
+    tree = _kat_tree()
+    assert tree.num_nodes == 32 and tree.num_nonleaf_nodes == 20 and tree.num_stages == 5
+    assert tree.ancestor_of(0) == -1 and tree.ancestor_of(1) == 0 and tree.ancestor_of(2) == 0
+    assert list(tree.children_of(0)) == [1, 2]
+    assert list(tree.children_of(1)) == [3, 4, 5] and list(tree.children_of(2)) == [6, 7]
+    assert tree.value_at_node(3) == 0 and tree.value_at_node(5) == 2 and tree.value_at_node(7) == 1
+    for t in range(tree.num_stages):
+        nodes = tree.nodes_at_stage(t)
+        assert np.array_equal(nodes, np.arange(nodes[0], nodes[0] + nodes.size))      # contiguous stage ranges
+    assert [tree.nodes_at_stage(t).size for t in range(5)] == [1, 2, 5, 12, 12]
+    assert np.isclose(tree.probability_of_node(1), 0.5) and np.isclose(tree.probability_of_node(3), 0.05)
+    for t in range(5):
+        assert np.isclose(sum(tree.probability_of_node(i) for i in tree.nodes_at_stage(t)), 1.0)
+    assert np.allclose(tree.conditional_probabilities_of_children(1), [0.1, 0.8, 0.1])
+    # after the stopping time every node has exactly one child with the same mode and probability
+    for i in tree.nodes_at_stage(3):
+        (j,) = tree.children_of(i)
+        assert tree.value_at_node(j) == tree.value_at_node(i)
+        assert tree.probability_of_node(j) == tree.probability_of_node(i)
+    with pytest.raises(ValueError):
+        tree.stage_of(-1)
+
+
+def test_tree_input_validation():
+    p = np.array([[0.5, 0.5], [0.3, 0.7]])
+    with pytest.raises(ValueError):
+        r.core.MarkovChainScenarioTreeFactory(p, np.array([0.6, 0.6]), 3, 2)
+    with pytest.raises(ValueError):
+        r.core.MarkovChainScenarioTreeFactory(p, np.array([0.5, 0.5]), 3, 4)
+    with pytest.raises(ValueError):
+        r.core.MarkovChainScenarioTreeFactory(np.array([[0.5, 0.6], [0.3, 0.7]]), np.array([0.5, 0.5]), 3, 2)
+
+
+@pytest.mark.reference
+@pytest.mark.skipif(not ref_loader.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("shape", [(3, 4, 3), (3, 5, 5), (2, 4, 1), (4, 6, 2)])
+def test_tree_equals_reference_factory(shape):
+    api = ref_loader.RefApi()
+    modes, horizon, tau = shape
+    rng = np.random.default_rng(modes * 100 + horizon)
+    p = rng.uniform(0.0, 1.0, (modes, modes))
+    p[rng.uniform(size=p.shape) < 0.25] = 0.0
+    p[np.arange(modes), np.arange(modes)] += 0.1
+    p /= p.sum(axis=1, keepdims=True)
+    v = rng.uniform(0.1, 1.0, modes)
+    v[0] = 0.0
+    v /= v.sum()
+    mine = r.core.MarkovChainScenarioTreeFactory(p, v, horizon, tau).create()
+    ref = api.MarkovChainScenarioTreeFactory(p, v, horizon, tau).create()
+    assert mine.num_nodes == ref.num_nodes and mine.num_nonleaf_nodes == ref.num_nonleaf_nodes
+    for i in range(ref.num_nodes):
+        assert mine.ancestor_of(i) == ref.ancestor_of(i) and mine.stage_of(i) == ref.stage_of(i)
+        assert mine.value_at_node(i) == ref.value_at_node(i)
+        assert np.isclose(mine.probability_of_node(i), ref.probability_of_node(i), rtol=1e-14)
+    for i in range(ref.num_nonleaf_nodes):
+        assert np.array_equal(mine.children_of(i), ref.children_of(i))
+
+
+# ---- builder, risks, rectangles, costs -----------------------------------------------------------------------------------
+def test_builder_and_component_shapes():
+    s = problems.spec("mini2")
+    problem = problems.build(s, r.core)
+    tree = problem.tree
+    assert problem.list_of_dynamics[0] is None and problem.list_of_nonleaf_costs[0] is None
+    for j in range(1, tree.num_nodes):
+        w = tree.value_at_node(j)
+        assert problem.state_dynamics_at_node(j) is s["a"][w] and problem.control_dynamics_at_node(j) is s["b"][w]
+        assert np.allclose(problem.nonleaf_cost_at_node(j).sqrt_state_weights @
+                           problem.nonleaf_cost_at_node(j).sqrt_state_weights, s["q"][w])
+    risk = problem.risk_at_node(0)
+    c = len(tree.children_of(0))
+    assert risk.matrix_e.shape == (2 * c + 1, c) and risk.matrix_f.shape == (2 * c + 1, 0)
+    assert risk.vector_b.shape == (2 * c + 1, 1) and risk.cone.dimension == 2 * c + 1
+    assert np.allclose(risk.vector_b[:c, 0], tree.conditional_probabilities_of_children(0))
+    assert risk.vector_b[-1, 0] == 1 and np.all(risk.vector_b[c:2 * c] == 0)
+    rect = problem.nonleaf_constraint_at_node(0)
+    nx, nu = s["nx"], s["nu"]
+    assert rect.is_active and rect.state_matrix.shape == (nx + nu, nx) and rect.control_matrix.shape == (nx + nu, nu)
+    assert np.array_equal(rect.state_matrix[:nx], np.eye(nx)) and np.array_equal(rect.control_matrix[nx:], np.eye(nu))
+    leaf_rect = problem.leaf_constraint_at_node(tree.num_nodes - 1)
+    assert leaf_rect.state_matrix.shape == (nx, nx)
+    with pytest.raises(ValueError):
+        r.core.AVaR(1.5)
+    with pytest.raises(Exception):
+        r.core.RAOCP(tree).with_all_nonleaf_constraints(r.core.Rectangle(r.core.Nonleaf(), -np.ones((3, 1)), np.ones((3, 1))))
+    with pytest.raises(Exception):
+        r.core.Quadratic(r.core.Leaf(), np.eye(2), np.eye(2))
+    with pytest.raises(Exception):
+        r.core.Rectangle(r.core.Leaf(), np.ones((2, 1)), -np.ones((2, 1)))
+
+
+# ---- flattening ------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,np_,nd_", [("cfg1", 214, 381), ("cfg2", 30120, 58040)])
+def test_flatten_sizes_match_survey(name, np_, nd_):
+    flat = FlatProblem(problems.build(problems.spec(name), r.core))
+    assert (flat.np_, flat.nd_) == (np_, nd_)
+    assert flat.stage_off[0] == 0 and flat.stage_off[-1] == flat.n and flat.stage_off[-2] == flat.m
+    assert np.array_equal(flat.child_first[1:], flat.child_first[:-1] + flat.child_count[:-1])
+    # children's classes are larger than their parents' (offline processes the largest ids first)
+    for i in range(flat.m):
+        for j in range(flat.child_first[i], flat.child_first[i] + flat.child_count[i]):
+            if j < flat.m:
+                assert flat.cls[j] > flat.cls[i]
+
+
+def test_block_list_round_trip():
+    flat = FlatProblem(problems.build(problems.spec("mini2"), r.core))
+    rng = np.random.default_rng(0)
+    p, d = rng.standard_normal(flat.np_), rng.standard_normal(flat.nd_)
+    pb, db = flat.primal_to_blocks(p), flat.dual_to_blocks(d)
+    n, m = flat.n, flat.m
+    assert len(pb) == 3 * n + 2 * m and len(db) == 11 * n                    # cache.py:127-132,142-156
+    assert all(b.shape[1] == 1 for b in pb + db)
+    assert db[2 * n].shape == (1, 1) and db[2 * n][0, 0] == 0.0               # segment 3 of the root is a placeholder
+    assert db[2 * n + 1].shape == (flat.nx, 1)
+    assert np.array_equal(flat.primal_from_blocks(pb), p) and np.array_equal(flat.dual_from_blocks(db), d)
+
+
+def test_dedup_classes_count():
+    flat = FlatProblem(problems.build(problems.spec("cfg2"), r.core))
+    assert flat.num_cls <= 3 * 10          # at most (modes x stages) classes on a Markov tree
+    nodedup = FlatProblem(problems.build(problems.spec("cfg1"), r.core), dedup=False)
+    assert nodedup.num_cls == nodedup.m and np.array_equal(nodedup.cls, np.arange(nodedup.m))
+
+
+def test_unsupported_inputs_fail_loudly():
+    s = problems.spec("cfg1")
+    problem = problems.build(s, r.core)
+    problem.list_of_risks[0] = object()
+    with pytest.raises(Exception, match="Risk at node 0 not defined"):
+        FlatProblem(problem)
+    problem = problems.build(s, r.core)
+    problem.list_of_nonleaf_constraints[0] = r.core.No()
+    with pytest.raises(Exception, match="mixed"):
+        FlatProblem(problem)
+
+
+# ---- the C-ABI library -----------------------------------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "raocp_b200.h")).read()
+    declared = set(re.findall(r"\b(rb_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 30
+    lib = _lib.load()
+    bound = {name for name, _, _ in _lib.SYMBOLS}
+    assert declared == bound, declared ^ bound
+    for name in declared:
+        assert isinstance(getattr(lib, name), ctypes._CFuncPtr)
+
+
+def test_compute_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(Exception, match="no CUDA device"):
+        r.core.Cache(problems.build(problems.spec("cfg1"), r.core))
+    with pytest.raises(Exception):
+        r.core.SecondOrderCone().project(np.ones((3, 1)))
