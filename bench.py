@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- Chambolle-Pock iterations/sec of the raocp_b200 CUDA path (and of the CPU restatement of the reference).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg3] [--batch B]
+
+One "step" = one full CP iteration (primal half step, prox_f, dual half step, prox_g*, all six residual norms and the
+stopping test, reference solver.py:124-161) over the synthetic, seeded problem of oracle/problems.py.
+Default workload: BASELINE.json configs[2] ("cfg3": 62 805-node tree, nx=20, nu=10), the tree the north-star target is
+quoted on; it fits one GPU.  Rank 0 prints ONE JSON line.
+
+Timing (device, CUDA events on the launching stream, max over ranks):
+  value    cold iterations/s: every timed iteration runs after an L2 flush (a 256 MiB buffer is overwritten), each
+           iteration bracketed by its own event pair -> this is the number the HBM roofline fraction is quoted on
+  warm     the same K iterations back to back with no flush (what a real solve sees: the 50 MB of iterates of cfg3
+           stay L2-resident on a B200), reported beside it
+  e2e      through the host API with HOST buffers: every step copies x0 from pinned host memory to the device, runs
+           one iteration and reads the six residual norms back (synchronised)
+With N > 1 (torchrun) every rank solves its own instance(s) of the workload ("independent problem instances",
+BASELINE.json north_star) -- no data-path collective, scaling "weak".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (os.path.join(ROOT, "raocp-toolbox_b200"), ROOT):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "CP iterations/sec"
+# bounded CPU samples: same modes / nx / nu as the workload on a shorter tree, so the node-by-node CPU port (55 s per
+# iteration on the full cfg3 tree) finishes in seconds; scaled to the full tree by node count (cost is linear in nodes)
+CPU_SAMPLE = {"cfg1": None, "cfg2": (3, 7, 4), "cfg3": (4, 8, 4), "cfg4": None, "cfg5": (3, 6, 4)}  # (modes, N, tau)
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        return json.load(open(path))["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(flat, batch, dedup):
+    """every iterate entry read once and written once, plus the node-specific DP operators (K twice,
+    R~ factor once) when they are streamed per node; with (mode, stage) de-duplicated operators that term is dropped"""
+    state = 8 * batch * 2 * (flat.np_ + flat.nd_)
+    ops = 0 if dedup else 8 * flat.m * (2 * flat.nu * flat.nx + flat.nu * flat.nu)
+    return state + ops
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, reasons = [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                sm.append(float(f[1]))
+                out["sm_max_mhz"] = float(f[2])
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = float(np.median(sm))
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def cpu_baseline(workload, budget_iters=4):
+    """Times the node-by-node CPU port of the reference (oracle/cp_node_oracle.py, kind "port") on a bounded sample."""
+    from oracle import problems
+    from oracle.cp_node_oracle import NodeOracle
+    import raocp_b200 as r
+    full = problems.spec(workload)
+    sample_shape = CPU_SAMPLE.get(workload)
+    s = dict(full)
+    if sample_shape is not None:
+        modes, horizon, tau = sample_shape
+        s["horizon"], s["tau"] = horizon, tau
+    problem = problems.build(s, r.core)
+    n_sample = problem.tree.num_nodes
+    n_full = problems.build(full, r.core).tree.num_nodes if sample_shape is not None else n_sample
+    t0 = time.perf_counter()
+    orc = NodeOracle(problem)
+    t_setup = time.perf_counter() - t0
+    orc.cache_initial_state(full["x0"][:, :1])
+    from oracle.cp_flat_oracle import FlatOracle
+    orc.alpha = FlatOracle(problem).step_size()
+    orc.iterate()  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(budget_iters):
+        orc.iterate()
+    dt = (time.perf_counter() - t0) / budget_iters
+    its_sample = 1.0 / dt
+    value = its_sample * n_sample / n_full
+    return {"value": value, "unit": "it/s", "cores": 1, "kind": "port",
+            "sample": f"{budget_iters} iterations of oracle/cp_node_oracle.py (NumPy, node-by-node like the reference) on "
+                      f"a {n_sample}-node tree with the workload's modes/nx/nu: {its_sample:.3f} it/s, scaled by "
+                      f"{n_sample}/{n_full} nodes to the full tree; setup (offline + null spaces) {t_setup:.1f} s; "
+                      f"host cores available: {os.cpu_count()}"}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    base = cpu_baseline(args.workload, budget_iters=max(1, min(args.steps, 6)))
+    line = {"metric": METRIC, "value": base["value"], "unit": "it/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload, "batch": 1, "note": "CPU port of the reference, bounded sample"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import raocp_b200 as r
+    from oracle import problems
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (raocp_b200 has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    K, W, batch = args.steps, max(3, args.warmup), args.batch
+    spec = problems.spec(args.workload, seed=0, batch=batch * world)
+    t0 = time.perf_counter()
+    problem = problems.build(spec, r.core)
+    t_build = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    solver = r.core.Solver(problem, batch=batch, dedup=not args.no_dedup, device=local_rank, verbose=False)
+    dev = solver.cache.device_solver
+    dev.synchronize()
+    t_setup = time.perf_counter() - t0
+    flat = solver.cache.flat_problem
+    alpha = solver.compute_step_size()
+    stream = torch.cuda.Stream()
+    dev.set_stream(stream.cuda_stream)
+    x0_host = torch.from_numpy(np.ascontiguousarray(spec["x0"][:, rank * batch:(rank + 1) * batch].T)).pin_memory()
+    norms_host = torch.zeros(batch, 6, dtype=torch.float64).pin_memory()
+    dev.set_initial_state(x0_host.numpy().T if batch > 1 else x0_host.numpy().reshape(-1))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        # ---- warm-up ---------------------------------------------------------------------------------------------
+        dev.loop_begin(alpha, 1 << 30, -1.0, 0)
+        dev.loop_enqueue(W)
+        phases = np.array([dev.profile_iteration() for _ in range(3)]).mean(axis=0)
+        barrier()
+        launches0 = dev.launch_count()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        # ---- cold: L2 flushed before every timed iteration --------------------------------------------------------
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        barrier()
+        for k in range(K):
+            flush.zero_()
+            starts[k].record(stream)
+            dev.loop_enqueue(1)
+            ends[k].record(stream)
+        barrier()
+        cold_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, ends)])
+        # ---- warm: back to back ------------------------------------------------------------------------------------
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        dev.loop_enqueue(K)
+        ev1.record(stream)
+        barrier()
+        warm_ms = ev0.elapsed_time(ev1)
+        launches = dev.launch_count() - launches0
+        clocks = sampler.stop()
+        # ---- end to end through the host API: pinned x0 -> device, one iteration, norms -> host, per step ----------------
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            dev.step(x0_host.data_ptr(), norms_host.data_ptr())
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        iters_done, _, last_norms = dev.loop_poll()
+        dev.loop_end()
+        # whole-solve call for context: Solver.chock(x0_host, K iterations) incl. x0 upload + residual history download
+        t0 = time.perf_counter()
+        solver.chock(spec["x0"][:, rank * batch:(rank + 1) * batch] if batch > 1 else spec["x0"][:, :1],
+                     max_iters=K - 1, tol=0.0, alpha=alpha)
+        solve_s = time.perf_counter() - t0
+
+    cold_total, e2e_t = float(cold_ms.sum()), e2e_s
+    if dist is not None:
+        t = torch.tensor([cold_total, warm_ms, e2e_t, solve_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cold_total, warm_ms, e2e_t, solve_s = t.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    units = batch * world  # problem instances advanced by one iteration per step
+    value = units * K / (cold_total * 1e-3)
+    peak, peak_src = peaks()
+    b_alg = algorithmic_bytes(flat, batch, not args.no_dedup)
+    ms_iter = cold_total / K
+    achieved = b_alg / (ms_iter * 1e-3) / 1e9
+    b_dual = 8 * batch * (2 * flat.np_ + 2 * flat.nd_)
+    line = {
+        "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_iter, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {flat.n}-node scenario tree ({flat.m} nonleaf), nx={flat.nx}, "
+                               f"nu={flat.nu}, AVaR(0.5), rectangles, seed 0", "instances_per_gpu": batch,
+                   "parallelism": "single GPU" if world == 1 else f"{world} x independent instances (no collective)",
+                   "l2": "flushed (256 MiB overwrite) before every timed iteration", "dedup_operators": not args.no_dedup,
+                   "residuals": "all six norms + stopping test every iteration", "alpha": alpha},
+        "warm": {"value": units * K / (warm_ms * 1e-3), "unit": "it/s", "ms_per_step": warm_ms / K,
+                 "note": "same K iterations back to back, no L2 flush (iterates L2-resident when they fit)"},
+        "e2e": {"value": units * K / e2e_t, "unit": "it/s", "h2d_bytes_per_step": int(x0_host.numel() * 8),
+                "d2h_bytes_per_step": int(norms_host.numel() * 8),
+                "note": "rb_step per iteration: x0 from pinned host memory, one iteration, residual norms to the host, "
+                        "synchronised every step",
+                "solve_call_it_s": units * K / solve_s},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "one CP iteration (all launches)",
+                     "algorithmic_bytes": b_alg,
+                     "dominant_kernel": {"name": "k_fused_dual", "algorithmic_bytes": b_dual, "ms": float(phases[3]),
+                                         "achieved": b_dual / (phases[3] * 1e-3) / 1e9,
+                                         "frac": b_dual / (phases[3] * 1e-3) / 1e9 / peak, "note": "warm L2"},
+                     "phases_ms": {"primal": float(phases[0]), "backward_sweep": float(phases[1]),
+                                   "forward_sweep": float(phases[2]), "dual_and_check": float(phases[3])}},
+        "clocks": clocks,
+        "setup": {"problem_build_s": t_build, "flatten_upload_offline_s": t_setup, "factorisation_classes": flat.num_cls},
+        "residuals_last": [float(v) for v in last_norms[0]],
+    }
+    if not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args.workload)
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg1", "cfg2", "cfg3", "cfg4", "cfg5"])
+    ap.add_argument("--batch", type=int, default=1, help="problem instances per GPU")
+    ap.add_argument("--no-dedup", action="store_true", help="stream per-node K / R~ (one factorisation class per node)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch multi-GPU runs with torchrun (python -m torch.distributed.run --nproc-per-node N ...)")
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -141,9 +141,28 @@ int rb_residuals(rb_solver *s, double alpha, double *norms, double *vectors);
  * (0 converged, 1 not) and the number of iterations executed in *iters. */
 int rb_iterate(rb_solver *s, double alpha, int32_t max_iters, double tol, int32_t check_every,
                double *xi_hist, double *delta_hist, int32_t hist_capacity, int32_t *iters, int32_t *status);
-/* benchmark hook: exactly `iters` fused iterations, no host synchronisation inside, residual norms of the last
- * iteration in norms[batch][6]. */
+/* exactly `iters` fused iterations, no host synchronisation inside, residual norms of the last iteration in
+ * norms[batch][6] (may be NULL). */
 int rb_iterate_fixed(rb_solver *s, double alpha, int32_t iters, double *norms);
+/* The same loop in pieces, for hosts that pipeline (rb_iterate is built from these):
+ *   rb_loop_begin   arms the device-side stopping test (max_iters, tol as in chock; tol < 0 never stops early) and the
+ *                   residual history (hist_capacity rows, 0 = none); iteration 0 starts from the OLD iterate like
+ *                   Solver.chock (solver.py:29-37).
+ *   rb_loop_enqueue enqueues `count` iterations (one CUDA-graph launch each) without synchronising; iterations after
+ *                   the stopping test fired are no-ops.
+ *   rb_loop_poll    synchronises and reports iterations executed, the stop flag and the last residual norms [batch][6].
+ *   rb_step         one end-to-end step for a host caller: x0 (host, may be NULL = unchanged) -> device, one
+ *                   iteration, the six residual norms -> host, synchronised.
+ *   rb_loop_end     closes the loop: current == old == newest iterate (no copy), history to the host. */
+int rb_loop_begin(rb_solver *s, double alpha, int32_t max_iters, double tol, int32_t hist_capacity);
+int rb_loop_enqueue(rb_solver *s, int32_t count);
+int rb_loop_poll(rb_solver *s, int32_t *iters, int32_t *done, double *last_norms);
+int rb_step(rb_solver *s, const double *x0, double *norms);
+int rb_loop_end(rb_solver *s, double *xi_hist, double *delta_hist, int32_t *iters, int32_t *status);
+/* measurement hook: one iteration with CUDA events between its phases, ms[4] = primal pass, backward sweep, forward
+ * sweep, dual pass (+ stopping test); advances the loop by one iteration. */
+int rb_profile_iteration(rb_solver *s, float *ms);
+int rb_use_graphs(rb_solver *s, int32_t enable); /* 1 (default): one CUDA graph per iteration; 0: plain launches */
 int rb_launch_count(const rb_solver *s, int64_t *kernels_launched); /* kernels launched by this handle so far */
 
 /* -- stand-alone projections (cones.py:30-132, rectangle.py:29-59): host vector in, host vector out ----------------

@@ -17,16 +17,6 @@ namespace {
 
 thread_local std::string g_create_error;
 
-struct DevBuf {
-    void *p = nullptr;
-    size_t bytes = 0;
-};
-
-// control block in device memory: kernels.cuh Ctrl + the parameters of the stopping test
-struct HostCtrl {
-    Ctrl c;
-};
-
 }  // namespace
 
 struct rb_solver {
@@ -45,9 +35,17 @@ struct rb_solver {
         int64_t compact, padded, len;
     };
     std::vector<Seg> pseg, dseg;
-    // iterates: index 0 = current, 1 = old (API semantics)
+    // iterates: two device copies.  cur_i / old_i say which copy plays "current" (Cache.__primal/__dual) and which
+    // "old" (Cache.__old_primal/__old_dual).  After update_cache() or a fused loop both views show the same
+    // iterate: instead of copying, `collapsed` marks that only buffer old_i is meaningful; the copy is made lazily by
+    // materialise() when a step-by-step method needs two distinct buffers.
     double *prim[2] = {nullptr, nullptr};
     double *dual[2] = {nullptr, nullptr};
+    int cur_i = 0, old_i = 1;
+    bool collapsed = true;
+    bool in_loop = false;
+    int loop_old0 = 1;  // which buffer was "old" when the fused loop began
+    double *h_pinned = nullptr;  // pinned staging for control block / residual read-back
     double *q = nullptr, *r = nullptr, *x0 = nullptr;
     Ctrl *ctrl = nullptr;
     double *slots = nullptr, *last = nullptr, *hist = nullptr;
@@ -62,9 +60,16 @@ struct rb_solver {
     double *tp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *td[4] = {nullptr, nullptr, nullptr, nullptr};
     double *staging_p = nullptr, *staging_d = nullptr;  // device staging for host-vector operator calls
+    // node tiles of the fused passes (fused.cu)
+    TilePlan tiles{};
+    size_t primal_smem = 0, dual_smem = 0;
+    // DP sweeps in three launches (sweeps.cu)
+    SweepPlan plan{};
+    int sub_warps = 1, top_warps = 16;
+    size_t sub_smem = 0, top_smem = 0;
     // fused loop
-    cudaGraphExec_t graph[2] = {nullptr, nullptr};
-    double graph_alpha = 0.0;
+    cudaGraphExec_t graph[2] = {nullptr, nullptr};  // graph[src]: one iteration reading buffer src, writing 1-src
+    bool use_graphs = true;
     int64_t launches = 0;
     int kernels_per_iter = 0;
 };
@@ -167,6 +172,38 @@ int launch_ok(rb_solver *s, const char *what) {
         int rc_ = launch_ok((s), (what));          \
         if (rc_ != RB_OK) return rc_;              \
     } while (0)
+
+// make "current" a distinct copy of "old" (see rb_solver::collapsed)
+int materialise(rb_solver *s) {
+    if (!s->collapsed) return RB_OK;
+    const Layout &L = s->P.L;
+    RB_CUDA(s, cudaMemcpyAsync(s->prim[s->cur_i], s->prim[s->old_i], (size_t)L.batch * L.np_pad * sizeof(double),
+                               cudaMemcpyDeviceToDevice, s->stream));
+    RB_CUDA(s, cudaMemcpyAsync(s->dual[s->cur_i], s->dual[s->old_i], (size_t)L.batch * L.nd_pad * sizeof(double),
+                               cudaMemcpyDeviceToDevice, s->stream));
+    s->collapsed = false;
+    return RB_OK;
+}
+inline double *view_p(rb_solver *s, int which) { return s->prim[(which == 0 && !s->collapsed) ? s->cur_i : s->old_i]; }
+inline double *view_d(rb_solver *s, int which) { return s->dual[(which == 0 && !s->collapsed) ? s->cur_i : s->old_i]; }
+#define RB_MATERIALISE(s)               \
+    do {                                \
+        int rc_ = materialise(s);       \
+        if (rc_ != RB_OK) return rc_;   \
+    } while (0)
+
+// the three launches of the DP sweeps on `prim` (x, u rows hold xbar, ubar on entry and the projection on exit)
+int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st, cudaEvent_t mid = nullptr) {
+    const SweepPlan &pl = s->plan;
+    const unsigned batch = (unsigned)s->P.L.batch;
+    if (pl.num_sub > 0)
+        k_sweep_sub_bwd<<<dim3(pl.num_sub, batch), 32 * s->sub_warps, s->sub_smem, st>>>(s->P, ctrl, pl, prim, s->q, s->r);
+    k_sweep_top<<<batch, 32 * s->top_warps, s->top_smem, st>>>(s->P, ctrl, pl, prim, s->q, s->r, s->x0);
+    if (mid) cudaEventRecord(mid, st);
+    if (pl.num_sub > 0)
+        k_sweep_sub_fwd<<<dim3(pl.num_sub, batch), 32 * s->sub_warps, s->sub_smem, st>>>(s->P, ctrl, pl, prim, s->r);
+    return launch_ok(s, "DP sweeps");
+}
 
 int need_offline(rb_solver *s) {
     if (!s->have_offline) return fail(s, RB_ERR_STATE, "rb_offline() has not been run");
@@ -391,7 +428,91 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
     TRY(dev_zero(s, B * 6, &s->slots));
     TRY(dev_zero(s, B * 6, &s->last));
     TRY(dev_zero(s, 1, &s->status));
-    s->kernels_per_iter = 1 + 2 * (L.num_stages - 1) + 1 + 1 + 1;
+    // ---- sweep plan: cut at the first stage with >= 64 nodes; one CTA per subtree below it
+    {
+        SweepPlan &pl = s->plan;
+        int t_s = L.num_stages;
+        for (int t = 0; t < L.num_stages; ++t)
+            if (s->stage_off[t + 1] - s->stage_off[t] >= 64) {
+                t_s = t;
+                break;
+            }
+        pl.t_s = t_s;
+        pl.depth = L.num_stages - t_s;
+        pl.num_sub = t_s < L.num_stages ? s->stage_off[t_s + 1] - s->stage_off[t_s] : 0;
+        std::vector<int> lo((size_t)pl.num_sub * std::max(pl.depth, 1)), hi(lo.size());
+        int max_width = 1;
+        for (int c = 0; c < pl.num_sub; ++c) {
+            int a = s->stage_off[t_s] + c, b = a + 1;
+            for (int d = 0; d < pl.depth; ++d) {
+                lo[(size_t)c * pl.depth + d] = a;
+                hi[(size_t)c * pl.depth + d] = b;
+                max_width = std::max(max_width, b - a);
+                if (d + 1 < pl.depth) {   // children of [a, b) are one contiguous range of the next stage
+                    const int na = s->child_first[a], nb = s->child_first[b - 1] + s->child_count[b - 1];
+                    a = na;
+                    b = nb;
+                }
+            }
+        }
+        int *d_lo = nullptr, *d_hi = nullptr, *d_so = nullptr;
+        TRY(upload(s, lo.data(), lo.size(), &d_lo));
+        TRY(upload(s, hi.data(), hi.size(), &d_hi));
+        TRY(upload(s, s->stage_off.data(), s->stage_off.size(), &d_so));
+        pl.sub_lo = d_lo; pl.sub_hi = d_hi; pl.stage_off = d_so;
+        pl.num_dyn = pb->num_dyn;
+        const size_t tab_bytes = sizeof(double) * 2 * ((size_t)pb->num_dyn * nx * nx + (size_t)pb->num_dyn * nx * nu);
+        pl.tabs_in_smem = tab_bytes <= 96 * 1024;
+        s->sub_warps = std::min(8, std::max(1, max_width));
+        const int top_nodes_max = t_s > 0 ? s->stage_off[t_s] - s->stage_off[t_s - 1] : 1;
+        s->top_warps = std::min(16, std::max(1, top_nodes_max));
+        const size_t extra = pl.tabs_in_smem ? tab_bytes : 0;
+        s->sub_smem = (size_t)s->sub_warps * 4 * kMaxDim * sizeof(double) + extra;
+        s->top_smem = (size_t)s->top_warps * 4 * kMaxDim * sizeof(double) + extra;
+        TRYC(cudaFuncSetAttribute(k_sweep_sub_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sub_smem));
+        TRYC(cudaFuncSetAttribute(k_sweep_sub_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sub_smem));
+        TRYC(cudaFuncSetAttribute(k_sweep_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->top_smem));
+    }
+    // ---- node tiles: runs of consecutive nodes (<= 32 nodes and <= 64 edges; leaves: <= 64 nodes) -----------------
+    {
+        std::vector<int2> tiles;
+        const int kTileNodes = 32, kTileEdges = 64, kTileLeaves = 64;
+        size_t need_p = 0, need_d = 0;
+        auto ev = [](long long c) { return (size_t)((c + 1) & ~1LL); };
+        int i = 0;
+        while (i < m) {
+            int j = i, edges = 0;
+            while (j < m && j - i < kTileNodes && (j == i || edges + s->child_count[j] <= kTileEdges)) edges += s->child_count[j++];
+            tiles.push_back(make_int2(i, j));
+            const long long nN = j - i, nE = edges, ny = 2 * nE + nN;
+            need_p = std::max(need_p, ev(nN * nx) + ev(nN * nu) + 2 * ev(ny) + 2 * ev(nE) + ev(nN) + 3 * ev(nE) +
+                                          ev(nE * nx) + ev(nE * nu) + 2 * ev(nE) + ev(nN * (nx + nu)));
+            need_d = std::max(need_d, 2 * ev(nN * nx) + 2 * ev(nN * nu) + 3 * ev(ny) + 2 * ev(nE) + 3 * ev(nN) +
+                                          ev(nE * nx) + ev(nE * nu) + 2 * ev(nE) + ev(nN * (nx + nu)));
+            i = j;
+        }
+        for (i = m; i < n; i += kTileLeaves) {
+            const int j = std::min(n, i + kTileLeaves);
+            tiles.push_back(make_int2(i, j));
+            const long long nN = j - i;
+            need_p = std::max(need_p, 3 * ev(nN * nx));
+            need_d = std::max(need_d, 4 * ev(nN * nx) + 4 * ev(nN));
+        }
+        int2 *d_tiles = nullptr;
+        TRY(upload(s, tiles.data(), tiles.size(), &d_tiles));
+        s->tiles.tiles = d_tiles;
+        s->tiles.num_tiles = (int)tiles.size();
+        s->tiles.rowlen = (std::max(nx, nu) + 1) & ~1;
+        s->primal_smem = sizeof(double) * (need_p + (size_t)8 * 4 * s->tiles.rowlen);
+        s->dual_smem = sizeof(double) * (need_d + (size_t)8 * kDualRowsHost * s->tiles.rowlen);
+        if (s->dual_smem > 200 * 1024 || s->primal_smem > 200 * 1024) {
+            s->err = "tile does not fit in shared memory";
+            return bail(RB_ERR_INVALID);
+        }
+        TRYC(cudaFuncSetAttribute(k_primal_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->primal_smem));
+        TRYC(cudaFuncSetAttribute(k_dual_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dual_smem));
+    }
+    s->kernels_per_iter = 1 + (s->plan.num_sub > 0 ? 3 : 1) + 1 + 1;
     *out = s;
     return RB_OK;
 #undef TRY
@@ -406,6 +527,7 @@ void rb_destroy(rb_solver *s) {
         if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
     for (void *p : s->allocs) cudaFree(p);
     if (s->hist) cudaFree(s->hist);
+    if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -489,27 +611,30 @@ int rb_get_offline(rb_solver *s, double *Pm, double *K, double *Rinv) {
 // ---- iterate access -------------------------------------------------------------------------------------------------
 int rb_set_primal(rb_solver *s, int which, const double *compact) {
     if (!s || !compact || which < 0 || which > 1) return RB_ERR_INVALID;
-    return copy_segments(s, s->pseg, s->np, s->P.L.np_pad, s->prim[which], compact, nullptr);
+    RB_MATERIALISE(s);
+    return copy_segments(s, s->pseg, s->np, s->P.L.np_pad, view_p(s, which), compact, nullptr);
 }
 int rb_get_primal(rb_solver *s, int which, double *compact) {
     if (!s || !compact || which < 0 || which > 1) return RB_ERR_INVALID;
-    return copy_segments(s, s->pseg, s->np, s->P.L.np_pad, s->prim[which], nullptr, compact);
+    return copy_segments(s, s->pseg, s->np, s->P.L.np_pad, view_p(s, which), nullptr, compact);
 }
 int rb_set_dual(rb_solver *s, int which, const double *compact) {
     if (!s || !compact || which < 0 || which > 1) return RB_ERR_INVALID;
-    return copy_segments(s, s->dseg, s->nd, s->P.L.nd_pad, s->dual[which], compact, nullptr);
+    RB_MATERIALISE(s);
+    return copy_segments(s, s->dseg, s->nd, s->P.L.nd_pad, view_d(s, which), compact, nullptr);
 }
 int rb_get_dual(rb_solver *s, int which, double *compact) {
     if (!s || !compact || which < 0 || which > 1) return RB_ERR_INVALID;
-    return copy_segments(s, s->dseg, s->nd, s->P.L.nd_pad, s->dual[which], nullptr, compact);
+    return copy_segments(s, s->dseg, s->nd, s->P.L.nd_pad, view_d(s, which), nullptr, compact);
 }
 
 int rb_set_initial_state(rb_solver *s, const double *x0) {
     if (!s || !x0) return RB_ERR_INVALID;
     const Layout &L = s->P.L;
     RB_CUDA(s, cudaMemcpyAsync(s->x0, x0, (size_t)L.batch * L.nx * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    // old_primal[0] = state (cache.py:81)
-    RB_CUDA(s, cudaMemcpy2DAsync(s->prim[1] + L.px, L.np_pad * sizeof(double), x0, L.nx * sizeof(double),
+    // old_primal[0] = state (cache.py:81); the current iterate keeps its own x_0 like the reference
+    RB_MATERIALISE(s);
+    RB_CUDA(s, cudaMemcpy2DAsync(s->prim[s->old_i] + L.px, L.np_pad * sizeof(double), x0, L.nx * sizeof(double),
                                  L.nx * sizeof(double), L.batch, cudaMemcpyHostToDevice, s->stream));
     RB_CUDA(s, cudaStreamSynchronize(s->stream));
     s->have_x0 = true;
@@ -518,11 +643,10 @@ int rb_set_initial_state(rb_solver *s, const double *x0) {
 
 int rb_update_cache(rb_solver *s) {
     if (!s) return RB_ERR_INVALID;
-    const Layout &L = s->P.L;
-    RB_CUDA(s, cudaMemcpyAsync(s->prim[1], s->prim[0], (size_t)L.batch * L.np_pad * sizeof(double), cudaMemcpyDeviceToDevice,
-                               s->stream));
-    RB_CUDA(s, cudaMemcpyAsync(s->dual[1], s->dual[0], (size_t)L.batch * L.nd_pad * sizeof(double), cudaMemcpyDeviceToDevice,
-                               s->stream));
+    if (s->collapsed) return RB_OK;
+    // old <- current without moving data: the current buffer becomes the (only meaningful) old one
+    std::swap(s->cur_i, s->old_i);
+    s->collapsed = true;
     return RB_OK;
 }
 
@@ -602,14 +726,17 @@ int rb_lambda_max(rb_solver *s, double *lambda_max) {
 // ---- half steps -------------------------------------------------------------------------------------------------------
 int rb_primal_half(rb_solver *s, double alpha) {
     if (!s) return RB_ERR_INVALID;
-    k_lt_axpby<<<node_grid(s, s->P.L.n), kThreads, 0, s->stream>>>(s->P, s->dual[1], s->prim[1], s->prim[0], 1.0, -alpha);
+    RB_MATERIALISE(s);
+    k_lt_axpby<<<node_grid(s, s->P.L.n), kThreads, 0, s->stream>>>(s->P, view_d(s, 1), view_p(s, 1), view_p(s, 0), 1.0,
+                                                                  -alpha);
     RB_LAUNCHED(s, "k_lt_axpby");
     return RB_OK;
 }
 
 int rb_s0_shift(rb_solver *s, double alpha) {
     if (!s) return RB_ERR_INVALID;
-    k_s0_shift<<<(s->P.L.batch + 127) / 128, 128, 0, s->stream>>>(s->P, s->prim[0], alpha);
+    RB_MATERIALISE(s);
+    k_s0_shift<<<(s->P.L.batch + 127) / 128, 128, 0, s->stream>>>(s->P, view_p(s, 0), alpha);
     RB_LAUNCHED(s, "k_s0_shift");
     return RB_OK;
 }
@@ -620,24 +747,18 @@ int rb_project_dynamics(rb_solver *s) {
     if (rc != RB_OK) return rc;
     if (!s->have_x0) return fail(s, RB_ERR_STATE, "initial state not set (cache_initial_state)");
     const Layout &L = s->P.L;
-    for (int t = L.num_stages - 1; t >= 0; --t) {
-        const int lo = s->stage_off[t], hi = s->stage_off[t + 1];
-        k_dyn_bwd<<<node_grid(s, hi - lo), kThreads, 0, s->stream>>>(s->P, s->prim[0], s->q, s->r, lo, hi);
-        RB_LAUNCHED(s, "k_dyn_bwd");
-    }
-    k_set_root<<<std::min(L.batch, 1024), 64, 0, s->stream>>>(s->P, s->prim[0], s->x0);
-    RB_LAUNCHED(s, "k_set_root");
-    for (int t = 0; t < L.num_stages - 1; ++t) {
-        const int lo = s->stage_off[t], hi = s->stage_off[t + 1];
-        k_dyn_fwd<<<node_grid(s, hi - lo), kThreads, 0, s->stream>>>(s->P, s->prim[0], s->r, lo, hi);
-        RB_LAUNCHED(s, "k_dyn_fwd");
-    }
+    RB_MATERIALISE(s);
+    (void)L;
+    int rc2 = launch_sweeps(s, nullptr, view_p(s, 0), s->stream);
+    if (rc2 != RB_OK) return rc2;
+    s->launches += s->plan.num_sub > 0 ? 3 : 1;
     return RB_OK;
 }
 
 int rb_project_kernel(rb_solver *s) {
     if (!s) return RB_ERR_INVALID;
-    k_kernel_proj<<<node_grid(s, s->P.L.m), kThreads, 0, s->stream>>>(s->P, s->prim[0]);
+    RB_MATERIALISE(s);
+    k_kernel_proj<<<node_grid(s, s->P.L.m), kThreads, 0, s->stream>>>(s->P, view_p(s, 0));
     RB_LAUNCHED(s, "k_kernel_proj");
     return RB_OK;
 }
@@ -652,15 +773,17 @@ int rb_prox_f(rb_solver *s, double alpha) {
 
 int rb_dual_half(rb_solver *s, double alpha) {
     if (!s) return RB_ERR_INVALID;
-    k_l_axpby<<<node_grid(s, s->P.L.n), kThreads, 0, s->stream>>>(s->P, s->prim[0], s->prim[1], 2.0, -1.0, s->dual[1],
-                                                                 s->dual[0], 1.0, alpha);
+    RB_MATERIALISE(s);
+    k_l_axpby<<<node_grid(s, s->P.L.n), kThreads, 0, s->stream>>>(s->P, view_p(s, 0), view_p(s, 1), 2.0, -1.0, view_d(s, 1),
+                                                                 view_d(s, 0), 1.0, alpha);
     RB_LAUNCHED(s, "k_l_axpby");
     return RB_OK;
 }
 
 static int prox_g_mode(rb_solver *s, double alpha, int mode) {
     if (!s) return RB_ERR_INVALID;
-    k_prox_g<<<node_grid(s, s->P.L.n), kThreads, 0, s->stream>>>(s->P, s->dual[0], alpha, mode, s->status);
+    RB_MATERIALISE(s);
+    k_prox_g<<<node_grid(s, s->P.L.n), kThreads, 0, s->stream>>>(s->P, view_d(s, 0), alpha, mode, s->status);
     RB_LAUNCHED(s, "k_prox_g");
     return (mode & 12) ? check_status(s) : RB_OK;
 }
@@ -677,8 +800,9 @@ int rb_modify_projection(rb_solver *s, double alpha, const double *modified_dual
     rc = copy_segments(s, s->dseg, s->nd, s->P.L.nd_pad, s->staging_d, modified_dual, nullptr);
     if (rc != RB_OK) return rc;
     const long long count = (long long)s->P.L.batch * s->P.L.nd_pad;
+    RB_MATERIALISE(s);
     // d = alpha * (w - d)   (cache.py:392-393)
-    k_axpby<<<1184, 256, 0, s->stream>>>(s->dual[0], alpha, s->staging_d, -alpha, s->dual[0], count);
+    k_axpby<<<1184, 256, 0, s->stream>>>(view_d(s, 0), alpha, s->staging_d, -alpha, view_d(s, 0), count);
     RB_LAUNCHED(s, "k_axpby");
     return RB_OK;
 }
@@ -702,16 +826,17 @@ int rb_residuals(rb_solver *s, double alpha, double *norms, double *vectors) {
     double *dd = s->td[0], *lp = s->td[1], *xi2 = s->td[2], *delta2 = s->td[3];
     const dim3 g = node_grid(s, L.n);
     cudaStream_t st = s->stream;
-    k_axpby<<<1184, 256, 0, st>>>(dp, 1.0, s->prim[1], -1.0, s->prim[0], pc);            // p - p_new
-    k_axpby<<<1184, 256, 0, st>>>(dd, 1.0, s->dual[1], -1.0, s->dual[0], dc);            // d - d_new
+    double *p_cur = view_p(s, 0), *p_old = view_p(s, 1), *d_cur = view_d(s, 0), *d_old = view_d(s, 1);
+    k_axpby<<<1184, 256, 0, st>>>(dp, 1.0, p_old, -1.0, p_cur, pc);                      // p - p_new
+    k_axpby<<<1184, 256, 0, st>>>(dd, 1.0, d_old, -1.0, d_cur, dc);                      // d - d_new
     k_lt_axpby<<<g, kThreads, 0, st>>>(s->P, dd, nullptr, lt, 0.0, 1.0);                 // L*(d - d_new)
     k_div_add<<<1184, 256, 0, st>>>(xi1, dp, alpha, -1.0, lt, pc);                       // xi1
-    k_axpby<<<1184, 256, 0, st>>>(pn, 1.0, s->prim[0], -1.0, s->prim[1], pc);            // p_new - p = delta1
+    k_axpby<<<1184, 256, 0, st>>>(pn, 1.0, p_cur, -1.0, p_old, pc);                      // p_new - p = delta1
     k_l_axpby<<<g, kThreads, 0, st>>>(s->P, pn, nullptr, 1.0, 0.0, nullptr, lp, 0.0, 1.0);  // L(p_new - p)
     k_div_add<<<1184, 256, 0, st>>>(xi2, dd, alpha, 1.0, lp, dc);                        // xi2
     k_lt_axpby<<<g, kThreads, 0, st>>>(s->P, xi2, nullptr, lt, 0.0, 1.0);                // L* xi2
     k_axpby<<<1184, 256, 0, st>>>(xi0, 1.0, xi1, 1.0, lt, pc);                           // xi0
-    k_axpby<<<1184, 256, 0, st>>>(delta2, 1.0, s->dual[0], -1.0, s->dual[1], dc);        // delta2
+    k_axpby<<<1184, 256, 0, st>>>(delta2, 1.0, d_cur, -1.0, d_old, dc);                  // delta2
     k_lt_axpby<<<g, kThreads, 0, st>>>(s->P, delta2, nullptr, lt, 0.0, 1.0);             // L* delta2
     k_axpby<<<1184, 256, 0, st>>>(delta0, 1.0, pn, -1.0, lt, pc);                        // delta0
     s->launches += 12;
@@ -746,116 +871,247 @@ int rb_residuals(rb_solver *s, double alpha, double *norms, double *vectors) {
 // ---- fused loop -------------------------------------------------------------------------------------------------------
 namespace {
 
-// enqueue the kernels of one iteration reading (prim[src], dual[src]) and writing (prim[dst], dual[dst])
-int enqueue_iteration(rb_solver *s, double alpha, int src, int dst, int max_iters, double tol) {
+// the kernels of one iteration reading buffer src and writing buffer 1-src
+int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st) {
     const Layout &L = s->P.L;
-    cudaStream_t st = s->stream;
-    k_fused_primal<<<node_grid(s, L.n), kThreads, 0, st>>>(s->P, s->ctrl, s->prim[src], s->dual[src], s->prim[dst], alpha);
-    for (int t = L.num_stages - 1; t >= 0; --t) {
-        const int lo = s->stage_off[t], hi = s->stage_off[t + 1];
-        k_fused_bwd<<<node_grid(s, hi - lo), kThreads, 0, st>>>(s->P, s->ctrl, s->prim[dst], s->q, s->r, lo, hi);
-    }
-    for (int t = 0; t < L.num_stages - 1; ++t) {
-        const int lo = s->stage_off[t], hi = s->stage_off[t + 1];
-        k_fused_fwd<<<node_grid(s, hi - lo), kThreads, 0, st>>>(s->P, s->ctrl, s->prim[dst], s->r, s->x0, lo, hi);
-    }
-    k_fused_dual<<<node_grid(s, L.n), kThreads, 0, st>>>(s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src],
-                                                        s->dual[dst], alpha, s->slots);
-    k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last, s->hist, s->hist_capacity, max_iters, tol);
+    const int dst = 1 - src;
+    const dim3 tg(s->tiles.num_tiles, L.batch);
+    k_primal_tile<<<tg, 256, s->primal_smem, st>>>(s->P, s->ctrl, s->tiles, s->prim[src], s->dual[src], s->prim[dst]);
+    int rc = launch_sweeps(s, s->ctrl, s->prim[dst], st);
+    if (rc != RB_OK) return rc;
+    k_dual_tile<<<tg, 256, s->dual_smem, st>>>(s->P, s->ctrl, s->tiles, s->prim[src], s->prim[dst], s->dual[src],
+                                              s->dual[dst], s->slots);
+    k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
     return launch_ok(s, "fused iteration");
 }
 
-int run_fused(rb_solver *s, double alpha, int max_iters, double tol, int fixed_iters, double *xi_hist, double *delta_hist,
-              int hist_capacity, int *iters_out, int *status_out) {
-    int rc = need_offline(s);
-    if (rc != RB_OK) return rc;
-    if (!s->have_x0) return fail(s, RB_ERR_STATE, "initial state not set (cache_initial_state)");
-    const Layout &L = s->P.L;
-    cudaStream_t st = s->stream;
-    const bool want_hist = xi_hist || delta_hist;
-    const int total = fixed_iters > 0 ? fixed_iters : max_iters + 1;
-    if (s->hist) {
-        RB_CUDA(s, cudaStreamSynchronize(st));
-        cudaFree(s->hist);
-        s->hist = nullptr;
-    }
-    s->hist_capacity = 0;
-    if (want_hist) {
-        s->hist_capacity = std::min(total, hist_capacity);
-        RB_CUDA(s, cudaMalloc((void **)&s->hist, (size_t)std::max(1, s->hist_capacity) * L.batch * 6 * sizeof(double)));
-    }
-    RB_CUDA(s, cudaMemsetAsync(s->ctrl, 0, sizeof(Ctrl), st));
-    RB_CUDA(s, cudaMemsetAsync(s->slots, 0, (size_t)L.batch * 6 * sizeof(double), st));
-    const int eff_max = fixed_iters > 0 ? fixed_iters - 1 : max_iters;
-    const double eff_tol = fixed_iters > 0 ? -1.0 : tol;
-    // iteration k reads buffer (k even ? old : current) and writes the other one
-    int launched = 0;
-    Ctrl hc{};
-    const int chunk = 64;
-    while (launched < total) {
-        const int todo = std::min(chunk, total - launched);
-        for (int k = 0; k < todo; ++k) {
-            const int it = launched + k;
-            const int src = (it % 2 == 0) ? 1 : 0, dst = 1 - src;
-            rc = enqueue_iteration(s, alpha, src, dst, eff_max, eff_tol);
-            if (rc != RB_OK) return rc;
-        }
-        launched += todo;
-        s->launches += (int64_t)todo * s->kernels_per_iter;
-        if (fixed_iters > 0) continue;  // benchmark mode: never synchronise inside
-        RB_CUDA(s, cudaMemcpyAsync(&hc, s->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
-        RB_CUDA(s, cudaStreamSynchronize(st));
-        if (hc.done) break;
-    }
-    RB_CUDA(s, cudaMemcpyAsync(&hc, s->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
-    RB_CUDA(s, cudaStreamSynchronize(st));
-    const int iters = hc.iters;
-    // the last executed iteration (index iters-1) wrote buffer dst; make current == old == final iterate
-    const int final_buf = ((iters - 1) % 2 == 0) ? 0 : 1;
-    const int other = 1 - final_buf;
-    RB_CUDA(s, cudaMemcpyAsync(s->prim[other], s->prim[final_buf], (size_t)L.batch * L.np_pad * sizeof(double),
-                               cudaMemcpyDeviceToDevice, st));
-    RB_CUDA(s, cudaMemcpyAsync(s->dual[other], s->dual[final_buf], (size_t)L.batch * L.nd_pad * sizeof(double),
-                               cudaMemcpyDeviceToDevice, st));
-    if (want_hist) {
-        const int rows = std::min(iters, s->hist_capacity);
-        std::vector<double> h((size_t)rows * L.batch * 6);
-        RB_CUDA(s, cudaMemcpyAsync(h.data(), s->hist, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-        RB_CUDA(s, cudaStreamSynchronize(st));
-        for (size_t i = 0; i < (size_t)rows * L.batch; ++i)
-            for (int k = 0; k < 3; ++k) {
-                if (xi_hist) xi_hist[i * 3 + k] = h[i * 6 + k];
-                if (delta_hist) delta_hist[i * 3 + k] = h[i * 6 + 3 + k];
-            }
-    }
-    RB_CUDA(s, cudaStreamSynchronize(st));
-    if (iters_out) *iters_out = iters;
-    // reference status (solver.py:166-169): 0 if the final iteration index is < max_iters
-    if (status_out) *status_out = (iters - 1 < max_iters) ? 0 : 1;
-    if (hc.status) {
-        RB_CUDA(s, cudaMemsetAsync(s->ctrl, 0, sizeof(Ctrl), st));
-        if (hc.status & 1) return fail(s, RB_ERR_NUMERIC, "Rectangle constraint - 'nan' value cannot be constrained");
-        return fail(s, RB_ERR_NUMERIC, "non-finite value in the residuals");
+// capture one iteration per buffer parity into a CUDA graph (the kernel arguments never change afterwards: step size
+// and stopping parameters live in the device control block)
+int build_graphs(rb_solver *s) {
+    for (int src = 0; src < 2; ++src) {
+        if (s->graph[src]) continue;
+        cudaStream_t cap = nullptr;
+        RB_CUDA(s, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        RB_CUDA(s, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_iteration_kernels(s, src, cap);
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(cap, &g);
+        cudaStreamDestroy(cap);
+        if (rc != RB_OK) return rc;
+        if (e != cudaSuccess) return fail(s, RB_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&s->graph[src], g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) return fail(s, RB_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
     }
     return RB_OK;
 }
 
 }  // namespace
 
+int rb_loop_begin(rb_solver *s, double alpha, int32_t max_iters, double tol, int32_t hist_capacity) {
+    if (!s || max_iters < 0 || hist_capacity < 0) return RB_ERR_INVALID;
+    int rc = need_offline(s);
+    if (rc != RB_OK) return rc;
+    if (!s->have_x0) return fail(s, RB_ERR_STATE, "initial state not set (cache_initial_state)");
+    const Layout &L = s->P.L;
+    cudaStream_t st = s->stream;
+    if (s->use_graphs) {
+        rc = build_graphs(s);
+        if (rc != RB_OK) return rc;
+    }
+    if (s->hist && s->hist_capacity < hist_capacity) {
+        RB_CUDA(s, cudaStreamSynchronize(st));
+        cudaFree(s->hist);
+        s->hist = nullptr;
+    }
+    if (hist_capacity > 0 && !s->hist) {
+        RB_CUDA(s, cudaMalloc((void **)&s->hist, (size_t)hist_capacity * L.batch * 6 * sizeof(double)));
+        s->hist_capacity = hist_capacity;
+    }
+    if (!s->h_pinned) RB_CUDA(s, cudaMallocHost((void **)&s->h_pinned, 4096));
+    Ctrl *hc = reinterpret_cast<Ctrl *>(s->h_pinned);
+    std::memset(hc, 0, sizeof(Ctrl));
+    hc->max_iters = max_iters;
+    hc->tol = tol;
+    hc->alpha = alpha;
+    hc->hist = hist_capacity > 0 ? s->hist : nullptr;
+    hc->hist_capacity = hist_capacity;
+    RB_CUDA(s, cudaMemcpyAsync(s->ctrl, hc, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
+    RB_CUDA(s, cudaMemsetAsync(s->slots, 0, (size_t)L.batch * 6 * sizeof(double), st));
+    // Solver.chock iterates from the OLD iterate (solver.py:29-37); the current one is scratch from here on
+    s->collapsed = false;
+    s->in_loop = true;
+    s->loop_old0 = s->old_i;
+    return RB_OK;
+}
+
+int rb_loop_enqueue(rb_solver *s, int32_t count) {
+    if (!s || count < 0) return RB_ERR_INVALID;
+    if (!s->in_loop) return fail(s, RB_ERR_STATE, "rb_loop_begin() has not been called");
+    for (int k = 0; k < count; ++k) {
+        const int src = s->old_i;
+        if (s->use_graphs) {
+            RB_CUDA(s, cudaGraphLaunch(s->graph[src], s->stream));
+        } else {
+            int rc = enqueue_iteration_kernels(s, src, s->stream);
+            if (rc != RB_OK) return rc;
+        }
+        // the buffer just written holds the newest iterate: it is the next iteration's "old"
+        std::swap(s->cur_i, s->old_i);
+    }
+    s->launches += (int64_t)count * s->kernels_per_iter;
+    return RB_OK;
+}
+
+int rb_loop_poll(rb_solver *s, int32_t *iters, int32_t *done, double *last_norms) {
+    if (!s) return RB_ERR_INVALID;
+    if (!s->in_loop) return fail(s, RB_ERR_STATE, "rb_loop_begin() has not been called");
+    const Layout &L = s->P.L;
+    Ctrl *hc = reinterpret_cast<Ctrl *>(s->h_pinned);
+    double *hn = s->h_pinned + 64;
+    if ((size_t)L.batch * 6 > (4096 - 512) / sizeof(double)) hn = nullptr;
+    RB_CUDA(s, cudaMemcpyAsync(hc, s->ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, s->stream));
+    if (last_norms) {
+        if (hn) RB_CUDA(s, cudaMemcpyAsync(hn, s->last, (size_t)L.batch * 6 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        else RB_CUDA(s, cudaMemcpyAsync(last_norms, s->last, (size_t)L.batch * 6 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    }
+    RB_CUDA(s, cudaStreamSynchronize(s->stream));
+    if (last_norms && hn) std::memcpy(last_norms, hn, (size_t)L.batch * 6 * sizeof(double));
+    if (iters) *iters = hc->iters;
+    if (done) *done = hc->done;
+    if (hc->status) {
+        RB_CUDA(s, cudaMemsetAsync(&s->ctrl->status, 0, sizeof(int), s->stream));
+        if (hc->status & 1) return fail(s, RB_ERR_NUMERIC, "Rectangle constraint - 'nan' value cannot be constrained");
+        return fail(s, RB_ERR_NUMERIC, "non-finite value in the residuals");
+    }
+    return RB_OK;
+}
+
+int rb_loop_end(rb_solver *s, double *xi_hist, double *delta_hist, int32_t *iters_out, int32_t *status_out) {
+    if (!s) return RB_ERR_INVALID;
+    if (!s->in_loop) return fail(s, RB_ERR_STATE, "rb_loop_begin() has not been called");
+    const Layout &L = s->P.L;
+    int32_t iters = 0, done = 0;
+    int rc = rb_loop_poll(s, &iters, &done, nullptr);
+    s->in_loop = false;
+    if (rc != RB_OK && rc != RB_ERR_NUMERIC) return rc;
+    // iterations enqueued after the stopping test fired were no-ops, but the host kept swapping roles while
+    // enqueueing: iteration k read buffer (k even ? loop_old0 : 1 - loop_old0) and wrote the other one, so the
+    // newest iterate is in the buffer written by iteration iters-1
+    const int newest = iters == 0 ? s->loop_old0 : (((iters - 1) % 2 == 0) ? 1 - s->loop_old0 : s->loop_old0);
+    s->old_i = newest;
+    s->cur_i = 1 - newest;
+    s->collapsed = true;
+    Ctrl *hc = reinterpret_cast<Ctrl *>(s->h_pinned);
+    if ((xi_hist || delta_hist) && hc->hist_capacity > 0) {
+        const int rows = std::min(iters, hc->hist_capacity);
+        std::vector<double> h((size_t)rows * L.batch * 6);
+        RB_CUDA(s, cudaMemcpyAsync(h.data(), s->hist, h.size() * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        RB_CUDA(s, cudaStreamSynchronize(s->stream));
+        for (size_t i = 0; i < (size_t)rows * L.batch; ++i)
+            for (int k = 0; k < 3; ++k) {
+                if (xi_hist) xi_hist[i * 3 + k] = h[i * 6 + k];
+                if (delta_hist) delta_hist[i * 3 + k] = h[i * 6 + 3 + k];
+            }
+    }
+    if (iters_out) *iters_out = iters;
+    // reference status (solver.py:166-169): 0 if the final iteration index is < max_iters
+    if (status_out) *status_out = (iters - 1 < hc->max_iters) ? 0 : 1;
+    return rc;
+}
+
 int rb_iterate(rb_solver *s, double alpha, int32_t max_iters, double tol, int32_t check_every, double *xi_hist,
                double *delta_hist, int32_t hist_capacity, int32_t *iters, int32_t *status) {
     if (!s || max_iters < 0) return RB_ERR_INVALID;
-    (void)check_every;  // the stopping test runs on the device after every iteration
-    return run_fused(s, alpha, max_iters, tol, 0, xi_hist, delta_hist, hist_capacity, iters, status);
+    const bool want_hist = xi_hist || delta_hist;
+    const int total = max_iters + 1;
+    int rc = rb_loop_begin(s, alpha, max_iters, tol, want_hist ? std::min(total, (int)hist_capacity) : 0);
+    if (rc != RB_OK) return rc;
+    // the stopping test runs on the device after every iteration; the host only polls every `chunk` iterations and
+    // the iterations enqueued past the stopping point are no-ops
+    const int chunk = std::max(1, check_every <= 1 ? 64 : (int)check_every);
+    int launched = 0;
+    while (launched < total) {
+        const int todo = std::min(chunk, total - launched);
+        rc = rb_loop_enqueue(s, todo);
+        if (rc != RB_OK) return rc;
+        launched += todo;
+        int32_t it = 0, done = 0;
+        rc = rb_loop_poll(s, &it, &done, nullptr);
+        if (rc != RB_OK) {
+            s->in_loop = false;
+            return rc;
+        }
+        if (done) break;
+    }
+    return rb_loop_end(s, xi_hist, delta_hist, iters, status);
 }
 
 int rb_iterate_fixed(rb_solver *s, double alpha, int32_t iters, double *norms) {
     if (!s || iters < 1) return RB_ERR_INVALID;
-    int rc = run_fused(s, alpha, iters - 1, -1.0, iters, nullptr, nullptr, 0, nullptr, nullptr);
+    int rc = rb_loop_begin(s, alpha, iters - 1, -1.0, 0);
     if (rc != RB_OK) return rc;
-    if (norms) {
-        RB_CUDA(s, cudaMemcpy(norms, s->last, (size_t)s->P.L.batch * 6 * sizeof(double), cudaMemcpyDeviceToHost));
+    rc = rb_loop_enqueue(s, iters);
+    if (rc != RB_OK) return rc;
+    int32_t it = 0, done = 0;
+    rc = rb_loop_poll(s, &it, &done, norms);
+    if (rc != RB_OK) {
+        s->in_loop = false;
+        return rc;
     }
+    return rb_loop_end(s, nullptr, nullptr, nullptr, nullptr);
+}
+
+// one end-to-end step for a host caller: pinned-host x0 -> device, one iteration, six residual norms -> host
+int rb_step(rb_solver *s, const double *x0, double *norms) {
+    if (!s || !norms) return RB_ERR_INVALID;
+    if (!s->in_loop) return fail(s, RB_ERR_STATE, "rb_loop_begin() has not been called");
+    const Layout &L = s->P.L;
+    if (x0) {
+        RB_CUDA(s, cudaMemcpyAsync(s->x0, x0, (size_t)L.batch * L.nx * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+        RB_CUDA(s, cudaMemcpy2DAsync(s->prim[s->old_i] + L.px, L.np_pad * sizeof(double), x0, L.nx * sizeof(double),
+                                     L.nx * sizeof(double), L.batch, cudaMemcpyHostToDevice, s->stream));
+    }
+    int rc = rb_loop_enqueue(s, 1);
+    if (rc != RB_OK) return rc;
+    RB_CUDA(s, cudaMemcpyAsync(norms, s->last, (size_t)L.batch * 6 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    RB_CUDA(s, cudaStreamSynchronize(s->stream));
+    return RB_OK;
+}
+
+// one iteration with CUDA events between its phases (plain launches): ms[0] primal pass, ms[1] backward sweep,
+// ms[2] forward sweep, ms[3] dual pass + stopping test.  Advances the loop by one iteration.
+int rb_profile_iteration(rb_solver *s, float *ms) {
+    if (!s || !ms) return RB_ERR_INVALID;
+    if (!s->in_loop) return fail(s, RB_ERR_STATE, "rb_loop_begin() has not been called");
+    const Layout &L = s->P.L;
+    cudaStream_t st = s->stream;
+    cudaEvent_t ev[5];
+    for (auto &e : ev) RB_CUDA(s, cudaEventCreate(&e));
+    const int src = s->old_i, dst = 1 - src;
+    RB_CUDA(s, cudaEventRecord(ev[0], st));
+    const dim3 tg(s->tiles.num_tiles, L.batch);
+    k_primal_tile<<<tg, 256, s->primal_smem, st>>>(s->P, s->ctrl, s->tiles, s->prim[src], s->dual[src], s->prim[dst]);
+    RB_CUDA(s, cudaEventRecord(ev[1], st));
+    int rcs = launch_sweeps(s, s->ctrl, s->prim[dst], st, ev[2]);
+    if (rcs != RB_OK) return rcs;
+    RB_CUDA(s, cudaEventRecord(ev[3], st));
+    k_dual_tile<<<tg, 256, s->dual_smem, st>>>(s->P, s->ctrl, s->tiles, s->prim[src], s->prim[dst], s->dual[src],
+                                              s->dual[dst], s->slots);
+    k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
+    RB_CUDA(s, cudaEventRecord(ev[4], st));
+    RB_CUDA(s, cudaStreamSynchronize(st));
+    int rc = launch_ok(s, "profiled iteration");
+    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    for (auto &e : ev) cudaEventDestroy(e);
+    std::swap(s->cur_i, s->old_i);
+    s->launches += s->kernels_per_iter;
+    return rc;
+}
+
+int rb_use_graphs(rb_solver *s, int32_t enable) {
+    if (!s) return RB_ERR_INVALID;
+    s->use_graphs = enable != 0;
     return RB_OK;
 }
 

@@ -62,24 +62,55 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// out[k] += scale * sum_l MT[l*rows + k] * v[l]   (k = lane, lane+32, ...; v and out are warp-private shared rows).
-// MT is the TRANSPOSE of the rows x cols matrix being applied, so lanes read consecutive addresses for every l.
+// One output row per lane: returns sum_l MT[l*rows + k] * v[l].  MT is the TRANSPOSE of the rows x cols matrix being
+// applied (so lanes read consecutive addresses for every l; conflict-free when MT is in shared memory), v is a
+// warp-private shared row.  Four independent accumulators / loads in flight per lane: the loop is latency-, not
+// throughput-bound, and the trip count is a run-time value.
+__device__ __forceinline__ double mv_row(const double *__restrict__ MT, const double *v, int rows, int cols, int k) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    const double *col = MT + k;
+    int l = 0;
+    for (; l + 4 <= cols; l += 4) {
+        const double m0 = col[(long long)l * rows], m1 = col[(long long)(l + 1) * rows];
+        const double m2 = col[(long long)(l + 2) * rows], m3 = col[(long long)(l + 3) * rows];
+        a0 = fma(m0, v[l], a0);
+        a1 = fma(m1, v[l + 1], a1);
+        a2 = fma(m2, v[l + 2], a2);
+        a3 = fma(m3, v[l + 3], a3);
+    }
+    for (; l < cols; ++l) a0 = fma(col[(long long)l * rows], v[l], a0);
+    return (a0 + a1) + (a2 + a3);
+}
+// the same matrix applied to two vectors at once (one pass over the matrix)
+__device__ __forceinline__ void mv_row2(const double *__restrict__ MT, const double *v, const double *w, int rows,
+                                        int cols, int k, double &rv, double &rw) {
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+    const double *col = MT + k;
+    int l = 0;
+    for (; l + 2 <= cols; l += 2) {
+        const double m0 = col[(long long)l * rows], m1 = col[(long long)(l + 1) * rows];
+        a0 = fma(m0, v[l], a0);
+        b0 = fma(m0, w[l], b0);
+        a1 = fma(m1, v[l + 1], a1);
+        b1 = fma(m1, w[l + 1], b1);
+    }
+    for (; l < cols; ++l) {
+        const double m0 = col[(long long)l * rows];
+        a0 = fma(m0, v[l], a0);
+        b0 = fma(m0, w[l], b0);
+    }
+    rv = a0 + a1;
+    rw = b0 + b1;
+}
+// out[k] += scale * (M v)[k]   (k = lane, lane+32, ...; out is a warp-private shared row)
 __device__ __forceinline__ void mv_acc(const double *__restrict__ MT, const double *v, int rows, int cols,
                                        double *out, double scale, int lane) {
-    for (int k = lane; k < rows; k += 32) {
-        double acc = 0.0;
-        for (int l = 0; l < cols; ++l) acc = fma(__ldg(MT + (long long)l * rows + k), v[l], acc);
-        out[k] += scale * acc;
-    }
+    for (int k = lane; k < rows; k += 32) out[k] += scale * mv_row(MT, v, rows, cols, k);
 }
-// out[k] = sum_l MT[l*rows+k] v[l]
+// out[k] = (M v)[k]
 __device__ __forceinline__ void mv_set(const double *__restrict__ MT, const double *v, int rows, int cols,
                                        double *out, int lane) {
-    for (int k = lane; k < rows; k += 32) {
-        double acc = 0.0;
-        for (int l = 0; l < cols; ++l) acc = fma(__ldg(MT + (long long)l * rows + k), v[l], acc);
-        out[k] = acc;
-    }
+    for (int k = lane; k < rows; k += 32) out[k] = mv_row(MT, v, rows, cols, k);
 }
 
 // ---- projections (device forms of reference cones.py / rectangle.py) -----------------------------------------------

@@ -10,11 +10,6 @@ __global__ void k_lt_axpby(const __grid_constant__ Params P, const double *__res
 __global__ void k_l_axpby(const __grid_constant__ Params P, const double *__restrict__ p1, const double *__restrict__ p2,
                           double c1, double c2, const double *__restrict__ base, double *__restrict__ out, double beta,
                           double gamma);
-__global__ void k_dyn_bwd(const __grid_constant__ Params P, const double *__restrict__ prim, double *__restrict__ q,
-                          double *__restrict__ r, int lo, int hi);
-__global__ void k_dyn_fwd(const __grid_constant__ Params P, double *__restrict__ prim, const double *__restrict__ r,
-                          int lo, int hi);
-__global__ void k_set_root(const __grid_constant__ Params P, double *__restrict__ prim, const double *__restrict__ x0);
 __global__ void k_kernel_proj(const __grid_constant__ Params P, double *__restrict__ prim);
 __global__ void k_s0_shift(const __grid_constant__ Params P, double *__restrict__ prim, double alpha);
 __global__ void k_prox_g(const __grid_constant__ Params P, double *__restrict__ dual, double alpha, int mode,
@@ -35,21 +30,48 @@ struct Ctrl {
     int done;        // set by k_check when the stopping test of solver.py:156-161 fires; later launches are no-ops
     int iters;       // iterations executed so far
     int status;      // bit 0: NaN met in a rectangle projection; bit 1: non-finite residual
+    int max_iters;   // stop when the iteration index reaches this (solver.py:156-157)
+    double tol;      // stop when max(xi0, xi1, xi2) <= tol for every instance (solver.py:158-159)
+    double alpha;    // step size alpha_1 = alpha_2 (solver.py:116-118)
+    double *hist;    // [hist_capacity][batch][6] residual history or null
+    int hist_capacity;
     int pad;
 };
-__global__ void k_fused_primal(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
-                               const double *__restrict__ p_old, const double *__restrict__ d_old,
-                               double *__restrict__ p_new, double alpha);
-__global__ void k_fused_bwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
-                            const double *__restrict__ prim, double *__restrict__ q, double *__restrict__ r, int lo, int hi);
-__global__ void k_fused_fwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, double *__restrict__ prim,
-                            const double *__restrict__ r, const double *__restrict__ x0, int lo, int hi);
-__global__ void k_fused_dual(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, const double *__restrict__ p_old,
-                             const double *__restrict__ p_new, const double *__restrict__ d_old,
-                             double *__restrict__ d_new, double alpha, double *__restrict__ slots);
+// tiles of consecutive nodes for the node-parallel passes (fused.cu): tiles[t] = (first node, one past the last);
+// a tile is either all nonleaf or all leaf nodes
+struct TilePlan {
+    const int2 *tiles;
+    int num_tiles;
+    int rowlen;      // doubles per warp-private scratch row (max(nx, nu) rounded up to even)
+};
+__global__ void k_primal_tile(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, TilePlan plan,
+                              const double *__restrict__ p_old, const double *__restrict__ d_old,
+                              double *__restrict__ p_new);
+__global__ void k_dual_tile(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, TilePlan plan,
+                            const double *__restrict__ p_old, const double *__restrict__ p_new,
+                            const double *__restrict__ d_old, double *__restrict__ d_new, double *__restrict__ slots);
+constexpr int kDualRowsHost = 15;   // must equal kDualRows in fused.cu
 __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, double *__restrict__ slots,
-                        double *__restrict__ last, double *__restrict__ hist, int hist_capacity, int max_iters,
-                        double tol);
+                        double *__restrict__ last);
+
+// ---- sweeps.cu: the DP sweeps in three launches ----------------------------------------------------------------------
+struct SweepPlan {
+    int t_s;               // cut stage: stages [0, t_s) belong to the top kernel, [t_s, num_stages) to the subtree CTAs
+    int num_sub;           // nodes at stage t_s = number of subtrees (0 if t_s == num_stages)
+    int depth;             // num_stages - t_s
+    const int *sub_lo;     // [num_sub][depth] first node of the subtree at stage t_s + d
+    const int *sub_hi;     // [num_sub][depth] one past the last
+    const int *stage_off;  // [num_stages + 1]
+    int tabs_in_smem;      // 1: A, A', B, B' staged in shared memory by every CTA
+    int num_dyn;
+};
+__global__ void k_sweep_sub_bwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, SweepPlan plan,
+                                const double *__restrict__ prim, double *__restrict__ q, double *__restrict__ r);
+__global__ void k_sweep_sub_fwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, SweepPlan plan,
+                                double *__restrict__ prim, const double *__restrict__ r);
+__global__ void k_sweep_top(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, SweepPlan plan,
+                            double *__restrict__ prim, double *__restrict__ q, double *__restrict__ r,
+                            const double *__restrict__ x0);
 
 // ---- offline.cu --------------------------------------------------------------------------------------------------
 struct ClassView {

@@ -9,9 +9,9 @@ namespace rb {
 //   nonleaf:  r_i = ubar_i - sum_j B_j' q_j;   q_i = -xbar_i - K_i' r_i + sum_j A_j' q_j
 // which equals the reference's q_i = -xbar_i + K_i'(d_i - ubar_i) + sum_j (A_j+B_jK_i)'(P_j B_j d_i + q_j) with
 // d_i = R~_i^-1 r_i (DESIGN.md "DP identities").  sm: 4 warp-private rows of kMaxDim doubles.
-__device__ __forceinline__ void dyn_bwd_node(const Params &P, const double *__restrict__ Pp, double *__restrict__ Q,
+__device__ __forceinline__ void dyn_bwd_node(const Layout &L, const Topo &T, const Tabs &M,
+                                             const double *__restrict__ Pp, double *__restrict__ Q,
                                              double *__restrict__ R, int node, int lane, double (*sm)[kMaxDim]) {
-    const Layout &L = P.L;
     const int nx = L.nx, nu = L.nu;
     if (node >= L.m) {
         for (int k = lane; k < nx; k += 32) Q[(long long)node * nx + k] = -Pp[L.px + (long long)node * nx + k];
@@ -20,13 +20,13 @@ __device__ __forceinline__ void dyn_bwd_node(const Params &P, const double *__re
     double *qj = sm[0], *sig = sm[1], *aq = sm[2], *rv = sm[3];
     for (int k = lane; k < nu; k += 32) sig[k] = 0.0;
     for (int k = lane; k < nx; k += 32) aq[k] = 0.0;
-    const int c0 = P.t.child_first[node], cc = P.t.child_count[node];
+    const int c0 = T.child_first[node], cc = T.child_count[node];
     for (int j = c0; j < c0 + cc; ++j) {
         for (int k = lane; k < nx; k += 32) qj[k] = Q[(long long)j * nx + k];
         __syncwarp();
-        const int di = P.t.dyn_idx[j];
-        mv_acc(P.m.B + (long long)di * nx * nu, qj, nu, nx, sig, 1.0, lane);   // B' q  (B row-major is (B')^T)
-        mv_acc(P.m.A + (long long)di * nx * nx, qj, nx, nx, aq, 1.0, lane);    // A' q
+        const int di = T.dyn_idx[j];
+        mv_acc(M.B + (long long)di * nx * nu, qj, nu, nx, sig, 1.0, lane);   // B' q  (B row-major is (B')^T)
+        mv_acc(M.A + (long long)di * nx * nx, qj, nx, nx, aq, 1.0, lane);    // A' q
         __syncwarp();
     }
     for (int k = lane; k < nu; k += 32) {
@@ -35,35 +35,34 @@ __device__ __forceinline__ void dyn_bwd_node(const Params &P, const double *__re
         R[(long long)node * nu + k] = rk;
     }
     __syncwarp();
-    const int cl = P.t.cls[node];
+    const int cl = T.cls[node];
     for (int k = lane; k < nx; k += 32) aq[k] -= Pp[L.px + (long long)node * nx + k];
-    mv_acc(P.m.K + (long long)cl * nu * nx, rv, nx, nu, aq, -1.0, lane);       // - K' r  (K row-major is (K')^T)
+    mv_acc(M.K + (long long)cl * nu * nx, rv, nx, nu, aq, -1.0, lane);       // - K' r  (K row-major is (K')^T)
     for (int k = lane; k < nx; k += 32) Q[(long long)node * nx + k] = aq[k];
     __syncwarp();
 }
 
 // Forward DP step at one nonleaf node (reference cache.py:282-288):
 //   u_i = K_i x_i + R~_i^-1 r_i;   x_j = A_j x_i + B_j u_i   ( = (A_j+B_jK_i) x_i + B_j d_i of the reference )
-__device__ __forceinline__ void dyn_fwd_node(const Params &P, double *__restrict__ Pp, const double *__restrict__ R,
-                                             int node, int lane, double (*sm)[kMaxDim]) {
-    const Layout &L = P.L;
+__device__ __forceinline__ void dyn_fwd_node(const Layout &L, const Topo &T, const Tabs &M, double *__restrict__ Pp,
+                                             const double *__restrict__ R, int node, int lane, double (*sm)[kMaxDim]) {
     const int nx = L.nx, nu = L.nu;
     double *xi = sm[0], *rv = sm[1], *ui = sm[2], *xj = sm[3];
     for (int k = lane; k < nx; k += 32) xi[k] = Pp[L.px + (long long)node * nx + k];
     for (int k = lane; k < nu; k += 32) rv[k] = R[(long long)node * nu + k];
     __syncwarp();
-    const int cl = P.t.cls[node];
-    mv_set(P.m.RinvT + (long long)cl * nu * nu, rv, nu, nu, ui, lane);         // d = R~^-1 r
+    const int cl = T.cls[node];
+    mv_set(M.RinvT + (long long)cl * nu * nu, rv, nu, nu, ui, lane);         // d = R~^-1 r
     __syncwarp();
-    mv_acc(P.m.KT + (long long)cl * nx * nu, xi, nu, nx, ui, 1.0, lane);       // + K x
+    mv_acc(M.KT + (long long)cl * nx * nu, xi, nu, nx, ui, 1.0, lane);       // + K x
     __syncwarp();
     for (int k = lane; k < nu; k += 32) Pp[L.pu + (long long)node * nu + k] = ui[k];
-    const int c0 = P.t.child_first[node], cc = P.t.child_count[node];
+    const int c0 = T.child_first[node], cc = T.child_count[node];
     for (int j = c0; j < c0 + cc; ++j) {
-        const int di = P.t.dyn_idx[j];
-        mv_set(P.m.AT + (long long)di * nx * nx, xi, nx, nx, xj, lane);
+        const int di = T.dyn_idx[j];
+        mv_set(M.AT + (long long)di * nx * nx, xi, nx, nx, xj, lane);
         __syncwarp();
-        mv_acc(P.m.BT + (long long)di * nu * nx, ui, nx, nu, xj, 1.0, lane);
+        mv_acc(M.BT + (long long)di * nu * nx, ui, nx, nu, xj, 1.0, lane);
         __syncwarp();
         for (int k = lane; k < nx; k += 32) Pp[L.px + (long long)j * nx + k] = xj[k];
         __syncwarp();
@@ -100,4 +99,16 @@ __device__ __forceinline__ void kernel_projection(const Params &P, double *Pp, i
 }
 
 
+}  // namespace rb
+
+namespace rb {
+// convenience overloads on the full parameter block
+__device__ __forceinline__ void dyn_bwd_node(const Params &P, const double *__restrict__ Pp, double *__restrict__ Q,
+                                             double *__restrict__ R, int node, int lane, double (*sm)[kMaxDim]) {
+    dyn_bwd_node(P.L, P.t, P.m, Pp, Q, R, node, lane, sm);
+}
+__device__ __forceinline__ void dyn_fwd_node(const Params &P, double *__restrict__ Pp, const double *__restrict__ R,
+                                             int node, int lane, double (*sm)[kMaxDim]) {
+    dyn_fwd_node(P.L, P.t, P.m, Pp, R, node, lane, sm);
+}
 }  // namespace rb

@@ -192,11 +192,14 @@ __global__ void k_gram_eig(const __grid_constant__ Params P, const int *__restri
     __syncwarp();
     // cyclic Jacobi (eigenvalues only): rotate rows/columns p, q until the off-diagonal mass vanishes
     for (int sweep = 0; sweep < 30; ++sweep) {
-        double off = 0.0;
-        for (int i = lane; i < dim * dim; i += 32)
+        double off = 0.0, diag = 0.0;
+        for (int i = lane; i < dim * dim; i += 32) {
             if (i / dim != i % dim) off = fma(G[i], G[i], off);
+            else diag = fma(G[i], G[i], diag);
+        }
         off = warp_sum(off);
-        if (off < 1e-300) break;
+        diag = warp_sum(diag);
+        if (off <= 1e-34 * diag) break;   // off-diagonal mass below (1e-17)^2 of the diagonal: converged
         for (int p = 0; p < dim - 1; ++p) {
             for (int q = p + 1; q < dim; ++q) {
                 const double apq = G[p * dim + q];

@@ -139,42 +139,7 @@ __global__ void __launch_bounds__(kThreads) k_l_axpby(const __grid_constant__ Pa
     }
 }
 
-// ----------------------------------------------------------------------------------------------------------------
-// projection onto the dynamics set, one launch per stage (cache.py:259-288).
-// Backward: r_i = ubar_i - sum_j B_j' q_j;  q_i = -xbar_i - K_i' r_i + sum_j A_j' q_j   (equal to the reference's
-// q_i = -xbar_i + K_i'(d_i - ubar_i) + sum_j (A_j+B_jK_i)'(P_j B_j d_i + q_j) with d_i = R~_i^-1 r_i).
-// ----------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_dyn_bwd(const __grid_constant__ Params P, const double *__restrict__ prim,
-                                                     double *__restrict__ q, double *__restrict__ r, int lo, int hi) {
-    __shared__ double sm[kWarpsPerBlock][4][kMaxDim];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int node = lo + blockIdx.x * kWarpsPerBlock + warp;
-    if (node >= hi) return;
-    dyn_bwd_node(P, prim + (long long)blockIdx.y * P.L.np_pad, q + (long long)blockIdx.y * P.L.n * P.L.nx,
-                 r + (long long)blockIdx.y * P.L.m * P.L.nu, node, lane, sm[warp]);
-}
-
-__global__ void __launch_bounds__(kThreads) k_dyn_fwd(const __grid_constant__ Params P, double *__restrict__ prim,
-                                                     const double *__restrict__ r, int lo, int hi) {
-    __shared__ double sm[kWarpsPerBlock][4][kMaxDim];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int node = lo + blockIdx.x * kWarpsPerBlock + warp;
-    if (node >= hi || node >= P.L.m) return;
-    dyn_fwd_node(P, prim + (long long)blockIdx.y * P.L.np_pad, r + (long long)blockIdx.y * P.L.m * P.L.nu, node, lane,
-                 sm[warp]);
-}
-
-// x_0 <- initial state (cache.py:282)
-__global__ void k_set_root(const __grid_constant__ Params P, double *__restrict__ prim, const double *__restrict__ x0) {
-    const Layout &L = P.L;
-    for (int b = blockIdx.x; b < L.batch; b += gridDim.x)
-        for (int k = threadIdx.x; k < L.nx; k += blockDim.x) prim[(long long)b * L.np_pad + L.px + k] = x0[b * L.nx + k];
-}
-
-// ----------------------------------------------------------------------------------------------------------------
-// projection of (y_i, tau_ch(i), s_ch(i)) onto ker [E' -I -I] (cache.py:290-317).  For AVaR (risks.py:28-35)
-// M = [a I, -I, 1, -I, -I], M M' = (a^2+3) I + 1 1', so proj = v - M' (M M')^-1 M v in closed form.
-// ----------------------------------------------------------------------------------------------------------------
+// the projection onto the dynamics set (cache.py:259-288) lives in sweeps.cu; the kernel projection follows
 __global__ void __launch_bounds__(kThreads) k_kernel_proj(const __grid_constant__ Params P, double *__restrict__ prim) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int node = blockIdx.x * kWarpsPerBlock + warp;

@@ -67,6 +67,13 @@ SYMBOLS = [
     ("rb_iterate", C.c_int, [_H, C.c_double, C.c_int32, C.c_double, C.c_int32, c_double_p, c_double_p, C.c_int32,
                              c_int_p, c_int_p]),
     ("rb_iterate_fixed", C.c_int, [_H, C.c_double, C.c_int32, c_double_p]),
+    ("rb_loop_begin", C.c_int, [_H, C.c_double, C.c_int32, C.c_double, C.c_int32]),
+    ("rb_loop_enqueue", C.c_int, [_H, C.c_int32]),
+    ("rb_loop_poll", C.c_int, [_H, c_int_p, c_int_p, c_double_p]),
+    ("rb_step", C.c_int, [_H, c_double_p, c_double_p]),
+    ("rb_loop_end", C.c_int, [_H, c_double_p, c_double_p, c_int_p, c_int_p]),
+    ("rb_profile_iteration", C.c_int, [_H, C.POINTER(C.c_float)]),
+    ("rb_use_graphs", C.c_int, [_H, C.c_int32]),
     ("rb_launch_count", C.c_int, [_H, C.POINTER(C.c_int64)]),
     ("rb_cone_project", C.c_int, [C.c_int32, C.c_int32, c_double_p, c_double_p]),
     ("rb_box_project", C.c_int, [C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]),

@@ -209,3 +209,34 @@ class DeviceSolver:
         norms = np.empty((self.batch, 6))
         self._call("rb_iterate_fixed", float(alpha), int(iters), _lib.dptr(norms))
         return norms
+
+    # ---- the fused loop in pieces (hosts that pipeline; bench.py) -----------------------------------------------------
+    def use_graphs(self, enable=True):
+        self._call("rb_use_graphs", 1 if enable else 0)
+
+    def loop_begin(self, alpha, max_iters, tol=-1.0, hist_capacity=0):
+        self._call("rb_loop_begin", float(alpha), int(max_iters), float(tol), int(hist_capacity))
+
+    def loop_enqueue(self, count=1):
+        self._call("rb_loop_enqueue", int(count))
+
+    def loop_poll(self):
+        iters, done = C.c_int32(), C.c_int32()
+        norms = np.empty((self.batch, 6))
+        self._call("rb_loop_poll", C.byref(iters), C.byref(done), _lib.dptr(norms))
+        return iters.value, bool(done.value), norms
+
+    def step(self, x0_ptr, norms_ptr):
+        """raw pointers (pinned host memory): x0 [batch][nx] in, norms [batch][6] out"""
+        self._call("rb_step", C.cast(x0_ptr, _lib.c_double_p), C.cast(norms_ptr, _lib.c_double_p))
+
+    def loop_end(self):
+        iters, status = C.c_int32(), C.c_int32()
+        self._call("rb_loop_end", None, None, C.byref(iters), C.byref(status))
+        return iters.value, status.value
+
+    def profile_iteration(self):
+        """ms of (primal pass, backward sweep, forward sweep, dual pass) of one iteration, CUDA events"""
+        ms = (C.c_float * 4)()
+        self._call("rb_profile_iteration", ms)
+        return list(ms)

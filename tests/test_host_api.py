@@ -163,7 +163,7 @@ def test_unsupported_inputs_fail_loudly():
 # ---- the C-ABI library -----------------------------------------------------------------------------------------------------
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "raocp_b200.h")).read()
-    declared = set(re.findall(r"\b(rb_[a-z_0-9]+)\s*\(", header))
+    declared = set(re.findall(r"\b(rb_[A-Za-z_0-9]+)\s*\(", header))
     assert len(declared) >= 30
     lib = _lib.load()
     bound = {name for name, _, _ in _lib.SYMBOLS}
