@@ -143,11 +143,14 @@ def cfg1_convergence(api):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--long", action="store_true")
+    ap.add_argument("--only", default=None, help="comma separated problem names")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     api = ref_loader.RefApi()
     parse_tex()
-    for nm in ("demo", "cfg1", "mini2", "mini3", "mini5"):
+    names = sys.argv[sys.argv.index("--only") + 1].split(",") if "--only" in sys.argv else \
+        ("demo", "cfg1", "mini2", "mini3", "mini5", "dense", "wide")
+    for nm in names:
         iterates(nm, api)
         ops(nm, api)
     if args.long:

@@ -18,6 +18,8 @@ SHAPES = {
     "mini2": (3, 5, 3, 4, 2),      # 3 modes, ragged-free, 94-ish nodes
     "mini3": (4, 7, 3, 6, 3),
     "mini5": (3, 6, 3, 16, 8),
+    "dense": (3, 5, 3, 5, 3),      # like mini2 but with NON-diagonal SPD cost weights (general matvec path)
+    "wide": (2, 3, 3, 40, 36),     # nx, nu > 32: more than one row per lane
 }
 
 
@@ -39,6 +41,15 @@ def spec(name, seed=0, batch=1):
         q_list.append(np.diag(rng.uniform(0.5, 2.0, size=nx)))
         r_list.append(np.diag(rng.uniform(0.5, 2.0, size=nu)))
     qf = np.diag(rng.uniform(0.5, 2.0, size=nx))
+    if name == "dense":   # random SPD weights with condition number <= 4
+
+        def spd(k):
+            g, _ = np.linalg.qr(rng.standard_normal((k, k)))
+            return g @ np.diag(rng.uniform(0.5, 2.0, size=k)) @ g.T
+
+        q_list = [spd(nx) for _ in range(modes)]
+        r_list = [spd(nu) for _ in range(modes)]
+        qf = spd(nx)
     x0 = rng.uniform(-1.0, 1.0, size=(nx, batch))
     return dict(name=name, seed=seed, p=p, v=v, horizon=horizon, tau=tau, nx=nx, nu=nu,
                 a=a_list, b=b_list, q=q_list, r=r_list, qf=qf, avar=0.5,

@@ -55,7 +55,8 @@ struct rb_solver {
     // offline
     std::vector<int> cls_child_ptr, cls_child_dyn, cls_child_cls, level_list, level_ptr;
     int *d_cls_child_ptr = nullptr, *d_cls_child_dyn = nullptr, *d_cls_child_cls = nullptr, *d_level_list = nullptr;
-    double *Ptab = nullptr, *Ktab = nullptr, *KTtab = nullptr, *RinvTtab = nullptr;
+    double *Ptab = nullptr, *Ktab = nullptr, *KRcatT = nullptr;
+    bool diag_costs = false;
     // residual temporaries (allocated on first use)
     double *tp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *td[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -65,8 +66,7 @@ struct rb_solver {
     size_t primal_smem = 0, dual_smem = 0;
     // DP sweeps in three launches (sweeps.cu)
     SweepPlan plan{};
-    int sub_warps = 1, top_warps = 16;
-    size_t sub_smem = 0, top_smem = 0;
+    int top_warps = 16;
     // fused loop
     cudaGraphExec_t graph[2] = {nullptr, nullptr};  // graph[src]: one iteration reading buffer src, writing 1-src
     bool use_graphs = true;
@@ -192,16 +192,25 @@ inline double *view_d(rb_solver *s, int which) { return s->dual[(which == 0 && !
         if (rc_ != RB_OK) return rc_;   \
     } while (0)
 
-// the three launches of the DP sweeps on `prim` (x, u rows hold xbar, ubar on entry and the projection on exit)
+// the launches of the DP sweeps on `prim` (x, u rows hold xbar, ubar on entry and the projection on exit)
 int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st, cudaEvent_t mid = nullptr) {
     const SweepPlan &pl = s->plan;
     const unsigned batch = (unsigned)s->P.L.batch;
-    if (pl.num_sub > 0)
-        k_sweep_sub_bwd<<<dim3(pl.num_sub, batch), 32 * s->sub_warps, s->sub_smem, st>>>(s->P, ctrl, pl, prim, s->q, s->r);
-    k_sweep_top<<<batch, 32 * s->top_warps, s->top_smem, st>>>(s->P, ctrl, pl, prim, s->q, s->r, s->x0);
+    const size_t per_warp = (size_t)(2 * s->P.L.nxu + 32) * sizeof(double);
+    auto grid = [&](const SweepLevel &lv) { return dim3((lv.num_sub + lv.subs_per_cta - 1) / lv.subs_per_cta, batch); };
+    auto threads = [&](const SweepLevel &lv) { return 32 * lv.warps_per_sub * lv.subs_per_cta; };
+    for (int v = pl.num_levels - 1; v >= 0; --v) {
+        const SweepLevel &lv = pl.lv[v];
+        k_sweep_sub_bwd<<<grid(lv), threads(lv), per_warp * lv.warps_per_sub * lv.subs_per_cta, st>>>(s->P, ctrl, lv, prim,
+                                                                                                   s->q, s->r);
+    }
+    k_sweep_top<<<batch, 32 * s->top_warps, per_warp * s->top_warps, st>>>(s->P, ctrl, pl, prim, s->q, s->r, s->x0);
     if (mid) cudaEventRecord(mid, st);
-    if (pl.num_sub > 0)
-        k_sweep_sub_fwd<<<dim3(pl.num_sub, batch), 32 * s->sub_warps, s->sub_smem, st>>>(s->P, ctrl, pl, prim, s->r);
+    for (int v = 0; v < pl.num_levels; ++v) {
+        const SweepLevel &lv = pl.lv[v];
+        k_sweep_sub_fwd<<<grid(lv), threads(lv), per_warp * lv.warps_per_sub * lv.subs_per_cta, st>>>(s->P, ctrl, lv, prim,
+                                                                                                   s->r);
+    }
     return launch_ok(s, "DP sweeps");
 }
 
@@ -354,10 +363,23 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
     TRY(upload(s, pb->A, (size_t)pb->num_dyn * nx * nx, &tmp_d)); M.A = tmp_d;
     TRY(upload(s, pb->B, (size_t)pb->num_dyn * nx * nu, &tmp_d)); M.B = tmp_d;
     {
-        auto at = transpose_tab(pb->A, pb->num_dyn, nx, nx);
-        TRY(upload(s, at.data(), at.size(), &tmp_d)); M.AT = tmp_d;
-        auto bt = transpose_tab(pb->B, pb->num_dyn, nx, nu);
-        TRY(upload(s, bt.data(), bt.size(), &tmp_d)); M.BT = tmp_d;
+        const int nxu = nx + nu;
+        std::vector<double> cat((size_t)pb->num_dyn * nx * nxu), catT(cat.size());
+        for (int t = 0; t < pb->num_dyn; ++t)
+            for (int l = 0; l < nx; ++l) {
+                for (int k = 0; k < nx; ++k) {
+                    const double a_lk = pb->A[((size_t)t * nx + l) * nx + k];
+                    cat[((size_t)t * nx + l) * nxu + k] = a_lk;            // row l = [A[l][:], B[l][:]]
+                    catT[((size_t)t * nxu + k) * nx + l] = a_lk;           // row k<nx = A[:][k]
+                }
+                for (int a = 0; a < nu; ++a) {
+                    const double b_la = pb->B[((size_t)t * nx + l) * nu + a];
+                    cat[((size_t)t * nx + l) * nxu + nx + a] = b_la;
+                    catT[((size_t)t * nxu + nx + a) * nx + l] = b_la;      // row nx+a = B[:][a]
+                }
+            }
+        TRY(upload(s, cat.data(), cat.size(), &tmp_d)); M.ABcat = tmp_d;
+        TRY(upload(s, catT.data(), catT.size(), &tmp_d)); M.ABcatT = tmp_d;
         auto sq = transpose_tab(pb->sqrtQ, pb->num_cost, nx, nx);
         TRY(upload(s, sq.data(), sq.size(), &tmp_d)); M.sqT = tmp_d;
         auto sr = transpose_tab(pb->sqrtR, pb->num_cost, nu, nu);
@@ -367,6 +389,18 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
         M.sq_diag = is_diag(pb->sqrtQ, pb->num_cost, nx);
         M.sr_diag = is_diag(pb->sqrtR, pb->num_cost, nu);
         M.sqf_diag = is_diag(pb->sqrtQf, pb->num_leafcost, nx);
+        s->diag_costs = M.sq_diag && M.sr_diag && M.sqf_diag;
+        auto diag_of = [](const double *tab, int count, int dim) {
+            std::vector<double> d((size_t)count * dim);
+            for (int t = 0; t < count; ++t)
+                for (int k = 0; k < dim; ++k) d[(size_t)t * dim + k] = tab[((size_t)t * dim + k) * dim + k];
+            return d;
+        };
+        auto dq = diag_of(pb->sqrtQ, pb->num_cost, nx), dr = diag_of(pb->sqrtR, pb->num_cost, nu),
+             df = diag_of(pb->sqrtQf, pb->num_leafcost, nx);
+        TRY(upload(s, dq.data(), dq.size(), &tmp_d)); M.sq_d = tmp_d;
+        TRY(upload(s, dr.data(), dr.size(), &tmp_d)); M.sr_d = tmp_d;
+        TRY(upload(s, df.data(), df.size(), &tmp_d)); M.sqf_d = tmp_d;
     }
     TRY(upload(s, L.has_nl_rect ? pb->nl_lo : nullptr, (size_t)pb->num_nl_rect * (nx + nu), &tmp_d)); M.nl_lo = tmp_d;
     TRY(upload(s, L.has_nl_rect ? pb->nl_hi : nullptr, (size_t)pb->num_nl_rect * (nx + nu), &tmp_d)); M.nl_hi = tmp_d;
@@ -412,9 +446,8 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
     }
     TRY(dev_zero(s, (size_t)s->num_cls * nx * nx, &s->Ptab));
     TRY(dev_zero(s, (size_t)s->num_cls * nu * nx, &s->Ktab));
-    TRY(dev_zero(s, (size_t)s->num_cls * nu * nx, &s->KTtab));
-    TRY(dev_zero(s, (size_t)s->num_cls * nu * nu, &s->RinvTtab));
-    M.K = s->Ktab; M.KT = s->KTtab; M.RinvT = s->RinvTtab;
+    TRY(dev_zero(s, (size_t)s->num_cls * (nx + nu) * nu, &s->KRcatT));
+    M.K = s->Ktab; M.KRcatT = s->KRcatT;
     // ---- iterates and scratch
     const size_t B = (size_t)L.batch;
     for (int w = 0; w < 2; ++w) {
@@ -428,57 +461,70 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
     TRY(dev_zero(s, B * 6, &s->slots));
     TRY(dev_zero(s, B * 6, &s->last));
     TRY(dev_zero(s, 1, &s->status));
-    // ---- sweep plan: cut at the first stage with >= 64 nodes; one CTA per subtree below it
+    // ---- sweep plan (sweeps.cu): cut at the first stage with >= 64 nodes and, if the tree keeps widening, again at the
+    //      first stage with >= 2048 nodes (and >= 8x the first cut): below a Markov tree's stopping time those are chains
     {
         SweepPlan &pl = s->plan;
-        int t_s = L.num_stages;
+        auto width = [&](int t) { return s->stage_off[t + 1] - s->stage_off[t]; };
+        int c1 = L.num_stages, c2 = L.num_stages;
         for (int t = 0; t < L.num_stages; ++t)
-            if (s->stage_off[t + 1] - s->stage_off[t] >= 64) {
-                t_s = t;
+            if (width(t) >= 64) {
+                c1 = t;
                 break;
             }
-        pl.t_s = t_s;
-        pl.depth = L.num_stages - t_s;
-        pl.num_sub = t_s < L.num_stages ? s->stage_off[t_s + 1] - s->stage_off[t_s] : 0;
-        std::vector<int> lo((size_t)pl.num_sub * std::max(pl.depth, 1)), hi(lo.size());
-        int max_width = 1;
-        for (int c = 0; c < pl.num_sub; ++c) {
-            int a = s->stage_off[t_s] + c, b = a + 1;
-            for (int d = 0; d < pl.depth; ++d) {
-                lo[(size_t)c * pl.depth + d] = a;
-                hi[(size_t)c * pl.depth + d] = b;
-                max_width = std::max(max_width, b - a);
-                if (d + 1 < pl.depth) {   // children of [a, b) are one contiguous range of the next stage
-                    const int na = s->child_first[a], nb = s->child_first[b - 1] + s->child_count[b - 1];
-                    a = na;
-                    b = nb;
+        for (int t = c1 + 1; t < L.num_stages; ++t)
+            if (width(t) >= 2048 && width(t) >= 8 * width(c1)) {
+                c2 = t;
+                break;
+            }
+        pl.t_top = c1;
+        pl.num_levels = c1 >= L.num_stages ? 0 : (c2 >= L.num_stages ? 1 : 2);
+        int *d_so = nullptr;
+        TRY(upload(s, s->stage_off.data(), s->stage_off.size(), &d_so));
+        pl.stage_off = d_so;
+        const int cuts[3] = {c1, c2, L.num_stages};
+        for (int v = 0; v < pl.num_levels; ++v) {
+            SweepLevel &lv = pl.lv[v];
+            lv.t_lo = cuts[v];
+            lv.depth = (v + 1 < pl.num_levels ? cuts[v + 1] : L.num_stages) - cuts[v];
+            lv.num_sub = width(lv.t_lo);
+            std::vector<int> lo((size_t)lv.num_sub * lv.depth), hi(lo.size());
+            int max_width = 1;
+            for (int c = 0; c < lv.num_sub; ++c) {
+                int a = s->stage_off[lv.t_lo] + c, b = a + 1;
+                for (int d = 0; d < lv.depth; ++d) {
+                    lo[(size_t)c * lv.depth + d] = a;
+                    hi[(size_t)c * lv.depth + d] = b;
+                    max_width = std::max(max_width, b - a);
+                    if (d + 1 < lv.depth) {   // children of [a, b) are one contiguous range of the next stage
+                        const int na = s->child_first[a], nb = s->child_first[b - 1] + s->child_count[b - 1];
+                        a = na;
+                        b = nb;
+                    }
                 }
             }
+            lv.warps_per_sub = std::min(16, max_width);
+            lv.subs_per_cta = std::max(1, 8 / lv.warps_per_sub);
+            int *d_lo = nullptr, *d_hi = nullptr;
+            TRY(upload(s, lo.data(), lo.size(), &d_lo));
+            TRY(upload(s, hi.data(), hi.size(), &d_hi));
+            lv.lo = d_lo;
+            lv.hi = d_hi;
         }
-        int *d_lo = nullptr, *d_hi = nullptr, *d_so = nullptr;
-        TRY(upload(s, lo.data(), lo.size(), &d_lo));
-        TRY(upload(s, hi.data(), hi.size(), &d_hi));
-        TRY(upload(s, s->stage_off.data(), s->stage_off.size(), &d_so));
-        pl.sub_lo = d_lo; pl.sub_hi = d_hi; pl.stage_off = d_so;
-        pl.num_dyn = pb->num_dyn;
-        const size_t tab_bytes = sizeof(double) * 2 * ((size_t)pb->num_dyn * nx * nx + (size_t)pb->num_dyn * nx * nu);
-        pl.tabs_in_smem = tab_bytes <= 96 * 1024;
-        s->sub_warps = std::min(8, std::max(1, max_width));
-        const int top_nodes_max = t_s > 0 ? s->stage_off[t_s] - s->stage_off[t_s - 1] : 1;
-        s->top_warps = std::min(16, std::max(1, top_nodes_max));
-        const size_t extra = pl.tabs_in_smem ? tab_bytes : 0;
-        s->sub_smem = (size_t)s->sub_warps * 4 * kMaxDim * sizeof(double) + extra;
-        s->top_smem = (size_t)s->top_warps * 4 * kMaxDim * sizeof(double) + extra;
-        TRYC(cudaFuncSetAttribute(k_sweep_sub_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sub_smem));
-        TRYC(cudaFuncSetAttribute(k_sweep_sub_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->sub_smem));
-        TRYC(cudaFuncSetAttribute(k_sweep_top, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->top_smem));
+        int top_max = 1;
+        for (int t = 0; t < pl.t_top; ++t) top_max = std::max(top_max, width(t));
+        s->top_warps = std::min(32, std::max(1, top_max));
+        const int sweep_smem = 32 * (2 * (nx + nu) + 32) * (int)sizeof(double);
+        TRYC(cudaFuncSetAttribute(k_sweep_sub_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
+        TRYC(cudaFuncSetAttribute(k_sweep_sub_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
+        TRYC(cudaFuncSetAttribute(k_sweep_top, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
     }
     // ---- node tiles: runs of consecutive nodes (<= 32 nodes and <= 64 edges; leaves: <= 64 nodes) -----------------
     {
         std::vector<int2> tiles;
         const int kTileNodes = 32, kTileEdges = 64, kTileLeaves = 64;
         size_t need_p = 0, need_d = 0;
-        auto ev = [](long long c) { return (size_t)((c + 1) & ~1LL); };
+        auto ev = [](long long c) { return (size_t)(c + 2); };   // chunks are widened to 16-byte boundaries
         int i = 0;
         while (i < m) {
             int j = i, edges = 0;
@@ -509,10 +555,9 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
             s->err = "tile does not fit in shared memory";
             return bail(RB_ERR_INVALID);
         }
-        TRYC(cudaFuncSetAttribute(k_primal_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->primal_smem));
-        TRYC(cudaFuncSetAttribute(k_dual_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->dual_smem));
+        TRYC(tile_kernels_set_smem(s->primal_smem, s->dual_smem));
     }
-    s->kernels_per_iter = 1 + (s->plan.num_sub > 0 ? 3 : 1) + 1 + 1;
+    s->kernels_per_iter = 1 + (1 + 2 * s->plan.num_levels) + 1 + 1;
     *out = s;
     return RB_OK;
 #undef TRY
@@ -581,8 +626,7 @@ int rb_offline(rb_solver *s) {
     for (int l = 0; l < levels; ++l) {
         const int begin = s->level_ptr[l], count = s->level_ptr[l + 1] - begin;
         if (count == 0) continue;
-        k_offline_level<<<count, 256, smem, s->stream>>>(s->P, cv, begin, count, s->Ptab, s->Ktab, s->KTtab, s->RinvTtab,
-                                                        s->status);
+        k_offline_level<<<count, 256, smem, s->stream>>>(s->P, cv, begin, count, s->Ptab, s->Ktab, s->KRcatT, s->status);
         RB_LAUNCHED(s, "k_offline_level");
     }
     int rc = check_status(s);
@@ -600,10 +644,12 @@ int rb_get_offline(rb_solver *s, double *Pm, double *K, double *Rinv) {
     if (Pm) RB_CUDA(s, cudaMemcpy(Pm, s->Ptab, (size_t)s->num_cls * nx * nx * sizeof(double), cudaMemcpyDeviceToHost));
     if (K) RB_CUDA(s, cudaMemcpy(K, s->Ktab, (size_t)s->num_cls * nu * nx * sizeof(double), cudaMemcpyDeviceToHost));
     if (Rinv) {
-        std::vector<double> t((size_t)s->num_cls * nu * nu);
-        RB_CUDA(s, cudaMemcpy(t.data(), s->RinvTtab, t.size() * sizeof(double), cudaMemcpyDeviceToHost));
-        auto tt = transpose_tab(t.data(), s->num_cls, nu, nu);
-        std::memcpy(Rinv, tt.data(), tt.size() * sizeof(double));
+        std::vector<double> t((size_t)s->num_cls * (nx + nu) * nu);
+        RB_CUDA(s, cudaMemcpy(t.data(), s->KRcatT, t.size() * sizeof(double), cudaMemcpyDeviceToHost));
+        for (int c = 0; c < s->num_cls; ++c)   // KRcatT[c][nx + b][a] = Rinv[a][b]
+            for (int a = 0; a < nu; ++a)
+                for (int b = 0; b < nu; ++b)
+                    Rinv[((size_t)c * nu + a) * nu + b] = t[((size_t)c * (nx + nu) + nx + b) * nu + a];
     }
     return RB_OK;
 }
@@ -751,7 +797,7 @@ int rb_project_dynamics(rb_solver *s) {
     (void)L;
     int rc2 = launch_sweeps(s, nullptr, view_p(s, 0), s->stream);
     if (rc2 != RB_OK) return rc2;
-    s->launches += s->plan.num_sub > 0 ? 3 : 1;
+    s->launches += 1 + 2 * s->plan.num_levels;
     return RB_OK;
 }
 
@@ -876,11 +922,11 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st) {
     const Layout &L = s->P.L;
     const int dst = 1 - src;
     const dim3 tg(s->tiles.num_tiles, L.batch);
-    k_primal_tile<<<tg, 256, s->primal_smem, st>>>(s->P, s->ctrl, s->tiles, s->prim[src], s->dual[src], s->prim[dst]);
+    launch_primal_tile(s->diag_costs, tg, s->primal_smem, st, s->P, s->ctrl, s->tiles, s->prim[src], s->dual[src], s->prim[dst]);
     int rc = launch_sweeps(s, s->ctrl, s->prim[dst], st);
     if (rc != RB_OK) return rc;
-    k_dual_tile<<<tg, 256, s->dual_smem, st>>>(s->P, s->ctrl, s->tiles, s->prim[src], s->prim[dst], s->dual[src],
-                                              s->dual[dst], s->slots);
+    launch_dual_tile(s->diag_costs, tg, s->dual_smem, st, s->P, s->ctrl, s->tiles, s->prim[src], s->prim[dst], s->dual[src],
+                     s->dual[dst], s->slots);
     k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
     return launch_ok(s, "fused iteration");
 }
@@ -1091,13 +1137,13 @@ int rb_profile_iteration(rb_solver *s, float *ms) {
     const int src = s->old_i, dst = 1 - src;
     RB_CUDA(s, cudaEventRecord(ev[0], st));
     const dim3 tg(s->tiles.num_tiles, L.batch);
-    k_primal_tile<<<tg, 256, s->primal_smem, st>>>(s->P, s->ctrl, s->tiles, s->prim[src], s->dual[src], s->prim[dst]);
+    launch_primal_tile(s->diag_costs, tg, s->primal_smem, st, s->P, s->ctrl, s->tiles, s->prim[src], s->dual[src], s->prim[dst]);
     RB_CUDA(s, cudaEventRecord(ev[1], st));
     int rcs = launch_sweeps(s, s->ctrl, s->prim[dst], st, ev[2]);
     if (rcs != RB_OK) return rcs;
     RB_CUDA(s, cudaEventRecord(ev[3], st));
-    k_dual_tile<<<tg, 256, s->dual_smem, st>>>(s->P, s->ctrl, s->tiles, s->prim[src], s->prim[dst], s->dual[src],
-                                              s->dual[dst], s->slots);
+    launch_dual_tile(s->diag_costs, tg, s->dual_smem, st, s->P, s->ctrl, s->tiles, s->prim[src], s->prim[dst], s->dual[src],
+                     s->dual[dst], s->slots);
     k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
     RB_CUDA(s, cudaEventRecord(ev[4], st));
     RB_CUDA(s, cudaStreamSynchronize(st));
@@ -1107,6 +1153,19 @@ int rb_profile_iteration(rb_solver *s, float *ms) {
     std::swap(s->cur_i, s->old_i);
     s->launches += s->kernels_per_iter;
     return rc;
+}
+
+int rb_force_dense_costs(rb_solver *s, int32_t enable) {
+    if (!s) return RB_ERR_INVALID;
+    // test hook: run the general (dense matrix) cost path even when sqrtQ, sqrtR, sqrtQf are all diagonal
+    const Tabs &M = s->P.m;
+    s->diag_costs = !enable && M.sq_diag && M.sr_diag && M.sqf_diag;
+    for (int i = 0; i < 2; ++i)
+        if (s->graph[i]) {
+            cudaGraphExecDestroy(s->graph[i]);
+            s->graph[i] = nullptr;
+        }
+    return RB_OK;
 }
 
 int rb_use_graphs(rb_solver *s, int32_t enable) {

@@ -31,16 +31,20 @@ struct Topo {
     const double *cond_prob, *risk_alpha;
 };
 
-// Operator tables.  "T" = stored transposed, so that the matrix-vector product with one output row per lane reads
-// consecutive addresses across lanes (see mv_acc below).
+// Operator tables.  Every matrix-vector product assigns one OUTPUT row per lane and walks the reduction index, so a
+// table is stored with the output index fastest (consecutive lanes read consecutive addresses; conflict-free when the
+// table sits in shared memory).  Matrices applied to the same vector are concatenated so that one pass keeps all
+// nx+nu lanes busy.
 struct Tabs {
-    const double *A, *AT;      // [num_dyn][nx][nx]
-    const double *B, *BT;      // B: [num_dyn][nx][nu], BT: [num_dyn][nu][nx]
-    const double *sqT, *srT;   // transposes of sqrtQ / sqrtR
-    const double *sqfT;        // transpose of sqrtQf
+    const double *A, *B;       // [num_dyn][nx][nx], [num_dyn][nx][nu] row-major (offline factorisation)
+    const double *ABcat;       // [num_dyn][nx][nx+nu]  row l = [A[l][:], B[l][:]]     ->  [A'q ; B'q]
+    const double *ABcatT;      // [num_dyn][nx+nu][nx]  row l<nx: A[:][l], row nx+a: B[:][a]   ->  A x + B u
+    const double *sqT, *srT;   // transposes of sqrtQ / sqrtR   [num_cost][..]
+    const double *sqfT;        // transpose of sqrtQf           [num_leafcost][nx][nx]
+    const double *sq_d, *sr_d, *sqf_d;   // their diagonals [..][nx] / [..][nu] (used when the *_diag flag is set)
     const double *nl_lo, *nl_hi, *leaf_lo, *leaf_hi;
-    const double *K, *KT;      // K: [num_cls][nu][nx], KT: [num_cls][nx][nu]
-    const double *RinvT;       // [num_cls][nu][nu] transpose of R~^-1
+    const double *K;           // [num_cls][nu][nx]                                    ->  K' r
+    const double *KRcatT;      // [num_cls][nx+nu][nu]  row l<nx: K[:][l], row nx+b: R~^-1[:][b]   ->  K x + R~^-1 r
     int sq_diag, sr_diag, sqf_diag;  // 1 if every matrix of the table is diagonal (fast path)
 };
 

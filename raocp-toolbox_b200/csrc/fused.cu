@@ -52,127 +52,163 @@ __device__ __forceinline__ DualOut dual_out(const Layout &L, double *d) {
     return {d + L.d1, d + L.d2, d + L.d3, d + L.d4, d + L.d5, d + L.d6, d + L.d7, d + L.d11, d + L.d12, d + L.d13, d + L.d14};
 }
 
-// bump allocator over the CTA's dynamic shared memory; stage() copies [first, first+count) of a segment with all threads
-// and returns a pointer re-based so that the segment's GLOBAL indices work
+// Asynchronous staging: cp.async (LDGSTS) 16-byte copies global -> shared, no register round trip, so every thread has
+// all of its copies of all chunks in flight before the single wait.
+__device__ __forceinline__ void cp_async16(double *smem_dst, const double *gsrc) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// bump allocator over the CTA's dynamic shared memory; stage() enqueues the copy of [first, first+count) of a segment
+// (widened to 16-byte boundaries: segment bases are 128-byte aligned and padded) and returns a pointer re-based so that
+// the segment's GLOBAL indices work.  finish() waits for all copies of the CTA.
 struct Stager {
     double *cursor;
     __device__ __forceinline__ const double *stage(const double *seg, long long first, long long count) {
         if (count <= 0) return seg;
+        const long long a = first & ~1LL, end = (first + count + 1) & ~1LL;
         double *dst = cursor;
-        cursor += (count + 1) & ~1LL;
-        const double *src = seg + first;
-        for (long long i = threadIdx.x; i < count; i += blockDim.x) dst[i] = src[i];
-        return dst - first;
+        cursor += end - a;
+        const double *src = seg + a;
+        for (long long i = 2 * (long long)threadIdx.x; i < end - a; i += 2 * (long long)blockDim.x) cp_async16(dst + i, src + i);
+        return dst - a;
+    }
+    __device__ __forceinline__ void finish() {
+        cp_async_wait_all();
+        __syncthreads();
     }
 };
-
-// cost-matrix application with a diagonal fast path (diagonal weights are the common case in MPC; the tables are
-// classified once at rb_create)
-__device__ __forceinline__ void cost_mv2(const double *__restrict__ MT, int diag, const double *v, const double *w, int dim,
-                                         int k, double &rv, double &rw) {
-    if (diag) {
-        const double m = MT[(long long)k * dim + k];
-        rv = m * v[k];
-        rw = m * w[k];
-    } else {
-        mv_row2(MT, v, w, dim, dim, k, rv, rw);
-    }
-}
-__device__ __forceinline__ double cost_mv(const double *__restrict__ MT, int diag, const double *v, int dim, int k) {
-    return diag ? MT[(long long)k * dim + k] * v[k] : mv_row(MT, v, dim, dim, k);
-}
 
 // ====================================================================================================================
 // primal pass
 // ====================================================================================================================
-// nonleaf node: xbar_i, ubar_i, ybar_i, and the children's taubar_j, sbar_j (edge quantities are owned by the parent's
-// warp) with the kernel projection (cache.py:290-317) fused in.  s_0 / tau_0 are handled by the caller.
-// rows: 4 warp-private shared rows of rowlen doubles.
+// nonleaf node: [xbar_i; ubar_i] (one concatenated pass, nx+nu lanes), ybar_i and the children's taubar_j, sbar_j (edge
+// quantities are owned by the parent's warp) with the kernel projection (cache.py:290-317) fused in.  s_0 / tau_0 are
+// handled by the caller.  DIAG: the cost square roots are diagonal (classified once at rb_create) -> no matvec.
+// scratch: 2 * (nx+nu) warp-private doubles.
+template <bool DIAG>
 __device__ __forceinline__ void primal_nonleaf_node(const Layout &L, const Topo &T, const Tabs &M, const PrimalView &po,
                                                     const DualView &d, const PrimalOut &pn, double alpha, int node,
-                                                    int lane, double *rows, int rowlen) {
-    const int nx = L.nx, nu = L.nu;
-    double *v3 = rows, *v4 = rows + rowlen, *ax = rows + 2 * rowlen, *au = rows + 3 * rowlen;
+                                                    int lane, double *scratch) {
+    const int nx = L.nx, nu = L.nu, nxu = L.nxu;
     const int c0 = T.child_first[node], cc = T.child_count[node];
-    for (int k = lane; k < nx; k += 32) ax[k] = L.has_nl_rect ? d.d7[(long long)node * L.nxu + k] : 0.0;
-    for (int k = lane; k < nu; k += 32) au[k] = L.has_nl_rect ? d.d7[(long long)node * L.nxu + nx + k] : 0.0;
-    for (int j = c0; j < c0 + cc; ++j) {
-        const long long e = j - 1;
-        for (int k = lane; k < nx; k += 32) v3[k] = d.d3[e * nx + k];
-        for (int k = lane; k < nu; k += 32) v4[k] = d.d4[e * nu + k];
-        __syncwarp();
-        const int ci = T.cost_idx[j];
-        for (int k = lane; k < nx; k += 32) ax[k] += cost_mv(M.sqT + (long long)ci * nx * nx, M.sq_diag, v3, nx, k);
-        for (int k = lane; k < nu; k += 32) au[k] += cost_mv(M.srT + (long long)ci * nu * nu, M.sr_diag, v4, nu, k);
-        __syncwarp();
-    }
-    for (int k = lane; k < nx; k += 32) {
-        const long long idx = (long long)node * nx + k;
-        pn.x[idx] = po.x[idx] - alpha * ax[k];
-    }
-    for (int k = lane; k < nu; k += 32) {
-        const long long idx = (long long)node * nu + k;
-        pn.u[idx] = po.u[idx] - alpha * au[k];
+    double *v = scratch, *acc = scratch + nxu;
+    const double *d7 = d.d7 + node * nxu;
+    if (DIAG) {
+        for (int k = lane; k < nxu; k += 32) {
+            const bool isx = k < nx;
+            double a = L.has_nl_rect ? d7[k] : 0.0;
+            for (int j = c0; j < c0 + cc; ++j) {
+                const int ci = T.cost_idx[j];
+                a += isx ? M.sq_d[ci * nx + k] * d.d3[(j - 1) * nx + k] : M.sr_d[ci * nu + k - nx] * d.d4[(j - 1) * nu + k - nx];
+            }
+            if (isx) pn.x[node * nx + k] = po.x[node * nx + k] - alpha * a;
+            else pn.u[node * nu + k - nx] = po.u[node * nu + k - nx] - alpha * a;
+        }
+    } else {
+        for (int k = lane; k < nxu; k += 32) acc[k] = L.has_nl_rect ? d7[k] : 0.0;
+        for (int j = c0; j < c0 + cc; ++j) {
+            for (int k = lane; k < nxu; k += 32) v[k] = k < nx ? d.d3[(j - 1) * nx + k] : d.d4[(j - 1) * nu + k - nx];
+            __syncwarp();
+            const int ci = T.cost_idx[j];
+            for (int k = lane; k < nxu; k += 32)
+                acc[k] += k < nx ? mv_row(M.sqT + (long long)ci * nx * nx, v, nx, nx, k)
+                                 : mv_row(M.srT + (long long)ci * nu * nu, v + nx, nu, nu, k - nx);
+            __syncwarp();
+        }
+        for (int k = lane; k < nxu; k += 32) {
+            if (k < nx) pn.x[node * nx + k] = po.x[node * nx + k] - alpha * acc[k];
+            else pn.u[node * nu + k - nx] = po.u[node * nu + k - nx] - alpha * acc[k];
+        }
     }
     const double d2v = d.d2[node];
     const int yo = T.yoff[node];
     const double a = T.risk_alpha[node];
     // For AVaR M = [a I, -I, 1, -I, -I] and M M' = (a^2+3) I + 1 1', so proj = v - M'(M M')^-1 M v in closed form
     const double ylast_bar = po.y[yo + 2 * cc] - alpha * (d.d1[yo + 2 * cc] - d2v);
-    double rsum = 0.0;
-    for (int e = lane; e < cc; e += 32) {
-        const int j = c0 + e;
-        const double ya = po.y[yo + e] - alpha * (d.d1[yo + e] - T.cond_prob[j] * d2v);
-        const double yb = po.y[yo + cc + e] - alpha * d.d1[yo + cc + e];
-        const double tj = po.tau[j] - alpha * (0.5 * (d.d5[j - 1] + d.d6[j - 1]));
-        const double lts = j < L.m ? d.d2c[j] : 0.5 * (d.d12[j - L.m] + d.d13[j - L.m]);
-        const double sj = po.s[j] - alpha * lts;
-        rsum += a * ya - yb + ylast_bar - tj - sj;
-    }
-    rsum = warp_sum(rsum);
     const double den = a * a + 3.0;
-    const double shift = rsum / (den + (double)cc);
-    double wsum = 0.0;
-    for (int e = lane; e < cc; e += 32) {   // same arithmetic as above, bit for bit
-        const int j = c0 + e;
-        const double ya = po.y[yo + e] - alpha * (d.d1[yo + e] - T.cond_prob[j] * d2v);
-        const double yb = po.y[yo + cc + e] - alpha * d.d1[yo + cc + e];
-        const double tj = po.tau[j] - alpha * (0.5 * (d.d5[j - 1] + d.d6[j - 1]));
-        const double lts = j < L.m ? d.d2c[j] : 0.5 * (d.d12[j - L.m] + d.d13[j - L.m]);
-        const double sj = po.s[j] - alpha * lts;
-        const double w = ((a * ya - yb + ylast_bar - tj - sj) - shift) / den;
-        pn.y[yo + e] = ya - a * w;
-        pn.y[yo + cc + e] = yb + w;
-        pn.tau[j] = tj + w;
-        pn.s[j] = sj + w;
-        wsum += w;
+    if (cc <= 32) {   // one child per lane: everything stays in registers
+        const int e = lane, j = c0 + e;
+        double ya = 0.0, yb = 0.0, tj = 0.0, sj = 0.0, res = 0.0;
+        if (e < cc) {
+            ya = po.y[yo + e] - alpha * (d.d1[yo + e] - T.cond_prob[j] * d2v);
+            yb = po.y[yo + cc + e] - alpha * d.d1[yo + cc + e];
+            tj = po.tau[j] - alpha * (0.5 * (d.d5[j - 1] + d.d6[j - 1]));
+            const double lts = j < L.m ? d.d2c[j] : 0.5 * (d.d12[j - L.m] + d.d13[j - L.m]);
+            sj = po.s[j] - alpha * lts;
+            res = a * ya - yb + ylast_bar - tj - sj;
+        }
+        const double rsum = cc == 1 ? __shfl_sync(0xffffffffu, res, 0) : warp_sum(res);
+        const double shift = rsum / (den + (double)cc);
+        double w = 0.0;
+        if (e < cc) {
+            w = (res - shift) / den;
+            pn.y[yo + e] = ya - a * w;
+            pn.y[yo + cc + e] = yb + w;
+            pn.tau[j] = tj + w;
+            pn.s[j] = sj + w;
+        }
+        const double wsum = cc == 1 ? __shfl_sync(0xffffffffu, w, 0) : warp_sum(w);
+        if (lane == 0) pn.y[yo + 2 * cc] = ylast_bar - wsum;
+    } else {
+        double rsum = 0.0;
+        for (int e = lane; e < cc; e += 32) {
+            const int j = c0 + e;
+            const double ya = po.y[yo + e] - alpha * (d.d1[yo + e] - T.cond_prob[j] * d2v);
+            const double yb = po.y[yo + cc + e] - alpha * d.d1[yo + cc + e];
+            const double tj = po.tau[j] - alpha * (0.5 * (d.d5[j - 1] + d.d6[j - 1]));
+            const double lts = j < L.m ? d.d2c[j] : 0.5 * (d.d12[j - L.m] + d.d13[j - L.m]);
+            const double sj = po.s[j] - alpha * lts;
+            rsum += a * ya - yb + ylast_bar - tj - sj;
+        }
+        rsum = warp_sum(rsum);
+        const double shift = rsum / (den + (double)cc);
+        double wsum = 0.0;
+        for (int e = lane; e < cc; e += 32) {   // same arithmetic as above, bit for bit
+            const int j = c0 + e;
+            const double ya = po.y[yo + e] - alpha * (d.d1[yo + e] - T.cond_prob[j] * d2v);
+            const double yb = po.y[yo + cc + e] - alpha * d.d1[yo + cc + e];
+            const double tj = po.tau[j] - alpha * (0.5 * (d.d5[j - 1] + d.d6[j - 1]));
+            const double lts = j < L.m ? d.d2c[j] : 0.5 * (d.d12[j - L.m] + d.d13[j - L.m]);
+            const double sj = po.s[j] - alpha * lts;
+            const double w = ((a * ya - yb + ylast_bar - tj - sj) - shift) / den;
+            pn.y[yo + e] = ya - a * w;
+            pn.y[yo + cc + e] = yb + w;
+            pn.tau[j] = tj + w;
+            pn.s[j] = sj + w;
+            wsum += w;
+        }
+        wsum = warp_sum(wsum);
+        if (lane == 0) pn.y[yo + 2 * cc] = ylast_bar - wsum;
     }
-    wsum = warp_sum(wsum);
-    if (lane == 0) pn.y[yo + 2 * cc] = ylast_bar - wsum;
     __syncwarp();
 }
 
+template <bool DIAG>
 __device__ __forceinline__ void primal_leaf_node(const Layout &L, const Topo &T, const Tabs &M, const PrimalView &po,
                                                  const DualView &d, const PrimalOut &pn, double alpha, int node, int lane,
-                                                 double *rows) {
+                                                 double *scratch) {
     const int nx = L.nx;
-    const long long li = node - L.m;
-    double *v = rows;
-    for (int k = lane; k < nx; k += 32) v[k] = d.d11[li * nx + k];
-    __syncwarp();
-    const double *sqfT = M.sqfT + (long long)T.leafcost_idx[li] * nx * nx;
+    const int li = node - L.m;
+    const int lc = T.leafcost_idx[li];
+    if (!DIAG) {
+        for (int k = lane; k < nx; k += 32) scratch[k] = d.d11[li * nx + k];
+        __syncwarp();
+    }
     for (int k = lane; k < nx; k += 32) {
-        double acc = cost_mv(sqfT, M.sqf_diag, v, nx, k);
+        double acc = DIAG ? M.sqf_d[lc * nx + k] * d.d11[li * nx + k]
+                          : mv_row(M.sqfT + (long long)lc * nx * nx, scratch, nx, nx, k);
         if (L.has_leaf_rect) acc += d.d14[li * nx + k];
-        const long long idx = (long long)node * nx + k;
-        pn.x[idx] = po.x[idx] - alpha * acc;
+        pn.x[node * nx + k] = po.x[node * nx + k] - alpha * acc;
     }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(256) k_primal_tile(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
-                                                    TilePlan plan, const double *__restrict__ p_old,
-                                                    const double *__restrict__ d_old, double *__restrict__ p_new) {
+template <bool DIAG>
+__global__ void __launch_bounds__(256, 3) k_primal_tile(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
+                                                       TilePlan plan, const double *__restrict__ p_old,
+                                                       const double *__restrict__ d_old, double *__restrict__ p_new) {
     if (ctrl->done) return;
     const double alpha = ctrl->alpha;
     const Layout &L = P.L;
@@ -184,7 +220,7 @@ __global__ void __launch_bounds__(256) k_primal_tile(const __grid_constant__ Par
     const PrimalOut pn = primal_out(L, p_new + (long long)blockIdx.y * L.np_pad);
     const int nx = L.nx, nu = L.nu;
     const int rowlen = plan.rowlen;
-    double *rows = dsm + (size_t)warp * 4 * rowlen;
+    double *rows = dsm + (size_t)warp * 4 * rowlen;   // 4 * rowlen >= 2 * (nx + nu)
     Stager st{dsm + (size_t)warps * 4 * rowlen};
     PrimalView po = primal_view(L, Pg);
     DualView d = dual_view(L, Dg);
@@ -211,9 +247,9 @@ __global__ void __launch_bounds__(256) k_primal_tile(const __grid_constant__ Par
         d.d5 = st.stage(d.d5, c0 - 1, nE);
         d.d6 = st.stage(d.d6, c0 - 1, nE);
         if (L.has_nl_rect) d.d7 = st.stage(d.d7, (long long)lo * L.nxu, nN * L.nxu);
-        __syncthreads();
+        st.finish();
         for (int node = lo + warp; node < hi; node += warps) {
-            primal_nonleaf_node(L, P.t, P.m, po, d, pn, alpha, node, lane, rows, rowlen);
+            primal_nonleaf_node<DIAG>(L, P.t, P.m, po, d, pn, alpha, node, lane, rows);
             if (node == 0 && lane == 0) {
                 pn.s[0] = (Pg[L.ps] - alpha * d.d2[0]) - alpha;   // s_0: half step, then prox of alpha * identity
                 pn.tau[0] = Pg[L.ptau] - alpha * Pg[L.ptau];      // tau_0 (always 0; same arithmetic as the reference)
@@ -224,184 +260,194 @@ __global__ void __launch_bounds__(256) k_primal_tile(const __grid_constant__ Par
         po.x = st.stage(po.x, (long long)lo * nx, nN * nx);
         d.d11 = st.stage(d.d11, l0 * nx, nN * nx);
         if (L.has_leaf_rect) d.d14 = st.stage(d.d14, l0 * nx, nN * nx);
-        __syncthreads();
-        for (int node = lo + warp; node < hi; node += warps) primal_leaf_node(L, P.t, P.m, po, d, pn, alpha, node, lane, rows);
+        st.finish();
+        for (int node = lo + warp; node < hi; node += warps)
+            primal_leaf_node<DIAG>(L, P.t, P.m, po, d, pn, alpha, node, lane, rows);
     }
 }
 
 // ====================================================================================================================
 // dual pass + residuals
 // ====================================================================================================================
-// residual bookkeeping: six running maxima per lane (xi0, xi1, xi2, delta0, delta1, delta2)
+// residual bookkeeping: six running maxima per lane (xi0, xi1, xi2, delta0, delta1, delta2).  Non-negative doubles
+// order like their bit patterns and NaN patterns sit above +inf, so an integer max keeps a NaN instead of dropping it
+// (fmax would): a non-finite iterate reaches the stopping test as a NaN residual.
 struct Resid {
-    double v[6];
-    int nan;
+    unsigned long long v[6];
     __device__ __forceinline__ void init() {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) v[i] = 0.0;
-        nan = 0;
+        for (int i = 0; i < 6; ++i) v[i] = 0ull;
     }
     __device__ __forceinline__ void put(int slot, double x) {
-        nan |= (x != x);
-        v[slot] = fmax(v[slot], fabs(x));
+        const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(x));
+        v[slot] = b > v[slot] ? b : v[slot];
     }
-    // one dual entry: old value, new value, lpp = [L(p+ - p)] entry; gives dd = d - d+ and the xi2 entry
-    __device__ __forceinline__ void dual(double dold, double dnew, double lpp, double alpha, double &dd, double &xi2) {
-        dd = dold - dnew;
-        xi2 = dd / alpha + lpp;
+    // one dual entry: dd = d - d+, lpp = [L(p+ - p)] entry; returns the xi2 entry
+    __device__ __forceinline__ double dual(double dd, double lpp, double inv_alpha) {
+        const double xi2 = fma(dd, inv_alpha, lpp);
         put(2, xi2);
-        put(5, dnew - dold);
+        put(5, dd);        // |delta2| = |d+ - d|
+        return xi2;
     }
-    // one primal entry: old value po, new value pn, g1 = [L*(d - d+)] entry, g2 = [L* xi2] entry
-    __device__ __forceinline__ void primal(double po, double pn, double g1, double g2, double alpha) {
-        const double xi1 = (po - pn) / alpha - g1;
+    // one primal entry: dp = p+ - p, g1 = [L*(d - d+)] entry, g2 = [L* xi2] entry
+    __device__ __forceinline__ void primal(double dp, double g1, double g2, double inv_alpha) {
+        const double xi1 = -fma(dp, inv_alpha, g1);   // (p - p+)/alpha - L*(d - d+)
         put(1, xi1);
         put(0, xi1 + g2);
-        const double d1 = pn - po;
-        put(4, d1);
-        put(3, d1 + g1);   // delta0 = delta1 - L*(d+ - d) = delta1 + L*(d - d+)
+        put(4, dp);
+        put(3, dp + g1);   // delta0 = delta1 - L*(d+ - d) = delta1 + L*(d - d+)
     }
 };
 
-// Moreau step for one dual entry.  dbar = d_old + alpha * lz (solver.py:55-58); w = dbar / alpha (+ shift)
-// (cache.py:329-347).  Returns w.
-__device__ __forceinline__ double dual_w(double d_old, double lz, double alpha, double shift) {
-    const double dbar = d_old + lz * alpha;
-    return dbar / alpha + shift;
+// Moreau step for one dual entry: dbar = d_old + alpha * lz (solver.py:55-58); w = dbar / alpha (+ shift)
+// (cache.py:329-347).  The division is a multiplication by 1/alpha (<= 1 ulp from the reference's quotient).
+__device__ __forceinline__ double dual_w(double d_old, double lz, double alpha, double inv_alpha, double shift) {
+    return fma(lz, alpha, d_old) * inv_alpha + shift;
 }
 
-// warp-private scratch rows of the dual pass (W spans three rows: nx + nu + 2 <= 3 * rowlen)
-enum { ZX, DX, ZU, DU, V1, V2, V1U, V2U, G1, G2, G1U, G2U, WROW, kDualRows = WROW + 3 };
+// warp-private scratch of the dual pass, in units of rowlen doubles (rowlen >= max(nx, nu), even):
+//   Z, DL : [z_x; z_u] = 2 p+ - p and [d_x; d_u] = p+ - p of the node          (2 rows each: nx+nu <= 2 rowlen)
+//   G1, G2: child -> parent sums [L*(d - d+)] and [L* xi2] on the [x; u] rows    (2 rows each)
+//   W, LB : w and L(p+ - p) on one edge, nx+nu+2 entries                        (3 rows each; dense path: V1/V2 alias)
+enum { SZ = 0, SDL = 2, SG1 = 4, SG2 = 6, SW = 8, SLB = 11, kDualRows = 15 };
 static_assert(kDualRows == kDualRowsHost, "host shared-memory sizing out of sync");
 
+template <bool DIAG>
 __device__ __forceinline__ void dual_nonleaf_node(const Layout &L, const Topo &T, const Tabs &M, const PrimalView &po,
                                                   const PrimalView &pn, const DualView &dold, const DualOut &dn,
-                                                  double alpha, int node, int lane, double *rows, int rowlen, Resid &R,
-                                                  int &bad) {
-    const int nx = L.nx, nu = L.nu;
-    double *zx = rows + ZX * rowlen, *dx = rows + DX * rowlen, *zu = rows + ZU * rowlen, *du = rows + DU * rowlen;
-    double *v1 = rows + V1 * rowlen, *v2 = rows + V2 * rowlen, *v1u = rows + V1U * rowlen, *v2u = rows + V2U * rowlen;
-    double *g1 = rows + G1 * rowlen, *g2 = rows + G2 * rowlen, *g1u = rows + G1U * rowlen, *g2u = rows + G2U * rowlen;
-    double *w = rows + WROW * rowlen;
-    for (int k = lane; k < nx; k += 32) {
-        const double xo = po.x[(long long)node * nx + k], xn = pn.x[(long long)node * nx + k];
-        zx[k] = 2 * xn - xo;
-        dx[k] = xn - xo;
+                                                  double alpha, double inv_alpha, int node, int lane, double *rows,
+                                                  int rowlen, Resid &R, int &bad) {
+    const int nx = L.nx, nu = L.nu, nxu = L.nxu, E = nxu + 2;
+    double *z = rows + SZ * rowlen, *dl = rows + SDL * rowlen, *g1 = rows + SG1 * rowlen, *g2 = rows + SG2 * rowlen;
+    double *w = rows + SW * rowlen, *lbv = rows + SLB * rowlen;
+    const double *xo = po.x + node * nx, *xn = pn.x + node * nx, *uo = po.u + node * nu - nx, *un = pn.u + node * nu - nx;
+    for (int k = lane; k < nxu; k += 32) {
+        const double o = k < nx ? xo[k] : uo[k], nw = k < nx ? xn[k] : un[k];
+        z[k] = 2 * nw - o;
+        dl[k] = nw - o;
         g1[k] = 0.0;
         g2[k] = 0.0;
     }
-    for (int k = lane; k < nu; k += 32) {
-        const double uo = po.u[(long long)node * nu + k], un = pn.u[(long long)node * nu + k];
-        zu[k] = 2 * un - uo;
-        du[k] = un - uo;
-        g1u[k] = 0.0;
-        g2u[k] = 0.0;
-    }
     __syncwarp();
     const int c0 = T.child_first[node], cc = T.child_count[node];
-    const int dim = nx + nu + 2;
     for (int j = c0; j < c0 + cc; ++j) {
-        const long long e = j - 1;
-        const int ci = T.cost_idx[j];
-        const double *sqT = M.sqT + (long long)ci * nx * nx;
-        const double *srT = M.srT + (long long)ci * nu * nu;
-        // pass A: L z and L (p+ - p) on this edge, then w = (d + alpha L z) / alpha
-        for (int k = lane; k < nx; k += 32) {
-            double la, lb;
-            cost_mv2(sqT, M.sq_diag, zx, dx, nx, k, la, lb);
-            w[k] = dual_w(dold.d3[e * nx + k], la, alpha, 0.0);
-            v2[k] = lb;
-        }
-        for (int k = lane; k < nu; k += 32) {
-            double la, lb;
-            cost_mv2(srT, M.sr_diag, zu, du, nu, k, la, lb);
-            w[nx + k] = dual_w(dold.d4[e * nu + k], la, alpha, 0.0);
-            v2u[k] = lb;
-        }
+        const int e0 = j - 1, ci = T.cost_idx[j];
+        const double *d3 = dold.d3 + e0 * nx, *d4 = dold.d4 + e0 * nu - nx;
         const double to = po.tau[j], tn = pn.tau[j];
-        if (lane == 0) {
-            const double ht = 0.5 * (2 * tn - to);
-            w[nx + nu] = dual_w(dold.d5[e], ht, alpha, -0.5);
-            w[nx + nu + 1] = dual_w(dold.d6[e], ht, alpha, 0.5);
-        }
-        __syncwarp();
-        const SocResult sr = soc_classify(w, dim, lane);
-        for (int k = lane; k < nx; k += 32) {
-            const double dnew = alpha * (w[k] - soc_entry(sr, w[k], false));
-            dn.d3[e * nx + k] = dnew;
-            double dd, xi2;
-            R.dual(dold.d3[e * nx + k], dnew, v2[k], alpha, dd, xi2);
-            v1[k] = dd;
-            v2[k] = xi2;
-        }
-        for (int k = lane; k < nu; k += 32) {
-            const double dnew = alpha * (w[nx + k] - soc_entry(sr, w[nx + k], false));
-            dn.d4[e * nu + k] = dnew;
-            double dd, xi2;
-            R.dual(dold.d4[e * nu + k], dnew, v2u[k], alpha, dd, xi2);
-            v1u[k] = dd;
-            v2u[k] = xi2;
-        }
-        if (lane == 0) {
-            const double w5 = w[nx + nu], w6 = w[nx + nu + 1];
-            const double dn5 = alpha * (w5 - soc_entry(sr, w5, false));
-            const double dn6 = alpha * (w6 - soc_entry(sr, w6, true));
-            dn.d5[e] = dn5;
-            dn.d6[e] = dn6;
-            const double hdt = 0.5 * (tn - to);
-            double dd5, dd6, xi25, xi26;
-            R.dual(dold.d5[e], dn5, hdt, alpha, dd5, xi25);
-            R.dual(dold.d6[e], dn6, hdt, alpha, dd6, xi26);
-            R.primal(to, tn, 0.5 * (dd5 + dd6), 0.5 * (xi25 + xi26), alpha);
-        }
-        __syncwarp();
-        // pass B: child -> parent sums  g1 += sqrtQ_j dd3_j,  g2 += sqrtQ_j xi2_3j  (same for R / d4)
-        for (int k = lane; k < nx; k += 32) {
-            double a1, a2;
-            cost_mv2(sqT, M.sq_diag, v1, v2, nx, k, a1, a2);
-            g1[k] += a1;
-            g2[k] += a2;
-        }
-        for (int k = lane; k < nu; k += 32) {
-            double a1, a2;
-            cost_mv2(srT, M.sr_diag, v1u, v2u, nu, k, a1, a2);
-            g1u[k] += a1;
-            g2u[k] += a2;
-        }
-        __syncwarp();
-    }
-    // d7: rectangle on [x; u] (cache.py:367-371)
-    if (L.has_nl_rect) {
-        const long long ri = (long long)T.nl_rect_idx[node] * L.nxu;
-        for (int k = lane; k < L.nxu; k += 32) {
-            const bool isx = k < nx;
-            const double zk = isx ? zx[k] : zu[k - nx];
-            const double dk = isx ? dx[k] : du[k - nx];
-            const long long idx = (long long)node * L.nxu + k;
-            const double dol = dold.d7[idx];
-            const double wv = dual_w(dol, zk, alpha, 0.0);
-            const double dnew = alpha * (wv - box_clip(wv, M.nl_lo[ri + k], M.nl_hi[ri + k], &bad));
-            dn.d7[idx] = dnew;
-            double dd, xi2;
-            R.dual(dol, dnew, dk, alpha, dd, xi2);
-            if (isx) {
-                g1[k] += dd;
-                g2[k] += xi2;
+        // pass A over the concatenated edge vector [d3; d4; d5; d6]: w = (d + alpha L z) / alpha (+-1/2), |.|^2 of all
+        // but the last entry (the cone's t)
+        double ss = 0.0;
+        for (int e = lane; e < E; e += 32) {
+            double la, lb, dol, shift = 0.0;
+            if (e < nx) {
+                if (DIAG) {
+                    const double mm = M.sq_d[ci * nx + e];
+                    la = mm * z[e];
+                    lb = mm * dl[e];
+                } else {
+                    mv_row2(M.sqT + (long long)ci * nx * nx, z, dl, nx, nx, e, la, lb);
+                }
+                dol = d3[e];
+            } else if (e < nxu) {
+                if (DIAG) {
+                    const double mm = M.sr_d[ci * nu + e - nx];
+                    la = mm * z[e];
+                    lb = mm * dl[e];
+                } else {
+                    mv_row2(M.srT + (long long)ci * nu * nu, z + nx, dl + nx, nu, nu, e - nx, la, lb);
+                }
+                dol = d4[e];
             } else {
-                g1u[k - nx] += dd;
-                g2u[k - nx] += xi2;
+                la = 0.5 * (2 * tn - to);
+                lb = 0.5 * (tn - to);
+                dol = e == nxu ? dold.d5[e0] : dold.d6[e0];
+                shift = e == nxu ? -0.5 : 0.5;
+            }
+            const double wv = dual_w(dol, la, alpha, inv_alpha, shift);
+            w[e] = wv;
+            lbv[e] = lb;
+            if (e < E - 1) ss = fma(wv, wv, ss);
+        }
+        ss = warp_sum(ss);   // also orders the scratch writes above before the reads below
+        __syncwarp();
+        // SecondOrderCone.project (cones.py:113-132): same branch order
+        const double r = sqrt(ss), t = w[E - 1];
+        const int mode = r <= t ? 0 : (r <= -t ? 1 : 2);
+        const double t_new = (r + t) / 2;
+        const double scale = mode == 2 ? t_new / r : 0.0;   // reference: t_new * (w / r) entrywise
+        double tdd = 0.0, txi = 0.0;
+        for (int e = lane; e < E; e += 32) {
+            const double wv = w[e];
+            const double zv = mode == 0 ? wv : (mode == 1 ? 0.0 : (e == E - 1 ? t_new : scale * wv));
+            const double dnew = alpha * (wv - zv);
+            double dol;
+            if (e < nx) {
+                dol = d3[e];
+                dn.d3[e0 * nx + e] = dnew;
+            } else if (e < nxu) {
+                dol = d4[e];
+                dn.d4[e0 * nu + e - nx] = dnew;
+            } else if (e == nxu) {
+                dol = dold.d5[e0];
+                dn.d5[e0] = dnew;
+            } else {
+                dol = dold.d6[e0];
+                dn.d6[e0] = dnew;
+            }
+            const double dd = dol - dnew;
+            const double xi2 = R.dual(dd, lbv[e], inv_alpha);
+            if (e < nxu) {
+                if (DIAG) {   // child -> parent sums with a diagonal cost root: entrywise
+                    const double mm = e < nx ? M.sq_d[ci * nx + e] : M.sr_d[ci * nu + e - nx];
+                    g1[e] += mm * dd;
+                    g2[e] += mm * xi2;
+                } else {
+                    w[e] = dd;      // reuse as V1 / V2 for pass B (each lane rewrites only its own entries)
+                    lbv[e] = xi2;
+                }
+            } else {
+                tdd = dd;
+                txi = xi2;
+            }
+        }
+        // tau_j residual rows need d5 and d6 together: entries nxu and nxu+1 sit in neighbouring lanes
+        {
+            const int l5 = nxu & 31, l6 = (nxu + 1) & 31;
+            const double dd5 = __shfl_sync(0xffffffffu, tdd, l5), dd6 = __shfl_sync(0xffffffffu, tdd, l6);
+            const double x5 = __shfl_sync(0xffffffffu, txi, l5), x6 = __shfl_sync(0xffffffffu, txi, l6);
+            if (lane == 0) R.primal(tn - to, 0.5 * (dd5 + dd6), 0.5 * (x5 + x6), inv_alpha);
+        }
+        if (!DIAG) {
+            __syncwarp();
+            for (int k = lane; k < nxu; k += 32) {
+                double a1, a2;
+                if (k < nx) mv_row2(M.sqT + (long long)ci * nx * nx, w, lbv, nx, nx, k, a1, a2);
+                else mv_row2(M.srT + (long long)ci * nu * nu, w + nx, lbv + nx, nu, nu, k - nx, a1, a2);
+                g1[k] += a1;
+                g2[k] += a2;
             }
         }
         __syncwarp();
     }
-    for (int k = lane; k < nx; k += 32)
-        R.primal(po.x[(long long)node * nx + k], pn.x[(long long)node * nx + k], g1[k], g2[k], alpha);
-    for (int k = lane; k < nu; k += 32)
-        R.primal(po.u[(long long)node * nu + k], pn.u[(long long)node * nu + k], g1u[k], g2u[k], alpha);
+    // d7: rectangle on [x; u] (cache.py:367-371), then the x / u residual rows
+    const long long ri = L.has_nl_rect ? (long long)T.nl_rect_idx[node] * nxu : 0;
+    for (int k = lane; k < nxu; k += 32) {
+        double a1 = g1[k], a2 = g2[k];
+        if (L.has_nl_rect) {
+            const double dol = dold.d7[node * nxu + k];
+            const double wv = dual_w(dol, z[k], alpha, inv_alpha, 0.0);
+            const double dnew = alpha * (wv - box_clip(wv, M.nl_lo[ri + k], M.nl_hi[ri + k], &bad));
+            dn.d7[node * nxu + k] = dnew;
+            const double dd = dol - dnew;
+            a1 += dd;
+            a2 += R.dual(dd, dl[k], inv_alpha);
+        }
+        R.primal(dl[k], a1, a2, inv_alpha);
+    }
     // d1, d2 (risk blocks) and the y_i, s_i residual rows
-    const int yo = T.yoff[node];
+    const int yo = T.yoff[node], ny = 2 * cc + 1;
     double dot_z = 0.0, dot_d = 0.0;
-    for (int e = lane; e < 2 * cc + 1; e += 32) {
+    for (int e = lane; e < ny; e += 32) {
         const double yold = po.y[yo + e], ynew = pn.y[yo + e];
         const double b = e < cc ? T.cond_prob[c0 + e] : (e == 2 * cc ? 1.0 : 0.0);
         dot_z = fma(b, 2 * ynew - yold, dot_z);
@@ -411,110 +457,148 @@ __device__ __forceinline__ void dual_nonleaf_node(const Layout &L, const Topo &T
     dot_d = warp_sum(dot_d);
     const double so = po.s[node], sn = pn.s[node];
     const double do2 = dold.d2[node];
-    const double w2 = dual_w(do2, (2 * sn - so) - dot_z, alpha, 0.0);
+    const double w2 = dual_w(do2, (2 * sn - so) - dot_z, alpha, inv_alpha, 0.0);
     const double dn2 = alpha * (w2 - fmax(0.0, w2));
     const double dd2 = do2 - dn2;
-    const double xi22 = dd2 / alpha + ((sn - so) - dot_d);
+    const double xi22 = fma(dd2, inv_alpha, (sn - so) - dot_d);
     if (lane == 0) {
         dn.d2[node] = dn2;
         R.put(2, xi22);
-        R.put(5, dn2 - do2);
-        R.primal(so, sn, dd2, xi22, alpha);   // s_i of a nonleaf node: L* row is d2_i
+        R.put(5, dd2);
+        R.primal(sn - so, dd2, xi22, inv_alpha);   // s_i of a nonleaf node: its L* row is d2_i
     }
-    for (int e = lane; e < 2 * cc + 1; e += 32) {
+    for (int e = lane; e < ny; e += 32) {
         const double yold = po.y[yo + e], ynew = pn.y[yo + e];
         const double b = e < cc ? T.cond_prob[c0 + e] : (e == 2 * cc ? 1.0 : 0.0);
         const double do1 = dold.d1[yo + e];
-        const double wv = dual_w(do1, 2 * ynew - yold, alpha, 0.0);
+        const double wv = dual_w(do1, 2 * ynew - yold, alpha, inv_alpha, 0.0);
         const double zv = e < 2 * cc ? fmax(0.0, wv) : wv;
         const double dnew = alpha * (wv - zv);
         dn.d1[yo + e] = dnew;
-        double dd, xi2;
-        R.dual(do1, dnew, ynew - yold, alpha, dd, xi2);
-        R.primal(yold, ynew, dd - b * dd2, xi2 - b * xi22, alpha);
+        const double dd = do1 - dnew;
+        const double xi2 = R.dual(dd, ynew - yold, inv_alpha);
+        R.primal(ynew - yold, dd - b * dd2, xi2 - b * xi22, inv_alpha);
     }
     __syncwarp();
 }
 
+template <bool DIAG>
 __device__ __forceinline__ void dual_leaf_node(const Layout &L, const Topo &T, const Tabs &M, const PrimalView &po,
                                                const PrimalView &pn, const DualView &dold, const DualOut &dn, double alpha,
-                                               int node, int lane, double *rows, int rowlen, Resid &R, int &bad) {
-    const int nx = L.nx;
-    double *zx = rows + ZX * rowlen, *dx = rows + DX * rowlen, *v1 = rows + V1 * rowlen, *v2 = rows + V2 * rowlen;
-    double *w = rows + WROW * rowlen;
-    const long long li = node - L.m;
+                                               double inv_alpha, int node, int lane, double *rows, int rowlen, Resid &R,
+                                               int &bad) {
+    const int nx = L.nx, E = nx + 2;
+    double *z = rows + SZ * rowlen, *dl = rows + SDL * rowlen, *w = rows + SW * rowlen, *lbv = rows + SLB * rowlen;
+    double *g1 = rows + SG1 * rowlen, *g2 = rows + SG2 * rowlen;
+    const int li = node - L.m, lc = T.leafcost_idx[li];
+    const double *xo = po.x + node * nx, *xn = pn.x + node * nx, *d11 = dold.d11 + li * nx;
     for (int k = lane; k < nx; k += 32) {
-        const double xo = po.x[(long long)node * nx + k], xn = pn.x[(long long)node * nx + k];
-        zx[k] = 2 * xn - xo;
-        dx[k] = xn - xo;
+        z[k] = 2 * xn[k] - xo[k];
+        dl[k] = xn[k] - xo[k];
     }
     __syncwarp();
-    const double *sqfT = M.sqfT + (long long)T.leafcost_idx[li] * nx * nx;
-    const int dim = nx + 2;
-    for (int k = lane; k < nx; k += 32) {
-        double la, lb;
-        cost_mv2(sqfT, M.sqf_diag, zx, dx, nx, k, la, lb);
-        w[k] = dual_w(dold.d11[li * nx + k], la, alpha, 0.0);
-        v2[k] = lb;
-    }
     const double so = po.s[node], sn = pn.s[node];
-    if (lane == 0) {
-        const double hs = 0.5 * (2 * sn - so);
-        w[nx] = dual_w(dold.d12[li], hs, alpha, -0.5);
-        w[nx + 1] = dual_w(dold.d13[li], hs, alpha, 0.5);
+    double ss = 0.0;
+    for (int e = lane; e < E; e += 32) {   // concatenated [d11; d12; d13], SOC with t = d13 (cache.py:375-386)
+        double la, lb, dol, shift = 0.0;
+        if (e < nx) {
+            if (DIAG) {
+                const double mm = M.sqf_d[lc * nx + e];
+                la = mm * z[e];
+                lb = mm * dl[e];
+            } else {
+                mv_row2(M.sqfT + (long long)lc * nx * nx, z, dl, nx, nx, e, la, lb);
+            }
+            dol = d11[e];
+        } else {
+            la = 0.5 * (2 * sn - so);
+            lb = 0.5 * (sn - so);
+            dol = e == nx ? dold.d12[li] : dold.d13[li];
+            shift = e == nx ? -0.5 : 0.5;
+        }
+        const double wv = dual_w(dol, la, alpha, inv_alpha, shift);
+        w[e] = wv;
+        lbv[e] = lb;
+        if (e < E - 1) ss = fma(wv, wv, ss);
     }
+    ss = warp_sum(ss);
     __syncwarp();
-    const SocResult sr = soc_classify(w, dim, lane);
-    for (int k = lane; k < nx; k += 32) {
-        const double dnew = alpha * (w[k] - soc_entry(sr, w[k], false));
-        dn.d11[li * nx + k] = dnew;
-        double dd, xi2;
-        R.dual(dold.d11[li * nx + k], dnew, v2[k], alpha, dd, xi2);
-        v1[k] = dd;
-        v2[k] = xi2;
+    const double r = sqrt(ss), t = w[E - 1];
+    const int mode = r <= t ? 0 : (r <= -t ? 1 : 2);
+    const double t_new = (r + t) / 2;
+    const double scale = mode == 2 ? t_new / r : 0.0;
+    double tdd = 0.0, txi = 0.0;
+    for (int e = lane; e < E; e += 32) {
+        const double wv = w[e];
+        const double zv = mode == 0 ? wv : (mode == 1 ? 0.0 : (e == E - 1 ? t_new : scale * wv));
+        const double dnew = alpha * (wv - zv);
+        double dol;
+        if (e < nx) {
+            dol = d11[e];
+            dn.d11[li * nx + e] = dnew;
+        } else if (e == nx) {
+            dol = dold.d12[li];
+            dn.d12[li] = dnew;
+        } else {
+            dol = dold.d13[li];
+            dn.d13[li] = dnew;
+        }
+        const double dd = dol - dnew;
+        const double xi2 = R.dual(dd, lbv[e], inv_alpha);
+        if (e < nx) {
+            if (DIAG) {
+                const double mm = M.sqf_d[lc * nx + e];
+                g1[e] = mm * dd;
+                g2[e] = mm * xi2;
+            } else {
+                w[e] = dd;
+                lbv[e] = xi2;
+            }
+        } else {
+            tdd = dd;
+            txi = xi2;
+        }
     }
-    if (lane == 0) {
-        const double w12 = w[nx], w13 = w[nx + 1];
-        const double dn12 = alpha * (w12 - soc_entry(sr, w12, false));
-        const double dn13 = alpha * (w13 - soc_entry(sr, w13, true));
-        dn.d12[li] = dn12;
-        dn.d13[li] = dn13;
-        const double hds = 0.5 * (sn - so);
-        double dd12, dd13, xa, xb;
-        R.dual(dold.d12[li], dn12, hds, alpha, dd12, xa);
-        R.dual(dold.d13[li], dn13, hds, alpha, dd13, xb);
-        R.primal(so, sn, 0.5 * (dd12 + dd13), 0.5 * (xa + xb), alpha);
+    {
+        const int l12 = nx & 31, l13 = (nx + 1) & 31;
+        const double dd12 = __shfl_sync(0xffffffffu, tdd, l12), dd13 = __shfl_sync(0xffffffffu, tdd, l13);
+        const double xa = __shfl_sync(0xffffffffu, txi, l12), xb = __shfl_sync(0xffffffffu, txi, l13);
+        if (lane == 0) R.primal(sn - so, 0.5 * (dd12 + dd13), 0.5 * (xa + xb), inv_alpha);
     }
-    __syncwarp();
+    if (!DIAG) __syncwarp();
+    const long long ri = L.has_leaf_rect ? (long long)T.leaf_rect_idx[li] * nx : 0;
     for (int k = lane; k < nx; k += 32) {
         double a1, a2;
-        cost_mv2(sqfT, M.sqf_diag, v1, v2, nx, k, a1, a2);
-        if (L.has_leaf_rect) {
-            const long long ri = (long long)T.leaf_rect_idx[li] * nx;
-            const long long idx = li * nx + k;
-            const double dol = dold.d14[idx];
-            const double wv = dual_w(dol, zx[k], alpha, 0.0);
-            const double dnew = alpha * (wv - box_clip(wv, M.leaf_lo[ri + k], M.leaf_hi[ri + k], &bad));
-            dn.d14[idx] = dnew;
-            double dd, xi2;
-            R.dual(dol, dnew, dx[k], alpha, dd, xi2);
-            a1 += dd;
-            a2 += xi2;
+        if (DIAG) {
+            a1 = g1[k];
+            a2 = g2[k];
+        } else {
+            mv_row2(M.sqfT + (long long)lc * nx * nx, w, lbv, nx, nx, k, a1, a2);
         }
-        R.primal(po.x[(long long)node * nx + k], pn.x[(long long)node * nx + k], a1, a2, alpha);
+        if (L.has_leaf_rect) {
+            const double dol = dold.d14[li * nx + k];
+            const double wv = dual_w(dol, z[k], alpha, inv_alpha, 0.0);
+            const double dnew = alpha * (wv - box_clip(wv, M.leaf_lo[ri + k], M.leaf_hi[ri + k], &bad));
+            dn.d14[li * nx + k] = dnew;
+            const double dd = dol - dnew;
+            a1 += dd;
+            a2 += R.dual(dd, dl[k], inv_alpha);
+        }
+        R.primal(dl[k], a1, a2, inv_alpha);
     }
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(256) k_dual_tile(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
-                                                  TilePlan plan, const double *__restrict__ p_old,
-                                                  const double *__restrict__ p_new, const double *__restrict__ d_old,
-                                                  double *__restrict__ d_new, double *__restrict__ slots) {
+template <bool DIAG>
+__global__ void __launch_bounds__(256, 2) k_dual_tile(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
+                                                     TilePlan plan, const double *__restrict__ p_old,
+                                                     const double *__restrict__ p_new, const double *__restrict__ d_old,
+                                                     double *__restrict__ d_new, double *__restrict__ slots) {
     if (ctrl->done) return;
-    const double alpha = ctrl->alpha;
+    const double alpha = ctrl->alpha, inv_alpha = 1.0 / alpha;
     const Layout &L = P.L;
     extern __shared__ double dsm[];
-    __shared__ double blockmax[8][6];
+    __shared__ unsigned long long blockmax[8][6];
     __shared__ int blockflags;
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) blockflags = 0;
@@ -553,9 +637,9 @@ __global__ void __launch_bounds__(256) k_dual_tile(const __grid_constant__ Param
         d.d5 = st.stage(d.d5, c0 - 1, nE);
         d.d6 = st.stage(d.d6, c0 - 1, nE);
         if (L.has_nl_rect) d.d7 = st.stage(d.d7, (long long)lo * L.nxu, nN * L.nxu);
-        __syncthreads();
+        st.finish();
         for (int node = lo + warp; node < hi; node += warps)
-            dual_nonleaf_node(L, P.t, P.m, po, pn, d, dn, alpha, node, lane, rows, rowlen, R, bad);
+            dual_nonleaf_node<DIAG>(L, P.t, P.m, po, pn, d, dn, alpha, inv_alpha, node, lane, rows, rowlen, R, bad);
     } else {
         const long long nN = hi - lo, l0 = lo - L.m;
         po.x = st.stage(po.x, (long long)lo * nx, nN * nx);
@@ -566,27 +650,51 @@ __global__ void __launch_bounds__(256) k_dual_tile(const __grid_constant__ Param
         d.d12 = st.stage(d.d12, l0, nN);
         d.d13 = st.stage(d.d13, l0, nN);
         if (L.has_leaf_rect) d.d14 = st.stage(d.d14, l0 * nx, nN * nx);
-        __syncthreads();
+        st.finish();
         for (int node = lo + warp; node < hi; node += warps)
-            dual_leaf_node(L, P.t, P.m, po, pn, d, dn, alpha, node, lane, rows, rowlen, R, bad);
+            dual_leaf_node<DIAG>(L, P.t, P.m, po, pn, d, dn, alpha, inv_alpha, node, lane, rows, rowlen, R, bad);
     }
-    // block-level reduction of the six maxima, one atomic per slot per block
+    // block-level reduction of the six maxima (as bit patterns), one atomic per slot per block
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        const double mval = warp_max(R.v[i]);
+        unsigned long long mval = R.v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, mval, o);
+            mval = other > mval ? other : mval;
+        }
         if (lane == 0) blockmax[warp][i] = mval;
     }
-    const int anynan = __any_sync(0xffffffffu, R.nan);
     const int anybad = __any_sync(0xffffffffu, bad);
     __syncthreads();
-    if (lane == 0 && (anynan || anybad)) atomicOr(&blockflags, (anynan ? 2 : 0) | (anybad ? 1 : 0));
+    if (lane == 0 && anybad) atomicOr(&blockflags, 1);
     __syncthreads();
     if (threadIdx.x < 6) {
-        double mval = blockmax[0][threadIdx.x];
-        for (int wv = 1; wv < warps; ++wv) mval = fmax(mval, blockmax[wv][threadIdx.x]);
-        atomic_max_nonneg(slots + (long long)blockIdx.y * 6 + threadIdx.x, mval);
+        unsigned long long mval = blockmax[0][threadIdx.x];
+        for (int wv = 1; wv < warps; ++wv) mval = blockmax[wv][threadIdx.x] > mval ? blockmax[wv][threadIdx.x] : mval;
+        atomicMax(reinterpret_cast<unsigned long long *>(slots + (long long)blockIdx.y * 6 + threadIdx.x), mval);
     }
     if (threadIdx.x == 0 && blockflags) atomicOr(&ctrl->status, blockflags);
+}
+
+cudaError_t tile_kernels_set_smem(size_t primal_bytes, size_t dual_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(k_primal_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)primal_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_primal_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)primal_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dual_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dual_bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_dual_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dual_bytes);
+    return e;
+}
+
+void launch_primal_tile(bool diag, dim3 grid, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
+                        const TilePlan &plan, const double *p_old, const double *d_old, double *p_new) {
+    if (diag) k_primal_tile<true><<<grid, 256, smem, st>>>(P, ctrl, plan, p_old, d_old, p_new);
+    else k_primal_tile<false><<<grid, 256, smem, st>>>(P, ctrl, plan, p_old, d_old, p_new);
+}
+
+void launch_dual_tile(bool diag, dim3 grid, size_t smem, cudaStream_t st, const Params &P, Ctrl *ctrl, const TilePlan &plan,
+                      const double *p_old, const double *p_new, const double *d_old, double *d_new, double *slots) {
+    if (diag) k_dual_tile<true><<<grid, 256, smem, st>>>(P, ctrl, plan, p_old, p_new, d_old, d_new, slots);
+    else k_dual_tile<false><<<grid, 256, smem, st>>>(P, ctrl, plan, p_old, p_new, d_old, d_new, slots);
 }
 
 // ----------------------------------------------------------------------------------------------------------------
@@ -606,6 +714,8 @@ __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctr
         double *s = slots + (long long)b * 6;
         const double err = fmax(s[0], fmax(s[1], s[2]));
         if (!(err <= tol)) all_ok = false;
+        for (int i = 0; i < 6; ++i)
+            if (s[i] != s[i]) ctrl->status |= 2;   // a NaN maximum: some iterate entry is not finite
         if (hist && it < hist_capacity)
             for (int i = 0; i < 6; ++i) hist[((long long)it * P.L.batch + b) * 6 + i] = s[i];
         for (int i = 0; i < 6; ++i) {

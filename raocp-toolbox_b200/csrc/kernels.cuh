@@ -44,30 +44,34 @@ struct TilePlan {
     int num_tiles;
     int rowlen;      // doubles per warp-private scratch row (max(nx, nu) rounded up to even)
 };
-__global__ void k_primal_tile(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, TilePlan plan,
-                              const double *__restrict__ p_old, const double *__restrict__ d_old,
-                              double *__restrict__ p_new);
-__global__ void k_dual_tile(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, TilePlan plan,
-                            const double *__restrict__ p_old, const double *__restrict__ p_new,
-                            const double *__restrict__ d_old, double *__restrict__ d_new, double *__restrict__ slots);
+// host launchers of the tiled kernels (templates on DIAG = all cost square roots diagonal -> entrywise products
+// instead of matvecs; defined in fused.cu next to the kernels)
+cudaError_t tile_kernels_set_smem(size_t primal_bytes, size_t dual_bytes);
+void launch_primal_tile(bool diag, dim3 grid, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
+                        const TilePlan &plan, const double *p_old, const double *d_old, double *p_new);
+void launch_dual_tile(bool diag, dim3 grid, size_t smem, cudaStream_t st, const Params &P, Ctrl *ctrl, const TilePlan &plan,
+                      const double *p_old, const double *p_new, const double *d_old, double *d_new, double *slots);
 constexpr int kDualRowsHost = 15;   // must equal kDualRows in fused.cu
 __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, double *__restrict__ slots,
                         double *__restrict__ last);
 
-// ---- sweeps.cu: the DP sweeps in three launches ----------------------------------------------------------------------
-struct SweepPlan {
-    int t_s;               // cut stage: stages [0, t_s) belong to the top kernel, [t_s, num_stages) to the subtree CTAs
-    int num_sub;           // nodes at stage t_s = number of subtrees (0 if t_s == num_stages)
-    int depth;             // num_stages - t_s
-    const int *sub_lo;     // [num_sub][depth] first node of the subtree at stage t_s + d
-    const int *sub_hi;     // [num_sub][depth] one past the last
-    const int *stage_off;  // [num_stages + 1]
-    int tabs_in_smem;      // 1: A, A', B, B' staged in shared memory by every CTA
-    int num_dyn;
+// ---- sweeps.cu: the DP sweeps in a handful of launches ---------------------------------------------------------------
+struct SweepLevel {
+    int t_lo, depth;       // the level's subtrees are rooted at stage t_lo and cover stages [t_lo, t_lo + depth)
+    int num_sub;           // nodes at stage t_lo
+    int warps_per_sub;     // warps cooperating on one subtree (block barrier per stage if > 1)
+    int subs_per_cta;      // subtrees packed into one CTA
+    const int *lo, *hi;    // [num_sub][depth] node range of the subtree at stage t_lo + d
 };
-__global__ void k_sweep_sub_bwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, SweepPlan plan,
+struct SweepPlan {
+    SweepLevel lv[2];
+    int num_levels;        // 0, 1 or 2
+    int t_top;             // stages [0, t_top) belong to the top kernel
+    const int *stage_off;  // [num_stages + 1]
+};
+__global__ void k_sweep_sub_bwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, SweepLevel lv,
                                 const double *__restrict__ prim, double *__restrict__ q, double *__restrict__ r);
-__global__ void k_sweep_sub_fwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, SweepPlan plan,
+__global__ void k_sweep_sub_fwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, SweepLevel lv,
                                 double *__restrict__ prim, const double *__restrict__ r);
 __global__ void k_sweep_top(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, SweepPlan plan,
                             double *__restrict__ prim, double *__restrict__ q, double *__restrict__ r,
@@ -81,8 +85,8 @@ struct ClassView {
     const int *level_list;  // classes of the level being processed
 };
 __global__ void k_offline_level(const __grid_constant__ Params P, ClassView cv, int level_begin, int level_count,
-                                double *__restrict__ Ptab, double *__restrict__ Ktab, double *__restrict__ KTtab,
-                                double *__restrict__ RinvTtab, int *__restrict__ status);
+                                double *__restrict__ Ptab, double *__restrict__ Ktab, double *__restrict__ KRcatT,
+                                int *__restrict__ status);
 size_t offline_smem_bytes(int nx, int nu);
 
 // lambda_max(L* L) pieces

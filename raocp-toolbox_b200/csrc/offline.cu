@@ -22,8 +22,7 @@ size_t offline_smem_bytes(int nx, int nu) {
 __global__ void __launch_bounds__(kOffThreads) k_offline_level(const __grid_constant__ Params P, ClassView cv,
                                                               int level_begin, int level_count,
                                                               double *__restrict__ Ptab, double *__restrict__ Ktab,
-                                                              double *__restrict__ KTtab, double *__restrict__ RinvTtab,
-                                                              int *__restrict__ status) {
+                                                              double *__restrict__ KRcatT, int *__restrict__ status) {
     extern __shared__ double smem[];
     const int nx = P.L.nx, nu = P.L.nu;
     double *PB = smem;                 // nx x nu
@@ -151,14 +150,16 @@ __global__ void __launch_bounds__(kOffThreads) k_offline_level(const __grid_cons
         __syncthreads();
     }
     for (int i = tid; i < nx * nx; i += nt) Ptab[(long long)c * nx * nx + i] = Pa[i];
+    // K (for K' r) and the concatenation [K R~^-1] stored reduction-index-major (for u = K x + R~^-1 r)
+    double *KR = KRcatT + (long long)c * (nx + nu) * nu;
     for (int i = tid; i < nu * nx; i += nt) {
         const int a = i / nx, k = i % nx;
         Ktab[(long long)c * nu * nx + i] = Km[i];
-        KTtab[(long long)c * nu * nx + (long long)k * nu + a] = Km[i];
+        KR[(long long)k * nu + a] = Km[i];
     }
     for (int i = tid; i < nu * nu; i += nt) {
         const int a = i / nu, b = i % nu;
-        RinvTtab[(long long)c * nu * nu + (long long)b * nu + a] = Ri[i];
+        KR[(long long)(nx + b) * nu + a] = Ri[i];
     }
 }
 

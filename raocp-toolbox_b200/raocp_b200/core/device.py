@@ -214,6 +214,9 @@ class DeviceSolver:
     def use_graphs(self, enable=True):
         self._call("rb_use_graphs", 1 if enable else 0)
 
+    def force_dense_costs(self, enable=True):
+        self._call("rb_force_dense_costs", 1 if enable else 0)
+
     def loop_begin(self, alpha, max_iters, tol=-1.0, hist_capacity=0):
         self._call("rb_loop_begin", float(alpha), int(max_iters), float(tol), int(hist_capacity))
 

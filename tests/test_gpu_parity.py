@@ -21,7 +21,7 @@ def _build(name, **kw):
     return s, problems.build(s, r.core), r
 
 
-@pytest.fixture(scope="module", params=["demo", "cfg1", "mini2", "mini3", "mini5"])
+@pytest.fixture(scope="module", params=["demo", "cfg1", "mini2", "mini3", "mini5", "dense", "wide"])
 def case(request):
     s, problem, r = _build(request.param)
     cache = r.core.Cache(problem)
@@ -111,7 +111,7 @@ def test_prox_g_piecewise_equals_fused(case):
     assert seg_rel_err(flat, dev.get_dual(0)[0], g["proxg"][gather], dual=True) < 1e-12
 
 
-@pytest.mark.parametrize("mode", ["fused", "stepwise"])
+@pytest.mark.parametrize("mode", ["fused", "fused_dense_costs", "fused_no_graph", "stepwise"])
 def test_iterates_match_reference(case, mode):
     """first 100 iterates against the unmodified reference (same alpha, same x0), 1e-9 relative per segment"""
     g = golden(f"{case['name']}_iterates.npz")
@@ -122,9 +122,13 @@ def test_iterates_match_reference(case, mode):
     alpha = float(g["alpha"])
     keep = [int(k) for k in g["keep"]]
     worst = 0.0
-    if mode == "fused":
+    if mode.startswith("fused"):
         for k in keep:
             fresh = r.core.Solver(problem, verbose=False)
+            if mode == "fused_dense_costs":
+                fresh.cache.device_solver.force_dense_costs(True)
+            if mode == "fused_no_graph":
+                fresh.cache.device_solver.use_graphs(False)
             status = fresh.chock(g["x0"], max_iters=k - 1, tol=0.0, alpha=alpha)
             assert status == 1 and fresh.iterations == k
             d2 = fresh.cache.device_solver

@@ -13,7 +13,7 @@ from oracle.cp_node_oracle import NodeOracle
 
 import raocp_b200 as r
 
-NAMES = ["demo", "cfg1", "mini2", "mini3", "mini5"]
+NAMES = ["demo", "cfg1", "mini2", "mini3", "mini5", "dense", "wide"]
 
 
 def _problem(name):
