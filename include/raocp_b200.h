@@ -163,6 +163,8 @@ int rb_loop_end(rb_solver *s, double *xi_hist, double *delta_hist, int32_t *iter
  * sweep, dual pass (+ stopping test); advances the loop by one iteration. */
 int rb_profile_iteration(rb_solver *s, float *ms);
 int rb_use_graphs(rb_solver *s, int32_t enable);
+/* test hook: 0 = never use the one-thread-per-node passes (lane.cu), always the warp-per-node tile kernels */
+int rb_use_lane_kernels(rb_solver *s, int32_t enable);
 /* test hook: 1 = use the general dense-matrix cost path even if sqrtQ, sqrtR, sqrtQf are all diagonal */
 int rb_force_dense_costs(rb_solver *s, int32_t enable); /* 1 (default): one CUDA graph per iteration; 0: plain launches */
 int rb_launch_count(const rb_solver *s, int64_t *kernels_launched); /* kernels launched by this handle so far */

@@ -57,6 +57,8 @@ struct rb_solver {
     int *d_cls_child_ptr = nullptr, *d_cls_child_dyn = nullptr, *d_cls_child_cls = nullptr, *d_level_list = nullptr;
     double *Ptab = nullptr, *Ktab = nullptr, *KRcatT = nullptr;
     bool diag_costs = false;
+    int max_children = 1;
+    bool allow_lane = true;   // one-thread-per-node passes (lane.cu) when the problem qualifies
     // residual temporaries (allocated on first use)
     double *tp[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     double *td[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -192,6 +194,30 @@ inline double *view_d(rb_solver *s, int which) { return s->dual[(which == 0 && !
         if (rc_ != RB_OK) return rc_;   \
     } while (0)
 
+bool use_lane(const rb_solver *s) { return s->allow_lane && s->diag_costs && s->max_children <= kLaneMaxChildren; }
+
+void launch_primal(rb_solver *s, cudaStream_t st, int src, int dst) {
+    const Layout &L = s->P.L;
+    if (use_lane(s)) {
+        k_primal_lane<<<dim3((L.n + kLaneThreads - 1) / kLaneThreads, L.batch), kLaneThreads, 0, st>>>(
+            s->P, s->ctrl, s->prim[src], s->dual[src], s->prim[dst]);
+    } else {
+        launch_primal_tile(s->diag_costs, dim3(s->tiles.num_tiles, L.batch), s->primal_smem, st, s->P, s->ctrl, s->tiles,
+                           s->prim[src], s->dual[src], s->prim[dst]);
+    }
+}
+
+void launch_dual(rb_solver *s, cudaStream_t st, int src, int dst) {
+    const Layout &L = s->P.L;
+    if (use_lane(s)) {
+        k_dual_lane<<<dim3((L.n + kLaneThreads - 1) / kLaneThreads, L.batch), kLaneThreads, 0, st>>>(
+            s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots);
+    } else {
+        launch_dual_tile(s->diag_costs, dim3(s->tiles.num_tiles, L.batch), s->dual_smem, st, s->P, s->ctrl, s->tiles,
+                         s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots);
+    }
+}
+
 // the launches of the DP sweeps on `prim` (x, u rows hold xbar, ubar on entry and the projection on exit)
 int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st, cudaEvent_t mid = nullptr) {
     const SweepPlan &pl = s->plan;
@@ -321,6 +347,7 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
     std::vector<int> yoff(m + 1, 0);
     for (int i = 0; i < m; ++i) yoff[i + 1] = yoff[i] + 2 * s->child_count[i] + 1;
     L.ysz = yoff[m];
+    for (int i = 0; i < m; ++i) s->max_children = std::max(s->max_children, s->child_count[i]);
     {
         int64_t pc = 0, pp = 0;  // compact / padded cursors
         auto addp = [&](long long &field, int64_t len) {
@@ -921,12 +948,11 @@ namespace {
 int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st) {
     const Layout &L = s->P.L;
     const int dst = 1 - src;
-    const dim3 tg(s->tiles.num_tiles, L.batch);
-    launch_primal_tile(s->diag_costs, tg, s->primal_smem, st, s->P, s->ctrl, s->tiles, s->prim[src], s->dual[src], s->prim[dst]);
+    (void)L;
+    launch_primal(s, st, src, dst);
     int rc = launch_sweeps(s, s->ctrl, s->prim[dst], st);
     if (rc != RB_OK) return rc;
-    launch_dual_tile(s->diag_costs, tg, s->dual_smem, st, s->P, s->ctrl, s->tiles, s->prim[src], s->prim[dst], s->dual[src],
-                     s->dual[dst], s->slots);
+    launch_dual(s, st, src, dst);
     k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
     return launch_ok(s, "fused iteration");
 }
@@ -1136,14 +1162,13 @@ int rb_profile_iteration(rb_solver *s, float *ms) {
     for (auto &e : ev) RB_CUDA(s, cudaEventCreate(&e));
     const int src = s->old_i, dst = 1 - src;
     RB_CUDA(s, cudaEventRecord(ev[0], st));
-    const dim3 tg(s->tiles.num_tiles, L.batch);
-    launch_primal_tile(s->diag_costs, tg, s->primal_smem, st, s->P, s->ctrl, s->tiles, s->prim[src], s->dual[src], s->prim[dst]);
+    (void)L;
+    launch_primal(s, st, src, dst);
     RB_CUDA(s, cudaEventRecord(ev[1], st));
     int rcs = launch_sweeps(s, s->ctrl, s->prim[dst], st, ev[2]);
     if (rcs != RB_OK) return rcs;
     RB_CUDA(s, cudaEventRecord(ev[3], st));
-    launch_dual_tile(s->diag_costs, tg, s->dual_smem, st, s->P, s->ctrl, s->tiles, s->prim[src], s->prim[dst], s->dual[src],
-                     s->dual[dst], s->slots);
+    launch_dual(s, st, src, dst);
     k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
     RB_CUDA(s, cudaEventRecord(ev[4], st));
     RB_CUDA(s, cudaStreamSynchronize(st));
@@ -1160,6 +1185,17 @@ int rb_force_dense_costs(rb_solver *s, int32_t enable) {
     // test hook: run the general (dense matrix) cost path even when sqrtQ, sqrtR, sqrtQf are all diagonal
     const Tabs &M = s->P.m;
     s->diag_costs = !enable && M.sq_diag && M.sr_diag && M.sqf_diag;
+    for (int i = 0; i < 2; ++i)
+        if (s->graph[i]) {
+            cudaGraphExecDestroy(s->graph[i]);
+            s->graph[i] = nullptr;
+        }
+    return RB_OK;
+}
+
+int rb_use_lane_kernels(rb_solver *s, int32_t enable) {
+    if (!s) return RB_ERR_INVALID;
+    s->allow_lane = enable != 0;
     for (int i = 0; i < 2; ++i)
         if (s->graph[i]) {
             cudaGraphExecDestroy(s->graph[i]);

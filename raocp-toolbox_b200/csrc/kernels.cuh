@@ -51,7 +51,17 @@ void launch_primal_tile(bool diag, dim3 grid, size_t smem, cudaStream_t st, cons
                         const TilePlan &plan, const double *p_old, const double *d_old, double *p_new);
 void launch_dual_tile(bool diag, dim3 grid, size_t smem, cudaStream_t st, const Params &P, Ctrl *ctrl, const TilePlan &plan,
                       const double *p_old, const double *p_new, const double *d_old, double *d_new, double *slots);
-constexpr int kDualRowsHost = 15;   // must equal kDualRows in fused.cu
+constexpr int kDualRowsHost = 15;
+
+// ---- lane.cu: one thread per node (diagonal cost square roots, <= kLaneMaxChildren children per node) ---------------
+constexpr int kLaneThreads = 128;
+constexpr int kLaneMaxChildren = 8;
+__global__ void k_primal_lane(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
+                              const double *__restrict__ p_old, const double *__restrict__ d_old,
+                              double *__restrict__ p_new);
+__global__ void k_dual_lane(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, const double *__restrict__ p_old,
+                            const double *__restrict__ p_new, const double *__restrict__ d_old,
+                            double *__restrict__ d_new, double *__restrict__ slots);   // must equal kDualRows in fused.cu
 __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, double *__restrict__ slots,
                         double *__restrict__ last);
 

@@ -1,0 +1,374 @@
+// lane.cu -- the node-parallel passes of one Chambolle-Pock iteration with ONE THREAD PER TREE NODE (FP64, sm_100a).
+//
+// The warp-per-node tile kernels of fused.cu spend >85 % of their instructions on index arithmetic, shuffles and
+// divergent per-lane branches (ncu, profiles/r1_tile_kernels.md): a node carries only ~130 doubles.  Here every thread
+// owns a node and streams its rows sequentially, so all 32 lanes do identical useful work, there are no shuffles and
+// no shared-memory scratch rows.  Consecutive lanes own consecutive nodes, i.e. rows that are contiguous in the
+// node-major layout: a warp request touches 32 neighbouring rows, every 32-byte sector fetched from HBM is consumed
+// completely within a few loop iterations out of L1, and the per-node work (~3 k thread instructions) is spread over
+// enough warps to keep HBM busy.  Used when the cost square roots are diagonal (rb_create classifies the tables) and no
+// node has more than kLaneMaxChildren children; otherwise the general tile kernels run.
+//
+//   k_primal_lane : pbar = p - alpha L* d (solver.py:27-39), s_0 -= alpha (cache.py:253-257), kernel projection
+//                   (cache.py:290-317)
+//   k_dual_lane   : dbar = d + alpha L(2 p+ - p) (solver.py:44-58), prox of g* (cache.py:321-393), all six residual
+//                   inf-norms (solver.py:63-95,137-141)
+#include "kernels.cuh"
+
+namespace rb {
+
+namespace {
+
+struct ResidLane {
+    unsigned long long v[6];   // bit patterns of non-negative doubles order like the doubles; NaN sits above +inf
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < 6; ++i) v[i] = 0ull;
+    }
+    __device__ __forceinline__ void put(int slot, double x) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(x));
+        v[slot] = b > v[slot] ? b : v[slot];
+    }
+    __device__ __forceinline__ double dual(double dd, double lpp, double inv_alpha) {   // dd = d - d+
+        const double xi2 = fma(dd, inv_alpha, lpp);
+        put(2, xi2);
+        put(5, dd);
+        return xi2;
+    }
+    __device__ __forceinline__ void primal(double dp, double g1, double g2, double inv_alpha) {   // dp = p+ - p
+        const double xi1 = -fma(dp, inv_alpha, g1);
+        put(1, xi1);
+        put(0, xi1 + g2);
+        put(4, dp);
+        put(3, dp + g1);
+    }
+};
+
+__device__ __forceinline__ double dual_w(double d_old, double lz, double alpha, double inv_alpha) {
+    return fma(lz, alpha, d_old) * inv_alpha;
+}
+
+}  // namespace
+
+// ====================================================================================================================
+__global__ void __launch_bounds__(kLaneThreads) k_primal_lane(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
+                                                             const double *__restrict__ p_old,
+                                                             const double *__restrict__ d_old, double *__restrict__ p_new) {
+    if (ctrl->done) return;
+    const double alpha = ctrl->alpha;
+    const Layout &L = P.L;
+    const Topo &T = P.t;
+    const Tabs &M = P.m;
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= L.n) return;
+    const double *Po = p_old + (long long)blockIdx.y * L.np_pad;
+    const double *D = d_old + (long long)blockIdx.y * L.nd_pad;
+    double *Pn = p_new + (long long)blockIdx.y * L.np_pad;
+    const int nx = L.nx, nu = L.nu, nxu = L.nxu;
+    if (node >= L.m) {   // leaf: xbar = x - alpha (sqrtQf d11 + d14)   (operators.py:89-92)
+        const int li = node - L.m;
+        const double *sq = M.sqf_d + T.leafcost_idx[li] * nx;
+        const double *d11 = D + L.d11 + (long long)li * nx, *d14 = D + L.d14 + (long long)li * nx;
+        const double *xo = Po + L.px + (long long)node * nx;
+        double *xn = Pn + L.px + (long long)node * nx;
+        for (int k = 0; k < nx; ++k) {
+            double acc = sq[k] * d11[k];
+            if (L.has_leaf_rect) acc += d14[k];
+            xn[k] = xo[k] - alpha * acc;
+        }
+        return;
+    }
+    const int c0 = T.child_first[node], cc = T.child_count[node];
+    {   // [xbar; ubar] = [x; u] - alpha (Gamma' d7 + sum_j sqrt(Q_j, R_j) [d3_j; d4_j])   (operators.py:74-87)
+        const double *xo = Po + L.px + (long long)node * nx, *uo = Po + L.pu + (long long)node * nu;
+        double *xn = Pn + L.px + (long long)node * nx, *un = Pn + L.pu + (long long)node * nu;
+        const double *d7 = D + L.d7 + (long long)node * nxu;
+        for (int k = 0; k < nx; ++k) {
+            double acc = L.has_nl_rect ? d7[k] : 0.0;
+            for (int j = c0; j < c0 + cc; ++j) acc = fma(M.sq_d[T.cost_idx[j] * nx + k], D[L.d3 + (long long)(j - 1) * nx + k], acc);
+            xn[k] = xo[k] - alpha * acc;
+        }
+        for (int k = 0; k < nu; ++k) {
+            double acc = L.has_nl_rect ? d7[nx + k] : 0.0;
+            for (int j = c0; j < c0 + cc; ++j) acc = fma(M.sr_d[T.cost_idx[j] * nu + k], D[L.d4 + (long long)(j - 1) * nu + k], acc);
+            un[k] = uo[k] - alpha * acc;
+        }
+    }
+    // ybar_i, the children's taubar_j / sbar_j, and the projection onto ker [E' -I -I] (cache.py:290-317).  For AVaR
+    // M = [a I, -I, 1, -I, -I], M M' = (a^2+3) I + 1 1', so proj = v - M'(M M')^-1 M v in closed form.
+    const double d2v = D[L.d2 + node];
+    const int yo = T.yoff[node];
+    const double a = T.risk_alpha[node];
+    const double *yold = Po + L.py + yo, *d1 = D + L.d1 + yo;
+    double *ynew = Pn + L.py + yo;
+    const double ylast_bar = yold[2 * cc] - alpha * (d1[2 * cc] - d2v);
+    const double den = a * a + 3.0;
+    double rsum = 0.0;
+    for (int e = 0; e < cc; ++e) {
+        const int j = c0 + e;
+        const double ya = yold[e] - alpha * (d1[e] - T.cond_prob[j] * d2v);
+        const double yb = yold[cc + e] - alpha * d1[cc + e];
+        const double tj = Po[L.ptau + j] - alpha * (0.5 * (D[L.d5 + j - 1] + D[L.d6 + j - 1]));
+        const double lts = j < L.m ? D[L.d2 + j] : 0.5 * (D[L.d12 + j - L.m] + D[L.d13 + j - L.m]);
+        const double sj = Po[L.ps + j] - alpha * lts;
+        rsum += a * ya - yb + ylast_bar - tj - sj;
+    }
+    const double shift = rsum / (den + (double)cc);
+    double wsum = 0.0;
+    for (int e = 0; e < cc; ++e) {   // the same arithmetic again, bit for bit
+        const int j = c0 + e;
+        const double ya = yold[e] - alpha * (d1[e] - T.cond_prob[j] * d2v);
+        const double yb = yold[cc + e] - alpha * d1[cc + e];
+        const double tj = Po[L.ptau + j] - alpha * (0.5 * (D[L.d5 + j - 1] + D[L.d6 + j - 1]));
+        const double lts = j < L.m ? D[L.d2 + j] : 0.5 * (D[L.d12 + j - L.m] + D[L.d13 + j - L.m]);
+        const double sj = Po[L.ps + j] - alpha * lts;
+        const double w = ((a * ya - yb + ylast_bar - tj - sj) - shift) / den;
+        ynew[e] = ya - a * w;
+        ynew[cc + e] = yb + w;
+        Pn[L.ptau + j] = tj + w;
+        Pn[L.ps + j] = sj + w;
+        wsum += w;
+    }
+    ynew[2 * cc] = ylast_bar - wsum;
+    if (node == 0) {
+        Pn[L.ps] = (Po[L.ps] - alpha * d2v) - alpha;   // s_0: half step, then prox of alpha * identity
+        Pn[L.ptau] = Po[L.ptau] - alpha * Po[L.ptau];  // tau_0 (always 0; same arithmetic as the reference)
+    }
+}
+
+// ====================================================================================================================
+__global__ void __launch_bounds__(kLaneThreads) k_dual_lane(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
+                                                           const double *__restrict__ p_old, const double *__restrict__ p_new,
+                                                           const double *__restrict__ d_old, double *__restrict__ d_new,
+                                                           double *__restrict__ slots) {
+    if (ctrl->done) return;
+    const double alpha = ctrl->alpha, inv_alpha = 1.0 / alpha;
+    const Layout &L = P.L;
+    const Topo &T = P.t;
+    const Tabs &M = P.m;
+    // per-thread SOC results of the children, [slot][thread]: scale (projection = scale * w on all but the last entry)
+    // and the projected last entry
+    __shared__ double soc_scale[kLaneMaxChildren][kLaneThreads];
+    __shared__ double soc_last[kLaneMaxChildren][kLaneThreads];
+    __shared__ unsigned long long blockmax[kLaneThreads / 32][6];
+    __shared__ int blockflags;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) blockflags = 0;
+    const int node = blockIdx.x * blockDim.x + tid;
+    const double *Po = p_old + (long long)blockIdx.y * L.np_pad;
+    const double *Pn = p_new + (long long)blockIdx.y * L.np_pad;
+    const double *Do = d_old + (long long)blockIdx.y * L.nd_pad;
+    double *Dn = d_new + (long long)blockIdx.y * L.nd_pad;
+    const int nx = L.nx, nu = L.nu, nxu = L.nxu;
+    ResidLane R;
+    R.init();
+    int bad = 0;
+
+    if (node < L.m) {
+        const int c0 = T.child_first[node], cc = T.child_count[node];
+        const double *xo = Po + L.px + (long long)node * nx, *xn = Pn + L.px + (long long)node * nx;
+        const double *uo = Po + L.pu + (long long)node * nu, *un = Pn + L.pu + (long long)node * nu;
+        // ---- phase 1: classify the second-order-cone block of every child edge (cones.py:113-132) ---------------------
+        for (int jj = 0; jj < cc; ++jj) {
+            const int j = c0 + jj;
+            const long long e0 = j - 1;
+            const double *sq = M.sq_d + T.cost_idx[j] * nx, *sr = M.sr_d + T.cost_idx[j] * nu;
+            const double *d3 = Do + L.d3 + e0 * nx, *d4 = Do + L.d4 + e0 * nu;
+            double ss = 0.0;
+            for (int k = 0; k < nx; ++k) {
+                const double wv = dual_w(d3[k], sq[k] * (2 * xn[k] - xo[k]), alpha, inv_alpha);
+                ss = fma(wv, wv, ss);
+            }
+            for (int k = 0; k < nu; ++k) {
+                const double wv = dual_w(d4[k], sr[k] * (2 * un[k] - uo[k]), alpha, inv_alpha);
+                ss = fma(wv, wv, ss);
+            }
+            const double to = Po[L.ptau + j], tn = Pn[L.ptau + j];
+            const double ht = 0.5 * (2 * tn - to);
+            const double w5 = dual_w(Do[L.d5 + e0], ht, alpha, inv_alpha) - 0.5;
+            const double w6 = dual_w(Do[L.d6 + e0], ht, alpha, inv_alpha) + 0.5;
+            ss = fma(w5, w5, ss);
+            const double r = sqrt(ss);
+            double scale, last;
+            if (r <= w6) {          // inside the cone: projection = w
+                scale = 1.0;
+                last = w6;
+            } else if (r <= -w6) {  // inside the polar cone: projection = 0
+                scale = 0.0;
+                last = 0.0;
+            } else {
+                last = (r + w6) / 2;
+                scale = last / r;   // reference: last * (w / r) entrywise
+            }
+            soc_scale[jj][tid] = scale;
+            soc_last[jj][tid] = last;
+        }
+        // ---- phase 2: one pass over the [x; u] rows: d3/d4 of every child, d7, and the x / u residual rows ----------------
+        const long long ri = L.has_nl_rect ? (long long)T.nl_rect_idx[node] * nxu : 0;
+        const double *d7o = Do + L.d7 + (long long)node * nxu;
+        double *d7n = Dn + L.d7 + (long long)node * nxu;
+        for (int k = 0; k < nxu; ++k) {
+            const bool isx = k < nx;
+            const int kk = isx ? k : k - nx;
+            const double o = isx ? xo[kk] : uo[kk], nw = isx ? xn[kk] : un[kk];
+            const double z = 2 * nw - o, dlt = nw - o;
+            double g1 = 0.0, g2 = 0.0;
+            for (int jj = 0; jj < cc; ++jj) {
+                const int j = c0 + jj;
+                const long long e0 = j - 1;
+                const double mm = isx ? M.sq_d[T.cost_idx[j] * nx + kk] : M.sr_d[T.cost_idx[j] * nu + kk];
+                const long long idx = isx ? L.d3 + e0 * nx + kk : L.d4 + e0 * nu + kk;
+                const double dol = Do[idx];
+                const double wv = dual_w(dol, mm * z, alpha, inv_alpha);
+                const double dnew = alpha * (wv - soc_scale[jj][tid] * wv);
+                Dn[idx] = dnew;
+                const double dd = dol - dnew;
+                const double xi2 = R.dual(dd, mm * dlt, inv_alpha);
+                g1 = fma(mm, dd, g1);
+                g2 = fma(mm, xi2, g2);
+            }
+            if (L.has_nl_rect) {   // rectangle on [x; u] (cache.py:367-371)
+                const double dol = d7o[k];
+                const double wv = dual_w(dol, z, alpha, inv_alpha);
+                const double dnew = alpha * (wv - box_clip(wv, M.nl_lo[ri + k], M.nl_hi[ri + k], &bad));
+                d7n[k] = dnew;
+                const double dd = dol - dnew;
+                g1 += dd;
+                g2 += R.dual(dd, dlt, inv_alpha);
+            }
+            R.primal(dlt, g1, g2, inv_alpha);
+        }
+        // ---- d5, d6 and the tau_j residual rows ----------------------------------------------------------------------------
+        for (int jj = 0; jj < cc; ++jj) {
+            const int j = c0 + jj;
+            const long long e0 = j - 1;
+            const double to = Po[L.ptau + j], tn = Pn[L.ptau + j];
+            const double ht = 0.5 * (2 * tn - to), hdt = 0.5 * (tn - to);
+            const double do5 = Do[L.d5 + e0], do6 = Do[L.d6 + e0];
+            const double w5 = dual_w(do5, ht, alpha, inv_alpha) - 0.5;
+            const double w6 = dual_w(do6, ht, alpha, inv_alpha) + 0.5;
+            const double dn5 = alpha * (w5 - soc_scale[jj][tid] * w5);
+            const double dn6 = alpha * (w6 - soc_last[jj][tid]);
+            Dn[L.d5 + e0] = dn5;
+            Dn[L.d6 + e0] = dn6;
+            const double dd5 = do5 - dn5, dd6 = do6 - dn6;
+            const double x5 = R.dual(dd5, hdt, inv_alpha), x6 = R.dual(dd6, hdt, inv_alpha);
+            R.primal(tn - to, 0.5 * (dd5 + dd6), 0.5 * (x5 + x6), inv_alpha);
+        }
+        // ---- d1, d2 (risk blocks) and the y_i, s_i residual rows ----------------------------------------------------------
+        const int yo = T.yoff[node], ny = 2 * cc + 1;
+        const double *yold = Po + L.py + yo, *ynew = Pn + L.py + yo, *d1o = Do + L.d1 + yo;
+        double *d1n = Dn + L.d1 + yo;
+        double dot_z = 0.0, dot_d = 0.0;
+        for (int e = 0; e < cc; ++e) {
+            const double b = T.cond_prob[c0 + e];
+            dot_z = fma(b, 2 * ynew[e] - yold[e], dot_z);
+            dot_d = fma(b, ynew[e] - yold[e], dot_d);
+        }
+        dot_z += 2 * ynew[2 * cc] - yold[2 * cc];
+        dot_d += ynew[2 * cc] - yold[2 * cc];
+        const double so = Po[L.ps + node], sn = Pn[L.ps + node];
+        const double do2 = Do[L.d2 + node];
+        const double w2 = dual_w(do2, (2 * sn - so) - dot_z, alpha, inv_alpha);
+        const double dn2 = alpha * (w2 - fmax(0.0, w2));
+        Dn[L.d2 + node] = dn2;
+        const double dd2 = do2 - dn2;
+        const double xi22 = fma(dd2, inv_alpha, (sn - so) - dot_d);
+        R.put(2, xi22);
+        R.put(5, dd2);
+        R.primal(sn - so, dd2, xi22, inv_alpha);   // s_i of a nonleaf node: its L* row is d2_i
+        for (int e = 0; e < ny; ++e) {
+            const double b = e < cc ? T.cond_prob[c0 + e] : (e == 2 * cc ? 1.0 : 0.0);
+            const double dy = ynew[e] - yold[e];
+            const double do1 = d1o[e];
+            const double wv = dual_w(do1, 2 * ynew[e] - yold[e], alpha, inv_alpha);
+            const double zv = e < 2 * cc ? fmax(0.0, wv) : wv;   // dual of R_+^{2c} x {0} (risks.py:32-33)
+            const double dnew = alpha * (wv - zv);
+            d1n[e] = dnew;
+            const double dd = do1 - dnew;
+            const double xi2 = R.dual(dd, dy, inv_alpha);
+            R.primal(dy, dd - b * dd2, xi2 - b * xi22, inv_alpha);
+        }
+    } else if (node < L.n) {
+        // ---- leaf: SOC on [d11; d12; d13] (cache.py:375-386), rectangle on d14, x_i and s_i residual rows -----------------
+        const int li = node - L.m;
+        const double *sq = M.sqf_d + T.leafcost_idx[li] * nx;
+        const double *xo = Po + L.px + (long long)node * nx, *xn = Pn + L.px + (long long)node * nx;
+        const double *d11o = Do + L.d11 + (long long)li * nx, *d14o = Do + L.d14 + (long long)li * nx;
+        double *d11n = Dn + L.d11 + (long long)li * nx, *d14n = Dn + L.d14 + (long long)li * nx;
+        const double so = Po[L.ps + node], sn = Pn[L.ps + node];
+        const double hs = 0.5 * (2 * sn - so), hds = 0.5 * (sn - so);
+        const double do12 = Do[L.d12 + li], do13 = Do[L.d13 + li];
+        double ss = 0.0;
+        for (int k = 0; k < nx; ++k) {
+            const double wv = dual_w(d11o[k], sq[k] * (2 * xn[k] - xo[k]), alpha, inv_alpha);
+            ss = fma(wv, wv, ss);
+        }
+        const double w12 = dual_w(do12, hs, alpha, inv_alpha) - 0.5;
+        const double w13 = dual_w(do13, hs, alpha, inv_alpha) + 0.5;
+        ss = fma(w12, w12, ss);
+        const double r = sqrt(ss);
+        double scale, last;
+        if (r <= w13) {
+            scale = 1.0;
+            last = w13;
+        } else if (r <= -w13) {
+            scale = 0.0;
+            last = 0.0;
+        } else {
+            last = (r + w13) / 2;
+            scale = last / r;
+        }
+        const long long ri = L.has_leaf_rect ? (long long)T.leaf_rect_idx[li] * nx : 0;
+        for (int k = 0; k < nx; ++k) {
+            const double z = 2 * xn[k] - xo[k], dlt = xn[k] - xo[k];
+            const double mm = sq[k];
+            const double dol = d11o[k];
+            const double wv = dual_w(dol, mm * z, alpha, inv_alpha);
+            const double dnew = alpha * (wv - scale * wv);
+            d11n[k] = dnew;
+            const double dd = dol - dnew;
+            const double xi2 = R.dual(dd, mm * dlt, inv_alpha);
+            double g1 = mm * dd, g2 = mm * xi2;
+            if (L.has_leaf_rect) {
+                const double dol14 = d14o[k];
+                const double wv14 = dual_w(dol14, z, alpha, inv_alpha);
+                const double dn14 = alpha * (wv14 - box_clip(wv14, M.leaf_lo[ri + k], M.leaf_hi[ri + k], &bad));
+                d14n[k] = dn14;
+                const double dd14 = dol14 - dn14;
+                g1 += dd14;
+                g2 += R.dual(dd14, dlt, inv_alpha);
+            }
+            R.primal(dlt, g1, g2, inv_alpha);
+        }
+        const double dn12 = alpha * (w12 - scale * w12), dn13 = alpha * (w13 - last);
+        Dn[L.d12 + li] = dn12;
+        Dn[L.d13 + li] = dn13;
+        const double dd12 = do12 - dn12, dd13 = do13 - dn13;
+        const double xa = R.dual(dd12, hds, inv_alpha), xb = R.dual(dd13, hds, inv_alpha);
+        R.primal(sn - so, 0.5 * (dd12 + dd13), 0.5 * (xa + xb), inv_alpha);
+    }
+    // block-level reduction of the six maxima (as bit patterns), one atomic per slot per block
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        unsigned long long mval = R.v[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, mval, o);
+            mval = other > mval ? other : mval;
+        }
+        if (lane == 0) blockmax[warp][i] = mval;
+    }
+    const int anybad = __any_sync(0xffffffffu, bad);
+    __syncthreads();
+    if (lane == 0 && anybad) atomicOr(&blockflags, 1);
+    __syncthreads();
+    if (tid < 6) {
+        unsigned long long mval = blockmax[0][tid];
+        for (int wv = 1; wv < kLaneThreads / 32; ++wv) mval = blockmax[wv][tid] > mval ? blockmax[wv][tid] : mval;
+        atomicMax(reinterpret_cast<unsigned long long *>(slots + (long long)blockIdx.y * 6 + tid), mval);
+    }
+    if (tid == 0 && blockflags) atomicOr(&ctrl->status, blockflags);
+}
+
+}  // namespace rb

@@ -75,6 +75,7 @@ SYMBOLS = [
     ("rb_profile_iteration", C.c_int, [_H, C.POINTER(C.c_float)]),
     ("rb_use_graphs", C.c_int, [_H, C.c_int32]),
     ("rb_force_dense_costs", C.c_int, [_H, C.c_int32]),
+    ("rb_use_lane_kernels", C.c_int, [_H, C.c_int32]),
     ("rb_launch_count", C.c_int, [_H, C.POINTER(C.c_int64)]),
     ("rb_cone_project", C.c_int, [C.c_int32, C.c_int32, c_double_p, c_double_p]),
     ("rb_box_project", C.c_int, [C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]),

@@ -217,6 +217,9 @@ class DeviceSolver:
     def force_dense_costs(self, enable=True):
         self._call("rb_force_dense_costs", 1 if enable else 0)
 
+    def use_lane_kernels(self, enable=True):
+        self._call("rb_use_lane_kernels", 1 if enable else 0)
+
     def loop_begin(self, alpha, max_iters, tol=-1.0, hist_capacity=0):
         self._call("rb_loop_begin", float(alpha), int(max_iters), float(tol), int(hist_capacity))
 

@@ -111,7 +111,7 @@ def test_prox_g_piecewise_equals_fused(case):
     assert seg_rel_err(flat, dev.get_dual(0)[0], g["proxg"][gather], dual=True) < 1e-12
 
 
-@pytest.mark.parametrize("mode", ["fused", "fused_dense_costs", "fused_no_graph", "stepwise"])
+@pytest.mark.parametrize("mode", ["fused", "fused_tile_kernels", "fused_dense_costs", "fused_no_graph", "stepwise"])
 def test_iterates_match_reference(case, mode):
     """first 100 iterates against the unmodified reference (same alpha, same x0), 1e-9 relative per segment"""
     g = golden(f"{case['name']}_iterates.npz")
@@ -127,6 +127,8 @@ def test_iterates_match_reference(case, mode):
             fresh = r.core.Solver(problem, verbose=False)
             if mode == "fused_dense_costs":
                 fresh.cache.device_solver.force_dense_costs(True)
+            if mode == "fused_tile_kernels":
+                fresh.cache.device_solver.use_lane_kernels(False)
             if mode == "fused_no_graph":
                 fresh.cache.device_solver.use_graphs(False)
             status = fresh.chock(g["x0"], max_iters=k - 1, tol=0.0, alpha=alpha)
