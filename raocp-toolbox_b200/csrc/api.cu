@@ -194,7 +194,9 @@ inline double *view_d(rb_solver *s, int which) { return s->dual[(which == 0 && !
         if (rc_ != RB_OK) return rc_;   \
     } while (0)
 
-bool use_lane(const rb_solver *s) { return s->allow_lane && s->diag_costs && s->max_children <= kLaneMaxChildren; }
+bool use_lane(const rb_solver *s) {
+    return s->allow_lane && s->diag_costs && s->max_children <= kLaneMaxChildren && s->P.L.nx % 2 == 0 && s->P.L.nu % 2 == 0;
+}
 
 void launch_primal(rb_solver *s, cudaStream_t st, int src, int dst) {
     const Layout &L = s->P.L;

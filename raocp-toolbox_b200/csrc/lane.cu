@@ -48,6 +48,15 @@ __device__ __forceinline__ double dual_w(double d_old, double lz, double alpha, 
     return fma(lz, alpha, d_old) * inv_alpha;
 }
 
+// Rows are walked two doubles (16 bytes) at a time: nx and nu are even on this path, so every row start is 16-byte
+// aligned, a lane consumes a 32-byte sector in two consecutive loads, and a warp request moves 512 useful bytes.
+__device__ __forceinline__ double2 ld2(const double *__restrict__ p, int k2) {
+    return *reinterpret_cast<const double2 *>(p + 2 * k2);
+}
+__device__ __forceinline__ void st2(double *__restrict__ p, int k2, double a, double b) {
+    *reinterpret_cast<double2 *>(p + 2 * k2) = make_double2(a, b);
+}
+
 }  // namespace
 
 // ====================================================================================================================
@@ -71,10 +80,16 @@ __global__ void __launch_bounds__(kLaneThreads) k_primal_lane(const __grid_const
         const double *d11 = D + L.d11 + (long long)li * nx, *d14 = D + L.d14 + (long long)li * nx;
         const double *xo = Po + L.px + (long long)node * nx;
         double *xn = Pn + L.px + (long long)node * nx;
-        for (int k = 0; k < nx; ++k) {
-            double acc = sq[k] * d11[k];
-            if (L.has_leaf_rect) acc += d14[k];
-            xn[k] = xo[k] - alpha * acc;
+#pragma unroll 2
+        for (int k2 = 0; k2 < nx / 2; ++k2) {
+            const double2 m2 = ld2(sq, k2), a2 = ld2(d11, k2), o2 = ld2(xo, k2);
+            double acc0 = m2.x * a2.x, acc1 = m2.y * a2.y;
+            if (L.has_leaf_rect) {
+                const double2 b2 = ld2(d14, k2);
+                acc0 += b2.x;
+                acc1 += b2.y;
+            }
+            st2(xn, k2, o2.x - alpha * acc0, o2.y - alpha * acc1);
         }
         return;
     }
@@ -83,15 +98,27 @@ __global__ void __launch_bounds__(kLaneThreads) k_primal_lane(const __grid_const
         const double *xo = Po + L.px + (long long)node * nx, *uo = Po + L.pu + (long long)node * nu;
         double *xn = Pn + L.px + (long long)node * nx, *un = Pn + L.pu + (long long)node * nu;
         const double *d7 = D + L.d7 + (long long)node * nxu;
-        for (int k = 0; k < nx; ++k) {
-            double acc = L.has_nl_rect ? d7[k] : 0.0;
-            for (int j = c0; j < c0 + cc; ++j) acc = fma(M.sq_d[T.cost_idx[j] * nx + k], D[L.d3 + (long long)(j - 1) * nx + k], acc);
-            xn[k] = xo[k] - alpha * acc;
+#pragma unroll 2
+        for (int k2 = 0; k2 < nx / 2; ++k2) {
+            const double2 o2 = ld2(xo, k2);
+            double2 acc = L.has_nl_rect ? ld2(d7, k2) : make_double2(0.0, 0.0);
+            for (int j = c0; j < c0 + cc; ++j) {
+                const double2 m2 = ld2(M.sq_d + T.cost_idx[j] * nx, k2), v2 = ld2(D + L.d3 + (long long)(j - 1) * nx, k2);
+                acc.x = fma(m2.x, v2.x, acc.x);
+                acc.y = fma(m2.y, v2.y, acc.y);
+            }
+            st2(xn, k2, o2.x - alpha * acc.x, o2.y - alpha * acc.y);
         }
-        for (int k = 0; k < nu; ++k) {
-            double acc = L.has_nl_rect ? d7[nx + k] : 0.0;
-            for (int j = c0; j < c0 + cc; ++j) acc = fma(M.sr_d[T.cost_idx[j] * nu + k], D[L.d4 + (long long)(j - 1) * nu + k], acc);
-            un[k] = uo[k] - alpha * acc;
+#pragma unroll 2
+        for (int k2 = 0; k2 < nu / 2; ++k2) {
+            const double2 o2 = ld2(uo, k2);
+            double2 acc = L.has_nl_rect ? ld2(d7 + nx, k2) : make_double2(0.0, 0.0);
+            for (int j = c0; j < c0 + cc; ++j) {
+                const double2 m2 = ld2(M.sr_d + T.cost_idx[j] * nu, k2), v2 = ld2(D + L.d4 + (long long)(j - 1) * nu, k2);
+                acc.x = fma(m2.x, v2.x, acc.x);
+                acc.y = fma(m2.y, v2.y, acc.y);
+            }
+            st2(un, k2, o2.x - alpha * acc.x, o2.y - alpha * acc.y);
         }
     }
     // ybar_i, the children's taubar_j / sbar_j, and the projection onto ker [E' -I -I] (cache.py:290-317).  For AVaR
@@ -174,15 +201,24 @@ __global__ void __launch_bounds__(kLaneThreads) k_dual_lane(const __grid_constan
             const long long e0 = j - 1;
             const double *sq = M.sq_d + T.cost_idx[j] * nx, *sr = M.sr_d + T.cost_idx[j] * nu;
             const double *d3 = Do + L.d3 + e0 * nx, *d4 = Do + L.d4 + e0 * nu;
-            double ss = 0.0;
-            for (int k = 0; k < nx; ++k) {
-                const double wv = dual_w(d3[k], sq[k] * (2 * xn[k] - xo[k]), alpha, inv_alpha);
-                ss = fma(wv, wv, ss);
+            double ss = 0.0, ss1 = 0.0;
+#pragma unroll 4
+            for (int k2 = 0; k2 < nx / 2; ++k2) {
+                const double2 o2 = ld2(xo, k2), n2 = ld2(xn, k2), d2 = ld2(d3, k2), m2 = ld2(sq, k2);
+                const double w0 = dual_w(d2.x, m2.x * (2 * n2.x - o2.x), alpha, inv_alpha);
+                const double w1 = dual_w(d2.y, m2.y * (2 * n2.y - o2.y), alpha, inv_alpha);
+                ss = fma(w0, w0, ss);
+                ss1 = fma(w1, w1, ss1);
             }
-            for (int k = 0; k < nu; ++k) {
-                const double wv = dual_w(d4[k], sr[k] * (2 * un[k] - uo[k]), alpha, inv_alpha);
-                ss = fma(wv, wv, ss);
+#pragma unroll 4
+            for (int k2 = 0; k2 < nu / 2; ++k2) {
+                const double2 o2 = ld2(uo, k2), n2 = ld2(un, k2), d2 = ld2(d4, k2), m2 = ld2(sr, k2);
+                const double w0 = dual_w(d2.x, m2.x * (2 * n2.x - o2.x), alpha, inv_alpha);
+                const double w1 = dual_w(d2.y, m2.y * (2 * n2.y - o2.y), alpha, inv_alpha);
+                ss = fma(w0, w0, ss);
+                ss1 = fma(w1, w1, ss1);
             }
+            ss += ss1;
             const double to = Po[L.ptau + j], tn = Pn[L.ptau + j];
             const double ht = 0.5 * (2 * tn - to);
             const double w5 = dual_w(Do[L.d5 + e0], ht, alpha, inv_alpha) - 0.5;
@@ -207,36 +243,59 @@ __global__ void __launch_bounds__(kLaneThreads) k_dual_lane(const __grid_constan
         const long long ri = L.has_nl_rect ? (long long)T.nl_rect_idx[node] * nxu : 0;
         const double *d7o = Do + L.d7 + (long long)node * nxu;
         double *d7n = Dn + L.d7 + (long long)node * nxu;
-        for (int k = 0; k < nxu; ++k) {
-            const bool isx = k < nx;
-            const int kk = isx ? k : k - nx;
-            const double o = isx ? xo[kk] : uo[kk], nw = isx ? xn[kk] : un[kk];
+        // one entry of the [x; u] rows: old / new primal value, old d7 value, bounds -> new d7 value, residual rows;
+        // d3 / d4 of the children are handled by the caller through `edge`
+        auto entry = [&](double o, double nw, double d7old, double lo_b, double hi_b, double g1, double g2, double &d7new) {
             const double z = 2 * nw - o, dlt = nw - o;
-            double g1 = 0.0, g2 = 0.0;
-            for (int jj = 0; jj < cc; ++jj) {
-                const int j = c0 + jj;
-                const long long e0 = j - 1;
-                const double mm = isx ? M.sq_d[T.cost_idx[j] * nx + kk] : M.sr_d[T.cost_idx[j] * nu + kk];
-                const long long idx = isx ? L.d3 + e0 * nx + kk : L.d4 + e0 * nu + kk;
-                const double dol = Do[idx];
-                const double wv = dual_w(dol, mm * z, alpha, inv_alpha);
-                const double dnew = alpha * (wv - soc_scale[jj][tid] * wv);
-                Dn[idx] = dnew;
-                const double dd = dol - dnew;
-                const double xi2 = R.dual(dd, mm * dlt, inv_alpha);
-                g1 = fma(mm, dd, g1);
-                g2 = fma(mm, xi2, g2);
-            }
             if (L.has_nl_rect) {   // rectangle on [x; u] (cache.py:367-371)
-                const double dol = d7o[k];
-                const double wv = dual_w(dol, z, alpha, inv_alpha);
-                const double dnew = alpha * (wv - box_clip(wv, M.nl_lo[ri + k], M.nl_hi[ri + k], &bad));
-                d7n[k] = dnew;
-                const double dd = dol - dnew;
+                const double wv = dual_w(d7old, z, alpha, inv_alpha);
+                d7new = alpha * (wv - box_clip(wv, lo_b, hi_b, &bad));
+                const double dd = d7old - d7new;
                 g1 += dd;
                 g2 += R.dual(dd, dlt, inv_alpha);
             }
             R.primal(dlt, g1, g2, inv_alpha);
+        };
+        auto edge = [&](double mm, double z, double dlt, double dol, double scale, double &dnew, double &g1, double &g2) {
+            const double wv = dual_w(dol, mm * z, alpha, inv_alpha);
+            dnew = alpha * (wv - scale * wv);
+            const double dd = dol - dnew;
+            const double xi2 = R.dual(dd, mm * dlt, inv_alpha);
+            g1 = fma(mm, dd, g1);
+            g2 = fma(mm, xi2, g2);
+        };
+        for (int part = 0; part < 2; ++part) {   // part 0: x rows with d3 / sqrtQ, part 1: u rows with d4 / sqrtR
+            const int w = part == 0 ? nx : nu, off7 = part == 0 ? 0 : nx;
+            const double *po_row = part == 0 ? xo : uo, *pn_row = part == 0 ? xn : un;
+            const double *mtab = part == 0 ? M.sq_d : M.sr_d;
+            const long long seg = part == 0 ? L.d3 : L.d4;
+#pragma unroll 2
+            for (int k2 = 0; k2 < w / 2; ++k2) {
+                const double2 o2 = ld2(po_row, k2), n2 = ld2(pn_row, k2);
+                double2 d7v = make_double2(0.0, 0.0), lo2 = d7v, hi2 = d7v;
+                if (L.has_nl_rect) {
+                    d7v = ld2(d7o + off7, k2);
+                    lo2 = ld2(M.nl_lo + ri + off7, k2);
+                    hi2 = ld2(M.nl_hi + ri + off7, k2);
+                }
+                const double z0 = 2 * n2.x - o2.x, z1 = 2 * n2.y - o2.y, dl0 = n2.x - o2.x, dl1 = n2.y - o2.y;
+                double g10 = 0.0, g20 = 0.0, g11 = 0.0, g21 = 0.0;
+                for (int jj = 0; jj < cc; ++jj) {
+                    const int j = c0 + jj;
+                    const double2 m2 = ld2(mtab + T.cost_idx[j] * w, k2);
+                    const double *dseg = Do + seg + (long long)(j - 1) * w;
+                    const double2 dol2 = ld2(dseg, k2);
+                    const double scale = soc_scale[jj][tid];
+                    double dn0, dn1;
+                    edge(m2.x, z0, dl0, dol2.x, scale, dn0, g10, g20);
+                    edge(m2.y, z1, dl1, dol2.y, scale, dn1, g11, g21);
+                    st2(Dn + seg + (long long)(j - 1) * w, k2, dn0, dn1);
+                }
+                double dn70 = 0.0, dn71 = 0.0;
+                entry(o2.x, n2.x, d7v.x, lo2.x, hi2.x, g10, g20, dn70);
+                entry(o2.y, n2.y, d7v.y, lo2.y, hi2.y, g11, g21, dn71);
+                if (L.has_nl_rect) st2(d7n + off7, k2, dn70, dn71);
+            }
         }
         // ---- d5, d6 and the tau_j residual rows ----------------------------------------------------------------------------
         for (int jj = 0; jj < cc; ++jj) {
@@ -299,11 +358,16 @@ __global__ void __launch_bounds__(kLaneThreads) k_dual_lane(const __grid_constan
         const double so = Po[L.ps + node], sn = Pn[L.ps + node];
         const double hs = 0.5 * (2 * sn - so), hds = 0.5 * (sn - so);
         const double do12 = Do[L.d12 + li], do13 = Do[L.d13 + li];
-        double ss = 0.0;
-        for (int k = 0; k < nx; ++k) {
-            const double wv = dual_w(d11o[k], sq[k] * (2 * xn[k] - xo[k]), alpha, inv_alpha);
-            ss = fma(wv, wv, ss);
+        double ss = 0.0, ss1 = 0.0;
+#pragma unroll 4
+        for (int k2 = 0; k2 < nx / 2; ++k2) {
+            const double2 o2 = ld2(xo, k2), n2 = ld2(xn, k2), d2 = ld2(d11o, k2), m2 = ld2(sq, k2);
+            const double w0 = dual_w(d2.x, m2.x * (2 * n2.x - o2.x), alpha, inv_alpha);
+            const double w1 = dual_w(d2.y, m2.y * (2 * n2.y - o2.y), alpha, inv_alpha);
+            ss = fma(w0, w0, ss);
+            ss1 = fma(w1, w1, ss1);
         }
+        ss += ss1;
         const double w12 = dual_w(do12, hs, alpha, inv_alpha) - 0.5;
         const double w13 = dual_w(do13, hs, alpha, inv_alpha) + 0.5;
         ss = fma(w12, w12, ss);
@@ -320,26 +384,37 @@ __global__ void __launch_bounds__(kLaneThreads) k_dual_lane(const __grid_constan
             scale = last / r;
         }
         const long long ri = L.has_leaf_rect ? (long long)T.leaf_rect_idx[li] * nx : 0;
-        for (int k = 0; k < nx; ++k) {
-            const double z = 2 * xn[k] - xo[k], dlt = xn[k] - xo[k];
-            const double mm = sq[k];
-            const double dol = d11o[k];
+        auto leaf_entry = [&](double o, double nw, double mm, double dol, double dol14, double lo_b, double hi_b,
+                              double &dnew, double &dn14) {
+            const double z = 2 * nw - o, dlt = nw - o;
             const double wv = dual_w(dol, mm * z, alpha, inv_alpha);
-            const double dnew = alpha * (wv - scale * wv);
-            d11n[k] = dnew;
+            dnew = alpha * (wv - scale * wv);
             const double dd = dol - dnew;
             const double xi2 = R.dual(dd, mm * dlt, inv_alpha);
             double g1 = mm * dd, g2 = mm * xi2;
             if (L.has_leaf_rect) {
-                const double dol14 = d14o[k];
                 const double wv14 = dual_w(dol14, z, alpha, inv_alpha);
-                const double dn14 = alpha * (wv14 - box_clip(wv14, M.leaf_lo[ri + k], M.leaf_hi[ri + k], &bad));
-                d14n[k] = dn14;
+                dn14 = alpha * (wv14 - box_clip(wv14, lo_b, hi_b, &bad));
                 const double dd14 = dol14 - dn14;
                 g1 += dd14;
                 g2 += R.dual(dd14, dlt, inv_alpha);
             }
             R.primal(dlt, g1, g2, inv_alpha);
+        };
+#pragma unroll 2
+        for (int k2 = 0; k2 < nx / 2; ++k2) {
+            const double2 o2 = ld2(xo, k2), n2 = ld2(xn, k2), m2 = ld2(sq, k2), dol2 = ld2(d11o, k2);
+            double2 d14v = make_double2(0.0, 0.0), lo2 = d14v, hi2 = d14v;
+            if (L.has_leaf_rect) {
+                d14v = ld2(d14o, k2);
+                lo2 = ld2(M.leaf_lo + ri, k2);
+                hi2 = ld2(M.leaf_hi + ri, k2);
+            }
+            double dn0, dn1, q0 = 0.0, q1 = 0.0;
+            leaf_entry(o2.x, n2.x, m2.x, dol2.x, d14v.x, lo2.x, hi2.x, dn0, q0);
+            leaf_entry(o2.y, n2.y, m2.y, dol2.y, d14v.y, lo2.y, hi2.y, dn1, q1);
+            st2(d11n, k2, dn0, dn1);
+            if (L.has_leaf_rect) st2(d14n, k2, q0, q1);
         }
         const double dn12 = alpha * (w12 - scale * w12), dn13 = alpha * (w13 - last);
         Dn[L.d12 + li] = dn12;
