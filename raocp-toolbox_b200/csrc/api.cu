@@ -69,6 +69,7 @@ struct rb_solver {
     // DP sweeps in three launches (sweeps.cu)
     SweepPlan plan{};
     int top_warps = 16;
+    size_t sweep_smem_max = 0;
     // fused loop
     cudaGraphExec_t graph[2] = {nullptr, nullptr};  // graph[src]: one iteration reading buffer src, writing 1-src
     bool use_graphs = true;
@@ -223,22 +224,21 @@ void launch_dual(rb_solver *s, cudaStream_t st, int src, int dst) {
 // the launches of the DP sweeps on `prim` (x, u rows hold xbar, ubar on entry and the projection on exit)
 int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st, cudaEvent_t mid = nullptr) {
     const SweepPlan &pl = s->plan;
-    const unsigned batch = (unsigned)s->P.L.batch;
-    const size_t per_warp = (size_t)(2 * s->P.L.nxu + 32) * sizeof(double);
+    const Layout &L = s->P.L;
+    const unsigned batch = (unsigned)L.batch;
+    const size_t per_warp = (size_t)(2 * L.nxu + 32) * sizeof(double);
     auto grid = [&](const SweepLevel &lv) { return dim3((lv.num_sub + lv.subs_per_cta - 1) / lv.subs_per_cta, batch); };
     auto threads = [&](const SweepLevel &lv) { return 32 * lv.warps_per_sub * lv.subs_per_cta; };
-    for (int v = pl.num_levels - 1; v >= 0; --v) {
-        const SweepLevel &lv = pl.lv[v];
-        k_sweep_sub_bwd<<<grid(lv), threads(lv), per_warp * lv.warps_per_sub * lv.subs_per_cta, st>>>(s->P, ctrl, lv, prim,
-                                                                                                   s->q, s->r);
-    }
-    k_sweep_top<<<batch, 32 * s->top_warps, per_warp * s->top_warps, st>>>(s->P, ctrl, pl, prim, s->q, s->r, s->x0);
+    auto smem = [&](const SweepLevel &lv) {
+        return per_warp * lv.warps_per_sub * lv.subs_per_cta + (size_t)lv.subs_per_cta * lv.stage_cap * L.nxu * sizeof(double);
+    };
+    for (int v = pl.num_levels - 1; v >= 0; --v)
+        launch_sweep_sub_bwd(grid(pl.lv[v]), threads(pl.lv[v]), smem(pl.lv[v]), st, s->P, ctrl, pl.lv[v], prim, s->q, s->r);
+    launch_sweep_top(batch, 32 * s->top_warps, per_warp * s->top_warps + (size_t)pl.top_cap * L.nxu * sizeof(double), st, s->P,
+                     ctrl, pl, prim, s->q, s->r, s->x0);
     if (mid) cudaEventRecord(mid, st);
-    for (int v = 0; v < pl.num_levels; ++v) {
-        const SweepLevel &lv = pl.lv[v];
-        k_sweep_sub_fwd<<<grid(lv), threads(lv), per_warp * lv.warps_per_sub * lv.subs_per_cta, st>>>(s->P, ctrl, lv, prim,
-                                                                                                   s->r);
-    }
+    for (int v = 0; v < pl.num_levels; ++v)
+        launch_sweep_sub_fwd(grid(pl.lv[v]), threads(pl.lv[v]), smem(pl.lv[v]), st, s->P, ctrl, pl.lv[v], prim, s->r);
     return launch_ok(s, "DP sweeps");
 }
 
@@ -532,7 +532,16 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
                     }
                 }
             }
-            lv.warps_per_sub = std::min(16, max_width);
+            // widest stage of any subtree, in nodes or in children (rows of the group-shared buffer)
+            int cap = 1;
+            for (int c = 0; c < lv.num_sub; ++c)
+                for (int d = 0; d < lv.depth; ++d) {
+                    const int a = lo[(size_t)c * lv.depth + d], b = hi[(size_t)c * lv.depth + d];
+                    cap = std::max(cap, b - a);
+                    if (a < m) cap = std::max(cap, s->child_first[b - 1] + s->child_count[b - 1] - s->child_first[a]);
+                }
+            lv.stage_cap = max_width == 1 ? 0 : cap;
+            lv.warps_per_sub = std::min(16, max_width == 1 ? 1 : cap);
             lv.subs_per_cta = std::max(1, 8 / lv.warps_per_sub);
             int *d_lo = nullptr, *d_hi = nullptr;
             TRY(upload(s, lo.data(), lo.size(), &d_lo));
@@ -541,12 +550,20 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
             lv.hi = d_hi;
         }
         int top_max = 1;
-        for (int t = 0; t < pl.t_top; ++t) top_max = std::max(top_max, width(t));
+        for (int t = 0; t < pl.t_top; ++t) top_max = std::max(top_max, std::max(width(t), t + 1 < L.num_stages ? width(t + 1) : 1));
+        pl.top_cap = top_max;
         s->top_warps = std::min(32, std::max(1, top_max));
-        const int sweep_smem = 32 * (2 * (nx + nu) + 32) * (int)sizeof(double);
-        TRYC(cudaFuncSetAttribute(k_sweep_sub_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
-        TRYC(cudaFuncSetAttribute(k_sweep_sub_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
-        TRYC(cudaFuncSetAttribute(k_sweep_top, cudaFuncAttributeMaxDynamicSharedMemorySize, sweep_smem));
+        const size_t per_warp = (size_t)(2 * (nx + nu) + 32) * sizeof(double);
+        size_t need = per_warp * s->top_warps + (size_t)pl.top_cap * (nx + nu) * sizeof(double);
+        for (int v = 0; v < pl.num_levels; ++v)
+            need = std::max(need, per_warp * pl.lv[v].warps_per_sub * pl.lv[v].subs_per_cta +
+                                      (size_t)pl.lv[v].subs_per_cta * pl.lv[v].stage_cap * (nx + nu) * sizeof(double));
+        if (need > 200 * 1024) {
+            s->err = "sweep stage buffers do not fit in shared memory";
+            return bail(RB_ERR_INVALID);
+        }
+        s->sweep_smem_max = need;
+        TRYC(sweep_kernels_set_smem((int)need));
     }
     // ---- node tiles: runs of consecutive nodes (<= 32 nodes and <= 64 edges; leaves: <= 64 nodes) -----------------
     {

@@ -69,23 +69,26 @@ __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctr
 struct SweepLevel {
     int t_lo, depth;       // the level's subtrees are rooted at stage t_lo and cover stages [t_lo, t_lo + depth)
     int num_sub;           // nodes at stage t_lo
-    int warps_per_sub;     // warps cooperating on one subtree (block barrier per stage if > 1)
+    int warps_per_sub;     // warps cooperating on one subtree (block barriers per stage if > 1)
     int subs_per_cta;      // subtrees packed into one CTA
+    int stage_cap;         // max over subtrees / stages of max(#nodes, #children) of one stage (group-shared buffer rows)
     const int *lo, *hi;    // [num_sub][depth] node range of the subtree at stage t_lo + d
 };
 struct SweepPlan {
     SweepLevel lv[2];
     int num_levels;        // 0, 1 or 2
     int t_top;             // stages [0, t_top) belong to the top kernel
+    int top_cap;           // widest stage (nodes or children) handled by the top kernel
     const int *stage_off;  // [num_stages + 1]
 };
-__global__ void k_sweep_sub_bwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, SweepLevel lv,
-                                const double *__restrict__ prim, double *__restrict__ q, double *__restrict__ r);
-__global__ void k_sweep_sub_fwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, SweepLevel lv,
-                                double *__restrict__ prim, const double *__restrict__ r);
-__global__ void k_sweep_top(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, SweepPlan plan,
-                            double *__restrict__ prim, double *__restrict__ q, double *__restrict__ r,
-                            const double *__restrict__ x0);
+// host launchers (templates on <NX, NU> are instantiated and dispatched in sweeps.cu)
+cudaError_t sweep_kernels_set_smem(int bytes);
+void launch_sweep_sub_bwd(dim3 grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
+                          const SweepLevel &lv, const double *prim, double *q, double *r);
+void launch_sweep_sub_fwd(dim3 grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
+                          const SweepLevel &lv, double *prim, const double *r);
+void launch_sweep_top(int grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
+                      const SweepPlan &plan, double *prim, double *q, double *r, const double *x0);
 
 // ---- offline.cu --------------------------------------------------------------------------------------------------
 struct ClassView {
