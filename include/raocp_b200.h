@@ -159,8 +159,9 @@ int rb_loop_enqueue(rb_solver *s, int32_t count);
 int rb_loop_poll(rb_solver *s, int32_t *iters, int32_t *done, double *last_norms);
 int rb_step(rb_solver *s, const double *x0, double *norms);
 int rb_loop_end(rb_solver *s, double *xi_hist, double *delta_hist, int32_t *iters, int32_t *status);
-/* measurement hook: one iteration with CUDA events between its phases, ms[4] = primal pass, backward sweep, forward
- * sweep, dual pass (+ stopping test); advances the loop by one iteration. */
+/* measurement hook: one iteration with a CUDA event after every launch; ms[8] = primal pass, the sweep launches in order
+ * (backward levels bottom-up, top, forward levels top-down), dual pass (+ stopping test); unused entries -1.  Advances
+ * the loop by one iteration. */
 int rb_profile_iteration(rb_solver *s, float *ms);
 int rb_use_graphs(rb_solver *s, int32_t enable);
 /* test hook: 0 = never use the one-thread-per-node passes (lane.cu), always the warp-per-node tile kernels */

@@ -222,7 +222,8 @@ void launch_dual(rb_solver *s, cudaStream_t st, int src, int dst) {
 }
 
 // the launches of the DP sweeps on `prim` (x, u rows hold xbar, ubar on entry and the projection on exit)
-int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st, cudaEvent_t mid = nullptr) {
+int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st, cudaEvent_t *evs = nullptr) {
+    int ne = 0;
     const SweepPlan &pl = s->plan;
     const Layout &L = s->P.L;
     const unsigned batch = (unsigned)L.batch;
@@ -232,13 +233,17 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
     auto smem = [&](const SweepLevel &lv) {
         return per_warp * lv.warps_per_sub * lv.subs_per_cta + (size_t)lv.subs_per_cta * lv.stage_cap * L.nxu * sizeof(double);
     };
-    for (int v = pl.num_levels - 1; v >= 0; --v)
+    for (int v = pl.num_levels - 1; v >= 0; --v) {
         launch_sweep_sub_bwd(grid(pl.lv[v]), threads(pl.lv[v]), smem(pl.lv[v]), st, s->P, ctrl, pl.lv[v], prim, s->q, s->r);
+        if (evs) cudaEventRecord(evs[ne++], st);
+    }
     launch_sweep_top(batch, 32 * s->top_warps, per_warp * s->top_warps + (size_t)pl.top_cap * L.nxu * sizeof(double), st, s->P,
                      ctrl, pl, prim, s->q, s->r, s->x0);
-    if (mid) cudaEventRecord(mid, st);
-    for (int v = 0; v < pl.num_levels; ++v)
+    if (evs) cudaEventRecord(evs[ne++], st);
+    for (int v = 0; v < pl.num_levels; ++v) {
         launch_sweep_sub_fwd(grid(pl.lv[v]), threads(pl.lv[v]), smem(pl.lv[v]), st, s->P, ctrl, pl.lv[v], prim, s->r);
+        if (evs) cudaEventRecord(evs[ne++], st);
+    }
     return launch_ok(s, "DP sweeps");
 }
 
@@ -541,6 +546,7 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
                     if (a < m) cap = std::max(cap, s->child_first[b - 1] + s->child_count[b - 1] - s->child_first[a]);
                 }
             lv.stage_cap = max_width == 1 ? 0 : cap;
+            lv.chain = (max_width == 1 && lv.depth <= 64 && lv.t_lo + lv.depth == L.num_stages) ? 1 : 0;
             lv.warps_per_sub = std::min(16, max_width == 1 ? 1 : cap);
             lv.subs_per_cta = std::max(1, 8 / lv.warps_per_sub);
             int *d_lo = nullptr, *d_hi = nullptr;
@@ -1170,29 +1176,29 @@ int rb_step(rb_solver *s, const double *x0, double *norms) {
     return RB_OK;
 }
 
-// one iteration with CUDA events between its phases (plain launches): ms[0] primal pass, ms[1] backward sweep,
-// ms[2] forward sweep, ms[3] dual pass + stopping test.  Advances the loop by one iteration.
+// one iteration with CUDA events after every launch (plain launches).  ms[0] primal pass; ms[1..] the sweep launches in
+// order (backward levels bottom-up, top, forward levels top-down: 1 + 2 * levels entries); then the dual pass (+ stopping
+// test).  Unused entries are -1.  Advances the loop by one iteration.
 int rb_profile_iteration(rb_solver *s, float *ms) {
     if (!s || !ms) return RB_ERR_INVALID;
     if (!s->in_loop) return fail(s, RB_ERR_STATE, "rb_loop_begin() has not been called");
-    const Layout &L = s->P.L;
     cudaStream_t st = s->stream;
-    cudaEvent_t ev[5];
+    const int nsweep = 1 + 2 * s->plan.num_levels;
+    cudaEvent_t ev[9];
     for (auto &e : ev) RB_CUDA(s, cudaEventCreate(&e));
     const int src = s->old_i, dst = 1 - src;
     RB_CUDA(s, cudaEventRecord(ev[0], st));
-    (void)L;
     launch_primal(s, st, src, dst);
     RB_CUDA(s, cudaEventRecord(ev[1], st));
-    int rcs = launch_sweeps(s, s->ctrl, s->prim[dst], st, ev[2]);
+    int rcs = launch_sweeps(s, s->ctrl, s->prim[dst], st, ev + 2);
     if (rcs != RB_OK) return rcs;
-    RB_CUDA(s, cudaEventRecord(ev[3], st));
     launch_dual(s, st, src, dst);
     k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
-    RB_CUDA(s, cudaEventRecord(ev[4], st));
+    RB_CUDA(s, cudaEventRecord(ev[2 + nsweep], st));
     RB_CUDA(s, cudaStreamSynchronize(st));
     int rc = launch_ok(s, "profiled iteration");
-    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    for (int i = 0; i < 8; ++i) ms[i] = -1.0f;
+    for (int i = 0; i < 2 + nsweep; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
     for (auto &e : ev) cudaEventDestroy(e);
     std::swap(s->cur_i, s->old_i);
     s->launches += s->kernels_per_iter;

@@ -71,6 +71,7 @@ struct SweepLevel {
     int num_sub;           // nodes at stage t_lo
     int warps_per_sub;     // warps cooperating on one subtree (block barriers per stage if > 1)
     int subs_per_cta;      // subtrees packed into one CTA
+    int chain;             // 1: every subtree is a chain down to the leaves (<= 64 nodes): prefetching chain walker
     int stage_cap;         // max over subtrees / stages of max(#nodes, #children) of one stage (group-shared buffer rows)
     const int *lo, *hi;    // [num_sub][depth] node range of the subtree at stage t_lo + d
 };

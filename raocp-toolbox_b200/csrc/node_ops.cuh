@@ -205,6 +205,167 @@ __device__ __forceinline__ void dyn_fwd_node(const Layout &L, const Topo &T, con
     __syncwarp();
 }
 
+// ---- chain walkers ------------------------------------------------------------------------------------------------------
+// Below the stopping time every subtree is a chain; one warp walks it.  Everything a step needs besides the previous
+// step's result is fetched ahead of time: the chain's node ids, dynamics rows and class ids are loaded once (lane d
+// holds depth d, broadcast by shuffle), the xbar / ubar / r rows of the NEXT step are prefetched into registers while
+// the current step computes, and q / x are carried in shared memory -- q of interior chain nodes never goes to HBM.
+// chain[d] = node at depth d (d = 0 is the head).  depth <= 64.
+template <int NX, int NU>
+__device__ __forceinline__ void chain_bwd(const Layout &L, const Topo &T, const Tabs &M, const double *__restrict__ X,
+                                          const double *__restrict__ U, double *__restrict__ Q, double *__restrict__ R,
+                                          const int *__restrict__ chain, int depth, int lane, double *scratch) {
+    const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
+    double *qj = scratch, *rv = scratch + nx, *acc = scratch + nxu;
+    // per-depth metadata: lanes hold depths lane and lane + 32
+    int node_a = lane < depth ? chain[lane] : 0, node_b = lane + 32 < depth ? chain[lane + 32] : 0;
+    int dyn_a = lane + 1 < depth ? T.dyn_idx[chain[lane + 1]] : 0, dyn_b = lane + 33 < depth ? T.dyn_idx[chain[lane + 33]] : 0;
+    int cls_a = (lane < depth && node_a < L.m) ? T.cls[node_a] : 0, cls_b = (lane + 32 < depth && node_b < L.m) ? T.cls[node_b] : 0;
+    auto at = [&](int va, int vb, int d) { return d < 32 ? __shfl_sync(0xffffffffu, va, d) : __shfl_sync(0xffffffffu, vb, d - 32); };
+    int d = depth - 1;
+    int node = at(node_a, node_b, d);
+    // rows of the current step (lane k: xbar[k], k < nx; ubar[k], k < nu; second register for widths > 32)
+    double xb0 = lane < nx ? X[node * nx + lane] : 0.0, xb1 = lane + 32 < nx ? X[node * nx + lane + 32] : 0.0;
+    double ub0 = 0.0, ub1 = 0.0;
+    if (node < L.m) {
+        ub0 = lane < nu ? U[node * nu + lane] : 0.0;
+        ub1 = lane + 32 < nu ? U[node * nu + lane + 32] : 0.0;
+    }
+    bool have_child = false;
+    for (; d >= 0; --d) {
+        // prefetch the rows of the next step (depth d - 1)
+        double nxb0 = 0.0, nxb1 = 0.0, nub0 = 0.0, nub1 = 0.0;
+        int next = 0;
+        if (d > 0) {
+            next = at(node_a, node_b, d - 1);
+            nxb0 = lane < nx ? X[next * nx + lane] : 0.0;
+            nxb1 = lane + 32 < nx ? X[next * nx + lane + 32] : 0.0;
+            nub0 = lane < nu ? U[next * nu + lane] : 0.0;
+            nub1 = lane + 32 < nu ? U[next * nu + lane + 32] : 0.0;
+        }
+        if (node >= L.m) {   // leaf: q = -xbar
+            if (lane < nx) qj[lane] = -xb0;
+            if (lane + 32 < nx) qj[lane + 32] = -xb1;
+        } else {
+            // acc = [A' q ; B' q] of the single child (the chain's previous node, q in shared memory) -- a node of a
+            // chain level always has its one child inside the chain
+            (void)have_child;
+            bwd_child_contrib<NX, NU>(L, M, at(dyn_a, dyn_b, d), qj, lane, acc, false);
+            __syncwarp();
+            // r = ubar - acc[nx:]  (lane a < nu)
+            if (lane < nu) {
+                const double rk = ub0 - acc[nx + lane];
+                rv[lane] = rk;
+                R[node * nu + lane] = rk;
+            }
+            if (lane + 32 < nu) {
+                const double rk = ub1 - acc[nx + lane + 32];
+                rv[lane + 32] = rk;
+                R[node * nu + lane + 32] = rk;
+            }
+            __syncwarp();
+            const double *Kc = M.K + (long long)at(cls_a, cls_b, d) * nu * nx;
+            double q0 = 0.0, q1 = 0.0;
+            if (lane < nx) {
+                double kr;
+                if constexpr (NX > 0) kr = mv_row_t<NX, NU>(Kc, rv, lane);
+                else kr = mv_row(Kc, rv, nx, nu, lane);
+                q0 = acc[lane] - xb0 - kr;
+            }
+            if (lane + 32 < nx) q1 = acc[lane + 32] - xb1 - mv_row(Kc, rv, nx, nu, lane + 32);
+            __syncwarp();
+            if (lane < nx) qj[lane] = q0;
+            if (lane + 32 < nx) qj[lane + 32] = q1;
+        }
+        have_child = true;
+        __syncwarp();
+        if (d == 0) {   // only the head's q is needed outside the chain
+            if (lane < nx) Q[node * nx + lane] = qj[lane];
+            if (lane + 32 < nx) Q[node * nx + lane + 32] = qj[lane + 32];
+        }
+        node = next;
+        xb0 = nxb0; xb1 = nxb1; ub0 = nub0; ub1 = nub1;
+    }
+}
+
+template <int NX, int NU>
+__device__ __forceinline__ void chain_fwd(const Layout &L, const Topo &T, const Tabs &M, double *__restrict__ X,
+                                          double *__restrict__ U, const double *__restrict__ R,
+                                          const int *__restrict__ chain, int depth, int lane, double *scratch) {
+    const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
+    double *v = scratch, *part = scratch + nxu, *xnext = scratch + nxu + 32;   // xnext: nx doubles
+    int node_a = lane < depth ? chain[lane] : 0, node_b = lane + 32 < depth ? chain[lane + 32] : 0;
+    int dyn_a = lane + 1 < depth ? T.dyn_idx[chain[lane + 1]] : 0, dyn_b = lane + 33 < depth ? T.dyn_idx[chain[lane + 33]] : 0;
+    int cls_a = (lane < depth && node_a < L.m) ? T.cls[node_a] : 0, cls_b = (lane + 32 < depth && node_b < L.m) ? T.cls[node_b] : 0;
+    auto at = [&](int va, int vb, int d) { return d < 32 ? __shfl_sync(0xffffffffu, va, d) : __shfl_sync(0xffffffffu, vb, d - 32); };
+    int node = at(node_a, node_b, 0);
+    // x of the head was written by the level above; r rows are prefetched one step ahead
+    if (lane < nx) v[lane] = X[node * nx + lane];
+    if (lane + 32 < nx) v[lane + 32] = X[node * nx + lane + 32];
+    double r0 = 0.0, r1 = 0.0;
+    if (node < L.m) {
+        r0 = lane < nu ? R[node * nu + lane] : 0.0;
+        r1 = lane + 32 < nu ? R[node * nu + lane + 32] : 0.0;
+    }
+    for (int d = 0; d + 1 < depth; ++d) {
+        if (node >= L.m) break;
+        const int child = at(node_a, node_b, d + 1);
+        double nr0 = 0.0, nr1 = 0.0;
+        if (child < L.m) {
+            nr0 = lane < nu ? R[child * nu + lane] : 0.0;
+            nr1 = lane + 32 < nu ? R[child * nu + lane + 32] : 0.0;
+        }
+        if (lane < nu) v[nx + lane] = r0;
+        if (lane + 32 < nu) v[nx + lane + 32] = r1;
+        __syncwarp();
+        const double *KR = M.KRcatT + (long long)at(cls_a, cls_b, d) * nxu * nu;
+        if (nu <= 32) {
+            double ua;
+            if constexpr (NX > 0) ua = mv_split_t<NU, NX + NU>(KR, v, lane, part);
+            else ua = mv_split(KR, v, nu, nxu, lane, part);
+            if (lane < nu) {
+                v[nx + lane] = ua;
+                U[node * nu + lane] = ua;
+            }
+        } else {
+            const double u0 = mv_row(KR, v, nu, nxu, lane), u1 = lane + 32 < nu ? mv_row(KR, v, nu, nxu, lane + 32) : 0.0;
+            __syncwarp();
+            v[nx + lane] = u0;
+            U[node * nu + lane] = u0;
+            if (lane + 32 < nu) {
+                v[nx + lane + 32] = u1;
+                U[node * nu + lane + 32] = u1;
+            }
+        }
+        __syncwarp();
+        // x_child = A x + B u, kept in shared memory for the next step and written out
+        const int dyn = at(dyn_a, dyn_b, d);
+        double x0 = 0.0, x1 = 0.0;
+        if constexpr (NX > 0) {
+            const double *C = M.ABcatT + dyn * ((NX + NU) * NX);
+            if (lane < NX) x0 = mv_row_t<NX, NX + NU>(C, v, lane);
+        } else {
+            const double *C = M.ABcatT + (long long)dyn * nxu * nx;
+            if (lane < nx) x0 = mv_row(C, v, nx, nxu, lane);
+            if (lane + 32 < nx) x1 = mv_row(C, v, nx, nxu, lane + 32);
+        }
+        __syncwarp();
+        if (lane < nx) {
+            v[lane] = x0;
+            X[child * nx + lane] = x0;
+        }
+        if (lane + 32 < nx) {
+            v[lane + 32] = x1;
+            X[child * nx + lane + 32] = x1;
+        }
+        (void)xnext;
+        node = child;
+        r0 = nr0;
+        r1 = nr1;
+    }
+    __syncwarp();
+}
+
 // Projection of (y_i, tau_ch(i), s_ch(i)) onto ker [E' -I -I] (reference cache.py:290-317), in place.  For AVaR
 // (risks.py:28-35) M = [a I, -I, 1, -I, -I] and M M' = (a^2+3) I + 1 1', hence proj = v - M'(M M')^-1 M v in closed form.
 __device__ __forceinline__ void kernel_projection(const Params &P, double *Pp, int node, int lane) {

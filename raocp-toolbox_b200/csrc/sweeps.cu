@@ -38,9 +38,10 @@ __device__ __forceinline__ void stage_bwd(const Layout &L, const Topo &T, const 
                                           const double *__restrict__ U, double *__restrict__ Q, double *__restrict__ R,
                                           int lo, int hi, const Group &g, int lane, bool live) {
     const int nx = NX > 0 ? NX : L.nx, nxu = NX > 0 ? NX + NU : L.nxu;
-    if (g.wps == 1) {   // a single warp owns the subtree (chains): no barriers at all
+    if (g.wps == 1) {   // a single warp owns the whole stage range (top of a tiny tree)
         if (live)
             for (int node = lo; node < hi; ++node) dyn_bwd_node<NX, NU>(L, T, M, X, U, Q, R, node, lane, g.scratch);
+        __syncwarp();
         return;
     }
     const bool leaves = lo >= L.m;
@@ -126,6 +127,10 @@ __global__ void __launch_bounds__(512) k_sweep_sub_bwd(const __grid_constant__ P
     const int sub = blockIdx.x * lv.subs_per_cta + warp / lv.warps_per_sub;
     const bool live = sub < lv.num_sub;
     const int *lo = lv.lo + (long long)(live ? sub : 0) * lv.depth, *hi = lv.hi + (long long)(live ? sub : 0) * lv.depth;
+    if (lv.chain) {   // chains: one warp walks one chain, no barriers
+        if (live) chain_bwd<NX, NU>(L, P.t, P.m, Pp + L.px, Pp + L.pu, Q, R, lo, lv.depth, lane, g.scratch);
+        return;
+    }
     for (int d = lv.depth - 1; d >= 0; --d)
         stage_bwd<NX, NU>(L, P.t, P.m, Pp + L.px, Pp + L.pu, Q, R, lo[d], hi[d], g, lane, live);
 }
@@ -144,6 +149,10 @@ __global__ void __launch_bounds__(512) k_sweep_sub_fwd(const __grid_constant__ P
     const int sub = blockIdx.x * lv.subs_per_cta + warp / lv.warps_per_sub;
     const bool live = sub < lv.num_sub;
     const int *lo = lv.lo + (long long)(live ? sub : 0) * lv.depth, *hi = lv.hi + (long long)(live ? sub : 0) * lv.depth;
+    if (lv.chain) {
+        if (live) chain_fwd<NX, NU>(L, P.t, P.m, Pp + L.px, Pp + L.pu, R, lo, lv.depth, lane, g.scratch);
+        return;
+    }
     for (int d = 0; d < lv.depth; ++d) stage_fwd<NX, NU>(L, P.t, P.m, Pp + L.px, Pp + L.pu, R, lo[d], hi[d], g, lane, live);
 }
 

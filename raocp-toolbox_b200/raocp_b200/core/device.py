@@ -242,7 +242,7 @@ class DeviceSolver:
         return iters.value, status.value
 
     def profile_iteration(self):
-        """ms of (primal pass, backward sweep, forward sweep, dual pass) of one iteration, CUDA events"""
-        ms = (C.c_float * 4)()
+        """ms per launch of one iteration (CUDA events): primal, sweep launches in order, dual + stopping test"""
+        ms = (C.c_float * 8)()
         self._call("rb_profile_iteration", ms)
-        return list(ms)
+        return [v for v in ms if v >= 0.0]
