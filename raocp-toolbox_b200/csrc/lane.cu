@@ -1,13 +1,15 @@
 // lane.cu -- the node-parallel passes of one Chambolle-Pock iteration with ONE THREAD PER TREE NODE (FP64, sm_100a).
 //
 // The warp-per-node tile kernels of fused.cu spend >85 % of their instructions on index arithmetic, shuffles and
-// divergent per-lane branches (ncu, profiles/r1_tile_kernels.md): a node carries only ~130 doubles.  Here every thread
-// owns a node and streams its rows sequentially, so all 32 lanes do identical useful work, there are no shuffles and
-// no shared-memory scratch rows.  Consecutive lanes own consecutive nodes, i.e. rows that are contiguous in the
-// node-major layout: a warp request touches 32 neighbouring rows, every 32-byte sector fetched from HBM is consumed
-// completely within a few loop iterations out of L1, and the per-node work (~3 k thread instructions) is spread over
-// enough warps to keep HBM busy.  Used when the cost square roots are diagonal (rb_create classifies the tables) and no
-// node has more than kLaneMaxChildren children; otherwise the general tile kernels run.
+// divergent per-lane branches (profiles/r1_kernel_evolution.md): a node carries only ~130 doubles.  Here every thread
+// owns a node and streams its rows sequentially with 16-byte loads: all 32 lanes do identical useful work, there are no
+// shuffles and no shared-memory scratch rows, and the instruction count is 5x lower (227 warp instructions per node
+// for the dual pass).  Consecutive lanes own consecutive nodes, i.e. rows that are contiguous in the node-major layout;
+// a 32-byte sector fetched for a lane is consumed by that lane's next load.  What bounds these kernels now is the
+// L1TEX wavefront rate (one wavefront per row touched by a request) and the small number of warps a 6e4-node tree
+// offers (13 per SM); a shared-memory staged variant measured no faster (profiles/r1_kernel_evolution.md), so the
+// simple form is kept.  Used when the cost square roots are diagonal (rb_create classifies the tables), nx and nu are
+// even and no node has more than kLaneMaxChildren children; otherwise the general warp-per-node tile kernels run.
 //
 //   k_primal_lane : pbar = p - alpha L* d (solver.py:27-39), s_0 -= alpha (cache.py:253-257), kernel projection
 //                   (cache.py:290-317)

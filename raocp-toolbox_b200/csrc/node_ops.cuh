@@ -11,11 +11,15 @@ namespace rb {
 // one output row per lane with compile-time shape: sum_l MT[l*ROWS + k] * v[l]
 template <int ROWS, int COLS>
 __device__ __forceinline__ double mv_row_t(const double *__restrict__ MT, const double *__restrict__ v, int k) {
+    // all matrix loads are issued before the first multiply-add: one L1/L2 round trip per product, not one per term
+    double mcol[COLS];
+#pragma unroll
+    for (int l = 0; l < COLS; ++l) mcol[l] = __ldg(MT + l * ROWS + k);
     double a0 = 0.0, a1 = 0.0;
 #pragma unroll
     for (int l = 0; l < COLS; ++l) {
-        if (l & 1) a1 = fma(MT[l * ROWS + k], v[l], a1);
-        else a0 = fma(MT[l * ROWS + k], v[l], a0);
+        if (l & 1) a1 = fma(mcol[l], v[l], a1);
+        else a0 = fma(mcol[l], v[l], a0);
     }
     return a0 + a1;
 }
@@ -126,10 +130,16 @@ __device__ __forceinline__ double mv_split_t(const double *__restrict__ MT, cons
         const int g = lane / ROWS, a = lane - g * ROWS;
         double p = 0.0;
         if (g < G) {
+            double mcol[SEG];
 #pragma unroll
             for (int i = 0; i < SEG; ++i) {
                 const int l = g * SEG + i;
-                if (l < COLS) p = fma(MT[l * ROWS + a], v[l], p);
+                mcol[i] = l < COLS ? __ldg(MT + l * ROWS + a) : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) {
+                const int l = g * SEG + i;
+                if (l < COLS) p = fma(mcol[i], v[l], p);
             }
         }
         part[lane] = p;
