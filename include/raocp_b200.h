@@ -81,6 +81,10 @@ typedef struct {
     int32_t num_cls;
     const int32_t *cls;        /* [m] */
     int32_t device;            /* CUDA device ordinal */
+    /* subtree sharding of ONE tree over the GPUs of a box: every rank passes the whole problem and its
+     * (rank, world); world <= 1 = not sharded.  Rank r owns a contiguous block of the subtrees below the first stage
+     * with >= 64 nodes and replicates the nodes above it; rb_shard_init must follow rb_create. */
+    int32_t shard_rank, shard_world;
 } rb_problem;
 
 /* -- lifetime ---------------------------------------------------------------------------------------------------- */
@@ -164,6 +168,12 @@ int rb_loop_end(rb_solver *s, double *xi_hist, double *delta_hist, int32_t *iter
  * the loop by one iteration. */
 int rb_profile_iteration(rb_solver *s, float *ms);
 int rb_use_graphs(rb_solver *s, int32_t enable);
+/* subtree sharding: rank 0 calls rb_shard_unique_id and distributes the 128 bytes (e.g. torch.distributed broadcast),
+ * every rank then calls rb_shard_init (collective: ncclCommInitRank).  Afterwards rb_iterate / rb_loop_* run the
+ * sharded loop: per iteration ONE all-gather of the cut-stage q_j, d2_j and the residual maxima; the iterates of a
+ * rank are valid on its own nodes and on the replicated top of the tree. */
+int rb_shard_unique_id(char *id128);
+int rb_shard_init(rb_solver *s, const char *id128);
 /* test hook: 0 = never use the one-thread-per-node passes (lane.cu), always the warp-per-node tile kernels */
 int rb_use_lane_kernels(rb_solver *s, int32_t enable);
 /* test hook: 1 = use the general dense-matrix cost path even if sqrtQ, sqrtR, sqrtQf are all diagonal */

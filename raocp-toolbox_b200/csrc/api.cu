@@ -70,6 +70,16 @@ struct rb_solver {
     SweepPlan plan{};
     int top_warps = 16;
     size_t sweep_smem_max = 0;
+    // subtree sharding over GPUs (shard.cu)
+    ShardPlan shard{};
+    bool sharded = false;
+    void *nccl_comm = nullptr;
+    int *owned_nodes = nullptr, *top_nodes = nullptr, *dual_nodes = nullptr;   // device node lists
+    int n_owned = 0, n_top = 0;
+    SweepLevel shard_lv[2]{};
+    double *xchg_send = nullptr, *xchg_recv = nullptr;
+    size_t xchg_count = 0;
+    bool shard_pending = false;   // an executed iteration whose residuals have not been gathered / tested yet
     // fused loop
     cudaGraphExec_t graph[2] = {nullptr, nullptr};  // graph[src]: one iteration reading buffer src, writing 1-src
     bool use_graphs = true;
@@ -199,22 +209,24 @@ bool use_lane(const rb_solver *s) {
     return s->allow_lane && s->diag_costs && s->max_children <= kLaneMaxChildren && s->P.L.nx % 2 == 0 && s->P.L.nu % 2 == 0;
 }
 
-void launch_primal(rb_solver *s, cudaStream_t st, int src, int dst) {
+void launch_primal(rb_solver *s, cudaStream_t st, int src, int dst, const int *nodes = nullptr, int count = -1) {
     const Layout &L = s->P.L;
+    if (count < 0) count = L.n;
     if (use_lane(s)) {
-        k_primal_lane<<<dim3((L.n + kLaneThreads - 1) / kLaneThreads, L.batch), kLaneThreads, 0, st>>>(
-            s->P, s->ctrl, s->prim[src], s->dual[src], s->prim[dst]);
+        k_primal_lane<<<dim3((count + kLaneThreads - 1) / kLaneThreads, L.batch), kLaneThreads, 0, st>>>(
+            s->P, s->ctrl, s->prim[src], s->dual[src], s->prim[dst], nodes, count);
     } else {
         launch_primal_tile(s->diag_costs, dim3(s->tiles.num_tiles, L.batch), s->primal_smem, st, s->P, s->ctrl, s->tiles,
                            s->prim[src], s->dual[src], s->prim[dst]);
     }
 }
 
-void launch_dual(rb_solver *s, cudaStream_t st, int src, int dst) {
+void launch_dual(rb_solver *s, cudaStream_t st, int src, int dst, const int *nodes = nullptr, int count = -1) {
     const Layout &L = s->P.L;
+    if (count < 0) count = L.n;
     if (use_lane(s)) {
-        k_dual_lane<<<dim3((L.n + kLaneThreads - 1) / kLaneThreads, L.batch), kLaneThreads, 0, st>>>(
-            s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots);
+        k_dual_lane<<<dim3((count + kLaneThreads - 1) / kLaneThreads, L.batch), kLaneThreads, 0, st>>>(
+            s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, nodes, count);
     } else {
         launch_dual_tile(s->diag_costs, dim3(s->tiles.num_tiles, L.batch), s->dual_smem, st, s->P, s->ctrl, s->tiles,
                          s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots);
@@ -610,6 +622,62 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
         TRYC(tile_kernels_set_smem(s->primal_smem, s->dual_smem));
     }
     s->kernels_per_iter = 1 + (1 + 2 * s->plan.num_levels) + 1 + 1;
+    // ---- subtree sharding: rank r owns a contiguous block of the level-0 subtrees, everybody replicates the top
+    if (pb->shard_world > 1) {
+        const SweepPlan &pl = s->plan;
+        const int W = pb->shard_world, R = pb->shard_rank;
+        if (R < 0 || R >= W || L.batch != 1 || pl.num_levels < 1 || pl.lv[0].num_sub < W) {
+            s->err = "subtree sharding needs batch == 1 and at least one cut-stage subtree per rank";
+            return bail(RB_ERR_INVALID);
+        }
+        const int C = pl.lv[0].num_sub;
+        std::vector<int> bounds(W + 1);
+        for (int r = 0; r <= W; ++r) bounds[r] = (int)((long long)r * C / W);
+        ShardPlan &sp = s->shard;
+        sp.rank = R; sp.world = W;
+        sp.cut_first = s->stage_off[pl.t_top];
+        sp.cut_lo = bounds[R]; sp.cut_hi = bounds[R + 1];
+        sp.cap = 0;
+        for (int r = 0; r < W; ++r) sp.cap = std::max(sp.cap, bounds[r + 1] - bounds[r]);
+        int *d_bounds = nullptr;
+        TRY(upload(s, bounds.data(), bounds.size(), &d_bounds));
+        sp.cut_bounds = d_bounds;
+        // owned nodes: the descendants of the owned cut nodes, one contiguous range per stage
+        std::vector<int> owned, top, both;
+        for (int i = 0; i < s->stage_off[pl.t_top]; ++i) top.push_back(i);
+        std::vector<std::pair<int, int>> stage_range(L.num_stages, {0, 0});
+        int a = sp.cut_first + sp.cut_lo, b = sp.cut_first + sp.cut_hi;
+        for (int t = pl.t_top; t < L.num_stages; ++t) {
+            stage_range[t] = {a, b};
+            for (int i = a; i < b; ++i) owned.push_back(i);
+            if (t + 1 < L.num_stages) {
+                const int na = s->child_first[a], nb = s->child_first[b - 1] + s->child_count[b - 1];
+                a = na;
+                b = nb;
+            }
+        }
+        both = top;
+        both.insert(both.end(), owned.begin(), owned.end());
+        TRY(upload(s, owned.data(), owned.size(), &s->owned_nodes));
+        TRY(upload(s, top.data(), top.size(), &s->top_nodes));
+        TRY(upload(s, both.data(), both.size(), &s->dual_nodes));
+        s->n_owned = (int)owned.size();
+        s->n_top = (int)top.size();
+        // sweep levels restricted to the owned subtrees (a contiguous block of every level)
+        for (int v = 0; v < pl.num_levels; ++v) {
+            SweepLevel lv = pl.lv[v];
+            const int first = s->stage_off[lv.t_lo];
+            const int sa = stage_range[lv.t_lo].first - first, sb = stage_range[lv.t_lo].second - first;
+            lv.lo += (size_t)sa * lv.depth;
+            lv.hi += (size_t)sa * lv.depth;
+            lv.num_sub = sb - sa;
+            s->shard_lv[v] = lv;
+        }
+        s->xchg_count = (size_t)sp.cap * (nx + 1) + 6;
+        TRY(dev_zero(s, s->xchg_count, &s->xchg_send));
+        TRY(dev_zero(s, s->xchg_count * W, &s->xchg_recv));
+        s->sharded = true;
+    }
     *out = s;
     return RB_OK;
 #undef TRY
@@ -623,6 +691,7 @@ void rb_destroy(rb_solver *s) {
     for (int i = 0; i < 2; ++i)
         if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
     for (void *p : s->allocs) cudaFree(p);
+    if (s->nccl_comm) nccl_comm_destroy(s->nccl_comm);
     if (s->hist) cudaFree(s->hist);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -982,6 +1051,50 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st) {
     return launch_ok(s, "fused iteration");
 }
 
+// the gather step of the sharded loop: q_j and d2_j of the cut nodes and the residual maxima of the previous iteration
+// cross NVLink, then the stopping test of the previous iteration runs (identically on every rank)
+int shard_exchange(rb_solver *s, int src, cudaStream_t st) {
+    k_shard_pack<<<8, 256, 0, st>>>(s->P, s->ctrl, s->shard, s->q, s->dual[src], s->slots, s->xchg_send);
+    const int rc = nccl_all_gather_f64(s->xchg_send, s->xchg_recv, s->xchg_count, s->nccl_comm, st);
+    if (rc != 0) return fail(s, RB_ERR_CUDA, std::string("ncclAllGather: ") + nccl_error(rc));
+    k_shard_unpack<<<8, 256, 0, st>>>(s->P, s->ctrl, s->shard, s->xchg_recv, s->q, s->dual[src], s->slots);
+    if (s->shard_pending) k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
+    s->shard_pending = false;
+    return launch_ok(s, "shard exchange");
+}
+
+// one iteration of the subtree-sharded loop (shard.cu): owned primal pass and backward sweep, ONE all-gather, replicated
+// top, owned forward sweep, dual pass on owned + top nodes
+int enqueue_iteration_sharded(rb_solver *s, int src, cudaStream_t st) {
+    if (!s->nccl_comm) return fail(s, RB_ERR_STATE, "rb_shard_init() has not been called");
+    if (!use_lane(s)) return fail(s, RB_ERR_INVALID, "subtree sharding currently needs the one-thread-per-node passes "
+                                                     "(diagonal cost roots, even nx / nu, <= 8 children per node)");
+    const SweepPlan &pl = s->plan;
+    const Layout &L = s->P.L;
+    const int dst = 1 - src;
+    const size_t per_warp = (size_t)(2 * L.nxu + 32) * sizeof(double);
+    auto grid = [&](const SweepLevel &lv) { return dim3((lv.num_sub + lv.subs_per_cta - 1) / lv.subs_per_cta, 1); };
+    auto threads = [&](const SweepLevel &lv) { return 32 * lv.warps_per_sub * lv.subs_per_cta; };
+    auto smem = [&](const SweepLevel &lv) {
+        return per_warp * lv.warps_per_sub * lv.subs_per_cta + (size_t)lv.subs_per_cta * lv.stage_cap * L.nxu * sizeof(double);
+    };
+    launch_primal(s, st, src, dst, s->owned_nodes, s->n_owned);
+    for (int v = pl.num_levels - 1; v >= 0; --v)
+        launch_sweep_sub_bwd(grid(s->shard_lv[v]), threads(s->shard_lv[v]), smem(s->shard_lv[v]), st, s->P, s->ctrl,
+                             s->shard_lv[v], s->prim[dst], s->q, s->r);
+    int rc = shard_exchange(s, src, st);
+    if (rc != RB_OK) return rc;
+    launch_primal(s, st, src, dst, s->top_nodes, s->n_top);
+    launch_sweep_top(1, 32 * s->top_warps, per_warp * s->top_warps + (size_t)pl.top_cap * L.nxu * sizeof(double), st, s->P,
+                     s->ctrl, pl, s->prim[dst], s->q, s->r, s->x0);
+    for (int v = 0; v < pl.num_levels; ++v)
+        launch_sweep_sub_fwd(grid(s->shard_lv[v]), threads(s->shard_lv[v]), smem(s->shard_lv[v]), st, s->P, s->ctrl,
+                             s->shard_lv[v], s->prim[dst], s->r);
+    launch_dual(s, st, src, dst, s->dual_nodes, s->n_top + s->n_owned);
+    s->shard_pending = true;
+    return launch_ok(s, "sharded iteration");
+}
+
 // capture one iteration per buffer parity into a CUDA graph (the kernel arguments never change afterwards: step size
 // and stopping parameters live in the device control block)
 int build_graphs(rb_solver *s) {
@@ -1012,10 +1125,11 @@ int rb_loop_begin(rb_solver *s, double alpha, int32_t max_iters, double tol, int
     if (!s->have_x0) return fail(s, RB_ERR_STATE, "initial state not set (cache_initial_state)");
     const Layout &L = s->P.L;
     cudaStream_t st = s->stream;
-    if (s->use_graphs) {
+    if (s->use_graphs && !s->sharded) {
         rc = build_graphs(s);
         if (rc != RB_OK) return rc;
     }
+    s->shard_pending = false;
     if (s->hist && s->hist_capacity < hist_capacity) {
         RB_CUDA(s, cudaStreamSynchronize(st));
         cudaFree(s->hist);
@@ -1047,7 +1161,10 @@ int rb_loop_enqueue(rb_solver *s, int32_t count) {
     if (!s->in_loop) return fail(s, RB_ERR_STATE, "rb_loop_begin() has not been called");
     for (int k = 0; k < count; ++k) {
         const int src = s->old_i;
-        if (s->use_graphs) {
+        if (s->sharded) {
+            int rc = enqueue_iteration_sharded(s, src, s->stream);
+            if (rc != RB_OK) return rc;
+        } else if (s->use_graphs) {
             RB_CUDA(s, cudaGraphLaunch(s->graph[src], s->stream));
         } else {
             int rc = enqueue_iteration_kernels(s, src, s->stream);
@@ -1064,6 +1181,10 @@ int rb_loop_poll(rb_solver *s, int32_t *iters, int32_t *done, double *last_norms
     if (!s) return RB_ERR_INVALID;
     if (!s->in_loop) return fail(s, RB_ERR_STATE, "rb_loop_begin() has not been called");
     const Layout &L = s->P.L;
+    if (s->sharded && s->shard_pending) {   // gather and test the residuals of the last enqueued iteration (all ranks)
+        int rcx = shard_exchange(s, s->old_i, s->stream);
+        if (rcx != RB_OK) return rcx;
+    }
     Ctrl *hc = reinterpret_cast<Ctrl *>(s->h_pinned);
     double *hn = s->h_pinned + 64;
     if ((size_t)L.batch * 6 > (4096 - 512) / sizeof(double)) hn = nullptr;
@@ -1215,6 +1336,30 @@ int rb_force_dense_costs(rb_solver *s, int32_t enable) {
             cudaGraphExecDestroy(s->graph[i]);
             s->graph[i] = nullptr;
         }
+    return RB_OK;
+}
+
+int rb_shard_unique_id(char *id128) {
+    if (!id128) return RB_ERR_INVALID;
+    const char *why = nccl_load();
+    if (why) return fail(nullptr, RB_ERR_INVALID, why);
+    NcclId id;
+    const int rc = nccl_unique_id(&id);
+    if (rc != 0) return fail(nullptr, RB_ERR_CUDA, std::string("ncclGetUniqueId: ") + nccl_error(rc));
+    std::memcpy(id128, id.internal, 128);
+    return RB_OK;
+}
+
+int rb_shard_init(rb_solver *s, const char *id128) {
+    if (!s || !id128) return RB_ERR_INVALID;
+    if (!s->sharded) return fail(s, RB_ERR_STATE, "the problem was not created with shard_world > 1");
+    const char *why = nccl_load();
+    if (why) return fail(s, RB_ERR_INVALID, why);
+    NcclId id;
+    std::memcpy(id.internal, id128, 128);
+    RB_CUDA(s, cudaSetDevice(s->device));
+    const int rc = nccl_comm_init(&s->nccl_comm, s->shard.world, id, s->shard.rank);
+    if (rc != 0) return fail(s, RB_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl_error(rc));
     return RB_OK;
 }
 

@@ -56,12 +56,14 @@ constexpr int kDualRowsHost = 15;
 // ---- lane.cu: one thread per node (diagonal cost square roots, <= kLaneMaxChildren children per node) ---------------
 constexpr int kLaneThreads = 128;
 constexpr int kLaneMaxChildren = 8;
+// node_list / count: the nodes to process (thread t takes node_list[t]); null = all nodes 0..n-1
 __global__ void k_primal_lane(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
                               const double *__restrict__ p_old, const double *__restrict__ d_old,
-                              double *__restrict__ p_new);
+                              double *__restrict__ p_new, const int *__restrict__ node_list, int count);
 __global__ void k_dual_lane(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, const double *__restrict__ p_old,
                             const double *__restrict__ p_new, const double *__restrict__ d_old,
-                            double *__restrict__ d_new, double *__restrict__ slots);   // must equal kDualRows in fused.cu
+                            double *__restrict__ d_new, double *__restrict__ slots, const int *__restrict__ node_list,
+                            int count);   // must equal kDualRows in fused.cu
 __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, double *__restrict__ slots,
                         double *__restrict__ last);
 
@@ -90,6 +92,30 @@ void launch_sweep_sub_fwd(dim3 grid, int threads, size_t smem, cudaStream_t st, 
                           const SweepLevel &lv, double *prim, const double *r);
 void launch_sweep_top(int grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
                       const SweepPlan &plan, double *prim, double *q, double *r, const double *x0);
+
+// ---- shard.cu: one tree sharded by subtree over the GPUs of a box ----------------------------------------------------------
+struct ShardPlan {
+    int rank, world;
+    int cut_first;          // first node of the cut stage (= first sweep level)
+    int cut_lo, cut_hi;     // this rank's block of cut nodes, as offsets into the cut stage
+    int cap;                // largest block of any rank (message rows)
+    const int *cut_bounds;  // [world + 1] block boundaries of all ranks (device)
+};
+struct NcclId {
+    char internal[128];
+};
+__global__ void k_shard_pack(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, ShardPlan sp,
+                             const double *__restrict__ q, const double *__restrict__ dual_src,
+                             const double *__restrict__ slots, double *__restrict__ send);
+__global__ void k_shard_unpack(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, ShardPlan sp,
+                               const double *__restrict__ recv, double *__restrict__ q, double *__restrict__ dual_src,
+                               double *__restrict__ slots);
+const char *nccl_load();   // nullptr on success, else the reason
+int nccl_unique_id(NcclId *id);
+int nccl_comm_init(void **comm, int world, const NcclId &id, int rank);
+int nccl_all_gather_f64(const double *send, double *recv, size_t count, void *comm, cudaStream_t st);
+void nccl_comm_destroy(void *comm);
+const char *nccl_error(int code);
 
 // ---- offline.cu --------------------------------------------------------------------------------------------------
 struct ClassView {

@@ -64,14 +64,16 @@ __device__ __forceinline__ void st2(double *__restrict__ p, int k2, double a, do
 // ====================================================================================================================
 __global__ void __launch_bounds__(kLaneThreads) k_primal_lane(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
                                                              const double *__restrict__ p_old,
-                                                             const double *__restrict__ d_old, double *__restrict__ p_new) {
+                                                             const double *__restrict__ d_old, double *__restrict__ p_new,
+                                                             const int *__restrict__ node_list, int count) {
     if (ctrl->done) return;
     const double alpha = ctrl->alpha;
     const Layout &L = P.L;
     const Topo &T = P.t;
     const Tabs &M = P.m;
-    const int node = blockIdx.x * blockDim.x + threadIdx.x;
-    if (node >= L.n) return;
+    const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= count) return;
+    const int node = node_list ? node_list[gid] : gid;
     const double *Po = p_old + (long long)blockIdx.y * L.np_pad;
     const double *D = d_old + (long long)blockIdx.y * L.nd_pad;
     double *Pn = p_new + (long long)blockIdx.y * L.np_pad;
@@ -169,7 +171,8 @@ __global__ void __launch_bounds__(kLaneThreads) k_primal_lane(const __grid_const
 __global__ void __launch_bounds__(kLaneThreads) k_dual_lane(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
                                                            const double *__restrict__ p_old, const double *__restrict__ p_new,
                                                            const double *__restrict__ d_old, double *__restrict__ d_new,
-                                                           double *__restrict__ slots) {
+                                                           double *__restrict__ slots, const int *__restrict__ node_list,
+                                                           int count) {
     if (ctrl->done) return;
     const double alpha = ctrl->alpha, inv_alpha = 1.0 / alpha;
     const Layout &L = P.L;
@@ -183,7 +186,8 @@ __global__ void __launch_bounds__(kLaneThreads) k_dual_lane(const __grid_constan
     __shared__ int blockflags;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) blockflags = 0;
-    const int node = blockIdx.x * blockDim.x + tid;
+    const int gid = blockIdx.x * blockDim.x + tid;
+    const int node = gid < count ? (node_list ? node_list[gid] : gid) : L.n;   // L.n = nothing to do
     const double *Po = p_old + (long long)blockIdx.y * L.np_pad;
     const double *Pn = p_new + (long long)blockIdx.y * L.np_pad;
     const double *Do = d_old + (long long)blockIdx.y * L.nd_pad;

@@ -28,6 +28,7 @@ class RbProblem(C.Structure):
         ("risk_alpha", c_double_p), ("cond_prob", c_double_p),
         ("num_cls", C.c_int32), ("cls", c_int_p),
         ("device", C.c_int32),
+        ("shard_rank", C.c_int32), ("shard_world", C.c_int32),
     ]
 
 
@@ -76,6 +77,8 @@ SYMBOLS = [
     ("rb_use_graphs", C.c_int, [_H, C.c_int32]),
     ("rb_force_dense_costs", C.c_int, [_H, C.c_int32]),
     ("rb_use_lane_kernels", C.c_int, [_H, C.c_int32]),
+    ("rb_shard_unique_id", C.c_int, [C.c_char_p]),
+    ("rb_shard_init", C.c_int, [_H, C.c_char_p]),
     ("rb_launch_count", C.c_int, [_H, C.POINTER(C.c_int64)]),
     ("rb_cone_project", C.c_int, [C.c_int32, C.c_int32, c_double_p, c_double_p]),
     ("rb_box_project", C.c_int, [C.c_int32, c_double_p, c_double_p, c_double_p, c_double_p]),

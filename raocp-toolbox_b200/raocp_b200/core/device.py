@@ -44,6 +44,7 @@ class DeviceSolver:
         pb.risk_alpha, pb.cond_prob = dp(f.risk_alpha), dp(f.cond_prob)
         pb.num_cls, pb.cls = f.num_cls, ip(f.cls)
         pb.device = f.device
+        pb.shard_rank, pb.shard_world = f.shard_rank, f.shard_world
         handle = C.c_void_p()
         _lib.check(self._lib.rb_create(C.byref(pb), C.byref(handle)))
         self._h = handle
@@ -246,3 +247,33 @@ class DeviceSolver:
         ms = (C.c_float * 8)()
         self._call("rb_profile_iteration", ms)
         return [v for v in ms if v >= 0.0]
+
+    # ---- subtree sharding over GPUs (one process per GPU) ------------------------------------------------------------------
+    def shard_init(self, unique_id=None):
+        """collective: rank 0 creates the NCCL id, torch.distributed carries it, every rank joins the communicator"""
+        import torch
+        import torch.distributed as dist
+        buf = (C.c_char * 128)()
+        if unique_id is None:
+            if dist.get_rank() == 0:
+                _lib.check(self._lib.rb_shard_unique_id(buf))
+            t = torch.tensor(list(buf.raw), dtype=torch.uint8)
+            if dist.get_backend() == "nccl":
+                t = t.cuda()
+            dist.broadcast(t, src=0)
+            unique_id = bytes(t.cpu().tolist())
+        self._call("rb_shard_init", C.c_char_p(unique_id))
+
+    def gather_sharded(self, which=0):
+        """assemble the full compact iterates on every rank from the ranks' authoritative parts (torch.distributed)"""
+        import torch
+        import torch.distributed as dist
+        f = self.flat
+        pm, dm = f.shard_masks(f.shard_rank, f.shard_world)
+        p = torch.from_numpy(np.where(pm, self.get_primal(which)[0], 0.0))
+        d = torch.from_numpy(np.where(dm, self.get_dual(which)[0], 0.0))
+        if dist.get_backend() == "nccl":
+            p, d = p.cuda(), d.cuda()
+        dist.all_reduce(p)
+        dist.all_reduce(d)
+        return p.cpu().numpy(), d.cpu().numpy()

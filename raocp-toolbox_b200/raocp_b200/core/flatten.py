@@ -39,7 +39,7 @@ def _table(objs, getters):
 
 
 class FlatProblem:
-    def __init__(self, problem, batch=1, dedup=True, device=0):
+    def __init__(self, problem, batch=1, dedup=True, device=0, shard=None):
         tree = problem.tree
         self.problem = problem
         self.n = n = int(tree.num_nodes)
@@ -48,6 +48,7 @@ class FlatProblem:
         self.num_stages = int(tree.num_stages)
         self.batch = int(batch)
         self.device = int(device)
+        self.shard_rank, self.shard_world = (int(shard[0]), int(shard[1])) if shard else (0, 1)
         if problem.list_of_dynamics[1] is None:
             raise Exception("RAOCP has no dynamics")
         self.nx = int(problem.state_dynamics_at_node(1).shape[1])
@@ -212,3 +213,53 @@ class FlatProblem:
         flat[mp["d_gather"]] = compact
         st = mp["d_starts"]
         return [flat[st[k]: st[k + 1]].reshape(-1, 1).copy() for k in range(len(st) - 1)]
+
+    # ---- subtree sharding (mirrors rb_create / shard.cu) ------------------------------------------------------------------
+    SHARD_CUT_WIDTH = 64   # the cut stage is the first stage with at least this many nodes (= first sweep level)
+
+    def shard_cut_stage(self):
+        widths = np.diff(self.stage_off)
+        wide = np.flatnonzero(widths >= self.SHARD_CUT_WIDTH)
+        if wide.size == 0:
+            raise Exception("the tree has no stage with >= 64 nodes: nothing to shard")
+        return int(wide[0])
+
+    def shard_owned_nodes(self, rank, world):
+        """bool[n]: nodes whose node-indexed quantities rank `rank` owns (its subtrees below the cut stage; rank 0 also
+        answers for the replicated top of the tree)"""
+        t_c = self.shard_cut_stage()
+        first, count = int(self.stage_off[t_c]), int(self.stage_off[t_c + 1] - self.stage_off[t_c])
+        if count < world:
+            raise Exception("fewer cut-stage subtrees than ranks")
+        a, b = first + rank * count // world, first + (rank + 1) * count // world
+        own = np.zeros(self.n, dtype=bool)
+        if rank == 0:
+            own[:first] = True
+        for t in range(t_c, self.num_stages):
+            own[a:b] = True
+            if t + 1 < self.num_stages:
+                a, b = int(self.child_first[a]), int(self.child_first[b - 1] + self.child_count[b - 1])
+        return own
+
+    def shard_masks(self, rank, world):
+        """(primal mask, dual mask) over the compact layouts: entries for which rank `rank` holds the authoritative
+        value after a sharded solve.  Node-indexed entries follow the node, edge-indexed entries (tau_j, s_j, d3..d6 of
+        edge j) follow the PARENT (they are computed by the parent's thread); the masks of all ranks partition both
+        vectors."""
+        own = self.shard_owned_nodes(rank, world)
+        n, m, nx, nu = self.n, self.m, self.nx, self.nu
+        par = self.parent.copy()
+        par[0] = 0
+        edge_own = own[par]              # entry j: owner of node j's parent (entry 0: the root itself)
+        edge_own[0] = own[0]
+        ymask = np.repeat(own[:m], self.ysize)
+        pm = np.concatenate((np.repeat(own, nx), np.repeat(own[:m], nu), ymask, edge_own, edge_own))
+        parts = [ymask, own[:m], np.repeat(edge_own[1:], nx), np.repeat(edge_own[1:], nu), edge_own[1:], edge_own[1:]]
+        if self.nl_rect:
+            parts.append(np.repeat(own[:m], nx + nu))
+        parts += [np.repeat(own[m:], nx), own[m:], own[m:]]
+        if self.leaf_rect:
+            parts.append(np.repeat(own[m:], nx))
+        dm = np.concatenate(parts)
+        assert pm.size == self.np_ and dm.size == self.nd_
+        return pm, dm

@@ -1,0 +1,82 @@
+"""Subtree-sharded solve on W GPUs vs the single-GPU solve (run under torchrun, one rank per GPU):
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multi_gpu_check.py
+
+Every rank solves the whole problem on its own GPU (single-GPU path) and takes part in the sharded solve; the
+assembled sharded iterate must agree with the single-GPU one (same kernels, same order of operations: 1e-12) and with the
+flat oracle (1e-9), and both must stop at the same iteration."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "raocp-toolbox_b200"), ROOT, os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import raocp_b200 as r
+    from oracle import problems
+    from oracle.cp_flat_oracle import FlatOracle
+    from helpers import seg_rel_err
+
+    ok = True
+    for name, iters in (("cfg2", 60), ("cfg3", 25)):
+        s = problems.spec(name)
+        problem = problems.build(s, r.core)
+        x0 = s["x0"][:, :1]
+        single = r.core.Solver(problem, device=local, verbose=False)
+        alpha = single.compute_step_size()
+        single.chock(x0, max_iters=iters - 1, tol=0.0, alpha=alpha)
+        sd = single.cache.device_solver
+        p1, d1 = sd.get_primal(0)[0], sd.get_dual(0)[0]
+        xi1, _ = single.residual_history
+
+        sharded = r.core.Solver(problem, device=local, verbose=False, shard=(rank, world))
+        dev = sharded.cache.device_solver
+        dev.shard_init()
+        sharded.chock(x0, max_iters=iters - 1, tol=0.0, alpha=alpha)
+        p2, d2 = dev.gather_sharded(0)
+        xi2, _ = sharded.residual_history
+        flat = sharded.cache.flat_problem
+        ep, ed = seg_rel_err(flat, p2, p1, dual=False), seg_rel_err(flat, d2, d1, dual=True)
+        er = float(np.max(np.abs(xi2 - xi1) / xi1))
+        line = f"[rank {rank}] {name}: sharded vs single GPU after {iters} iterations: primal {ep:.2e} dual {ed:.2e} residuals {er:.2e}"
+        if name == "cfg2":   # oracle check on the small case
+            orc = FlatOracle(problem)
+            orc.cache_initial_state(x0)
+            orc.alpha = alpha
+            for _ in range(iters):
+                orc.iterate()
+            eo = max(seg_rel_err(flat, p2, orc.flat_primal(orc.p), dual=False), seg_rel_err(flat, d2, orc.flat_dual(orc.d), dual=True))
+            line += f"; vs oracle {eo:.2e}"
+            ok &= eo < 1e-9
+        print(line, flush=True)
+        ok &= ep < 1e-12 and ed < 1e-12 and er < 1e-9 and sharded.iterations == single.iterations
+        # stopping at a tolerance: same iteration count on both paths
+        s1 = r.core.Solver(problem, device=local, verbose=False)
+        s2 = r.core.Solver(problem, device=local, verbose=False, shard=(rank, world))
+        s2.cache.device_solver.shard_init()
+        st1 = s1.chock(x0, max_iters=400, tol=xi1[-1].max() * 1.5, alpha=alpha)
+        st2 = s2.chock(x0, max_iters=400, tol=xi1[-1].max() * 1.5, alpha=alpha)
+        print(f"[rank {rank}] {name}: stop test single {s1.iterations} its (status {st1}) sharded {s2.iterations} its (status {st2})",
+              flush=True)
+        ok &= st1 == st2 and abs(s1.iterations - s2.iterations) <= 1
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", flush=True)
+    sys.exit(0 if int(t.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
