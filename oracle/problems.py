@@ -20,6 +20,7 @@ SHAPES = {
     "mini5": (3, 6, 3, 16, 8),
     "dense": (3, 5, 3, 5, 3),      # like mini2 but with NON-diagonal SPD cost weights (general matvec path)
     "wide": (2, 3, 3, 40, 36),     # nx, nu > 32: more than one row per lane
+    "shard": (3, 9, 5, 8, 4),      # 1 822 nodes, 81 subtrees below stage 4: multi-GPU subtree sharding checks
 }
 
 

@@ -29,7 +29,7 @@ def main():
     from helpers import seg_rel_err
 
     ok = True
-    for name, iters in (("cfg2", 60), ("cfg3", 25)):
+    for name, iters in (("shard", 60), ("cfg3", 25)):
         s = problems.spec(name)
         problem = problems.build(s, r.core)
         x0 = s["x0"][:, :1]
@@ -50,7 +50,7 @@ def main():
         ep, ed = seg_rel_err(flat, p2, p1, dual=False), seg_rel_err(flat, d2, d1, dual=True)
         er = float(np.max(np.abs(xi2 - xi1) / xi1))
         line = f"[rank {rank}] {name}: sharded vs single GPU after {iters} iterations: primal {ep:.2e} dual {ed:.2e} residuals {er:.2e}"
-        if name == "cfg2":   # oracle check on the small case
+        if name == "shard":   # oracle check on the small case
             orc = FlatOracle(problem)
             orc.cache_initial_state(x0)
             orc.alpha = alpha
@@ -65,8 +65,9 @@ def main():
         s1 = r.core.Solver(problem, device=local, verbose=False)
         s2 = r.core.Solver(problem, device=local, verbose=False, shard=(rank, world))
         s2.cache.device_solver.shard_init()
-        st1 = s1.chock(x0, max_iters=400, tol=xi1[-1].max() * 1.5, alpha=alpha)
-        st2 = s2.chock(x0, max_iters=400, tol=xi1[-1].max() * 1.5, alpha=alpha)
+        tol = float(np.sort(xi1.max(axis=1))[1]) * (1 + 1e-9)   # first reached somewhere inside the recorded history
+        st1 = s1.chock(x0, max_iters=400, tol=tol, alpha=alpha)
+        st2 = s2.chock(x0, max_iters=400, tol=tol, alpha=alpha)
         print(f"[rank {rank}] {name}: stop test single {s1.iterations} its (status {st1}) sharded {s2.iterations} its (status {st2})",
               flush=True)
         ok &= st1 == st2 and abs(s1.iterations - s2.iterations) <= 1
