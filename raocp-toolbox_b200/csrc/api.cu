@@ -213,8 +213,7 @@ void launch_primal(rb_solver *s, cudaStream_t st, int src, int dst, const int *n
     const Layout &L = s->P.L;
     if (count < 0) count = L.n;
     if (use_lane(s)) {
-        k_primal_lane<<<dim3((count + kLaneThreads - 1) / kLaneThreads, L.batch), kLaneThreads, 0, st>>>(
-            s->P, s->ctrl, s->prim[src], s->dual[src], s->prim[dst], nodes, count);
+        launch_primal_lane(dim3(1, L.batch), st, s->P, s->ctrl, s->prim[src], s->dual[src], s->prim[dst], nodes, count);
     } else {
         launch_primal_tile(s->diag_costs, dim3(s->tiles.num_tiles, L.batch), s->primal_smem, st, s->P, s->ctrl, s->tiles,
                            s->prim[src], s->dual[src], s->prim[dst]);
@@ -225,8 +224,8 @@ void launch_dual(rb_solver *s, cudaStream_t st, int src, int dst, const int *nod
     const Layout &L = s->P.L;
     if (count < 0) count = L.n;
     if (use_lane(s)) {
-        k_dual_lane<<<dim3((count + kLaneThreads - 1) / kLaneThreads, L.batch), kLaneThreads, 0, st>>>(
-            s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, nodes, count);
+        launch_dual_lane(dim3(1, L.batch), st, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
+                         nodes, count);
     } else {
         launch_dual_tile(s->diag_costs, dim3(s->tiles.num_tiles, L.batch), s->dual_smem, st, s->P, s->ctrl, s->tiles,
                          s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots);

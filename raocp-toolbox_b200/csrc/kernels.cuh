@@ -53,17 +53,17 @@ void launch_dual_tile(bool diag, dim3 grid, size_t smem, cudaStream_t st, const 
                       const double *p_old, const double *p_new, const double *d_old, double *d_new, double *slots);
 constexpr int kDualRowsHost = 15;
 
-// ---- lane.cu: one thread per node (diagonal cost square roots, <= kLaneMaxChildren children per node) ---------------
-constexpr int kLaneThreads = 128;
+// ---- lane.cu: eight lanes per node (diagonal cost square roots, even nx / nu, <= kLaneMaxChildren children per node) ---------------
+constexpr int kLaneThreads = 256;
+constexpr int kLaneOctet = 8;    // lanes that share one node
 constexpr int kLaneMaxChildren = 8;
-// node_list / count: the nodes to process (thread t takes node_list[t]); null = all nodes 0..n-1
-__global__ void k_primal_lane(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
-                              const double *__restrict__ p_old, const double *__restrict__ d_old,
-                              double *__restrict__ p_new, const int *__restrict__ node_list, int count);
-__global__ void k_dual_lane(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, const double *__restrict__ p_old,
-                            const double *__restrict__ p_new, const double *__restrict__ d_old,
-                            double *__restrict__ d_new, double *__restrict__ slots, const int *__restrict__ node_list,
-                            int count);   // must equal kDualRows in fused.cu
+// node_list / count: the nodes to process (lane group t takes node_list[t]); null = all nodes 0..n-1.  The kernels are
+// templates on the number of lanes per node (4 or 8); nodes_batch.y = batch
+void launch_primal_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, const double *p_old,
+                        const double *d_old, double *p_new, const int *node_list, int count);
+void launch_dual_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old,
+                      const double *p_new, const double *d_old, double *d_new, double *slots, const int *node_list,
+                      int count);
 __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, double *__restrict__ slots,
                         double *__restrict__ last);
 
