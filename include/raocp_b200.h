@@ -85,6 +85,10 @@ typedef struct {
      * (rank, world); world <= 1 = not sharded.  Rank r owns a contiguous block of the subtrees below the first stage
      * with >= 64 nodes and replicates the nodes above it; rb_shard_init must follow rb_create. */
     int32_t shard_rank, shard_world;
+    /* tuning / test hook for the cut stages of the DP sweeps (sweeps.cu); 0 = defaults (64 and 256 nodes): the first cut
+     * is the first stage with >= sweep_cut1_min nodes, the second the stage where the tree turns into chains if it has
+     * >= sweep_cut2_min of them.  Must be 0 when shard_world > 1. */
+    int32_t sweep_cut1_min, sweep_cut2_min;
 } rb_problem;
 
 /* -- lifetime ---------------------------------------------------------------------------------------------------- */
@@ -174,8 +178,11 @@ int rb_use_graphs(rb_solver *s, int32_t enable);
  * rank are valid on its own nodes and on the replicated top of the tree. */
 int rb_shard_unique_id(char *id128);
 int rb_shard_init(rb_solver *s, const char *id128);
-/* test hook: 0 = never use the one-thread-per-node passes (lane.cu), always the warp-per-node tile kernels */
+/* test hook: 0 = never use the lanes-per-node passes (lane.cu), always the warp-per-node tile kernels */
 int rb_use_lane_kernels(rb_solver *s, int32_t enable);
+/* test hook: 0 = walk chains with one warp per chain (sweeps.cu) instead of eight chains per warp on the FP64 tensor
+ * cores (chain_mma.cu); both implement cache.py:259-288 */
+int rb_use_mma_sweeps(rb_solver *s, int32_t enable);
 /* test hook: 1 = use the general dense-matrix cost path even if sqrtQ, sqrtR, sqrtQf are all diagonal */
 int rb_force_dense_costs(rb_solver *s, int32_t enable); /* 1 (default): one CUDA graph per iteration; 0: plain launches */
 int rb_launch_count(const rb_solver *s, int64_t *kernels_launched); /* kernels launched by this handle so far */

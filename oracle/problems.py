@@ -21,6 +21,12 @@ SHAPES = {
     "dense": (3, 5, 3, 5, 3),      # like mini2 but with NON-diagonal SPD cost weights (general matvec path)
     "wide": (2, 3, 3, 40, 36),     # nx, nu > 32: more than one row per lane
     "shard": (3, 9, 5, 8, 4),      # 1 822 nodes, 81 subtrees below stage 4: multi-GPU subtree sharding checks
+    # trees with a long chain part (stopping time << horizon): the cut-stage / chain kernels of the DP sweeps
+    "chain21": (2, 8, 3, 2, 1),
+    "chain32": (3, 7, 2, 3, 2),
+    "chain63": (4, 7, 3, 6, 3),
+    "chain105": (3, 9, 5, 10, 5),
+    "chain2010": (4, 9, 4, 20, 10),  # 1 621 nodes, 256 chains of 6 nodes: a small cfg3
 }
 
 

@@ -77,6 +77,8 @@ struct rb_solver {
     int *owned_nodes = nullptr, *top_nodes = nullptr, *dual_nodes = nullptr;   // device node lists
     int n_owned = 0, n_top = 0;
     SweepLevel shard_lv[2]{};
+    std::vector<int> chain_lo[2];   // host copy of lv.lo of chain levels (tile building)
+    bool allow_mma = true;   // chain levels on the FP64 tensor cores when the level carries tiles (rb_use_mma_sweeps)
     double *xchg_send = nullptr, *xchg_recv = nullptr;
     size_t xchg_count = 0;
     bool shard_pending = false;   // an executed iteration whose residuals have not been gathered / tested yet
@@ -245,17 +247,58 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
         return per_warp * lv.warps_per_sub * lv.subs_per_cta + (size_t)lv.subs_per_cta * lv.stage_cap * L.nxu * sizeof(double);
     };
     for (int v = pl.num_levels - 1; v >= 0; --v) {
-        launch_sweep_sub_bwd(grid(pl.lv[v]), threads(pl.lv[v]), smem(pl.lv[v]), st, s->P, ctrl, pl.lv[v], prim, s->q, s->r);
+        if (s->allow_mma && pl.lv[v].num_tiles > 0)
+            launch_chain_mma_bwd(st, s->P, ctrl, pl.lv[v], prim, s->q, s->r);
+        else
+            launch_sweep_sub_bwd(grid(pl.lv[v]), threads(pl.lv[v]), smem(pl.lv[v]), st, s->P, ctrl, pl.lv[v], prim, s->q, s->r);
         if (evs) cudaEventRecord(evs[ne++], st);
     }
     launch_sweep_top(batch, 32 * s->top_warps, per_warp * s->top_warps + (size_t)pl.top_cap * L.nxu * sizeof(double), st, s->P,
                      ctrl, pl, prim, s->q, s->r, s->x0);
     if (evs) cudaEventRecord(evs[ne++], st);
     for (int v = 0; v < pl.num_levels; ++v) {
-        launch_sweep_sub_fwd(grid(pl.lv[v]), threads(pl.lv[v]), smem(pl.lv[v]), st, s->P, ctrl, pl.lv[v], prim, s->r);
+        if (s->allow_mma && pl.lv[v].num_tiles > 0)
+            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r);
+        else
+            launch_sweep_sub_fwd(grid(pl.lv[v]), threads(pl.lv[v]), smem(pl.lv[v]), st, s->P, ctrl, pl.lv[v], prim, s->r);
         if (evs) cudaEventRecord(evs[ne++], st);
     }
     return launch_ok(s, "DP sweeps");
+}
+
+// Chains whose nodes share the dynamics row and the factorisation class at every depth are grouped eight to a tile
+// (chain_mma.cu).  `lo` = [num][depth] node ids.  The tiling is dropped (num_tiles = 0) when it would leave more than half
+// of the tile columns empty -- then the one-warp-per-chain walker is the better kernel.
+int build_chain_tiles(rb_solver *s, const std::vector<int> &lo, int depth, int first, int num, const int **tiles_out,
+                      int *num_tiles_out) {
+    *tiles_out = nullptr;
+    *num_tiles_out = 0;
+    if (num <= 0) return RB_OK;
+    const int m = s->P.L.m;
+    std::map<std::vector<int>, std::vector<int>> groups;
+    std::vector<int> sig((size_t)2 * depth);
+    for (int c = first; c < first + num; ++c) {
+        for (int d = 0; d < depth; ++d) {
+            const int node = lo[(size_t)c * depth + d];
+            sig[2 * d] = d == 0 ? 0 : s->dyn_idx[node];
+            sig[2 * d + 1] = node < m ? s->cls[node] : -1;
+        }
+        groups[sig].push_back(c);
+    }
+    std::vector<int> tiles;
+    for (auto &kv : groups) {
+        const std::vector<int> &cs = kv.second;
+        for (size_t i = 0; i < cs.size(); i += 8)
+            for (size_t k = 0; k < 8; ++k) tiles.push_back(i + k < cs.size() ? cs[i + k] : -1);
+    }
+    const int num_tiles = (int)(tiles.size() / 8);
+    if ((long long)num_tiles * 8 > 2LL * num) return RB_OK;
+    int *d_tiles = nullptr;
+    int rc = upload(s, tiles.data(), tiles.size(), &d_tiles);
+    if (rc != RB_OK) return rc;
+    *tiles_out = d_tiles;
+    *num_tiles_out = num_tiles;
+    return RB_OK;
 }
 
 int need_offline(rb_solver *s) {
@@ -506,22 +549,40 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
     TRY(dev_zero(s, B * 6, &s->slots));
     TRY(dev_zero(s, B * 6, &s->last));
     TRY(dev_zero(s, 1, &s->status));
-    // ---- sweep plan (sweeps.cu): cut at the first stage with >= 64 nodes and, if the tree keeps widening, again at the
-    //      first stage with >= 2048 nodes (and >= 8x the first cut): below a Markov tree's stopping time those are chains
+    // ---- sweep plan (sweeps.cu): first cut at the first stage with >= 64 nodes; second cut where the tree turns into
+    //      chains (below the stopping time of a Markov tree) if there are >= 256 of them, else -- if the tree keeps
+    //      branching -- at the first stage with >= 2048 nodes and >= 8x the first cut
     {
         SweepPlan &pl = s->plan;
         auto width = [&](int t) { return s->stage_off[t + 1] - s->stage_off[t]; };
+        if ((pb->sweep_cut1_min != 0 || pb->sweep_cut2_min != 0) && pb->shard_world > 1) {
+            s->err = "sweep_cut*_min must be 0 for a sharded problem";
+            return bail(RB_ERR_INVALID);
+        }
+        const int cut1_min = pb->sweep_cut1_min > 0 ? pb->sweep_cut1_min : 64;
+        const int cut2_min = pb->sweep_cut2_min > 0 ? pb->sweep_cut2_min : 256;
         int c1 = L.num_stages, c2 = L.num_stages;
         for (int t = 0; t < L.num_stages; ++t)
-            if (width(t) >= 64) {
+            if (width(t) >= cut1_min) {
                 c1 = t;
                 break;
             }
-        for (int t = c1 + 1; t < L.num_stages; ++t)
-            if (width(t) >= 2048 && width(t) >= 8 * width(c1)) {
-                c2 = t;
-                break;
-            }
+        int c_chain = L.num_stages - 1;   // first stage from which every node has at most one child
+        while (c_chain > 0) {
+            bool chains = true;
+            for (int i = s->stage_off[c_chain - 1]; i < s->stage_off[c_chain] && chains; ++i) chains = s->child_count[i] <= 1;
+            if (!chains) break;
+            --c_chain;
+        }
+        if (c_chain > c1 && c_chain < L.num_stages - 1 && L.num_stages - c_chain <= 64 && width(c_chain) >= cut2_min) {
+            c2 = c_chain;
+        } else {
+            for (int t = c1 + 1; t < L.num_stages; ++t)
+                if (width(t) >= std::max(2048, cut2_min) && width(t) >= 8 * width(c1)) {
+                    c2 = t;
+                    break;
+                }
+        }
         pl.t_top = c1;
         pl.num_levels = c1 >= L.num_stages ? 0 : (c2 >= L.num_stages ? 1 : 2);
         int *d_so = nullptr;
@@ -565,6 +626,12 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
             TRY(upload(s, hi.data(), hi.size(), &d_hi));
             lv.lo = d_lo;
             lv.hi = d_hi;
+            lv.tiles = nullptr;
+            lv.num_tiles = 0;
+            if (lv.chain && chain_mma_supported(nx, nu)) {
+                s->chain_lo[v] = lo;
+                TRY(build_chain_tiles(s, lo, lv.depth, 0, lv.num_sub, &lv.tiles, &lv.num_tiles));
+            }
         }
         int top_max = 1;
         for (int t = 0; t < pl.t_top; ++t) top_max = std::max(top_max, std::max(width(t), t + 1 < L.num_stages ? width(t + 1) : 1));
@@ -670,6 +737,10 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
             lv.lo += (size_t)sa * lv.depth;
             lv.hi += (size_t)sa * lv.depth;
             lv.num_sub = sb - sa;
+            if (lv.num_tiles > 0) {   // tiles of the owned chains only (indices relative to the shifted lo / hi)
+                std::vector<int> sub(s->chain_lo[v].begin() + (size_t)sa * lv.depth, s->chain_lo[v].begin() + (size_t)sb * lv.depth);
+                TRY(build_chain_tiles(s, sub, lv.depth, 0, lv.num_sub, &lv.tiles, &lv.num_tiles));
+            }
             s->shard_lv[v] = lv;
         }
         s->xchg_count = (size_t)sp.cap * (nx + 1) + 6;
@@ -1079,16 +1150,22 @@ int enqueue_iteration_sharded(rb_solver *s, int src, cudaStream_t st) {
     };
     launch_primal(s, st, src, dst, s->owned_nodes, s->n_owned);
     for (int v = pl.num_levels - 1; v >= 0; --v)
-        launch_sweep_sub_bwd(grid(s->shard_lv[v]), threads(s->shard_lv[v]), smem(s->shard_lv[v]), st, s->P, s->ctrl,
-                             s->shard_lv[v], s->prim[dst], s->q, s->r);
+        if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
+            launch_chain_mma_bwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->q, s->r);
+        else
+            launch_sweep_sub_bwd(grid(s->shard_lv[v]), threads(s->shard_lv[v]), smem(s->shard_lv[v]), st, s->P, s->ctrl,
+                                 s->shard_lv[v], s->prim[dst], s->q, s->r);
     int rc = shard_exchange(s, src, st);
     if (rc != RB_OK) return rc;
     launch_primal(s, st, src, dst, s->top_nodes, s->n_top);
     launch_sweep_top(1, 32 * s->top_warps, per_warp * s->top_warps + (size_t)pl.top_cap * L.nxu * sizeof(double), st, s->P,
                      s->ctrl, pl, s->prim[dst], s->q, s->r, s->x0);
     for (int v = 0; v < pl.num_levels; ++v)
-        launch_sweep_sub_fwd(grid(s->shard_lv[v]), threads(s->shard_lv[v]), smem(s->shard_lv[v]), st, s->P, s->ctrl,
-                             s->shard_lv[v], s->prim[dst], s->r);
+        if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
+            launch_chain_mma_fwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->r);
+        else
+            launch_sweep_sub_fwd(grid(s->shard_lv[v]), threads(s->shard_lv[v]), smem(s->shard_lv[v]), st, s->P, s->ctrl,
+                                 s->shard_lv[v], s->prim[dst], s->r);
     launch_dual(s, st, src, dst, s->dual_nodes, s->n_top + s->n_owned);
     s->shard_pending = true;
     return launch_ok(s, "sharded iteration");
@@ -1365,6 +1442,17 @@ int rb_shard_init(rb_solver *s, const char *id128) {
 int rb_use_lane_kernels(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
     s->allow_lane = enable != 0;
+    for (int i = 0; i < 2; ++i)
+        if (s->graph[i]) {
+            cudaGraphExecDestroy(s->graph[i]);
+            s->graph[i] = nullptr;
+        }
+    return RB_OK;
+}
+
+int rb_use_mma_sweeps(rb_solver *s, int32_t enable) {
+    if (!s) return RB_ERR_INVALID;
+    s->allow_mma = enable != 0;
     for (int i = 0; i < 2; ++i)
         if (s->graph[i]) {
             cudaGraphExecDestroy(s->graph[i]);

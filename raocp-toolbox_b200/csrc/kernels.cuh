@@ -76,6 +76,8 @@ struct SweepLevel {
     int chain;             // 1: every subtree is a chain down to the leaves (<= 64 nodes): prefetching chain walker
     int stage_cap;         // max over subtrees / stages of max(#nodes, #children) of one stage (group-shared buffer rows)
     const int *lo, *hi;    // [num_sub][depth] node range of the subtree at stage t_lo + d
+    const int *tiles;      // chain levels: [num_tiles][8] chains with identical dynamics / class sequences (-1 = padding)
+    int num_tiles;         //               0 = no tiling (chain_mma.cu is not used)
 };
 struct SweepPlan {
     SweepLevel lv[2];
@@ -92,6 +94,13 @@ void launch_sweep_sub_fwd(dim3 grid, int threads, size_t smem, cudaStream_t st, 
                           const SweepLevel &lv, double *prim, const double *r);
 void launch_sweep_top(int grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
                       const SweepPlan &plan, double *prim, double *q, double *r, const double *x0);
+
+// ---- chain_mma.cu: chain levels on the FP64 tensor cores, 8 chains per warp ---------------------------------------------------
+bool chain_mma_supported(int nx, int nu);
+void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, const double *prim,
+                          double *q, double *r);
+void launch_chain_mma_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, double *prim,
+                          const double *r);
 
 // ---- shard.cu: one tree sharded by subtree over the GPUs of a box ----------------------------------------------------------
 struct ShardPlan {

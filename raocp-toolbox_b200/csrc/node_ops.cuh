@@ -216,11 +216,34 @@ __device__ __forceinline__ void dyn_fwd_node(const Layout &L, const Topo &T, con
 }
 
 // ---- chain walkers ------------------------------------------------------------------------------------------------------
-// Below the stopping time every subtree is a chain; one warp walks it.  Everything a step needs besides the previous
-// step's result is fetched ahead of time: the chain's node ids, dynamics rows and class ids are loaded once (lane d
-// holds depth d, broadcast by shuffle), the xbar / ubar / r rows of the NEXT step are prefetched into registers while
-// the current step computes, and q / x are carried in shared memory -- q of interior chain nodes never goes to HBM.
+// Below the stopping time every subtree is a chain; one warp walks it, lane k owns output row k.  Everything a step
+// needs besides the previous step's result is fetched ahead of time:
+//   * the chain's node ids, dynamics rows and class ids are loaded once (lane d holds depth d, broadcast by shuffle);
+//   * with compile-time sizes the lane's column of the dynamics tables ([A | B] for the backward, [A ; B]' for the forward
+//     step) lives in REGISTERS for the whole chain (reloaded only if the dynamics row changes along the chain -- never on
+//     a Markov tree, where the mode is frozen after the stopping time);
+//   * the class-indexed K column / [K R~^-1] segment and the xbar / ubar / r rows of the NEXT step are prefetched into
+//     registers while the current step computes;
+//   * q / x are carried in shared memory -- q of interior chain nodes never goes to HBM.
 // chain[d] = node at depth d (d = 0 is the head).  depth <= 64.
+template <int COLS>
+__device__ __forceinline__ double dot_col(const double (&m)[COLS], const double *__restrict__ v) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+    for (int l = 0; l < COLS; ++l) {
+        if ((l & 3) == 0) a0 = fma(m[l], v[l], a0);
+        else if ((l & 3) == 1) a1 = fma(m[l], v[l], a1);
+        else if ((l & 3) == 2) a2 = fma(m[l], v[l], a2);
+        else a3 = fma(m[l], v[l], a3);
+    }
+    return (a0 + a1) + (a2 + a3);
+}
+template <int COLS>
+__device__ __forceinline__ void load_col(double (&m)[COLS], const double *__restrict__ MT, int rows, int k, bool active) {
+#pragma unroll
+    for (int l = 0; l < COLS; ++l) m[l] = active ? __ldg(MT + l * rows + k) : 0.0;
+}
+
 template <int NX, int NU>
 __device__ __forceinline__ void chain_bwd(const Layout &L, const Topo &T, const Tabs &M, const double *__restrict__ X,
                                           const double *__restrict__ U, double *__restrict__ Q, double *__restrict__ R,
@@ -241,9 +264,20 @@ __device__ __forceinline__ void chain_bwd(const Layout &L, const Topo &T, const 
         ub0 = lane < nu ? U[node * nu + lane] : 0.0;
         ub1 = lane + 32 < nu ? U[node * nu + lane + 32] : 0.0;
     }
-    bool have_child = false;
+    // register-resident table columns (compile-time sizes, nx + nu <= 32): ccol = column `lane` of [A | B] of the current
+    // dynamics row, kcol = column `lane` of K of the current step's class (prefetched one step ahead)
+    constexpr int CN = NX > 0 ? NX : 1, KN = NX > 0 ? NU : 1;
+    constexpr bool kRegs = NX > 0 && NX + NU <= 32;
+    double ccol[CN], kcol[KN], kcol_next[KN];
+    int dyn_loaded = -1;
+    if constexpr (kRegs) {
+        if (d > 0 || node < L.m) {
+            const int dn = node < L.m ? d : d - 1;   // first nonleaf step
+            if (dn >= 0) load_col<KN>(kcol, M.K + (long long)at(cls_a, cls_b, dn) * NU * NX, NX, lane, lane < NX);
+        }
+    }
     for (; d >= 0; --d) {
-        // prefetch the rows of the next step (depth d - 1)
+        // prefetch the rows (and the K column) of the next step (depth d - 1)
         double nxb0 = 0.0, nxb1 = 0.0, nub0 = 0.0, nub1 = 0.0;
         int next = 0;
         if (d > 0) {
@@ -252,15 +286,26 @@ __device__ __forceinline__ void chain_bwd(const Layout &L, const Topo &T, const 
             nxb1 = lane + 32 < nx ? X[next * nx + lane + 32] : 0.0;
             nub0 = lane < nu ? U[next * nu + lane] : 0.0;
             nub1 = lane + 32 < nu ? U[next * nu + lane + 32] : 0.0;
+            if constexpr (kRegs) {
+                if (node < L.m)   // (when the current node is a leaf, kcol already holds the next step's column)
+                    load_col<KN>(kcol_next, M.K + (long long)at(cls_a, cls_b, d - 1) * NU * NX, NX, lane, lane < NX);
+            }
         }
         if (node >= L.m) {   // leaf: q = -xbar
             if (lane < nx) qj[lane] = -xb0;
             if (lane + 32 < nx) qj[lane + 32] = -xb1;
         } else {
-            // acc = [A' q ; B' q] of the single child (the chain's previous node, q in shared memory) -- a node of a
-            // chain level always has its one child inside the chain
-            (void)have_child;
-            bwd_child_contrib<NX, NU>(L, M, at(dyn_a, dyn_b, d), qj, lane, acc, false);
+            // acc = [A' q ; B' q] of the single child (the chain's previous node, q in shared memory)
+            const int dyn = at(dyn_a, dyn_b, d);
+            if constexpr (kRegs) {
+                if (dyn != dyn_loaded) {
+                    load_col<CN>(ccol, M.ABcat + dyn * (NX * (NX + NU)), NX + NU, lane, lane < NX + NU);
+                    dyn_loaded = dyn;
+                }
+                if (lane < NX + NU) acc[lane] = dot_col<CN>(ccol, qj);
+            } else {
+                bwd_child_contrib<NX, NU>(L, M, dyn, qj, lane, acc, false);
+            }
             __syncwarp();
             // r = ubar - acc[nx:]  (lane a < nu)
             if (lane < nu) {
@@ -274,20 +319,27 @@ __device__ __forceinline__ void chain_bwd(const Layout &L, const Topo &T, const 
                 R[node * nu + lane + 32] = rk;
             }
             __syncwarp();
-            const double *Kc = M.K + (long long)at(cls_a, cls_b, d) * nu * nx;
             double q0 = 0.0, q1 = 0.0;
-            if (lane < nx) {
-                double kr;
-                if constexpr (NX > 0) kr = mv_row_t<NX, NU>(Kc, rv, lane);
-                else kr = mv_row(Kc, rv, nx, nu, lane);
-                q0 = acc[lane] - xb0 - kr;
+            if constexpr (kRegs) {
+                if (lane < NX) q0 = acc[lane] - xb0 - dot_col<KN>(kcol, rv);
+            } else {
+                const double *Kc = M.K + (long long)at(cls_a, cls_b, d) * nu * nx;
+                if (lane < nx) {
+                    double kr;
+                    if constexpr (NX > 0) kr = mv_row_t<NX, NU>(Kc, rv, lane);
+                    else kr = mv_row(Kc, rv, nx, nu, lane);
+                    q0 = acc[lane] - xb0 - kr;
+                }
+                if (lane + 32 < nx) q1 = acc[lane + 32] - xb1 - mv_row(Kc, rv, nx, nu, lane + 32);
             }
-            if (lane + 32 < nx) q1 = acc[lane + 32] - xb1 - mv_row(Kc, rv, nx, nu, lane + 32);
             __syncwarp();
             if (lane < nx) qj[lane] = q0;
             if (lane + 32 < nx) qj[lane + 32] = q1;
+            if constexpr (kRegs) {
+#pragma unroll
+                for (int l = 0; l < KN; ++l) kcol[l] = kcol_next[l];
+            }
         }
-        have_child = true;
         __syncwarp();
         if (d == 0) {   // only the head's q is needed outside the chain
             if (lane < nx) Q[node * nx + lane] = qj[lane];
@@ -303,7 +355,7 @@ __device__ __forceinline__ void chain_fwd(const Layout &L, const Topo &T, const 
                                           double *__restrict__ U, const double *__restrict__ R,
                                           const int *__restrict__ chain, int depth, int lane, double *scratch) {
     const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
-    double *v = scratch, *part = scratch + nxu, *xnext = scratch + nxu + 32;   // xnext: nx doubles
+    double *v = scratch, *part = scratch + nxu;
     int node_a = lane < depth ? chain[lane] : 0, node_b = lane + 32 < depth ? chain[lane + 32] : 0;
     int dyn_a = lane + 1 < depth ? T.dyn_idx[chain[lane + 1]] : 0, dyn_b = lane + 33 < depth ? T.dyn_idx[chain[lane + 33]] : 0;
     int cls_a = (lane < depth && node_a < L.m) ? T.cls[node_a] : 0, cls_b = (lane + 32 < depth && node_b < L.m) ? T.cls[node_b] : 0;
@@ -317,6 +369,25 @@ __device__ __forceinline__ void chain_fwd(const Layout &L, const Topo &T, const 
         r0 = lane < nu ? R[node * nu + lane] : 0.0;
         r1 = lane + 32 < nu ? R[node * nu + lane + 32] : 0.0;
     }
+    // register-resident tables (compile-time sizes, nu <= 16 so that the split product applies): ct = column `lane` of
+    // [A ; B]' of the current dynamics row; kr = this lane's segment of [K R~^-1] of the current class (prefetched)
+    constexpr bool kRegs = NX > 0 && NX + NU <= 32 && NU <= 16;
+    constexpr int TN = NX > 0 ? NX + NU : 1;
+    constexpr int G = kRegs ? 32 / (NU > 0 ? NU : 1) : 1, SEG = kRegs ? (NX + NU + G - 1) / G : 1;
+    double ct[TN], kr[SEG], kr_next[SEG];
+    int dyn_loaded = -1;
+    const int sg = kRegs ? lane / (NU > 0 ? NU : 1) : 0, sa = kRegs ? lane - sg * (NU > 0 ? NU : 1) : 0;
+    auto load_kr = [&](double (&dst)[SEG], int cls) {
+        const double *KR = M.KRcatT + (long long)cls * (NX + NU) * NU;
+#pragma unroll
+        for (int i = 0; i < SEG; ++i) {
+            const int l = sg * SEG + i;
+            dst[i] = (sg < G && l < NX + NU) ? __ldg(KR + l * NU + sa) : 0.0;
+        }
+    };
+    if constexpr (kRegs) {
+        if (node < L.m) load_kr(kr, at(cls_a, cls_b, 0));
+    }
     for (int d = 0; d + 1 < depth; ++d) {
         if (node >= L.m) break;
         const int child = at(node_a, node_b, d + 1);
@@ -324,34 +395,62 @@ __device__ __forceinline__ void chain_fwd(const Layout &L, const Topo &T, const 
         if (child < L.m) {
             nr0 = lane < nu ? R[child * nu + lane] : 0.0;
             nr1 = lane + 32 < nu ? R[child * nu + lane + 32] : 0.0;
+            if constexpr (kRegs) load_kr(kr_next, at(cls_a, cls_b, d + 1));
         }
         if (lane < nu) v[nx + lane] = r0;
         if (lane + 32 < nu) v[nx + lane + 32] = r1;
         __syncwarp();
-        const double *KR = M.KRcatT + (long long)at(cls_a, cls_b, d) * nxu * nu;
-        if (nu <= 32) {
-            double ua;
-            if constexpr (NX > 0) ua = mv_split_t<NU, NX + NU>(KR, v, lane, part);
-            else ua = mv_split(KR, v, nu, nxu, lane, part);
-            if (lane < nu) {
-                v[nx + lane] = ua;
-                U[node * nu + lane] = ua;
+        if constexpr (kRegs) {   // u = [K R~^-1] [x ; r], reduction split over G lane groups
+            double p = 0.0;
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) {
+                const int l = sg * SEG + i;
+                if (l < NX + NU) p = fma(kr[i], v[l], p);
+            }
+            part[lane] = p;
+            __syncwarp();
+            double ua = 0.0;
+            if (lane < NU) {
+#pragma unroll
+                for (int gg = 0; gg < G; ++gg) ua += part[gg * NU + lane];
+            }
+            __syncwarp();
+            if (lane < NU) {
+                v[NX + lane] = ua;
+                U[node * NU + lane] = ua;
             }
         } else {
-            const double u0 = mv_row(KR, v, nu, nxu, lane), u1 = lane + 32 < nu ? mv_row(KR, v, nu, nxu, lane + 32) : 0.0;
-            __syncwarp();
-            v[nx + lane] = u0;
-            U[node * nu + lane] = u0;
-            if (lane + 32 < nu) {
-                v[nx + lane + 32] = u1;
-                U[node * nu + lane + 32] = u1;
+            const double *KR = M.KRcatT + (long long)at(cls_a, cls_b, d) * nxu * nu;
+            if (nu <= 32) {
+                double ua;
+                if constexpr (NX > 0) ua = mv_split_t<NU, NX + NU>(KR, v, lane, part);
+                else ua = mv_split(KR, v, nu, nxu, lane, part);
+                if (lane < nu) {
+                    v[nx + lane] = ua;
+                    U[node * nu + lane] = ua;
+                }
+            } else {
+                const double u0 = mv_row(KR, v, nu, nxu, lane), u1 = lane + 32 < nu ? mv_row(KR, v, nu, nxu, lane + 32) : 0.0;
+                __syncwarp();
+                v[nx + lane] = u0;
+                U[node * nu + lane] = u0;
+                if (lane + 32 < nu) {
+                    v[nx + lane + 32] = u1;
+                    U[node * nu + lane + 32] = u1;
+                }
             }
         }
         __syncwarp();
         // x_child = A x + B u, kept in shared memory for the next step and written out
         const int dyn = at(dyn_a, dyn_b, d);
         double x0 = 0.0, x1 = 0.0;
-        if constexpr (NX > 0) {
+        if constexpr (kRegs) {
+            if (dyn != dyn_loaded) {
+                load_col<TN>(ct, M.ABcatT + dyn * ((NX + NU) * NX), NX, lane, lane < NX);
+                dyn_loaded = dyn;
+            }
+            if (lane < NX) x0 = dot_col<TN>(ct, v);
+        } else if constexpr (NX > 0) {
             const double *C = M.ABcatT + dyn * ((NX + NU) * NX);
             if (lane < NX) x0 = mv_row_t<NX, NX + NU>(C, v, lane);
         } else {
@@ -368,7 +467,10 @@ __device__ __forceinline__ void chain_fwd(const Layout &L, const Topo &T, const 
             v[lane + 32] = x1;
             X[child * nx + lane + 32] = x1;
         }
-        (void)xnext;
+        if constexpr (kRegs) {
+#pragma unroll
+            for (int i = 0; i < SEG; ++i) kr[i] = kr_next[i];
+        }
         node = child;
         r0 = nr0;
         r1 = nr1;

@@ -29,6 +29,7 @@ class RbProblem(C.Structure):
         ("num_cls", C.c_int32), ("cls", c_int_p),
         ("device", C.c_int32),
         ("shard_rank", C.c_int32), ("shard_world", C.c_int32),
+        ("sweep_cut1_min", C.c_int32), ("sweep_cut2_min", C.c_int32),
     ]
 
 
@@ -77,6 +78,7 @@ SYMBOLS = [
     ("rb_use_graphs", C.c_int, [_H, C.c_int32]),
     ("rb_force_dense_costs", C.c_int, [_H, C.c_int32]),
     ("rb_use_lane_kernels", C.c_int, [_H, C.c_int32]),
+    ("rb_use_mma_sweeps", C.c_int, [_H, C.c_int32]),
     ("rb_shard_unique_id", C.c_int, [C.c_char_p]),
     ("rb_shard_init", C.c_int, [_H, C.c_char_p]),
     ("rb_launch_count", C.c_int, [_H, C.POINTER(C.c_int64)]),

@@ -18,9 +18,11 @@ from .flatten import FlatProblem
 
 
 class Cache:
-    def __init__(self, problem_spec: ps.RAOCP, batch=1, dedup=True, device=0, keep_history=False, shard=None):
+    def __init__(self, problem_spec: ps.RAOCP, batch=1, dedup=True, device=0, keep_history=False, shard=None,
+                 sweep_cuts=None):
         self.__raocp = problem_spec
-        self.__flat = FlatProblem(problem_spec, batch=batch, dedup=dedup, device=device, shard=shard)
+        self.__flat = FlatProblem(problem_spec, batch=batch, dedup=dedup, device=device, shard=shard,
+                                  sweep_cuts=sweep_cuts)
         f = self.__flat
         self.__num_nodes = f.n
         self.__num_nonleaf_nodes = f.m

@@ -45,6 +45,7 @@ class DeviceSolver:
         pb.num_cls, pb.cls = f.num_cls, ip(f.cls)
         pb.device = f.device
         pb.shard_rank, pb.shard_world = f.shard_rank, f.shard_world
+        pb.sweep_cut1_min, pb.sweep_cut2_min = f.sweep_cuts
         handle = C.c_void_p()
         _lib.check(self._lib.rb_create(C.byref(pb), C.byref(handle)))
         self._h = handle
@@ -220,6 +221,9 @@ class DeviceSolver:
 
     def use_lane_kernels(self, enable=True):
         self._call("rb_use_lane_kernels", 1 if enable else 0)
+
+    def use_mma_sweeps(self, enable=True):
+        self._call("rb_use_mma_sweeps", 1 if enable else 0)
 
     def loop_begin(self, alpha, max_iters, tol=-1.0, hist_capacity=0):
         self._call("rb_loop_begin", float(alpha), int(max_iters), float(tol), int(hist_capacity))

@@ -39,7 +39,7 @@ def _table(objs, getters):
 
 
 class FlatProblem:
-    def __init__(self, problem, batch=1, dedup=True, device=0, shard=None):
+    def __init__(self, problem, batch=1, dedup=True, device=0, shard=None, sweep_cuts=None):
         tree = problem.tree
         self.problem = problem
         self.n = n = int(tree.num_nodes)
@@ -49,6 +49,7 @@ class FlatProblem:
         self.batch = int(batch)
         self.device = int(device)
         self.shard_rank, self.shard_world = (int(shard[0]), int(shard[1])) if shard else (0, 1)
+        self.sweep_cuts = (int(sweep_cuts[0]), int(sweep_cuts[1])) if sweep_cuts else (0, 0)   # rb_problem.sweep_cut*_min
         if problem.list_of_dynamics[1] is None:
             raise Exception("RAOCP has no dynamics")
         self.nx = int(problem.state_dynamics_at_node(1).shape[1])

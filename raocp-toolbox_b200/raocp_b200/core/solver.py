@@ -21,10 +21,10 @@ from . import raocp_spec as spec
 
 class Solver:
     def __init__(self, problem_spec: spec.RAOCP, batch=1, dedup=True, device=0, keep_history=False, verbose=True,
-                 shard=None):
+                 shard=None, sweep_cuts=None):
         self.__raocp = problem_spec
         self.__cache = cache.Cache(self.__raocp, batch=batch, dedup=dedup, device=device, keep_history=keep_history,
-                                   shard=shard)
+                                   shard=shard, sweep_cuts=sweep_cuts)
         self.__operator = ops.Operator(self.__cache)
         self.__dev = self.__cache.device_solver
         self.__initial_state = None

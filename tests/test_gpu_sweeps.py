@@ -1,0 +1,88 @@
+"""DP sweeps (cache.py:259-288) on trees big / chain-like enough to reach every kernel of the sweep plan: the subtree
+levels, the one-warp-per-chain walker (sweeps.cu) and the eight-chains-per-warp tensor-core walker (chain_mma.cu), each
+against the NumPy oracle (pinned to the reference by tests/test_oracle_pinning.py), through the C-ABI."""
+import numpy as np
+import pytest
+
+from helpers import seg_rel_err
+
+pytestmark = pytest.mark.gpu
+
+# (problem, sweep_cuts): cut stage minima so that small trees still get a top part, a branching level and a chain level
+CASES = [
+    ("chain21", (2, 8)),        # nx=2, nu=1 (scalar loads), 8 chains = exactly one tile
+    ("chain32", (3, 9)),        # odd nx, 9 chains: a full tile and a padded one
+    ("mini2", (9, 27)),         # nx=4, nu=2, level 0 of depth 1
+    ("chain63", (16, 64)),      # sizes without an instantiation: run-time-size walker
+    ("shard", (64, 200)),       # nx=8, nu=4
+    ("chain105", (64, 200)),    # nx=10, nu=5 (odd nu)
+    ("chain2010", None),        # default plan: cut at 64 nodes, 256 chains
+    ("cfg2", None),             # default plan, no chain level (243 chains < 256)
+]
+
+
+def _pair(name, cuts, mma, batch=1):
+    import raocp_b200 as r
+    from oracle import problems
+    from oracle.cp_flat_oracle import FlatOracle
+    s = problems.spec(name, batch=batch)
+    problem = problems.build(s, r.core)
+    solver = r.core.Solver(problem, verbose=False, sweep_cuts=cuts, batch=batch)
+    solver.cache.device_solver.use_mma_sweeps(mma)
+    return s, solver, FlatOracle(problem)
+
+
+@pytest.mark.parametrize("mma", [True, False], ids=["mma", "warp_per_chain"])
+@pytest.mark.parametrize("name,cuts", CASES, ids=[c[0] for c in CASES])
+def test_projection_on_dynamics(name, cuts, mma):
+    s, solver, oracle = _pair(name, cuts, mma)
+    cache, dev, flat = solver.cache, solver.cache.device_solver, solver.cache.flat_problem
+    x0 = s["x0"][:, :1]
+    rng = np.random.default_rng(5)
+    vec = rng.standard_normal(flat.np_)
+    cache.cache_initial_state(x0)
+    dev.set_primal(0, vec)
+    cache.project_on_dynamics()
+    oracle.cache_initial_state(x0)
+    p = oracle.unflat_primal(vec)
+    oracle.project_on_dynamics(p)
+    assert seg_rel_err(flat, dev.get_primal(0)[0], oracle.flat_primal(p), dual=False) < 1e-11
+
+
+@pytest.mark.parametrize("mma", [True, False], ids=["mma", "warp_per_chain"])
+@pytest.mark.parametrize("name,cuts", CASES, ids=[c[0] for c in CASES])
+def test_iterates(name, cuts, mma):
+    """30 Chambolle-Pock iterations, iterates within 1e-9 (north star) of the oracle"""
+    s, solver, oracle = _pair(name, cuts, mma)
+    flat, dev = solver.cache.flat_problem, solver.cache.device_solver
+    x0 = s["x0"][:, :1]
+    alpha = oracle.step_size()
+    assert abs(solver.compute_step_size() - alpha) <= 1e-11 * alpha
+    assert solver.chock(x0, max_iters=29, tol=0.0, alpha=alpha) == 1 and solver.iterations == 30
+    oracle.cache_initial_state(x0)
+    oracle.alpha = alpha
+    for _ in range(30):
+        xi, delta = oracle.iterate()
+    assert seg_rel_err(flat, dev.get_primal(0)[0], oracle.flat_primal(oracle.p), dual=False) < 1e-9
+    assert seg_rel_err(flat, dev.get_dual(0)[0], oracle.flat_dual(oracle.d), dual=True) < 1e-9
+    got = np.concatenate((solver.residual_history[0][-1], solver.residual_history[1][-1]))
+    want = np.concatenate((np.array(xi), np.array(delta)))
+    assert np.max(np.abs(got - want) / want) < 1e-6
+
+
+def test_batched_instances_through_chain_tiles():
+    """batch > 1: every instance walks the same tiles on its own rows"""
+    from oracle.cp_flat_oracle import FlatOracle
+    s, solver, oracle = _pair("chain2010", None, True, batch=3)
+    flat, dev = solver.cache.flat_problem, solver.cache.device_solver
+    alpha = oracle.step_size()
+    x0 = s["x0"][:, :3]
+    assert solver.chock(x0, max_iters=9, tol=0.0, alpha=alpha) == 1
+    for b in range(3):
+        oracle = FlatOracle(flat.problem)       # fresh zero iterates
+        oracle.cache_initial_state(x0[:, b:b + 1])
+        oracle.alpha = alpha
+        for _ in range(10):
+            oracle.iterate()
+        assert seg_rel_err(flat, dev.get_primal(0)[b], oracle.flat_primal(oracle.p), dual=False) < 1e-9
+        assert seg_rel_err(flat, dev.get_dual(0)[b], oracle.flat_dual(oracle.d), dual=True) < 1e-9
