@@ -278,11 +278,14 @@ int build_chain_tiles(rb_solver *s, const std::vector<int> &lo, int depth, int f
     std::map<std::vector<int>, std::vector<int>> groups;
     std::vector<int> sig((size_t)2 * depth);
     for (int c = first; c < first + num; ++c) {
+        bool one_dyn = true;   // the walkers keep ONE dynamics row in registers per tile
         for (int d = 0; d < depth; ++d) {
             const int node = lo[(size_t)c * depth + d];
             sig[2 * d] = d == 0 ? 0 : s->dyn_idx[node];
             sig[2 * d + 1] = node < m ? s->cls[node] : -1;
+            one_dyn = one_dyn && (d < 2 || sig[2 * d] == sig[2]);
         }
+        if (!one_dyn) return RB_OK;
         groups[sig].push_back(c);
     }
     std::vector<int> tiles;
@@ -648,6 +651,28 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
         }
         s->sweep_smem_max = need;
         TRYC(sweep_kernels_set_smem((int)need));
+        // lane-major MMA fragment tables for the tiled chain levels (filled by rb_offline)
+        bool tiled = false;
+        for (int v = 0; v < pl.num_levels; ++v) tiled = tiled || pl.lv[v].num_tiles > 0;
+        if (tiled) {
+            int f_ab, f_abt, f_k, f_kr;
+            chain_mma_frag_counts(nx, nu, &f_ab, &f_abt, &f_k, &f_kr);
+            double *t_ab = nullptr, *t_abt = nullptr, *t_k = nullptr, *t_kr = nullptr;
+            TRY(dev_zero(s, (size_t)s->num_dyn * f_ab * 32, &t_ab));
+            TRY(dev_zero(s, (size_t)s->num_dyn * f_abt * 32, &t_abt));
+            TRY(dev_zero(s, (size_t)s->num_cls * f_k * 32, &t_k));
+            TRY(dev_zero(s, (size_t)s->num_cls * f_kr * 32, &t_kr));
+            s->P.m.fragAB = t_ab;
+            s->P.m.fragABT = t_abt;
+            s->P.m.fragK = t_k;
+            s->P.m.fragKR = t_kr;
+            size_t mma_need = 0;
+            for (int v = 0; v < pl.num_levels; ++v)
+                if (pl.lv[v].num_tiles > 0)
+                    mma_need = std::max(mma_need, std::max(chain_mma_smem_bytes(nx, nu, pl.lv[v].depth, true),
+                                                           chain_mma_smem_bytes(nx, nu, pl.lv[v].depth, false)));
+            TRYC(chain_mma_set_smem((int)mma_need));
+        }
     }
     // ---- node tiles: runs of consecutive nodes (<= 32 nodes and <= 64 edges; leaves: <= 64 nodes) -----------------
     {
@@ -819,6 +844,10 @@ int rb_offline(rb_solver *s) {
         if (count == 0) continue;
         k_offline_level<<<count, 256, smem, s->stream>>>(s->P, cv, begin, count, s->Ptab, s->Ktab, s->KRcatT, s->status);
         RB_LAUNCHED(s, "k_offline_level");
+    }
+    if (s->P.m.fragK) {
+        launch_chain_mma_frags(s->stream, s->P.m, s->P.L.nx, s->P.L.nu, s->num_dyn, s->num_cls, true, true);
+        RB_LAUNCHED(s, "k_frag_table");
     }
     int rc = check_status(s);
     if (rc != RB_OK) return rc;

@@ -12,7 +12,7 @@
 // {8v + 2t + j : t = 0..3}, i.e. exactly what lane t already holds: no shuffle, no shared memory between the steps.  The
 // matrix fragments are gathered from the operator tables in that permuted order; the dynamics fragments stay in
 // registers for the whole chain, the class-indexed ones (K, [K R~^-1]) and the xbar / ubar / r rows of the next step are
-// prefetched while the current step's MMAs issue.
+// prefetched while the current step's MMAs issue.  All matrices come from lane-major fragment tables (k_frag_table).
 //
 // Slots: 0..nx-1 = the state-sized part (q or x), nx..nx+nu-1 = the input-sized part (r or u); nx + nu <= 32.
 // Measured on B200 (profiles/microbench/fp64_pipes.cu): DMMA m8n8k4 issues every 16 cycles from a single warp per SM
@@ -110,9 +110,31 @@ __device__ __forceinline__ void st_input(double *__restrict__ row, int t, const 
 // Fragment of a table for the B operand: lane (tk, n) = (lane % 4, lane / 4) supplies W[slot 8*kb + 2*tk + kj][slot 8*ob + n]
 // where W[l][o] = tab[(l - l_off) * ld + (o - o_off)] for l_off <= l < l_off + rows and o_off <= o < o_off + cols, else 0.
 __device__ __forceinline__ double frag(const double *__restrict__ tab, int ld, int l_off, int rows, int o_off, int cols, int kb,
-                                       int kj, int ob, int lane, double sign) {
+                                       int kj, int ob, int lane) {
     const int l = 8 * kb + 2 * (lane & 3) + kj - l_off, o = 8 * ob + (lane >> 2) - o_off;
-    return (l >= 0 && l < rows && o >= 0 && o < cols) ? sign * __ldg(tab + l * ld + o) : 0.0;
+    return (l >= 0 && l < rows && o >= 0 && o < cols) ? tab[l * ld + o] : 0.0;
+}
+
+// The fragments are gathered ONCE per table (after the offline factorisation) into lane-major tables, so that a walker
+// fetches its F fragment words of table entry e as one contiguous, unpredicated run: out[(e * 32 + lane) * F + f], with
+// f = (2 * kbi + kj) * nob + obi for k-blocks kb0 + kbi and output blocks ob0 + obi.
+__global__ void k_frag_table(const double *__restrict__ tab, long long entry_stride, int ld, int l_off, int rows, int o_off,
+                             int cols, int kb0, int ob0, int nob, double *__restrict__ out) {
+    const int e = blockIdx.x, f = blockIdx.y, F = gridDim.y, lane = threadIdx.x;
+    const int obi = f % nob, kj = (f / nob) & 1, kbi = f / (2 * nob);
+    out[((long long)e * 32 + lane) * F + f] =
+        frag(tab + e * entry_stride, ld, l_off, rows, o_off, cols, kb0 + kbi, kj, ob0 + obi, lane);
+}
+
+template <int F>
+__device__ __forceinline__ void ld_frags(double (&w)[F], const double *__restrict__ table, int entry, int lane) {
+    const double2 *b = reinterpret_cast<const double2 *>(table + ((long long)entry * 32 + lane) * F);
+#pragma unroll
+    for (int f = 0; f < F; f += 2) {
+        const double2 v = __ldg(b + f / 2);
+        w[f] = v.x;
+        w[f + 1] = v.y;
+    }
 }
 
 // per-warp metadata in shared memory: node ids [depth][8], then dynamics row and class of every depth (of chain 0 of
@@ -139,6 +161,74 @@ __device__ __forceinline__ TileMeta stage_meta(const Layout &L, const Topo &T, c
     return TileMeta{nodes, dyns, clss, g, t, own >= 0};
 }
 
+// ---- asynchronous row / fragment staging -----------------------------------------------------------------------------------
+// A step's inputs (xbar, ubar or r rows of the eight chains and the fragments of the step's class) are copied with
+// cp.async into a per-warp ring of kStages shared-memory stages two steps ahead.  Every lane copies exactly the words it
+// will read itself, so no warp barrier is needed -- only cp.async.wait_group -- and, unlike register prefetching, the
+// copies hold no register scoreboard: the tensor-core instructions of the current step never wait for a copy of a later one.
+constexpr int kStages = 3;
+// words per lane of one stage, padded to an odd number of 16-byte units: conflict-free 128-bit shared-memory reads
+__host__ __device__ constexpr int ring_lane_words(int words) { return (words / 2) % 2 == 0 ? words + 2 : words; }
+
+template <int BYTES>
+__device__ __forceinline__ void cp_async(double *smem_dst, const double *gsrc) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(gsrc), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// state-sized row: the lane's slots 8b + 2t + {0,1} (b < QT) -> dst[2b + {0,1}]; slots >= NX are never written (zeroed once)
+template <int NX, int NU>
+__device__ __forceinline__ void cp_state(double *dst, const double *__restrict__ row, int t) {
+    using D = ChainDims<NX, NU>;
+#pragma unroll
+    for (int b = 0; b < D::QT; ++b) {
+        const int s0 = 8 * b + 2 * t;
+        if constexpr (D::VEC) {
+            if (s0 < NX) cp_async<16>(dst + 2 * b, row + s0);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                if (s0 + j < NX) cp_async<8>(dst + 2 * b + j, row + s0 + j);
+        }
+    }
+}
+// input-sized row: the lane's slots of block RT0 + i -> dst[2i + {0,1}]
+template <int NX, int NU>
+__device__ __forceinline__ void cp_input(double *dst, const double *__restrict__ row, int t) {
+    using D = ChainDims<NX, NU>;
+#pragma unroll
+    for (int i = 0; i < D::RN; ++i) {
+        const int a0 = 8 * (D::RT0 + i) + 2 * t - NX;
+        if constexpr (D::VEC) {
+            if (a0 >= 0 && a0 < NU) cp_async<16>(dst + 2 * i, row + a0);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+                if (a0 + j >= 0 && a0 + j < NU) cp_async<8>(dst + 2 * i + j, row + a0 + j);
+        }
+    }
+}
+// the lane's F fragment words of one table entry (F is even: 16-byte copies)
+template <int F>
+__device__ __forceinline__ void cp_frags(double *dst, const double *__restrict__ table, int entry, int lane) {
+    const double *src = table + ((long long)entry * 32 + lane) * F;
+#pragma unroll
+    for (int f = 0; f < F; f += 2) cp_async<16>(dst + f, src + f);
+}
+template <int N>
+__device__ __forceinline__ void lds_vec(double (&v)[N], const double *src) {
+    static_assert(N % 2 == 0, "pairs");
+#pragma unroll
+    for (int k = 0; k < N; k += 2) {
+        const double2 w = *reinterpret_cast<const double2 *>(src + k);
+        v[k] = w.x;
+        v[k + 1] = w.y;
+    }
+}
+
 // ---- backward:  r = ubar - B'q_child,  q = A'q_child - xbar - K'r    -------------------------------
 template <int NX, int NU>
 __global__ void __launch_bounds__(128) k_chain_mma_bwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
@@ -146,71 +236,62 @@ __global__ void __launch_bounds__(128) k_chain_mma_bwd(const __grid_constant__ P
                                                       double *__restrict__ q, double *__restrict__ r) {
     using D = ChainDims<NX, NU>;
     if (ctrl && ctrl->done) return;
-    extern __shared__ int meta_smem[];
+    extern __shared__ __align__(16) double mma_smem[];
     const Layout &L = P.L;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    const int tile = blockIdx.x * warps + warp;
     if (tile >= lv.num_tiles) return;
-    const TileMeta tm = stage_meta(L, P.t, lv, tile, warp, lane, meta_smem);
+    constexpr int F1 = 2 * D::QT * D::NT, F2 = 2 * D::RN * D::QT;
+    constexpr int kLaneWords = ring_lane_words(2 * D::QT + 2 * D::RN + F2);   // per lane and stage: xbar | ubar | K fragments
+    double *ring = mma_smem + ((size_t)warp * kStages * 32 + lane) * kLaneWords;   // stage s: ring + s * 32 * kLaneWords
+    const TileMeta tm = stage_meta(L, P.t, lv, tile, warp, lane,
+                                   reinterpret_cast<int *>(mma_smem + (size_t)warps * kStages * 32 * kLaneWords));
     const int t = tm.t, g = tm.g;
     const double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
     double *Q = q + (long long)blockIdx.y * L.n * NX, *R = r + (long long)blockIdx.y * L.m * NU;
 
-    double w1[2 * D::QT][D::NT];                             // [A | B] of the chain's dynamics row
-    double w2[2 * D::RN][D::QT], w2n[2 * D::RN][D::QT];      // -K of the current / next class
-    double qs[D::QT][2], xb[D::QT][2], xbn[D::QT][2], ub[D::RN][2], ubn[D::RN][2];
-    int dyn_loaded = -1;
-    auto load_w2 = [&](double (&w)[2 * D::RN][D::QT], int cls) {
-        const double *K = P.m.K + (long long)cls * NU * NX;
 #pragma unroll
-        for (int i = 0; i < D::RN; ++i)
+    for (int s = 0; s < kStages; ++s)
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int ob = 0; ob < D::QT; ++ob) w[2 * i + j][ob] = frag(K, NX, NX, NU, 0, NX, D::RT0 + i, j, ob, lane, -1.0);
-    };
-#pragma unroll
-    for (int b = 0; b < D::QT; ++b) qs[b][0] = qs[b][1] = 0.0;
-#pragma unroll
-    for (int i = 0; i < D::RN; ++i) ub[i][0] = ub[i][1] = ubn[i][0] = ubn[i][1] = 0.0;
-
-    int d = lv.depth - 1;
-    int node = tm.nodes[d * 8 + g];
-    ld_state<NX, NU, true>(X + (long long)node * NX, t, xb);
-    if (tm.clss[d] >= 0) {
-        ld_input<NX, NU>(U + (long long)node * NU, t, ub);
-        load_w2(w2, tm.clss[d]);
-    }
-    for (; d >= 0; --d) {
-        const int cls = tm.clss[d];
-        int next = node;
-        if (d > 0) {   // prefetch the rows and the class fragments of the next step
-            next = tm.nodes[(d - 1) * 8 + g];
-            ld_state<NX, NU, true>(X + (long long)next * NX, t, xbn);
-            const int cn = tm.clss[d - 1];
-            if (cn >= 0) {
-                ld_input<NX, NU>(U + (long long)next * NU, t, ubn);
-                load_w2(w2n, cn);
+        for (int k = 0; k < 2 * D::QT + 2 * D::RN; ++k) ring[s * 32 * kLaneWords + k] = 0.0;   // padding slots stay zero
+    auto prefetch = [&](int d) {   // one commit group per step, possibly empty
+        if (d >= 0) {
+            double *dst = ring + (d % kStages) * 32 * kLaneWords;
+            const int node = tm.nodes[d * 8 + g], cls = tm.clss[d];
+            cp_state<NX, NU>(dst, X + (long long)node * NX, t);
+            if (cls >= 0) {
+                cp_input<NX, NU>(dst + 2 * D::QT, U + (long long)node * NU, t);
+                cp_frags<F2>(dst + 2 * D::QT + 2 * D::RN, P.m.fragK, cls, lane);
             }
         }
-        if (cls < 0) {   // leaf: q = -xbar
+        cp_async_commit();
+    };
+    int d = lv.depth - 1;
+    prefetch(d);
+    prefetch(d - 1);
+    double w1[F1];   // [A | B] of the chain's dynamics row (one row per tile: build_chain_tiles), fragment (2 kb + j) * NT + ob
+    if (lv.depth > 1) ld_frags<F1>(w1, P.m.fragAB, tm.dyns[1], lane);
+    double qs[D::QT][2];
+#pragma unroll
+    for (int b = 0; b < D::QT; ++b) qs[b][0] = qs[b][1] = 0.0;
+
+    for (; d >= 0; --d) {
+        prefetch(d - 2);
+        cp_async_wait<2>();   // the copies of step d have landed
+        const double *src = ring + (d % kStages) * 32 * kLaneWords;
+        const int node = tm.nodes[d * 8 + g];
+        double xb[2 * D::QT];
+        lds_vec(xb, src);
+        if (tm.clss[d] < 0) {   // leaf: q = -xbar
 #pragma unroll
             for (int b = 0; b < D::QT; ++b) {
-                qs[b][0] = -xb[b][0];
-                qs[b][1] = -xb[b][1];
+                qs[b][0] = -xb[2 * b];
+                qs[b][1] = -xb[2 * b + 1];
             }
         } else {
-            const int dyn = d + 1 < lv.depth ? tm.dyns[d + 1] : 0;
-            if (dyn != dyn_loaded) {
-                const double *C = P.m.ABcat + (long long)dyn * NX * D::S;
-#pragma unroll
-                for (int kb = 0; kb < D::QT; ++kb)
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-#pragma unroll
-                        for (int ob = 0; ob < D::NT; ++ob) w1[2 * kb + j][ob] = frag(C, D::S, 0, NX, 0, D::S, kb, j, ob, lane, 1.0);
-                dyn_loaded = dyn;
-            }
+            double ub[2 * D::RN], w2[F2];
+            lds_vec(ub, src + 2 * D::QT);
+            lds_vec(w2, src + 2 * D::QT + 2 * D::RN);
             // E = [A'q ; B'q]
             double E[D::NT][2];
 #pragma unroll
@@ -220,45 +301,31 @@ __global__ void __launch_bounds__(128) k_chain_mma_bwd(const __grid_constant__ P
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
-                    for (int ob = 0; ob < D::NT; ++ob) dmma(E[ob], qs[kb][j], w1[2 * kb + j][ob]);
-            // r = ubar - B'q  on the input slots
-            double rr[D::RN][2];
+                    for (int ob = 0; ob < D::NT; ++ob) dmma(E[ob], qs[kb][j], w1[(2 * kb + j) * D::NT + ob]);
+            // r = ubar - B'q  on the input slots (nr = -r feeds the second product)
+            double rr[D::RN][2], nr[D::RN][2];
 #pragma unroll
             for (int i = 0; i < D::RN; ++i)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int a = 8 * (D::RT0 + i) + 2 * t + j - NX;
-                    rr[i][j] = (a >= 0 && a < NU) ? ub[i][j] - E[D::RT0 + i][j] : 0.0;
+                    rr[i][j] = (a >= 0 && a < NU) ? ub[2 * i + j] - E[D::RT0 + i][j] : 0.0;
+                    nr[i][j] = -rr[i][j];
                 }
             if (tm.valid) st_input<NX, NU>(R + (long long)node * NU, t, rr);
             // q = A'q - xbar - K'r  on the state slots
 #pragma unroll
             for (int b = 0; b < D::QT; ++b)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) qs[b][j] = (8 * b + 2 * t + j < NX) ? E[b][j] - xb[b][j] : 0.0;
+                for (int j = 0; j < 2; ++j) qs[b][j] = (8 * b + 2 * t + j < NX) ? E[b][j] - xb[2 * b + j] : 0.0;
 #pragma unroll
             for (int i = 0; i < D::RN; ++i)
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
-                    for (int ob = 0; ob < D::QT; ++ob) dmma(qs[ob], rr[i][j], w2[2 * i + j][ob]);
+                    for (int ob = 0; ob < D::QT; ++ob) dmma(qs[ob], nr[i][j], w2[(2 * i + j) * D::QT + ob]);
         }
         if (d == 0 && tm.valid) st_state<NX, NU>(Q + (long long)node * NX, t, qs);   // only the head's q leaves the chain
-        node = next;
-#pragma unroll
-        for (int b = 0; b < D::QT; ++b) {
-            xb[b][0] = xbn[b][0];
-            xb[b][1] = xbn[b][1];
-        }
-#pragma unroll
-        for (int i = 0; i < D::RN; ++i) {
-            ub[i][0] = ubn[i][0];
-            ub[i][1] = ubn[i][1];
-        }
-#pragma unroll
-        for (int k = 0; k < 2 * D::RN; ++k)
-#pragma unroll
-            for (int ob = 0; ob < D::QT; ++ob) w2[k][ob] = w2n[k][ob];
     }
 }
 
@@ -268,44 +335,50 @@ __global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ P
                                                       SweepLevel lv, double *__restrict__ prim, const double *__restrict__ r) {
     using D = ChainDims<NX, NU>;
     if (ctrl && ctrl->done) return;
-    extern __shared__ int meta_smem[];
+    extern __shared__ __align__(16) double mma_smem[];
     const Layout &L = P.L;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * (blockDim.x >> 5) + warp;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    const int tile = blockIdx.x * warps + warp;
     if (tile >= lv.num_tiles) return;
-    const TileMeta tm = stage_meta(L, P.t, lv, tile, warp, lane, meta_smem);
+    constexpr int F4 = 2 * D::NT * D::QT, F3 = 2 * D::NT * D::RN;
+    constexpr int kLaneWords = ring_lane_words(2 * D::RN + F3);                // per lane and stage: r | [K R~^-1] fragments
+    double *ring = mma_smem + ((size_t)warp * kStages * 32 + lane) * kLaneWords;
+    const TileMeta tm = stage_meta(L, P.t, lv, tile, warp, lane,
+                                   reinterpret_cast<int *>(mma_smem + (size_t)warps * kStages * 32 * kLaneWords));
     const int t = tm.t, g = tm.g;
     double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
     const double *R = r + (long long)blockIdx.y * L.m * NU;
 
-    double w4[2 * D::NT][D::QT];                             // [A ; B]' of the chain's dynamics row
-    double w3[2 * D::NT][D::RN], w3n[2 * D::NT][D::RN];      // [K R~^-1] of the current / next class
-    double xs[D::QT][2], rr[D::RN][2], rrn[D::RN][2];
-    int dyn_loaded = -1;
-    auto load_w3 = [&](double (&w)[2 * D::NT][D::RN], int cls) {
-        const double *KR = P.m.KRcatT + (long long)cls * D::S * NU;
 #pragma unroll
-        for (int kb = 0; kb < D::NT; ++kb)
+    for (int s = 0; s < kStages; ++s)
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int i = 0; i < D::RN; ++i) w[2 * kb + j][i] = frag(KR, NU, 0, D::S, NX, NU, kb, j, D::RT0 + i, lane, 1.0);
-    };
-#pragma unroll
-    for (int i = 0; i < D::RN; ++i) rr[i][0] = rr[i][1] = rrn[i][0] = rrn[i][1] = 0.0;
-    int node = tm.nodes[g];
-    ld_state<NX, NU, false>(X + (long long)node * NX, t, xs);   // x of the head was written by the level above
-    if (tm.clss[0] >= 0) {
-        ld_input<NX, NU>(R + (long long)node * NU, t, rr);
-        load_w3(w3, tm.clss[0]);
-    }
-    for (int d = 0; d + 1 < lv.depth; ++d) {
-        if (tm.clss[d] < 0) break;
-        const int child = tm.nodes[(d + 1) * 8 + g], cn = tm.clss[d + 1];
-        if (cn >= 0) {
-            ld_input<NX, NU>(R + (long long)child * NU, t, rrn);
-            load_w3(w3n, cn);
+        for (int k = 0; k < 2 * D::RN; ++k) ring[s * 32 * kLaneWords + k] = 0.0;
+    auto prefetch = [&](int d) {
+        if (d < lv.depth) {
+            const int cls = tm.clss[d];
+            if (cls >= 0) {
+                double *dst = ring + (d % kStages) * 32 * kLaneWords;
+                cp_input<NX, NU>(dst, R + (long long)tm.nodes[d * 8 + g] * NU, t);
+                cp_frags<F3>(dst + 2 * D::RN, P.m.fragKR, cls, lane);
+            }
         }
+        cp_async_commit();
+    };
+    prefetch(0);
+    prefetch(1);
+    double w4[F4];   // [A ; B]' of the chain's dynamics row, fragment (2 kb + j) * QT + ob
+    if (lv.depth > 1) ld_frags<F4>(w4, P.m.fragABT, tm.dyns[1], lane);
+    double xs[D::QT][2];
+    ld_state<NX, NU, false>(X + (long long)tm.nodes[g] * NX, t, xs);   // x of the head was written by the level above
+
+    for (int d = 0; d + 1 < lv.depth && tm.clss[d] >= 0; ++d) {
+        prefetch(d + 2);
+        cp_async_wait<2>();
+        const double *src = ring + (d % kStages) * 32 * kLaneWords;
+        const int node = tm.nodes[d * 8 + g], child = tm.nodes[(d + 1) * 8 + g];
+        double rr[2 * D::RN], w3[F3];
+        lds_vec(rr, src);
+        lds_vec(w3, src + 2 * D::RN);
         // u = [K R~^-1] [x ; r]  (lands on the input slots)
         double ua[D::RN][2];
 #pragma unroll
@@ -317,23 +390,12 @@ __global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ P
                 const bool is_x = 8 * kb + 2 * t + j < NX;
                 double v = 0.0;
                 if (kb < D::QT) v = xs[kb < D::QT ? kb : 0][j];
-                if (kb >= D::RT0 && !is_x) v = rr[kb >= D::RT0 ? kb - D::RT0 : 0][j];
+                if (kb >= D::RT0 && !is_x) v = rr[2 * (kb >= D::RT0 ? kb - D::RT0 : 0) + j];
 #pragma unroll
-                for (int i = 0; i < D::RN; ++i) dmma(ua[i], v, w3[2 * kb + j][i]);
+                for (int i = 0; i < D::RN; ++i) dmma(ua[i], v, w3[(2 * kb + j) * D::RN + i]);
             }
         if (tm.valid) st_input<NX, NU>(U + (long long)node * NU, t, ua);
         // x_child = [A B] [x ; u]
-        const int dyn = tm.dyns[d + 1];
-        if (dyn != dyn_loaded) {
-            const double *C = P.m.ABcatT + (long long)dyn * D::S * NX;
-#pragma unroll
-            for (int kb = 0; kb < D::NT; ++kb)
-#pragma unroll
-                for (int j = 0; j < 2; ++j)
-#pragma unroll
-                    for (int ob = 0; ob < D::QT; ++ob) w4[2 * kb + j][ob] = frag(C, NX, 0, D::S, 0, NX, kb, j, ob, lane, 1.0);
-            dyn_loaded = dyn;
-        }
         double xn[D::QT][2];
 #pragma unroll
         for (int b = 0; b < D::QT; ++b) xn[b][0] = xn[b][1] = 0.0;
@@ -346,24 +408,14 @@ __global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ P
                 if (kb < D::QT) v = xs[kb < D::QT ? kb : 0][j];
                 if (kb >= D::RT0 && !is_x) v = ua[kb >= D::RT0 ? kb - D::RT0 : 0][j];
 #pragma unroll
-                for (int ob = 0; ob < D::QT; ++ob) dmma(xn[ob], v, w4[2 * kb + j][ob]);
+                for (int ob = 0; ob < D::QT; ++ob) dmma(xn[ob], v, w4[(2 * kb + j) * D::QT + ob]);
             }
         if (tm.valid) st_state<NX, NU>(X + (long long)child * NX, t, xn);
-        node = child;
 #pragma unroll
         for (int b = 0; b < D::QT; ++b) {
             xs[b][0] = xn[b][0];
             xs[b][1] = xn[b][1];
         }
-#pragma unroll
-        for (int i = 0; i < D::RN; ++i) {
-            rr[i][0] = rrn[i][0];
-            rr[i][1] = rrn[i][1];
-        }
-#pragma unroll
-        for (int k = 0; k < 2 * D::NT; ++k)
-#pragma unroll
-            for (int i = 0; i < D::RN; ++i) w3[k][i] = w3n[k][i];
     }
 }
 
@@ -380,14 +432,57 @@ bool chain_mma_supported(int nx, int nu) {
     return false;
 }
 
+// fragment tables of chain_mma (Tabs::fragAB, fragABT: per dynamics row; fragK, fragKR: per factorisation class)
+void chain_mma_frag_counts(int nx, int nu, int *f_ab, int *f_abt, int *f_k, int *f_kr) {
+    const int NT = (nx + nu + 7) / 8, QT = (nx + 7) / 8, RT0 = nx / 8, RN = NT - RT0;
+    *f_ab = 2 * QT * NT;
+    *f_abt = 2 * NT * QT;
+    *f_k = 2 * RN * QT;
+    *f_kr = 2 * NT * RN;
+}
+void launch_chain_mma_frags(cudaStream_t st, const Tabs &M, int nx, int nu, int num_dyn, int num_cls, bool dynamics,
+                            bool classes) {
+    const int S = nx + nu, NT = (S + 7) / 8, QT = (nx + 7) / 8, RT0 = nx / 8, RN = NT - RT0;
+    if (dynamics) {
+        // [A'q ; B'q]: rows = state slots of q, columns = all slots
+        k_frag_table<<<dim3(num_dyn, 2 * QT * NT), 32, 0, st>>>(M.ABcat, (long long)nx * S, S, 0, nx, 0, S, 0, 0, NT,
+                                                                const_cast<double *>(M.fragAB));
+        // A x + B u: rows = all slots of [x ; u], columns = state slots
+        k_frag_table<<<dim3(num_dyn, 2 * NT * QT), 32, 0, st>>>(M.ABcatT, (long long)S * nx, nx, 0, S, 0, nx, 0, 0, QT,
+                                                                const_cast<double *>(M.fragABT));
+    }
+    if (classes) {
+        // K'r: rows = input slots (r), columns = state slots
+        k_frag_table<<<dim3(num_cls, 2 * RN * QT), 32, 0, st>>>(M.K, (long long)nu * nx, nx, nx, nu, 0, nx, RT0, 0, QT,
+                                                                const_cast<double *>(M.fragK));
+        // K x + R~^-1 r: rows = all slots of [x ; r], columns = input slots
+        k_frag_table<<<dim3(num_cls, 2 * NT * RN), 32, 0, st>>>(M.KRcatT, (long long)S * nu, nu, 0, S, nx, nu, 0, RT0, RN,
+                                                                const_cast<double *>(M.fragKR));
+    }
+}
+
 static dim3 mma_grid(const SweepLevel &lv, int batch) { return dim3((lv.num_tiles + 3) / 4, batch); }
-static size_t mma_smem(const SweepLevel &lv) { return (size_t)4 * lv.depth * 10 * sizeof(int); }
+// dynamic shared memory of a 4-warp CTA: the cp.async rings + the tile metadata
+size_t chain_mma_smem_bytes(int nx, int nu, int depth, bool backward) {
+    const int NT = (nx + nu + 7) / 8, QT = (nx + 7) / 8, RT0 = nx / 8, RN = NT - RT0;
+    const int lane_words = ring_lane_words(backward ? 2 * QT + 2 * RN + 2 * RN * QT : 2 * RN + 2 * NT * RN);
+    return (size_t)4 * kStages * 32 * lane_words * sizeof(double) + (size_t)4 * depth * 10 * sizeof(int);
+}
+cudaError_t chain_mma_set_smem(int bytes) {
+    cudaError_t e = cudaSuccess;
+#define RB_SET(NX, NU)                                                                                                       \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_bwd<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_fwd<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    RB_MMA_DIMS(RB_SET)
+#undef RB_SET
+    return e;
+}
 
 void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, const double *prim,
                           double *q, double *r) {
 #define RB_GO(NX, NU)                                                                                             \
     if (P.L.nx == NX && P.L.nu == NU) {                                                                           \
-        k_chain_mma_bwd<NX, NU><<<mma_grid(lv, P.L.batch), 128, mma_smem(lv), st>>>(P, ctrl, lv, prim, q, r);     \
+        k_chain_mma_bwd<NX, NU><<<mma_grid(lv, P.L.batch), 128, chain_mma_smem_bytes(NX, NU, lv.depth, true), st>>>(P, ctrl, lv, prim, q, r);     \
         return;                                                                                                   \
     }
     RB_MMA_DIMS(RB_GO)
@@ -398,7 +493,7 @@ void launch_chain_mma_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, co
                           const double *r) {
 #define RB_GO(NX, NU)                                                                                             \
     if (P.L.nx == NX && P.L.nu == NU) {                                                                           \
-        k_chain_mma_fwd<NX, NU><<<mma_grid(lv, P.L.batch), 128, mma_smem(lv), st>>>(P, ctrl, lv, prim, r);        \
+        k_chain_mma_fwd<NX, NU><<<mma_grid(lv, P.L.batch), 128, chain_mma_smem_bytes(NX, NU, lv.depth, false), st>>>(P, ctrl, lv, prim, r);        \
         return;                                                                                                   \
     }
     RB_MMA_DIMS(RB_GO)

@@ -46,6 +46,9 @@ struct Tabs {
     const double *K;           // [num_cls][nu][nx]                                    ->  K' r
     const double *KRcatT;      // [num_cls][nx+nu][nu]  row l<nx: K[:][l], row nx+b: R~^-1[:][b]   ->  K x + R~^-1 r
     int sq_diag, sr_diag, sqf_diag;  // 1 if every matrix of the table is diagonal (fast path)
+    // MMA fragment images of ABcat / ABcatT ([num_dyn][F][32]) and K / KRcatT ([num_cls][F][32]) for chain_mma.cu; null
+    // when no sweep level is tiled
+    const double *fragAB, *fragABT, *fragK, *fragKR;
 };
 
 struct Params {

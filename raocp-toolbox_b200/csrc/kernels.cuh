@@ -97,6 +97,11 @@ void launch_sweep_top(int grid, int threads, size_t smem, cudaStream_t st, const
 
 // ---- chain_mma.cu: chain levels on the FP64 tensor cores, 8 chains per warp ---------------------------------------------------
 bool chain_mma_supported(int nx, int nu);
+size_t chain_mma_smem_bytes(int nx, int nu, int depth, bool backward);
+cudaError_t chain_mma_set_smem(int bytes);
+void chain_mma_frag_counts(int nx, int nu, int *f_ab, int *f_abt, int *f_k, int *f_kr);
+void launch_chain_mma_frags(cudaStream_t st, const Tabs &M, int nx, int nu, int num_dyn, int num_cls, bool dynamics,
+                            bool classes);
 void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, const double *prim,
                           double *q, double *r);
 void launch_chain_mma_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, double *prim,
