@@ -78,7 +78,10 @@ struct rb_solver {
     int n_owned = 0, n_top = 0;
     SweepLevel shard_lv[2]{};
     std::vector<int> chain_lo[2];   // host copy of lv.lo of chain levels (tile building)
-    bool allow_mma = true;   // chain levels on the FP64 tensor cores when the level carries tiles (rb_use_mma_sweeps)
+    bool allow_mma = true;
+    bool allow_tree = true;  // branching levels / top out of shared memory (tree_sweeps.cu) when they fit (rb_use_tree_kernels)
+    TreeLevel tree_top{}, tree_lv[2]{}, shard_tree_lv[2]{};
+    size_t tree_smem[3]{};   // dynamic shared memory of the top / level launches   // chain levels on the FP64 tensor cores when the level carries tiles (rb_use_mma_sweeps)
     double *xchg_send = nullptr, *xchg_recv = nullptr;
     size_t xchg_count = 0;
     bool shard_pending = false;   // an executed iteration whose residuals have not been gathered / tested yet
@@ -249,16 +252,25 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
     for (int v = pl.num_levels - 1; v >= 0; --v) {
         if (s->allow_mma && pl.lv[v].num_tiles > 0)
             launch_chain_mma_bwd(st, s->P, ctrl, pl.lv[v], prim, s->q, s->r);
+        else if (s->allow_tree && s->tree_lv[v].desc)
+            launch_tree_bwd(dim3(s->tree_lv[v].num_sub, batch), 32 * s->tree_lv[v].warps, s->tree_smem[1 + v], st, s->P, ctrl,
+                            s->tree_lv[v], prim, s->q, s->r);
         else
             launch_sweep_sub_bwd(grid(pl.lv[v]), threads(pl.lv[v]), smem(pl.lv[v]), st, s->P, ctrl, pl.lv[v], prim, s->q, s->r);
         if (evs) cudaEventRecord(evs[ne++], st);
     }
-    launch_sweep_top(batch, 32 * s->top_warps, per_warp * s->top_warps + (size_t)pl.top_cap * L.nxu * sizeof(double), st, s->P,
-                     ctrl, pl, prim, s->q, s->r, s->x0);
+    if (s->allow_tree && s->tree_top.desc)
+        launch_tree_top(batch, 32 * s->tree_top.warps, s->tree_smem[0], st, s->P, ctrl, s->tree_top, prim, s->q, s->r, s->x0);
+    else
+        launch_sweep_top(batch, 32 * s->top_warps, per_warp * s->top_warps + (size_t)pl.top_cap * L.nxu * sizeof(double), st,
+                         s->P, ctrl, pl, prim, s->q, s->r, s->x0);
     if (evs) cudaEventRecord(evs[ne++], st);
     for (int v = 0; v < pl.num_levels; ++v) {
         if (s->allow_mma && pl.lv[v].num_tiles > 0)
             launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r);
+        else if (s->allow_tree && s->tree_lv[v].desc)
+            launch_tree_fwd(dim3(s->tree_lv[v].num_sub, batch), 32 * s->tree_lv[v].warps, s->tree_smem[1 + v], st, s->P, ctrl,
+                            s->tree_lv[v], prim, s->r);
         else
             launch_sweep_sub_fwd(grid(pl.lv[v]), threads(pl.lv[v]), smem(pl.lv[v]), st, s->P, ctrl, pl.lv[v], prim, s->r);
         if (evs) cudaEventRecord(evs[ne++], st);
@@ -301,6 +313,88 @@ int build_chain_tiles(rb_solver *s, const std::vector<int> &lo, int depth, int f
     if (rc != RB_OK) return rc;
     *tiles_out = d_tiles;
     *num_tiles_out = num_tiles;
+    return RB_OK;
+}
+
+// Pack the topology of every subtree of a level into one contiguous descriptor per subtree (tree_sweeps.cu) and decide what
+// fits into shared memory.  lo / hi: [num_sub][depth] node ranges.  out->desc stays null if the level cannot be served.
+int build_tree_level(rb_solver *s, const std::vector<int> &lo, const std::vector<int> &hi, int depth, int num_sub, bool top,
+                     TreeLevel *out, size_t *smem_out) {
+    *out = TreeLevel{};
+    const Layout &L = s->P.L;
+    const int m = L.m;
+    if (depth <= 0 || num_sub <= 0) return RB_OK;
+    TreeLevel lv{};
+    lv.depth = depth;
+    lv.num_sub = num_sub;
+    lv.num_dyn = s->num_dyn;
+    std::vector<int> ns(num_sub), ne(num_sub, 0), xf(num_sub, 0);
+    for (int c = 0; c < num_sub; ++c) {
+        int tot = 0;
+        for (int d = 0; d < depth; ++d) {
+            const int a = lo[(size_t)c * depth + d], b = hi[(size_t)c * depth + d];
+            tot += b - a;
+            lv.max_row = std::max(lv.max_row, b - a);
+        }
+        ns[c] = tot;
+        const int a = lo[(size_t)c * depth + depth - 1], b = hi[(size_t)c * depth + depth - 1];
+        if (a < m) {
+            if (b > m) return RB_OK;   // a stage mixing leaves and nonleaf nodes: not handled here
+            xf[c] = s->child_first[a];
+            ne[c] = s->child_first[b - 1] + s->child_count[b - 1] - xf[c];
+        }
+        lv.max_nodes = std::max(lv.max_nodes, tot);
+        lv.max_ext = std::max(lv.max_ext, ne[c]);
+        lv.max_row = std::max(lv.max_row, ne[c]);
+    }
+    lv.desc_stride = 4 + 3 * depth + 5 * lv.max_nodes + 2 * lv.max_ext;
+    lv.warps = std::min(16, std::max(1, lv.max_row));
+    // what fits: operator tables resident in shared memory, or only the rows
+    const size_t limit = 200 * 1024;
+    bool fits = false;
+    for (int opt = 0; opt < 2 && !fits; ++opt) {
+        lv.resident = opt == 0;
+        fits = tree_smem_bytes(lv, L.nx, L.nu, lv.warps, top) <= limit;
+    }
+    if (!fits) return RB_OK;
+    std::vector<int> desc((size_t)num_sub * lv.desc_stride, 0);
+    for (int c = 0; c < num_sub; ++c) {
+        int *h = desc.data() + (size_t)c * lv.desc_stride;
+        int *dlo = h + 4, *dw = dlo + depth, *doff = dw + depth, *dyn = doff + depth, *cls = dyn + lv.max_nodes,
+            *cfirst = cls + lv.max_nodes, *ccount = cfirst + lv.max_nodes, *par = ccount + lv.max_nodes,
+            *xdyn = par + lv.max_nodes, *xpar = xdyn + lv.max_ext;
+        h[0] = ns[c];
+        h[1] = ne[c];
+        h[2] = xf[c];
+        int off = 0;
+        for (int d = 0; d < depth; ++d) {
+            dlo[d] = lo[(size_t)c * depth + d];
+            dw[d] = hi[(size_t)c * depth + d] - dlo[d];
+            doff[d] = off;
+            off += dw[d];
+        }
+        for (int d = 0; d < depth; ++d)
+            for (int p = 0; p < dw[d]; ++p) {
+                const int node = dlo[d] + p, i = doff[d] + p;
+                dyn[i] = s->dyn_idx[node];
+                cls[i] = node < m ? s->cls[node] : -1;
+                par[i] = d > 0 ? doff[d - 1] + (s->parent[node] - dlo[d - 1]) : -1;
+                if (node < m) {
+                    cfirst[i] = s->child_first[node] - (d + 1 < depth ? dlo[d + 1] : xf[c]);
+                    ccount[i] = s->child_count[node];
+                }
+            }
+        for (int e = 0; e < ne[c]; ++e) {
+            xdyn[e] = s->dyn_idx[xf[c] + e];
+            xpar[e] = doff[depth - 1] + (s->parent[xf[c] + e] - dlo[depth - 1]);
+        }
+    }
+    int *d_desc = nullptr;
+    int rc = upload(s, desc.data(), desc.size(), &d_desc);
+    if (rc != RB_OK) return rc;
+    lv.desc = d_desc;
+    *out = lv;
+    *smem_out = tree_smem_bytes(lv, L.nx, L.nu, lv.warps, top);
     return RB_OK;
 }
 
@@ -635,7 +729,17 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
                 s->chain_lo[v] = lo;
                 TRY(build_chain_tiles(s, lo, lv.depth, 0, lv.num_sub, &lv.tiles, &lv.num_tiles));
             }
+            if (!lv.chain) TRY(build_tree_level(s, lo, hi, lv.depth, lv.num_sub, false, &s->tree_lv[v], &s->tree_smem[1 + v]));
         }
+        {   // the top of the tree as one subtree: stages [0, t_top)
+            std::vector<int> lo(pl.t_top), hi(pl.t_top);
+            for (int t = 0; t < pl.t_top; ++t) {
+                lo[t] = s->stage_off[t];
+                hi[t] = s->stage_off[t + 1];
+            }
+            TRY(build_tree_level(s, lo, hi, pl.t_top, 1, true, &s->tree_top, &s->tree_smem[0]));
+        }
+        TRYC(tree_kernels_set_smem((int)std::max(s->tree_smem[0], std::max(s->tree_smem[1], s->tree_smem[2]))));
         int top_max = 1;
         for (int t = 0; t < pl.t_top; ++t) top_max = std::max(top_max, std::max(width(t), t + 1 < L.num_stages ? width(t + 1) : 1));
         pl.top_cap = top_max;
@@ -767,6 +871,11 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
                 TRY(build_chain_tiles(s, sub, lv.depth, 0, lv.num_sub, &lv.tiles, &lv.num_tiles));
             }
             s->shard_lv[v] = lv;
+            s->shard_tree_lv[v] = s->tree_lv[v];
+            if (s->tree_lv[v].desc) {
+                s->shard_tree_lv[v].desc += (size_t)sa * s->tree_lv[v].desc_stride;
+                s->shard_tree_lv[v].num_sub = sb - sa;
+            }
         }
         s->xchg_count = (size_t)sp.cap * (nx + 1) + 6;
         TRY(dev_zero(s, s->xchg_count, &s->xchg_send));
@@ -1181,17 +1290,27 @@ int enqueue_iteration_sharded(rb_solver *s, int src, cudaStream_t st) {
     for (int v = pl.num_levels - 1; v >= 0; --v)
         if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
             launch_chain_mma_bwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->q, s->r);
+        else if (s->allow_tree && s->shard_tree_lv[v].desc)
+            launch_tree_bwd(dim3(s->shard_tree_lv[v].num_sub, 1), 32 * s->shard_tree_lv[v].warps, s->tree_smem[1 + v], st, s->P,
+                            s->ctrl, s->shard_tree_lv[v], s->prim[dst], s->q, s->r);
         else
             launch_sweep_sub_bwd(grid(s->shard_lv[v]), threads(s->shard_lv[v]), smem(s->shard_lv[v]), st, s->P, s->ctrl,
                                  s->shard_lv[v], s->prim[dst], s->q, s->r);
     int rc = shard_exchange(s, src, st);
     if (rc != RB_OK) return rc;
     launch_primal(s, st, src, dst, s->top_nodes, s->n_top);
-    launch_sweep_top(1, 32 * s->top_warps, per_warp * s->top_warps + (size_t)pl.top_cap * L.nxu * sizeof(double), st, s->P,
-                     s->ctrl, pl, s->prim[dst], s->q, s->r, s->x0);
+    if (s->allow_tree && s->tree_top.desc)
+        launch_tree_top(1, 32 * s->tree_top.warps, s->tree_smem[0], st, s->P, s->ctrl, s->tree_top, s->prim[dst], s->q, s->r,
+                        s->x0);
+    else
+        launch_sweep_top(1, 32 * s->top_warps, per_warp * s->top_warps + (size_t)pl.top_cap * L.nxu * sizeof(double), st, s->P,
+                         s->ctrl, pl, s->prim[dst], s->q, s->r, s->x0);
     for (int v = 0; v < pl.num_levels; ++v)
         if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
             launch_chain_mma_fwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->r);
+        else if (s->allow_tree && s->shard_tree_lv[v].desc)
+            launch_tree_fwd(dim3(s->shard_tree_lv[v].num_sub, 1), 32 * s->shard_tree_lv[v].warps, s->tree_smem[1 + v], st, s->P,
+                            s->ctrl, s->shard_tree_lv[v], s->prim[dst], s->r);
         else
             launch_sweep_sub_fwd(grid(s->shard_lv[v]), threads(s->shard_lv[v]), smem(s->shard_lv[v]), st, s->P, s->ctrl,
                                  s->shard_lv[v], s->prim[dst], s->r);
@@ -1482,6 +1601,17 @@ int rb_use_lane_kernels(rb_solver *s, int32_t enable) {
 int rb_use_mma_sweeps(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
     s->allow_mma = enable != 0;
+    for (int i = 0; i < 2; ++i)
+        if (s->graph[i]) {
+            cudaGraphExecDestroy(s->graph[i]);
+            s->graph[i] = nullptr;
+        }
+    return RB_OK;
+}
+
+int rb_use_tree_kernels(rb_solver *s, int32_t enable) {
+    if (!s) return RB_ERR_INVALID;
+    s->allow_tree = enable != 0;
     for (int i = 0; i < 2; ++i)
         if (s->graph[i]) {
             cudaGraphExecDestroy(s->graph[i]);

@@ -95,6 +95,26 @@ void launch_sweep_sub_fwd(dim3 grid, int threads, size_t smem, cudaStream_t st, 
 void launch_sweep_top(int grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
                       const SweepPlan &plan, double *prim, double *q, double *r, const double *x0);
 
+// ---- tree_sweeps.cu: branching subtrees with everything resident in shared memory ---------------------------------------------
+struct TreeLevel {
+    int depth, num_sub;      // stages per subtree, subtrees (one CTA each)
+    int desc_stride;         // ints per subtree descriptor
+    int max_nodes, max_ext;  // largest subtree (nodes) / largest set of children below a subtree
+    int max_row;             // widest stage or child set (rows of the ping-pong / contribution buffers)
+    int num_dyn;
+    int resident;            // the dynamics tables and the per-node K, [K R~^-1] are staged in shared memory (they fit)
+    int warps;
+    const int *desc;         // [num_sub][desc_stride]; null = level not served by tree_sweeps.cu
+};
+size_t tree_smem_bytes(const TreeLevel &lv, int nx, int nu, int warps, bool top);
+cudaError_t tree_kernels_set_smem(int bytes);
+void launch_tree_bwd(dim3 grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl, const TreeLevel &lv,
+                     const double *prim, double *q, double *r);
+void launch_tree_fwd(dim3 grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl, const TreeLevel &lv,
+                     double *prim, const double *r);
+void launch_tree_top(int grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl, const TreeLevel &lv,
+                     double *prim, double *q, double *r, const double *x0);
+
 // ---- chain_mma.cu: chain levels on the FP64 tensor cores, 8 chains per warp ---------------------------------------------------
 bool chain_mma_supported(int nx, int nu);
 size_t chain_mma_smem_bytes(int nx, int nu, int depth, bool backward);

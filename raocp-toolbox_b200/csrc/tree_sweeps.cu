@@ -1,0 +1,501 @@
+// tree_sweeps.cu -- the BRANCHING part of the DP sweeps (reference cache.py:259-288): the top of the tree and the subtree
+// level(s) above the chains, with everything a CTA touches resident in shared memory.
+//
+// A CTA owns one subtree (breadth-first numbering: one contiguous node range per stage).  What made the first version
+// of these kernels slow was not arithmetic but a chain of ~8 dependent global-memory round trips per stage (topology,
+// q of the children, operator tables, xbar / ubar, ...) at ~800 cycles each.  Here the host packs the topology of every
+// subtree into one contiguous DESCRIPTOR; the CTA reads it (round trip 1), then issues cp.async copies of all rows it
+// will need -- xbar, ubar (or r), the q of the children below the subtree, the dynamics tables and the K (or [K R~^-1])
+// of its nodes -- (round trip 2), and walks the stages out of shared memory with two block barriers per stage.  q of
+// interior nodes never goes to HBM; r, u, x are written as they are produced and never read back by the same kernel.
+//
+// Per stage one warp per parent does the whole step with the parent's children in flight together (independent
+// accumulator chains), so a stage costs one matrix-vector latency and ONE block barrier.  The top kernel runs backward
+// to the root and forward again inside one launch, r staying in shared memory in between.
+//
+// Subtrees that do not fit into shared memory (very wide stages or nx, nu beyond ~48) keep using sweeps.cu.
+#include "kernels.cuh"
+
+namespace rb {
+
+namespace {
+
+template <int BYTES>
+__device__ __forceinline__ void cpa(void *smem_dst, const void *gsrc) {
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(gsrc), "n"(BYTES) : "memory");
+}
+// block-wide asynchronous copy of `count` doubles; vec: both sides are 16-byte aligned (decided once per kernel from the
+// parities of nx / nu, not per call)
+__device__ __forceinline__ void stage_rows(double *dst, const double *__restrict__ src, int count, bool vec) {
+    if (vec) {
+        for (int i = 2 * threadIdx.x; i + 1 < count; i += 2 * blockDim.x) cpa<16>(dst + i, src + i);
+        if ((count & 1) && threadIdx.x == 0) cpa<8>(dst + count - 1, src + count - 1);
+    } else {
+        for (int i = threadIdx.x; i < count; i += blockDim.x) cpa<8>(dst + i, src + i);
+    }
+}
+// one warp per node: the node's class-indexed matrix (len doubles, len even => 16-byte copies) into its own slot
+__device__ __forceinline__ void stage_node_tables(double *dst, const double *__restrict__ table, const int *cls, int ns, int len) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    for (int i = warp; i < ns; i += warps) {
+        const int c = cls[i];
+        if (c < 0) continue;
+        const double *src = table + (long long)c * len;
+        double *d = dst + (long long)i * len;
+        if ((len & 1) == 0) {
+            for (int k = 2 * lane; k < len; k += 64) cpa<16>(d + k, src + k);
+        } else {
+            for (int k = lane; k < len; k += 32) cpa<8>(d + k, src + k);
+        }
+    }
+}
+__device__ __forceinline__ void stage_wait() {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+}
+
+// out_k = sum_l MT[l * stride + k] * v[l];  COLS > 0: compile-time length (fully unrolled, loads first)
+template <int COLS>
+__device__ __forceinline__ double dot_col(const double *MT, int stride, const double *v, int k, int cols) {
+    if constexpr (COLS > 0) {
+        double m[COLS];
+#pragma unroll
+        for (int l = 0; l < COLS; ++l) m[l] = MT[l * stride + k];
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+        for (int l = 0; l < COLS; ++l) {
+            if ((l & 3) == 0) a0 = fma(m[l], v[l], a0);
+            else if ((l & 3) == 1) a1 = fma(m[l], v[l], a1);
+            else if ((l & 3) == 2) a2 = fma(m[l], v[l], a2);
+            else a3 = fma(m[l], v[l], a3);
+        }
+        return (a0 + a1) + (a2 + a3);
+    } else {
+        double a0 = 0.0, a1 = 0.0;
+        int l = 0;
+        for (; l + 1 < cols; l += 2) {
+            a0 = fma(MT[l * stride + k], v[l], a0);
+            a1 = fma(MT[(l + 1) * stride + k], v[l + 1], a1);
+        }
+        if (l < cols) a0 = fma(MT[l * stride + k], v[l], a0);
+        return a0 + a1;
+    }
+}
+
+// shared-memory view of one subtree
+struct Sub {
+    const int *hdr;        // descriptor header: [0] nodes, [1] external children, [2] first external child (global id)
+    const int *lo, *w, *off;            // per depth: first global node id, width, first local index
+    const int *dyn, *cls, *cfirst, *ccount, *par;   // per local node
+    const int *xdyn, *xpar;             // per external child: dynamics row, local index of the parent
+    int depth, ns, ne, ext_first;
+};
+__device__ __forceinline__ Sub sub_view(const int *desc, const TreeLevel &lv) {
+    Sub s;
+    s.hdr = desc;
+    s.depth = lv.depth;
+    s.ns = desc[0];
+    s.ne = desc[1];
+    s.ext_first = desc[2];
+    s.lo = desc + 4;
+    s.w = s.lo + lv.depth;
+    s.off = s.w + lv.depth;
+    s.dyn = s.off + lv.depth;
+    s.cls = s.dyn + lv.max_nodes;
+    s.cfirst = s.cls + lv.max_nodes;
+    s.ccount = s.cfirst + lv.max_nodes;
+    s.par = s.ccount + lv.max_nodes;
+    s.xdyn = s.par + lv.max_nodes;
+    s.xpar = s.xdyn + lv.max_ext;
+    return s;
+}
+
+// carve the dynamic shared memory (all sizes in doubles; the host computes the same total in tree_smem_bytes)
+struct Carve {
+    double *p;
+    __device__ __forceinline__ double *take(long long count) {
+        double *r = p;
+        p += (count + 1) & ~1LL;
+        return r;
+    }
+};
+
+// sum over a node's children c of  sum_l M_c[l * stride + k] * v_c[l]   with four children in flight (independent
+// accumulator chains: the latency of a parent's step is that of ONE matrix-vector product, whatever the branching factor).
+// tab: table of matrices (len doubles each) indexed by cdyn[c]; rows: the children's vectors (row_len apart).
+template <int COLS>
+__device__ __forceinline__ double child_sum(const double *tab, long long len, int stride, const int *cdyn, const double *rows,
+                                            int row_len, int c0, int cc, int k, int cols) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int c = c0;
+    for (; c + 3 < c0 + cc; c += 4) {
+        const double *m0 = tab + cdyn[c] * len + k, *m1 = tab + cdyn[c + 1] * len + k, *m2 = tab + cdyn[c + 2] * len + k,
+                     *m3 = tab + cdyn[c + 3] * len + k;
+        const double *v0 = rows + (long long)c * row_len, *v1 = v0 + row_len, *v2 = v1 + row_len, *v3 = v2 + row_len;
+        if constexpr (COLS > 0) {
+#pragma unroll
+            for (int l = 0; l < COLS; ++l) {
+                a0 = fma(m0[l * stride], v0[l], a0);
+                a1 = fma(m1[l * stride], v1[l], a1);
+                a2 = fma(m2[l * stride], v2[l], a2);
+                a3 = fma(m3[l * stride], v3[l], a3);
+            }
+        } else {
+            for (int l = 0; l < cols; ++l) {
+                a0 = fma(m0[l * stride], v0[l], a0);
+                a1 = fma(m1[l * stride], v1[l], a1);
+                a2 = fma(m2[l * stride], v2[l], a2);
+                a3 = fma(m3[l * stride], v3[l], a3);
+            }
+        }
+    }
+    for (; c < c0 + cc; ++c) a0 += dot_col<COLS>(tab + cdyn[c] * len, stride, rows + (long long)c * row_len, k, cols);
+    return (a0 + a1) + (a2 + a3);
+}
+
+// ---- backward over the subtree --------------------------------------------------------------------------------------------
+// One warp per parent, one block barrier per stage.  xb, ub: staged rows (local node order); qa holds the q of the
+// external children on entry; rbuf (optional) keeps r for a forward pass in the same kernel.  The root stage's q is
+// written to global memory if Qglob.
+// RES: the dynamics table (Ctab) and the per-node K (Ktab, indexed by local node) are in shared memory; otherwise both are
+// the global tables (Ktab indexed by class).
+template <int NX, int NU, bool RES>
+__device__ __forceinline__ void tree_backward(const Layout &L, const Sub &s, const TreeLevel &lv, const double *xb,
+                                              const double *ub, double *qa, double *qb, double *scratch, double *rbuf,
+                                              const double *Ctab, const double *Ktab, double *__restrict__ Qglob,
+                                              double *__restrict__ Rglob) {
+    const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    double *qchild = qa, *qcur = qb;
+    double *rv = scratch + (long long)warp * 2 * nxu, *acc = rv + nxu;
+    for (int d = s.depth - 1; d >= 0; --d) {
+        const int w = s.w[d], off = s.off[d], lo = s.lo[d];
+        if (s.cls[off] < 0) {   // leaves: q = -xbar
+            for (int i = threadIdx.x; i < w * nx; i += blockDim.x) qcur[i] = -xb[off * nx + i];
+        } else {
+            const bool bottom = d == s.depth - 1;
+            const int *cdyn = bottom ? s.xdyn : s.dyn + s.off[d + 1];
+            for (int p = warp; p < w; p += warps) {
+                const int i = off + p, c0 = s.cfirst[i], cc = s.ccount[i];
+                const double *K = Ktab + (long long)(RES ? i : s.cls[i]) * nu * nx;
+                if (NX > 0 && NX + NU <= 32) {   // lane k: entry k of [A'q ; B'q] summed over the children
+                    double a = 0.0;
+                    if (lane < nxu) a = child_sum<NX>(Ctab, (long long)nx * nxu, nxu, cdyn, qchild, nx, c0, cc, lane, nx);
+                    if (lane >= nx && lane < nxu) {
+                        const double rk = ub[i * nu + lane - nx] - a;
+                        rv[lane - nx] = rk;
+                        if (rbuf) rbuf[i * nu + lane - nx] = rk;
+                        Rglob[(long long)(lo + p) * nu + lane - nx] = rk;
+                    }
+                    __syncwarp();
+                    if (lane < nx) qcur[p * nx + lane] = a - xb[i * nx + lane] - dot_col<NU>(K, nx, rv, lane, nu);
+                } else {
+                    for (int k = lane; k < nxu; k += 32)
+                        acc[k] = child_sum<NX>(Ctab, (long long)nx * nxu, nxu, cdyn, qchild, nx, c0, cc, k, nx);
+                    __syncwarp();
+                    for (int a = lane; a < nu; a += 32) {
+                        const double rk = ub[i * nu + a] - acc[nx + a];
+                        rv[a] = rk;
+                        if (rbuf) rbuf[i * nu + a] = rk;
+                        Rglob[(long long)(lo + p) * nu + a] = rk;
+                    }
+                    __syncwarp();
+                    for (int k = lane; k < nx; k += 32)
+                        qcur[p * nx + k] = acc[k] - xb[i * nx + k] - dot_col<NU>(K, nx, rv, k, nu);
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (d == 0 && Qglob)
+            for (int i = threadIdx.x; i < w * nx; i += blockDim.x) Qglob[(long long)lo * nx + i] = qcur[i];
+        double *tmp = qchild;
+        qchild = qcur;
+        qcur = tmp;
+    }
+}
+
+// ---- forward over the subtree ----------------------------------------------------------------------------------------------
+// One warp per parent: u = K x + R~^-1 r, then x of each child = A x + B u (all children in flight); one block barrier per
+// stage.  xa holds x of the root stage on entry; rbuf: r rows (local node order).  Writes u of all nonleaf nodes and x of
+// all nodes below the root stage (including the external children) to global memory.
+template <int NX, int NU, bool RES>
+__device__ __forceinline__ void tree_forward(const Layout &L, const Sub &s, const TreeLevel &lv, double *xa, double *xbuf,
+                                             double *scratch, const double *rbuf, const double *CTtab, const double *KRtab,
+                                             double *__restrict__ Xglob, double *__restrict__ Uglob) {
+    const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    double *xcur = xa, *xnext = xbuf;
+    double *v = scratch + (long long)warp * 2 * nxu;
+    for (int d = 0; d < s.depth; ++d) {
+        const int w = s.w[d], off = s.off[d], lo = s.lo[d];
+        if (s.cls[off] < 0) break;   // leaves
+        const bool bottom = d == s.depth - 1;
+        const int *cdyn = bottom ? s.xdyn : s.dyn + s.off[d + 1];
+        const long long cglob = bottom ? s.ext_first : s.lo[d + 1];
+        for (int p = warp; p < w; p += warps) {
+            const int i = off + p, c0 = s.cfirst[i], cc = s.ccount[i];
+            for (int k = lane; k < nx; k += 32) v[k] = xcur[p * nx + k];
+            for (int a = lane; a < nu; a += 32) v[nx + a] = rbuf[i * nu + a];
+            __syncwarp();
+            const double *KR = KRtab + (long long)(RES ? i : s.cls[i]) * nxu * nu;
+            double ua[2];
+            int cnt = 0;
+            for (int a = lane; a < nu; a += 32) ua[cnt++] = dot_col<(NX > 0 ? NX + NU : 0)>(KR, nu, v, a, nxu);
+            __syncwarp();
+            cnt = 0;
+            for (int a = lane; a < nu; a += 32) {
+                v[nx + a] = ua[cnt];
+                Uglob[(long long)(lo + p) * nu + a] = ua[cnt++];
+            }
+            __syncwarp();
+            // the children: four at a time, lane k = entry k of x_child
+            int c = c0;
+            for (; c + 3 < c0 + cc; c += 4) {
+                for (int k = lane; k < nx; k += 32) {
+                    const double *m0 = CTtab + (long long)cdyn[c] * nxu * nx + k, *m1 = CTtab + (long long)cdyn[c + 1] * nxu * nx + k,
+                                 *m2 = CTtab + (long long)cdyn[c + 2] * nxu * nx + k, *m3 = CTtab + (long long)cdyn[c + 3] * nxu * nx + k;
+                    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+                    if constexpr (NX > 0) {
+#pragma unroll
+                        for (int l = 0; l < NX + NU; ++l) {
+                            const double vl = v[l];
+                            a0 = fma(m0[l * NX], vl, a0);
+                            a1 = fma(m1[l * NX], vl, a1);
+                            a2 = fma(m2[l * NX], vl, a2);
+                            a3 = fma(m3[l * NX], vl, a3);
+                        }
+                    } else {
+                        for (int l = 0; l < nxu; ++l) {
+                            const double vl = v[l];
+                            a0 = fma(m0[l * nx], vl, a0);
+                            a1 = fma(m1[l * nx], vl, a1);
+                            a2 = fma(m2[l * nx], vl, a2);
+                            a3 = fma(m3[l * nx], vl, a3);
+                        }
+                    }
+                    if (!bottom) {
+                        xnext[(c + 0) * nx + k] = a0;
+                        xnext[(c + 1) * nx + k] = a1;
+                        xnext[(c + 2) * nx + k] = a2;
+                        xnext[(c + 3) * nx + k] = a3;
+                    }
+                    Xglob[(cglob + c + 0) * nx + k] = a0;
+                    Xglob[(cglob + c + 1) * nx + k] = a1;
+                    Xglob[(cglob + c + 2) * nx + k] = a2;
+                    Xglob[(cglob + c + 3) * nx + k] = a3;
+                }
+            }
+            for (; c < c0 + cc; ++c)
+                for (int k = lane; k < nx; k += 32) {
+                    const double xk = dot_col<(NX > 0 ? NX + NU : 0)>(CTtab + (long long)cdyn[c] * nxu * nx, nx, v, k, nxu);
+                    if (!bottom) xnext[c * nx + k] = xk;
+                    Xglob[(cglob + c) * nx + k] = xk;
+                }
+            __syncwarp();
+        }
+        __syncthreads();
+        double *tmp = xcur;
+        xcur = xnext;
+        xnext = tmp;
+    }
+}
+
+// stage the subtree descriptor, then everything the sweep needs
+__device__ __forceinline__ const int *stage_desc(const TreeLevel &lv, int sub, Carve &cv) {
+    int *desc = reinterpret_cast<int *>(cv.take((lv.desc_stride + 1) / 2));
+    const int *src = lv.desc + (long long)sub * lv.desc_stride;
+    for (int i = threadIdx.x; i < lv.desc_stride; i += blockDim.x) desc[i] = __ldg(src + i);
+    __syncthreads();
+    return desc;
+}
+
+}  // namespace
+
+template <int NX, int NU, bool RES>
+__global__ void __launch_bounds__(512) k_tree_bwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, TreeLevel lv,
+                                                 const double *__restrict__ prim, double *__restrict__ q,
+                                                 double *__restrict__ r) {
+    if (ctrl && ctrl->done) return;
+    extern __shared__ __align__(16) double tree_smem[];
+    const Layout &L = P.L;
+    const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
+    const bool vx = (nx & 1) == 0, vu = (nu & 1) == 0;
+    Carve cv{tree_smem};
+    const Sub s = sub_view(stage_desc(lv, blockIdx.x, cv), lv);
+    const double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
+    double *Q = q + (long long)blockIdx.y * L.n * nx, *R = r + (long long)blockIdx.y * L.m * nu;
+    double *xb = cv.take((long long)lv.max_nodes * nx), *ub = cv.take((long long)lv.max_nodes * nu);
+    double *qa = cv.take((long long)lv.max_row * nx), *qb = cv.take((long long)lv.max_row * nx);
+    double *scratch = cv.take((long long)(blockDim.x >> 5) * 2 * nxu);
+    for (int d = 0; d < s.depth; ++d) {
+        stage_rows(xb + s.off[d] * nx, X + (long long)s.lo[d] * nx, s.w[d] * nx, vx);
+        if (s.cls[s.off[d]] >= 0) stage_rows(ub + s.off[d] * nu, U + (long long)s.lo[d] * nu, s.w[d] * nu, vu);
+    }
+    stage_rows(qa, Q + (long long)s.ext_first * nx, s.ne * nx, vx);
+    if constexpr (RES) {
+        double *ctab = cv.take((long long)lv.num_dyn * nx * nxu), *knode = cv.take((long long)lv.max_nodes * nu * nx);
+        stage_rows(ctab, P.m.ABcat, lv.num_dyn * nx * nxu, ((nx * nxu) & 1) == 0);
+        stage_node_tables(knode, P.m.K, s.cls, s.ns, nu * nx);
+        stage_wait();
+        tree_backward<NX, NU, true>(L, s, lv, xb, ub, qa, qb, scratch, nullptr, ctab, knode, Q, R);
+    } else {
+        stage_wait();
+        tree_backward<NX, NU, false>(L, s, lv, xb, ub, qa, qb, scratch, nullptr, P.m.ABcat, P.m.K, Q, R);
+    }
+}
+
+template <int NX, int NU, bool RES>
+__global__ void __launch_bounds__(512) k_tree_fwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, TreeLevel lv,
+                                                 double *__restrict__ prim, const double *__restrict__ r) {
+    if (ctrl && ctrl->done) return;
+    extern __shared__ __align__(16) double tree_smem[];
+    const Layout &L = P.L;
+    const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
+    const bool vx = (nx & 1) == 0, vu = (nu & 1) == 0;
+    Carve cv{tree_smem};
+    const Sub s = sub_view(stage_desc(lv, blockIdx.x, cv), lv);
+    double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
+    const double *R = r + (long long)blockIdx.y * L.m * nu;
+    double *rbuf = cv.take((long long)lv.max_nodes * nu);
+    double *xa = cv.take((long long)lv.max_row * nx), *xbuf = cv.take((long long)lv.max_row * nx);
+    double *scratch = cv.take((long long)(blockDim.x >> 5) * 2 * nxu);
+    for (int d = 0; d < s.depth; ++d)
+        if (s.cls[s.off[d]] >= 0) stage_rows(rbuf + s.off[d] * nu, R + (long long)s.lo[d] * nu, s.w[d] * nu, vu);
+    stage_rows(xa, X + (long long)s.lo[0] * nx, s.w[0] * nx, vx);   // x of the root stage comes from the level above
+    if constexpr (RES) {
+        double *cttab = cv.take((long long)lv.num_dyn * nxu * nx), *krnode = cv.take((long long)lv.max_nodes * nxu * nu);
+        stage_rows(cttab, P.m.ABcatT, lv.num_dyn * nxu * nx, ((nx * nxu) & 1) == 0);
+        stage_node_tables(krnode, P.m.KRcatT, s.cls, s.ns, nxu * nu);
+        stage_wait();
+        tree_forward<NX, NU, true>(L, s, lv, xa, xbuf, scratch, rbuf, cttab, krnode, X, U);
+    } else {
+        stage_wait();
+        tree_forward<NX, NU, false>(L, s, lv, xa, xbuf, scratch, rbuf, P.m.ABcatT, P.m.KRcatT, X, U);
+    }
+}
+
+// top of the tree: one CTA per problem instance, backward to the root, x_0 <- initial state (cache.py:282), forward again
+template <int NX, int NU, bool RES>
+__global__ void __launch_bounds__(512) k_tree_top(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, TreeLevel lv,
+                                                 double *__restrict__ prim, double *__restrict__ q, double *__restrict__ r,
+                                                 const double *__restrict__ x0) {
+    if (ctrl && ctrl->done) return;
+    extern __shared__ __align__(16) double tree_smem[];
+    const Layout &L = P.L;
+    const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
+    const bool vx = (nx & 1) == 0, vu = (nu & 1) == 0;
+    Carve cv{tree_smem};
+    const Sub s = sub_view(stage_desc(lv, 0, cv), lv);
+    double *X = prim + (long long)blockIdx.x * L.np_pad + L.px, *U = prim + (long long)blockIdx.x * L.np_pad + L.pu;
+    double *Q = q + (long long)blockIdx.x * L.n * nx, *R = r + (long long)blockIdx.x * L.m * nu;
+    double *xb = cv.take((long long)lv.max_nodes * nx), *ub = cv.take((long long)lv.max_nodes * nu);
+    double *qa = cv.take((long long)lv.max_row * nx), *qb = cv.take((long long)lv.max_row * nx);
+    double *scratch = cv.take((long long)(blockDim.x >> 5) * 2 * nxu);
+    double *rbuf = cv.take((long long)lv.max_nodes * nu);
+    for (int d = 0; d < s.depth; ++d) {
+        stage_rows(xb + s.off[d] * nx, X + (long long)s.lo[d] * nx, s.w[d] * nx, vx);
+        if (s.cls[s.off[d]] >= 0) stage_rows(ub + s.off[d] * nu, U + (long long)s.lo[d] * nu, s.w[d] * nu, vu);
+    }
+    stage_rows(qa, Q + (long long)s.ext_first * nx, s.ne * nx, vx);
+    const double *ct = P.m.ABcat, *ctt = P.m.ABcatT, *kt = P.m.K, *krt = P.m.KRcatT;
+    if constexpr (RES) {
+        double *ctab = cv.take((long long)lv.num_dyn * nx * nxu), *cttab = cv.take((long long)lv.num_dyn * nxu * nx);
+        double *knode = cv.take((long long)lv.max_nodes * nu * nx), *krnode = cv.take((long long)lv.max_nodes * nxu * nu);
+        stage_rows(ctab, P.m.ABcat, lv.num_dyn * nx * nxu, ((nx * nxu) & 1) == 0);
+        stage_rows(cttab, P.m.ABcatT, lv.num_dyn * nxu * nx, ((nx * nxu) & 1) == 0);
+        stage_node_tables(knode, P.m.K, s.cls, s.ns, nu * nx);
+        stage_node_tables(krnode, P.m.KRcatT, s.cls, s.ns, nxu * nu);
+        ct = ctab;
+        ctt = cttab;
+        kt = knode;
+        krt = krnode;
+    }
+    stage_wait();
+    tree_backward<NX, NU, RES>(L, s, lv, xb, ub, qa, qb, scratch, rbuf, ct, kt, Q, R);
+    // forward: the q ping-pong buffers of the backward pass become the x ping-pong
+    __syncthreads();
+    for (int k = threadIdx.x; k < nx; k += blockDim.x) {
+        const double v = x0[(long long)blockIdx.x * nx + k];
+        qa[k] = v;
+        X[k] = v;
+    }
+    __syncthreads();
+    tree_forward<NX, NU, RES>(L, s, lv, qa, qb, scratch, rbuf, ctt, krt, X, U);
+}
+
+// ---- host side ----------------------------------------------------------------------------------------------------------------
+#define RB_TREE_DIMS(X) X(2, 1) X(3, 2) X(4, 2) X(8, 4) X(10, 5) X(20, 10)
+
+// bytes of dynamic shared memory of the three kernels for a level (the maximum: one attribute for all)
+size_t tree_smem_bytes(const TreeLevel &lv, int nx, int nu, int warps, bool top) {
+    auto ev = [](long long c) { return (size_t)((c + 1) & ~1LL); };
+    const long long nxu = nx + nu;
+    size_t tot = ev((lv.desc_stride + 1) / 2);
+    const size_t scr = ev((long long)warps * 2 * nxu);
+    size_t bwd = ev((long long)lv.max_nodes * nx) + ev((long long)lv.max_nodes * nu) + 2 * ev((long long)lv.max_row * nx) + scr;
+    size_t fwd = ev((long long)lv.max_nodes * nu) + 2 * ev((long long)lv.max_row * nx) + scr;
+    const size_t tab = lv.resident ? ev((long long)lv.num_dyn * nx * nxu) : 0;
+    const size_t kb = lv.resident ? ev((long long)lv.max_nodes * nu * nx) : 0, kf = lv.resident ? ev((long long)lv.max_nodes * nxu * nu) : 0;
+    if (top) return (tot + bwd + ev((long long)lv.max_nodes * nu) + 2 * tab + kb + kf) * sizeof(double);
+    return (tot + std::max(bwd + tab + kb, fwd + tab + kf)) * sizeof(double);
+}
+
+cudaError_t tree_kernels_set_smem(int bytes) {
+    cudaError_t e = cudaSuccess;
+#define RB_SET1(NX, NU, RES)                                                                                                  \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_bwd<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_fwd<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_top<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+#define RB_SET(NX, NU) RB_SET1(NX, NU, true) RB_SET1(NX, NU, false)
+    RB_TREE_DIMS(RB_SET)
+    RB_SET(0, 0)
+#undef RB_SET1
+#undef RB_SET
+    return e;
+}
+
+void launch_tree_bwd(dim3 grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl, const TreeLevel &lv,
+                     const double *prim, double *q, double *r) {
+#define RB_GO(NX, NU)                                                                    \
+    if (P.L.nx == NX && P.L.nu == NU) {                                                  \
+        if (lv.resident) k_tree_bwd<NX, NU, true><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r);   \
+        else k_tree_bwd<NX, NU, false><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r);        \
+        return;                                                                          \
+    }
+    RB_TREE_DIMS(RB_GO)
+#undef RB_GO
+    if (lv.resident) k_tree_bwd<0, 0, true><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r);
+    else k_tree_bwd<0, 0, false><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r);
+}
+
+void launch_tree_fwd(dim3 grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl, const TreeLevel &lv,
+                     double *prim, const double *r) {
+#define RB_GO(NX, NU)                                                                    \
+    if (P.L.nx == NX && P.L.nu == NU) {                                                  \
+        if (lv.resident) k_tree_fwd<NX, NU, true><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, r);   \
+        else k_tree_fwd<NX, NU, false><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, r);           \
+        return;                                                                          \
+    }
+    RB_TREE_DIMS(RB_GO)
+#undef RB_GO
+    if (lv.resident) k_tree_fwd<0, 0, true><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, r);
+    else k_tree_fwd<0, 0, false><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, r);
+}
+
+void launch_tree_top(int grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl, const TreeLevel &lv,
+                     double *prim, double *q, double *r, const double *x0) {
+#define RB_GO(NX, NU)                                                                    \
+    if (P.L.nx == NX && P.L.nu == NU) {                                                  \
+        if (lv.resident) k_tree_top<NX, NU, true><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0);   \
+        else k_tree_top<NX, NU, false><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0);    \
+        return;                                                                          \
+    }
+    RB_TREE_DIMS(RB_GO)
+#undef RB_GO
+    if (lv.resident) k_tree_top<0, 0, true><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0);
+    else k_tree_top<0, 0, false><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0);
+}
+
+}  // namespace rb

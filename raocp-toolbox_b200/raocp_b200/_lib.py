@@ -79,6 +79,7 @@ SYMBOLS = [
     ("rb_force_dense_costs", C.c_int, [_H, C.c_int32]),
     ("rb_use_lane_kernels", C.c_int, [_H, C.c_int32]),
     ("rb_use_mma_sweeps", C.c_int, [_H, C.c_int32]),
+    ("rb_use_tree_kernels", C.c_int, [_H, C.c_int32]),
     ("rb_shard_unique_id", C.c_int, [C.c_char_p]),
     ("rb_shard_init", C.c_int, [_H, C.c_char_p]),
     ("rb_launch_count", C.c_int, [_H, C.POINTER(C.c_int64)]),

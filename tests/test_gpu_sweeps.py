@@ -1,5 +1,6 @@
 """DP sweeps (cache.py:259-288) on trees big / chain-like enough to reach every kernel of the sweep plan: the subtree
-levels, the one-warp-per-chain walker (sweeps.cu) and the eight-chains-per-warp tensor-core walker (chain_mma.cu), each
+levels out of shared memory (tree_sweeps.cu) or global memory (sweeps.cu), the one-warp-per-chain walker (sweeps.cu) and
+the eight-chains-per-warp tensor-core walker (chain_mma.cu), each
 against the NumPy oracle (pinned to the reference by tests/test_oracle_pinning.py), through the C-ABI."""
 import numpy as np
 import pytest
@@ -18,24 +19,30 @@ CASES = [
     ("chain105", (64, 200)),    # nx=10, nu=5 (odd nu)
     ("chain2010", None),        # default plan: cut at 64 nodes, 256 chains
     ("cfg2", None),             # default plan, no chain level (243 chains < 256)
+    ("wide", (2, 4)),           # nx=40, nu=36: rows wider than a warp, run-time-size kernels
+    ("cfg1", None),             # 31 nodes: the whole tree is the "top"
 ]
 
 
-def _pair(name, cuts, mma, batch=1):
+MODES = ["mma", "warp_per_chain", "global_stage_kernels"]
+
+
+def _pair(name, cuts, mode, batch=1):
     import raocp_b200 as r
     from oracle import problems
     from oracle.cp_flat_oracle import FlatOracle
     s = problems.spec(name, batch=batch)
     problem = problems.build(s, r.core)
     solver = r.core.Solver(problem, verbose=False, sweep_cuts=cuts, batch=batch)
-    solver.cache.device_solver.use_mma_sweeps(mma)
+    solver.cache.device_solver.use_mma_sweeps(mode == "mma")                     # chain_mma.cu vs sweeps.cu chain walker
+    solver.cache.device_solver.use_tree_kernels(mode != "global_stage_kernels")  # tree_sweeps.cu vs sweeps.cu stage kernels
     return s, solver, FlatOracle(problem)
 
 
-@pytest.mark.parametrize("mma", [True, False], ids=["mma", "warp_per_chain"])
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name,cuts", CASES, ids=[c[0] for c in CASES])
-def test_projection_on_dynamics(name, cuts, mma):
-    s, solver, oracle = _pair(name, cuts, mma)
+def test_projection_on_dynamics(name, cuts, mode):
+    s, solver, oracle = _pair(name, cuts, mode)
     cache, dev, flat = solver.cache, solver.cache.device_solver, solver.cache.flat_problem
     x0 = s["x0"][:, :1]
     rng = np.random.default_rng(5)
@@ -49,11 +56,11 @@ def test_projection_on_dynamics(name, cuts, mma):
     assert seg_rel_err(flat, dev.get_primal(0)[0], oracle.flat_primal(p), dual=False) < 1e-11
 
 
-@pytest.mark.parametrize("mma", [True, False], ids=["mma", "warp_per_chain"])
+@pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("name,cuts", CASES, ids=[c[0] for c in CASES])
-def test_iterates(name, cuts, mma):
+def test_iterates(name, cuts, mode):
     """30 Chambolle-Pock iterations, iterates within 1e-9 (north star) of the oracle"""
-    s, solver, oracle = _pair(name, cuts, mma)
+    s, solver, oracle = _pair(name, cuts, mode)
     flat, dev = solver.cache.flat_problem, solver.cache.device_solver
     x0 = s["x0"][:, :1]
     alpha = oracle.step_size()
@@ -73,7 +80,7 @@ def test_iterates(name, cuts, mma):
 def test_batched_instances_through_chain_tiles():
     """batch > 1: every instance walks the same tiles on its own rows"""
     from oracle.cp_flat_oracle import FlatOracle
-    s, solver, oracle = _pair("chain2010", None, True, batch=3)
+    s, solver, oracle = _pair("chain2010", None, "mma", batch=3)
     flat, dev = solver.cache.flat_problem, solver.cache.device_solver
     alpha = oracle.step_size()
     x0 = s["x0"][:, :3]
