@@ -183,9 +183,10 @@ int rb_use_lane_kernels(rb_solver *s, int32_t enable);
 /* test hook: 0 = walk chains with one warp per chain (sweeps.cu) instead of eight chains per warp on the FP64 tensor
  * cores (chain_mma.cu); both implement cache.py:259-288 */
 int rb_use_mma_sweeps(rb_solver *s, int32_t enable);
-/* test hook: 0 = branching levels and the top of the tree with the global-memory stage kernels (sweeps.cu) instead of
- * the shared-memory-resident subtree kernels (tree_sweeps.cu) */
-int rb_use_tree_kernels(rb_solver *s, int32_t enable);
+/* test hook for the branching levels and the top of the tree: 0 = global-memory stage kernels (sweeps.cu); 1 = the
+ * shared-memory-resident subtree kernels (tree_sweeps.cu), one launch per level; 2 (default) = additionally the first
+ * level and the top fused into one cooperative launch when all its CTAs can be co-resident */
+int rb_use_tree_kernels(rb_solver *s, int32_t mode);
 /* test hook: 1 = use the general dense-matrix cost path even if sqrtQ, sqrtR, sqrtQf are all diagonal */
 int rb_force_dense_costs(rb_solver *s, int32_t enable); /* 1 (default): one CUDA graph per iteration; 0: plain launches */
 int rb_launch_count(const rb_solver *s, int64_t *kernels_launched); /* kernels launched by this handle so far */

@@ -79,7 +79,11 @@ struct rb_solver {
     SweepLevel shard_lv[2]{};
     std::vector<int> chain_lo[2];   // host copy of lv.lo of chain levels (tile building)
     bool allow_mma = true;
-    bool allow_tree = true;  // branching levels / top out of shared memory (tree_sweeps.cu) when they fit (rb_use_tree_kernels)
+    int tree_mode = 2;       // 0: sweeps.cu stage kernels; 1: tree_sweeps.cu, one launch per level; 2: + level 0 fused with the top
+    bool fuse_ok = false;    // the fused launch is possible (co-residency, same residency mode, one smem footprint)
+    size_t fuse_smem = 0;
+    int fuse_threads = 0;
+    int *tree_sync = nullptr;
     TreeLevel tree_top{}, tree_lv[2]{}, shard_tree_lv[2]{};
     size_t tree_smem[3]{};   // dynamic shared memory of the top / level launches   // chain levels on the FP64 tensor cores when the level carries tiles (rb_use_mma_sweeps)
     double *xchg_send = nullptr, *xchg_recv = nullptr;
@@ -237,8 +241,16 @@ void launch_dual(rb_solver *s, cudaStream_t st, int src, int dst, const int *nod
     }
 }
 
-// the launches of the DP sweeps on `prim` (x, u rows hold xbar, ubar on entry and the projection on exit)
-int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st, cudaEvent_t *evs = nullptr) {
+// kernels launched per iteration of the fused loop: primal pass, sweeps, dual pass, stopping test
+int iter_launches(const rb_solver *s) {
+    const SweepPlan &pl = s->plan;
+    const bool fused = s->tree_mode > 1 && s->fuse_ok && !(s->allow_mma && pl.lv[0].num_tiles > 0) && !s->sharded;
+    return 1 + (1 + 2 * pl.num_levels - (fused ? 2 : 0)) + 1 + 1;
+}
+
+// the launches of the DP sweeps on `prim` (x, u rows hold xbar, ubar on entry and the projection on exit); evs / nev:
+// optional event after every launch
+int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st, cudaEvent_t *evs = nullptr, int *nev = nullptr) {
     int ne = 0;
     const SweepPlan &pl = s->plan;
     const Layout &L = s->P.L;
@@ -249,32 +261,42 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
     auto smem = [&](const SweepLevel &lv) {
         return per_warp * lv.warps_per_sub * lv.subs_per_cta + (size_t)lv.subs_per_cta * lv.stage_cap * L.nxu * sizeof(double);
     };
-    for (int v = pl.num_levels - 1; v >= 0; --v) {
+    const bool tree = s->tree_mode > 0;
+    const bool fused = s->tree_mode > 1 && s->fuse_ok && !(s->allow_mma && pl.lv[0].num_tiles > 0);
+    auto bwd = [&](int v) {
         if (s->allow_mma && pl.lv[v].num_tiles > 0)
             launch_chain_mma_bwd(st, s->P, ctrl, pl.lv[v], prim, s->q, s->r);
-        else if (s->allow_tree && s->tree_lv[v].desc)
+        else if (tree && s->tree_lv[v].desc)
             launch_tree_bwd(dim3(s->tree_lv[v].num_sub, batch), 32 * s->tree_lv[v].warps, s->tree_smem[1 + v], st, s->P, ctrl,
                             s->tree_lv[v], prim, s->q, s->r);
         else
             launch_sweep_sub_bwd(grid(pl.lv[v]), threads(pl.lv[v]), smem(pl.lv[v]), st, s->P, ctrl, pl.lv[v], prim, s->q, s->r);
         if (evs) cudaEventRecord(evs[ne++], st);
-    }
-    if (s->allow_tree && s->tree_top.desc)
-        launch_tree_top(batch, 32 * s->tree_top.warps, s->tree_smem[0], st, s->P, ctrl, s->tree_top, prim, s->q, s->r, s->x0);
-    else
-        launch_sweep_top(batch, 32 * s->top_warps, per_warp * s->top_warps + (size_t)pl.top_cap * L.nxu * sizeof(double), st,
-                         s->P, ctrl, pl, prim, s->q, s->r, s->x0);
-    if (evs) cudaEventRecord(evs[ne++], st);
-    for (int v = 0; v < pl.num_levels; ++v) {
+    };
+    auto fwd = [&](int v) {
         if (s->allow_mma && pl.lv[v].num_tiles > 0)
             launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r);
-        else if (s->allow_tree && s->tree_lv[v].desc)
+        else if (tree && s->tree_lv[v].desc)
             launch_tree_fwd(dim3(s->tree_lv[v].num_sub, batch), 32 * s->tree_lv[v].warps, s->tree_smem[1 + v], st, s->P, ctrl,
                             s->tree_lv[v], prim, s->r);
         else
             launch_sweep_sub_fwd(grid(pl.lv[v]), threads(pl.lv[v]), smem(pl.lv[v]), st, s->P, ctrl, pl.lv[v], prim, s->r);
         if (evs) cudaEventRecord(evs[ne++], st);
+    };
+    for (int v = pl.num_levels - 1; v >= (fused ? 1 : 0); --v) bwd(v);
+    if (fused) {
+        cudaError_t e = launch_tree_fused((int)batch, s->fuse_threads, s->fuse_smem, st, s->P, ctrl, s->tree_lv[0], s->tree_top,
+                                          prim, s->q, s->r, s->x0, s->tree_sync);
+        if (e != cudaSuccess) return fail(s, RB_ERR_CUDA, std::string("fused tree launch: ") + cudaGetErrorString(e));
+    } else if (tree && s->tree_top.desc) {
+        launch_tree_top(batch, 32 * s->tree_top.warps, s->tree_smem[0], st, s->P, ctrl, s->tree_top, prim, s->q, s->r, s->x0);
+    } else {
+        launch_sweep_top(batch, 32 * s->top_warps, per_warp * s->top_warps + (size_t)pl.top_cap * L.nxu * sizeof(double), st,
+                         s->P, ctrl, pl, prim, s->q, s->r, s->x0);
     }
+    if (evs) cudaEventRecord(evs[ne++], st);
+    for (int v = fused ? 1 : 0; v < pl.num_levels; ++v) fwd(v);
+    if (nev) *nev = ne;
     return launch_ok(s, "DP sweeps");
 }
 
@@ -739,7 +761,23 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
             }
             TRY(build_tree_level(s, lo, hi, pl.t_top, 1, true, &s->tree_top, &s->tree_smem[0]));
         }
-        TRYC(tree_kernels_set_smem((int)std::max(s->tree_smem[0], std::max(s->tree_smem[1], s->tree_smem[2]))));
+        size_t tree_need = std::max(s->tree_smem[0], std::max(s->tree_smem[1], s->tree_smem[2]));
+        if (s->tree_top.desc && pl.num_levels > 0 && s->tree_lv[0].desc && s->tree_top.resident == s->tree_lv[0].resident) {
+            // level 0 with the footprint of a two-way pass (tables of both directions, r kept)
+            s->fuse_threads = 32 * std::max(s->tree_top.warps, s->tree_lv[0].warps);
+            s->fuse_smem = std::max(tree_smem_bytes(s->tree_top, nx, nu, s->fuse_threads / 32, true),
+                                    tree_smem_bytes(s->tree_lv[0], nx, nu, s->fuse_threads / 32, true));
+            if (s->fuse_smem <= 200 * 1024) {
+                tree_need = std::max(tree_need, s->fuse_smem);
+                s->fuse_ok = true;
+            }
+        }
+        TRYC(tree_kernels_set_smem((int)tree_need));
+        if (s->fuse_ok) {
+            s->fuse_ok = tree_fused_fits(nx, nu, s->tree_top.resident != 0, s->fuse_threads, s->fuse_smem,
+                                         (s->tree_lv[0].num_sub + 1) * L.batch);
+            if (s->fuse_ok) TRY(dev_zero(s, (size_t)2 * L.batch, &s->tree_sync));
+        }
         int top_max = 1;
         for (int t = 0; t < pl.t_top; ++t) top_max = std::max(top_max, std::max(width(t), t + 1 < L.num_stages ? width(t + 1) : 1));
         pl.top_cap = top_max;
@@ -816,7 +854,7 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
         }
         TRYC(tile_kernels_set_smem(s->primal_smem, s->dual_smem));
     }
-    s->kernels_per_iter = 1 + (1 + 2 * s->plan.num_levels) + 1 + 1;
+    s->kernels_per_iter = 0;   // see iter_launches()
     // ---- subtree sharding: rank r owns a contiguous block of the level-0 subtrees, everybody replicates the top
     if (pb->shard_world > 1) {
         const SweepPlan &pl = s->plan;
@@ -1290,7 +1328,7 @@ int enqueue_iteration_sharded(rb_solver *s, int src, cudaStream_t st) {
     for (int v = pl.num_levels - 1; v >= 0; --v)
         if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
             launch_chain_mma_bwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->q, s->r);
-        else if (s->allow_tree && s->shard_tree_lv[v].desc)
+        else if (s->tree_mode > 0 && s->shard_tree_lv[v].desc)
             launch_tree_bwd(dim3(s->shard_tree_lv[v].num_sub, 1), 32 * s->shard_tree_lv[v].warps, s->tree_smem[1 + v], st, s->P,
                             s->ctrl, s->shard_tree_lv[v], s->prim[dst], s->q, s->r);
         else
@@ -1299,7 +1337,7 @@ int enqueue_iteration_sharded(rb_solver *s, int src, cudaStream_t st) {
     int rc = shard_exchange(s, src, st);
     if (rc != RB_OK) return rc;
     launch_primal(s, st, src, dst, s->top_nodes, s->n_top);
-    if (s->allow_tree && s->tree_top.desc)
+    if (s->tree_mode > 0 && s->tree_top.desc)
         launch_tree_top(1, 32 * s->tree_top.warps, s->tree_smem[0], st, s->P, s->ctrl, s->tree_top, s->prim[dst], s->q, s->r,
                         s->x0);
     else
@@ -1308,7 +1346,7 @@ int enqueue_iteration_sharded(rb_solver *s, int src, cudaStream_t st) {
     for (int v = 0; v < pl.num_levels; ++v)
         if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
             launch_chain_mma_fwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->r);
-        else if (s->allow_tree && s->shard_tree_lv[v].desc)
+        else if (s->tree_mode > 0 && s->shard_tree_lv[v].desc)
             launch_tree_fwd(dim3(s->shard_tree_lv[v].num_sub, 1), 32 * s->shard_tree_lv[v].warps, s->tree_smem[1 + v], st, s->P,
                             s->ctrl, s->shard_tree_lv[v], s->prim[dst], s->r);
         else
@@ -1397,7 +1435,7 @@ int rb_loop_enqueue(rb_solver *s, int32_t count) {
         // the buffer just written holds the newest iterate: it is the next iteration's "old"
         std::swap(s->cur_i, s->old_i);
     }
-    s->launches += (int64_t)count * s->kernels_per_iter;
+    s->launches += (int64_t)count * iter_launches(s);
     return RB_OK;
 }
 
@@ -1528,14 +1566,14 @@ int rb_profile_iteration(rb_solver *s, float *ms) {
     if (!s || !ms) return RB_ERR_INVALID;
     if (!s->in_loop) return fail(s, RB_ERR_STATE, "rb_loop_begin() has not been called");
     cudaStream_t st = s->stream;
-    const int nsweep = 1 + 2 * s->plan.num_levels;
+    int nsweep = 0;
     cudaEvent_t ev[9];
     for (auto &e : ev) RB_CUDA(s, cudaEventCreate(&e));
     const int src = s->old_i, dst = 1 - src;
     RB_CUDA(s, cudaEventRecord(ev[0], st));
     launch_primal(s, st, src, dst);
     RB_CUDA(s, cudaEventRecord(ev[1], st));
-    int rcs = launch_sweeps(s, s->ctrl, s->prim[dst], st, ev + 2);
+    int rcs = launch_sweeps(s, s->ctrl, s->prim[dst], st, ev + 2, &nsweep);
     if (rcs != RB_OK) return rcs;
     launch_dual(s, st, src, dst);
     k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
@@ -1546,7 +1584,7 @@ int rb_profile_iteration(rb_solver *s, float *ms) {
     for (int i = 0; i < 2 + nsweep; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
     for (auto &e : ev) cudaEventDestroy(e);
     std::swap(s->cur_i, s->old_i);
-    s->launches += s->kernels_per_iter;
+    s->launches += iter_launches(s);
     return rc;
 }
 
@@ -1611,7 +1649,7 @@ int rb_use_mma_sweeps(rb_solver *s, int32_t enable) {
 
 int rb_use_tree_kernels(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
-    s->allow_tree = enable != 0;
+    s->tree_mode = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
     for (int i = 0; i < 2; ++i)
         if (s->graph[i]) {
             cudaGraphExecDestroy(s->graph[i]);

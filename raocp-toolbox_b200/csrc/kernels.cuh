@@ -112,6 +112,10 @@ void launch_tree_bwd(dim3 grid, int threads, size_t smem, cudaStream_t st, const
                      const double *prim, double *q, double *r);
 void launch_tree_fwd(dim3 grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl, const TreeLevel &lv,
                      double *prim, const double *r);
+cudaError_t launch_tree_fused(int batch, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
+                              const TreeLevel &lvs, const TreeLevel &lvt, double *prim, double *q, double *r, const double *x0,
+                              int *sync);
+bool tree_fused_fits(int nx, int nu, bool resident, int threads, size_t smem, int ctas);
 void launch_tree_top(int grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl, const TreeLevel &lv,
                      double *prim, double *q, double *r, const double *x0);
 

@@ -425,6 +425,101 @@ __global__ void __launch_bounds__(512) k_tree_top(const __grid_constant__ Params
     tree_forward<NX, NU, RES>(L, s, lv, qa, qb, scratch, rbuf, ctt, krt, X, U);
 }
 
+// ---- level 0 backward + top + level 0 forward in ONE launch ---------------------------------------------------------------------
+// CTAs 0..num_sub-1 own the level-0 subtrees, CTA num_sub the top of the tree (all co-resident: cooperative launch).  A
+// subtree CTA stages everything for both directions once, walks backward, publishes its root's q and bumps a counter; the
+// top CTA (which staged its own data meanwhile) waits for the counter, runs backward and forward, publishes x of the cut
+// stage and flips a flag; the subtree CTAs then walk forward with r still in shared memory.  Two launches, two
+// descriptor / table stagings and the r round trip through HBM disappear.  sync: [2 * instance] = counter,
+// [2 * instance + 1] = flag generation (both self-resetting across launches).
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+// block-wide copy of rows that ANOTHER CTA of this launch wrote (L2 path, never the non-coherent L1)
+__device__ __forceinline__ void load_peer_rows(double *dst, const double *src, int count) {
+    for (int i = threadIdx.x; i < count; i += blockDim.x) dst[i] = __ldcg(src + i);
+}
+
+template <int NX, int NU, bool RES>
+__global__ void __launch_bounds__(512) k_tree_fused(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, TreeLevel lvs,
+                                                   TreeLevel lvt, double *__restrict__ prim, double *__restrict__ q,
+                                                   double *__restrict__ r, const double *__restrict__ x0, int *__restrict__ sync) {
+    if (ctrl && ctrl->done) return;
+    extern __shared__ __align__(16) double tree_smem[];
+    const Layout &L = P.L;
+    const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
+    const bool vx = (nx & 1) == 0, vu = (nu & 1) == 0;
+    const bool is_top = blockIdx.x == (unsigned)lvs.num_sub;
+    const TreeLevel &lv = is_top ? lvt : lvs;
+    int *counter = sync + 2 * blockIdx.y, *flag = counter + 1;
+    int flag0 = 0;
+    if (!is_top && threadIdx.x == 0) flag0 = ld_acquire(flag);   // before this launch's top CTA can have flipped it
+    Carve cv{tree_smem};
+    const Sub s = sub_view(stage_desc(lv, is_top ? 0 : blockIdx.x, cv), lv);
+    double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
+    double *Q = q + (long long)blockIdx.y * L.n * nx, *R = r + (long long)blockIdx.y * L.m * nu;
+    double *xb = cv.take((long long)lv.max_nodes * nx), *ub = cv.take((long long)lv.max_nodes * nu);
+    double *qa = cv.take((long long)lv.max_row * nx), *qb = cv.take((long long)lv.max_row * nx);
+    double *scratch = cv.take((long long)(blockDim.x >> 5) * 2 * nxu);
+    double *rbuf = cv.take((long long)lv.max_nodes * nu);
+    for (int d = 0; d < s.depth; ++d) {
+        stage_rows(xb + s.off[d] * nx, X + (long long)s.lo[d] * nx, s.w[d] * nx, vx);
+        if (s.cls[s.off[d]] >= 0) stage_rows(ub + s.off[d] * nu, U + (long long)s.lo[d] * nu, s.w[d] * nu, vu);
+    }
+    if (!is_top) stage_rows(qa, Q + (long long)s.ext_first * nx, s.ne * nx, vx);   // written by the previous launch
+    const double *ct = P.m.ABcat, *ctt = P.m.ABcatT, *kt = P.m.K, *krt = P.m.KRcatT;
+    if constexpr (RES) {
+        double *ctab = cv.take((long long)lv.num_dyn * nx * nxu), *cttab = cv.take((long long)lv.num_dyn * nxu * nx);
+        double *knode = cv.take((long long)lv.max_nodes * nu * nx), *krnode = cv.take((long long)lv.max_nodes * nxu * nu);
+        stage_rows(ctab, P.m.ABcat, lv.num_dyn * nx * nxu, ((nx * nxu) & 1) == 0);
+        stage_rows(cttab, P.m.ABcatT, lv.num_dyn * nxu * nx, ((nx * nxu) & 1) == 0);
+        stage_node_tables(knode, P.m.K, s.cls, s.ns, nu * nx);
+        stage_node_tables(krnode, P.m.KRcatT, s.cls, s.ns, nxu * nu);
+        ct = ctab;
+        ctt = cttab;
+        kt = knode;
+        krt = krnode;
+    }
+    stage_wait();
+    if (!is_top) {
+        tree_backward<NX, NU, RES>(L, s, lv, xb, ub, qa, qb, scratch, rbuf, ct, kt, Q, R);
+        __syncthreads();   // the root's q is written
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicAdd(counter, 1);
+            while (ld_acquire(flag) == flag0) __nanosleep(64);
+        }
+        __syncthreads();
+        load_peer_rows(qa, X + (long long)s.lo[0] * nx, s.w[0] * nx);   // x of the root, from the top CTA
+        __syncthreads();
+        tree_forward<NX, NU, RES>(L, s, lv, qa, qb, scratch, rbuf, ctt, krt, X, U);
+    } else {
+        if (threadIdx.x == 0)
+            while (ld_acquire(counter) < lvs.num_sub) __nanosleep(64);
+        __syncthreads();
+        load_peer_rows(qa, Q + (long long)s.ext_first * nx, s.ne * nx);
+        __syncthreads();
+        tree_backward<NX, NU, RES>(L, s, lv, xb, ub, qa, qb, scratch, rbuf, ct, kt, Q, R);
+        __syncthreads();
+        for (int k = threadIdx.x; k < nx; k += blockDim.x) {
+            const double v = x0[(long long)blockIdx.y * nx + k];
+            qa[k] = v;
+            X[k] = v;
+        }
+        __syncthreads();
+        tree_forward<NX, NU, RES>(L, s, lv, qa, qb, scratch, rbuf, ctt, krt, X, U);
+        __syncthreads();   // x of the cut stage is written
+        if (threadIdx.x == 0) {
+            __threadfence();
+            atomicExch(counter, 0);
+            st_release(flag, ld_acquire(flag) + 1);
+        }
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------------------------------------
 #define RB_TREE_DIMS(X) X(2, 1) X(3, 2) X(4, 2) X(8, 4) X(10, 5) X(20, 10)
 
@@ -447,7 +542,8 @@ cudaError_t tree_kernels_set_smem(int bytes) {
 #define RB_SET1(NX, NU, RES)                                                                                                  \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_bwd<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_fwd<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_top<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_top<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_fused<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 #define RB_SET(NX, NU) RB_SET1(NX, NU, true) RB_SET1(NX, NU, false)
     RB_TREE_DIMS(RB_SET)
     RB_SET(0, 0)
@@ -496,6 +592,56 @@ void launch_tree_top(int grid, int threads, size_t smem, cudaStream_t st, const 
 #undef RB_GO
     if (lv.resident) k_tree_top<0, 0, true><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0);
     else k_tree_top<0, 0, false><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0);
+}
+
+// cooperative launch: all (num_sub + 1) x batch CTAs must be co-resident (the top CTA spins on the others)
+template <typename K>
+static cudaError_t launch_coop(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
+                               const TreeLevel &lvs, const TreeLevel &lvt, double *prim, double *q, double *r, const double *x0,
+                               int *sync) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, P, ctrl, lvs, lvt, prim, q, r, x0, sync);
+}
+
+cudaError_t launch_tree_fused(int batch, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
+                              const TreeLevel &lvs, const TreeLevel &lvt, double *prim, double *q, double *r, const double *x0,
+                              int *sync) {
+    const dim3 grid(lvs.num_sub + 1, batch);
+#define RB_GO(NX, NU)                                                                                                       \
+    if (P.L.nx == NX && P.L.nu == NU)                                                                                        \
+        return lvs.resident ? launch_coop(k_tree_fused<NX, NU, true>, grid, threads, smem, st, P, ctrl, lvs, lvt, prim, q, r, x0, sync) \
+                            : launch_coop(k_tree_fused<NX, NU, false>, grid, threads, smem, st, P, ctrl, lvs, lvt, prim, q, r, x0, sync);
+    RB_TREE_DIMS(RB_GO)
+#undef RB_GO
+    return lvs.resident ? launch_coop(k_tree_fused<0, 0, true>, grid, threads, smem, st, P, ctrl, lvs, lvt, prim, q, r, x0, sync)
+                        : launch_coop(k_tree_fused<0, 0, false>, grid, threads, smem, st, P, ctrl, lvs, lvt, prim, q, r, x0, sync);
+}
+
+// can the fused launch run?  (co-residency of all CTAs at this block size and shared-memory footprint)
+bool tree_fused_fits(int nx, int nu, bool resident, int threads, size_t smem, int ctas) {
+    int dev = 0, sms = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
+    cudaError_t e = cudaErrorInvalidValue;
+#define RB_OCC(NX, NU)                                                                                                   \
+    if (e != cudaSuccess && nx == NX && nu == NU)                                                                        \
+        e = resident ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree_fused<NX, NU, true>, threads, smem) \
+                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree_fused<NX, NU, false>, threads, smem);
+    RB_TREE_DIMS(RB_OCC)
+#undef RB_OCC
+    if (e != cudaSuccess)
+        e = resident ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree_fused<0, 0, true>, threads, smem)
+                     : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_tree_fused<0, 0, false>, threads, smem);
+    return e == cudaSuccess && (long long)per_sm * sms >= ctas;
 }
 
 }  // namespace rb

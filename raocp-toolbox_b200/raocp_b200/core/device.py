@@ -225,8 +225,9 @@ class DeviceSolver:
     def use_mma_sweeps(self, enable=True):
         self._call("rb_use_mma_sweeps", 1 if enable else 0)
 
-    def use_tree_kernels(self, enable=True):
-        self._call("rb_use_tree_kernels", 1 if enable else 0)
+    def use_tree_kernels(self, mode=2):
+        """0: sweeps.cu stage kernels; 1: tree_sweeps.cu per level; 2: level 0 + top fused (default)"""
+        self._call("rb_use_tree_kernels", int(mode))
 
     def loop_begin(self, alpha, max_iters, tol=-1.0, hist_capacity=0):
         self._call("rb_loop_begin", float(alpha), int(max_iters), float(tol), int(hist_capacity))

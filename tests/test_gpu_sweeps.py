@@ -24,7 +24,7 @@ CASES = [
 ]
 
 
-MODES = ["mma", "warp_per_chain", "global_stage_kernels"]
+MODES = ["mma", "warp_per_chain", "tree_per_level", "global_stage_kernels"]
 
 
 def _pair(name, cuts, mode, batch=1):
@@ -35,7 +35,8 @@ def _pair(name, cuts, mode, batch=1):
     problem = problems.build(s, r.core)
     solver = r.core.Solver(problem, verbose=False, sweep_cuts=cuts, batch=batch)
     solver.cache.device_solver.use_mma_sweeps(mode == "mma")                     # chain_mma.cu vs sweeps.cu chain walker
-    solver.cache.device_solver.use_tree_kernels(mode != "global_stage_kernels")  # tree_sweeps.cu vs sweeps.cu stage kernels
+    # tree_sweeps.cu fused with the top (default) / one launch per level, or the sweeps.cu stage kernels
+    solver.cache.device_solver.use_tree_kernels({"global_stage_kernels": 0, "tree_per_level": 1}.get(mode, 2))
     return s, solver, FlatOracle(problem)
 
 
