@@ -171,6 +171,8 @@ def run_ours(args, rank, world, local_rank):
     t_build = time.perf_counter() - t0
     t0 = time.perf_counter()
     solver = r.core.Solver(problem, batch=batch, dedup=not args.no_dedup, device=local_rank, verbose=False)
+    solver.cache.device_solver.use_tree_kernels(args.tree_mode)
+    solver.cache.device_solver.use_mma_sweeps(not args.no_mma)
     dev = solver.cache.device_solver
     dev.synchronize()
     t_setup = time.perf_counter() - t0
@@ -331,6 +333,9 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="problem instances per GPU")
     ap.add_argument("--no-dedup", action="store_true", help="stream per-node K / R~ (one factorisation class per node)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tree-mode", type=int, default=2, choices=[0, 1, 2],
+                    help="ablation: branching sweep levels with sweeps.cu (0), tree_sweeps.cu per level (1), fused with the top (2)")
+    ap.add_argument("--no-mma", action="store_true", help="ablation: chains with one warp per chain instead of chain_mma.cu")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

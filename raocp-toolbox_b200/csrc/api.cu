@@ -304,9 +304,10 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
 // (chain_mma.cu).  `lo` = [num][depth] node ids.  The tiling is dropped (num_tiles = 0) when it would leave more than half
 // of the tile columns empty -- then the one-warp-per-chain walker is the better kernel.
 int build_chain_tiles(rb_solver *s, const std::vector<int> &lo, int depth, int first, int num, const int **tiles_out,
-                      int *num_tiles_out) {
+                      int *num_tiles_out, const int **meta_out) {
     *tiles_out = nullptr;
     *num_tiles_out = 0;
+    *meta_out = nullptr;
     if (num <= 0) return RB_OK;
     const int m = s->P.L.m;
     std::map<std::vector<int>, std::vector<int>> groups;
@@ -333,8 +334,29 @@ int build_chain_tiles(rb_solver *s, const std::vector<int> &lo, int depth, int f
     int *d_tiles = nullptr;
     int rc = upload(s, tiles.data(), tiles.size(), &d_tiles);
     if (rc != RB_OK) return rc;
+    // the image of the per-warp metadata the walkers keep in shared memory
+    const int stride = depth * 10 + 8;
+    std::vector<int> meta((size_t)num_tiles * stride);
+    for (int t = 0; t < num_tiles; ++t) {
+        int *mt = meta.data() + (size_t)t * stride;
+        const int c0 = tiles[(size_t)t * 8];
+        for (int g = 0; g < 8; ++g) {
+            const int own = tiles[(size_t)t * 8 + g], c = own >= 0 ? own : c0;
+            for (int d = 0; d < depth; ++d) mt[d * 8 + g] = lo[(size_t)c * depth + d];
+            mt[depth * 10 + g] = own >= 0 ? 1 : 0;
+        }
+        for (int d = 0; d < depth; ++d) {
+            const int node = lo[(size_t)c0 * depth + d];
+            mt[depth * 8 + d] = s->dyn_idx[node];
+            mt[depth * 9 + d] = node < m ? s->cls[node] : -1;
+        }
+    }
+    int *d_meta = nullptr;
+    rc = upload(s, meta.data(), meta.size(), &d_meta);
+    if (rc != RB_OK) return rc;
     *tiles_out = d_tiles;
     *num_tiles_out = num_tiles;
+    *meta_out = d_meta;
     return RB_OK;
 }
 
@@ -746,10 +768,11 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
             lv.lo = d_lo;
             lv.hi = d_hi;
             lv.tiles = nullptr;
+            lv.tile_meta = nullptr;
             lv.num_tiles = 0;
             if (lv.chain && chain_mma_supported(nx, nu)) {
                 s->chain_lo[v] = lo;
-                TRY(build_chain_tiles(s, lo, lv.depth, 0, lv.num_sub, &lv.tiles, &lv.num_tiles));
+                TRY(build_chain_tiles(s, lo, lv.depth, 0, lv.num_sub, &lv.tiles, &lv.num_tiles, &lv.tile_meta));
             }
             if (!lv.chain) TRY(build_tree_level(s, lo, hi, lv.depth, lv.num_sub, false, &s->tree_lv[v], &s->tree_smem[1 + v]));
         }
@@ -906,7 +929,7 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
             lv.num_sub = sb - sa;
             if (lv.num_tiles > 0) {   // tiles of the owned chains only (indices relative to the shifted lo / hi)
                 std::vector<int> sub(s->chain_lo[v].begin() + (size_t)sa * lv.depth, s->chain_lo[v].begin() + (size_t)sb * lv.depth);
-                TRY(build_chain_tiles(s, sub, lv.depth, 0, lv.num_sub, &lv.tiles, &lv.num_tiles));
+                TRY(build_chain_tiles(s, sub, lv.depth, 0, lv.num_sub, &lv.tiles, &lv.num_tiles, &lv.tile_meta));
             }
             s->shard_lv[v] = lv;
             s->shard_tree_lv[v] = s->tree_lv[v];

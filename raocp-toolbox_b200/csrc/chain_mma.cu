@@ -137,28 +137,38 @@ __device__ __forceinline__ void ld_frags(double (&w)[F], const double *__restric
     }
 }
 
-// per-warp metadata in shared memory: node ids [depth][8], then dynamics row and class of every depth (of chain 0 of
-// the tile; the host only groups chains for which they coincide)
+// per-warp metadata in shared memory, copied from the host-built image of the tile (SweepLevel::tile_meta): node ids
+// [depth][8] (padding columns shadow chain 0: loads only, stores are masked), the dynamics row and the class of every depth
+// (the host only groups chains for which they coincide), 8 validity flags.  One global round trip, overlapped with the
+// read of the loop's "done" flag; returns false if the loop has stopped.
 struct TileMeta {
     const int *nodes, *dyns, *clss;
     int g, t;
     bool valid;
 };
-__device__ __forceinline__ TileMeta stage_meta(const Layout &L, const Topo &T, const SweepLevel &lv, int tile, int warp, int lane,
-                                               int *smem) {
-    int *nodes = smem + warp * (lv.depth * 10), *dyns = nodes + lv.depth * 8, *clss = dyns + lv.depth;
-    const int g = lane >> 2, t = lane & 3;
-    const int own = lv.tiles[tile * 8 + g];
-    const int c = own >= 0 ? own : lv.tiles[tile * 8];   // padding columns shadow chain 0 (loads only, stores are masked)
-    for (int d = t; d < lv.depth; d += 4) nodes[d * 8 + g] = lv.lo[(long long)c * lv.depth + d];
+__device__ __forceinline__ int tile_meta_ints(int depth) { return depth * 10 + 8; }
+__device__ __forceinline__ bool stage_meta(const SweepLevel &lv, const Ctrl *ctrl, int tile, int warp, int lane, int *smem,
+                                           TileMeta &tm) {
+    const int n = tile_meta_ints(lv.depth);
+    int *dst = smem + warp * n;
+    const int *src = lv.tile_meta + (long long)tile * n;
+    int mine[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (lane + 32 * i < n) mine[i] = __ldg(src + lane + 32 * i);
+    const int done = ctrl ? *reinterpret_cast<const volatile int *>(&ctrl->done) : 0;
+    for (int i = lane + 128; i < n; i += 32) dst[i] = __ldg(src + i);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (lane + 32 * i < n) dst[lane + 32 * i] = mine[i];
     __syncwarp();
-    for (int d = lane; d < lv.depth; d += 32) {
-        const int n0 = nodes[d * 8];
-        dyns[d] = T.dyn_idx[n0];
-        clss[d] = n0 < L.m ? T.cls[n0] : -1;
-    }
-    __syncwarp();
-    return TileMeta{nodes, dyns, clss, g, t, own >= 0};
+    tm.nodes = dst;
+    tm.dyns = dst + lv.depth * 8;
+    tm.clss = tm.dyns + lv.depth;
+    tm.g = lane >> 2;
+    tm.t = lane & 3;
+    tm.valid = dst[lv.depth * 10 + tm.g] != 0;
+    return done == 0;
 }
 
 // ---- asynchronous row / fragment staging -----------------------------------------------------------------------------------
@@ -235,7 +245,6 @@ __global__ void __launch_bounds__(128) k_chain_mma_bwd(const __grid_constant__ P
                                                       SweepLevel lv, const double *__restrict__ prim,
                                                       double *__restrict__ q, double *__restrict__ r) {
     using D = ChainDims<NX, NU>;
-    if (ctrl && ctrl->done) return;
     extern __shared__ __align__(16) double mma_smem[];
     const Layout &L = P.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
@@ -244,8 +253,9 @@ __global__ void __launch_bounds__(128) k_chain_mma_bwd(const __grid_constant__ P
     constexpr int F1 = 2 * D::QT * D::NT, F2 = 2 * D::RN * D::QT;
     constexpr int kLaneWords = ring_lane_words(2 * D::QT + 2 * D::RN + F2);   // per lane and stage: xbar | ubar | K fragments
     double *ring = mma_smem + ((size_t)warp * kStages * 32 + lane) * kLaneWords;   // stage s: ring + s * 32 * kLaneWords
-    const TileMeta tm = stage_meta(L, P.t, lv, tile, warp, lane,
-                                   reinterpret_cast<int *>(mma_smem + (size_t)warps * kStages * 32 * kLaneWords));
+    TileMeta tm;
+    if (!stage_meta(lv, ctrl, tile, warp, lane, reinterpret_cast<int *>(mma_smem + (size_t)warps * kStages * 32 * kLaneWords), tm))
+        return;
     const int t = tm.t, g = tm.g;
     const double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
     double *Q = q + (long long)blockIdx.y * L.n * NX, *R = r + (long long)blockIdx.y * L.m * NU;
@@ -334,7 +344,6 @@ template <int NX, int NU>
 __global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
                                                       SweepLevel lv, double *__restrict__ prim, const double *__restrict__ r) {
     using D = ChainDims<NX, NU>;
-    if (ctrl && ctrl->done) return;
     extern __shared__ __align__(16) double mma_smem[];
     const Layout &L = P.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
@@ -343,8 +352,9 @@ __global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ P
     constexpr int F4 = 2 * D::NT * D::QT, F3 = 2 * D::NT * D::RN;
     constexpr int kLaneWords = ring_lane_words(2 * D::RN + F3);                // per lane and stage: r | [K R~^-1] fragments
     double *ring = mma_smem + ((size_t)warp * kStages * 32 + lane) * kLaneWords;
-    const TileMeta tm = stage_meta(L, P.t, lv, tile, warp, lane,
-                                   reinterpret_cast<int *>(mma_smem + (size_t)warps * kStages * 32 * kLaneWords));
+    TileMeta tm;
+    if (!stage_meta(lv, ctrl, tile, warp, lane, reinterpret_cast<int *>(mma_smem + (size_t)warps * kStages * 32 * kLaneWords), tm))
+        return;
     const int t = tm.t, g = tm.g;
     double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
     const double *R = r + (long long)blockIdx.y * L.m * NU;
@@ -466,7 +476,7 @@ static dim3 mma_grid(const SweepLevel &lv, int batch) { return dim3((lv.num_tile
 size_t chain_mma_smem_bytes(int nx, int nu, int depth, bool backward) {
     const int NT = (nx + nu + 7) / 8, QT = (nx + 7) / 8, RT0 = nx / 8, RN = NT - RT0;
     const int lane_words = ring_lane_words(backward ? 2 * QT + 2 * RN + 2 * RN * QT : 2 * RN + 2 * NT * RN);
-    return (size_t)4 * kStages * 32 * lane_words * sizeof(double) + (size_t)4 * depth * 10 * sizeof(int);
+    return (size_t)4 * kStages * 32 * lane_words * sizeof(double) + (size_t)4 * (depth * 10 + 8) * sizeof(int);
 }
 cudaError_t chain_mma_set_smem(int bytes) {
     cudaError_t e = cudaSuccess;

@@ -78,6 +78,7 @@ struct SweepLevel {
     const int *lo, *hi;    // [num_sub][depth] node range of the subtree at stage t_lo + d
     const int *tiles;      // chain levels: [num_tiles][8] chains with identical dynamics / class sequences (-1 = padding)
     int num_tiles;         //               0 = no tiling (chain_mma.cu is not used)
+    const int *tile_meta;  // [num_tiles][depth * 10 + 8]: node ids [depth][8], dynamics row [depth], class [depth], valid [8]
 };
 struct SweepPlan {
     SweepLevel lv[2];

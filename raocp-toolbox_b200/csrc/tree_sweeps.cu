@@ -15,6 +15,9 @@
 //
 // Subtrees that do not fit into shared memory (very wide stages or nx, nu beyond ~48) keep using sweeps.cu.
 #include "kernels.cuh"
+#ifdef RB_TRACE
+#include <cstdio>
+#endif
 
 namespace rb {
 
@@ -62,6 +65,7 @@ __device__ __forceinline__ double dot_col(const double *MT, int stride, const do
         double m[COLS];
 #pragma unroll
         for (int l = 0; l < COLS; ++l) m[l] = MT[l * stride + k];
+        asm volatile("" ::: "memory");   // loads first (see schedule_fence)
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
         for (int l = 0; l < COLS; ++l) {
@@ -121,6 +125,15 @@ struct Carve {
     }
 };
 
+// chunk length for the batched loads below: the largest of 5, 4, 3, 2 that divides COLS
+template <int COLS>
+struct Chunk {
+    static constexpr int value = COLS % 5 == 0 ? 5 : COLS % 4 == 0 ? 4 : COLS % 3 == 0 ? 3 : COLS % 2 == 0 ? 2 : 1;
+};
+// keeps the shared-memory loads of a chunk together and ahead of the multiply-adds that use them (ptxas otherwise
+// schedules each LDS right before its DFMA and every DFMA eats a full shared-memory latency)
+__device__ __forceinline__ void schedule_fence() { asm volatile("" ::: "memory"); }
+
 // sum over a node's children c of  sum_l M_c[l * stride + k] * v_c[l]   with four children in flight (independent
 // accumulator chains: the latency of a parent's step is that of ONE matrix-vector product, whatever the branching factor).
 // tab: table of matrices (len doubles each) indexed by cdyn[c]; rows: the children's vectors (row_len apart).
@@ -134,12 +147,29 @@ __device__ __forceinline__ double child_sum(const double *tab, long long len, in
                      *m3 = tab + cdyn[c + 3] * len + k;
         const double *v0 = rows + (long long)c * row_len, *v1 = v0 + row_len, *v2 = v1 + row_len, *v3 = v2 + row_len;
         if constexpr (COLS > 0) {
+            constexpr int CH = Chunk<COLS>::value;
 #pragma unroll
-            for (int l = 0; l < COLS; ++l) {
-                a0 = fma(m0[l * stride], v0[l], a0);
-                a1 = fma(m1[l * stride], v1[l], a1);
-                a2 = fma(m2[l * stride], v2[l], a2);
-                a3 = fma(m3[l * stride], v3[l], a3);
+            for (int l0 = 0; l0 < COLS; l0 += CH) {
+                double m[4][CH], v[4][CH];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    m[0][i] = m0[(l0 + i) * stride];
+                    m[1][i] = m1[(l0 + i) * stride];
+                    m[2][i] = m2[(l0 + i) * stride];
+                    m[3][i] = m3[(l0 + i) * stride];
+                    v[0][i] = v0[l0 + i];
+                    v[1][i] = v1[l0 + i];
+                    v[2][i] = v2[l0 + i];
+                    v[3][i] = v3[l0 + i];
+                }
+                schedule_fence();
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    a0 = fma(m[0][i], v[0][i], a0);
+                    a1 = fma(m[1][i], v[1][i], a1);
+                    a2 = fma(m[2][i], v[2][i], a2);
+                    a3 = fma(m[3][i], v[3][i], a3);
+                }
             }
         } else {
             for (int l = 0; l < cols; ++l) {
@@ -169,7 +199,13 @@ __device__ __forceinline__ void tree_backward(const Layout &L, const Sub &s, con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
     double *qchild = qa, *qcur = qb;
     double *rv = scratch + (long long)warp * 2 * nxu, *acc = rv + nxu;
+#ifdef RB_TRACE
+    __shared__ long long st_b[8];
+#endif
     for (int d = s.depth - 1; d >= 0; --d) {
+#ifdef RB_TRACE
+        if (threadIdx.x == 0 && d < 8) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(st_b[d]));
+#endif
         const int w = s.w[d], off = s.off[d], lo = s.lo[d];
         if (s.cls[off] < 0) {   // leaves: q = -xbar
             for (int i = threadIdx.x; i < w * nx; i += blockDim.x) qcur[i] = -xb[off * nx + i];
@@ -214,6 +250,13 @@ __device__ __forceinline__ void tree_backward(const Layout &L, const Sub &s, con
         qchild = qcur;
         qcur = tmp;
     }
+#ifdef RB_TRACE
+    if (threadIdx.x == 0 && gridDim.x > 1 && blockIdx.x == gridDim.x - 1) {
+        long long t_;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));
+        printf("top bwd stages (deep->root): %lld %lld %lld ns\n", st_b[1] - st_b[2], st_b[0] - st_b[1], t_ - st_b[0]);
+    }
+#endif
 }
 
 // ---- forward over the subtree ----------------------------------------------------------------------------------------------
@@ -258,13 +301,26 @@ __device__ __forceinline__ void tree_forward(const Layout &L, const Sub &s, cons
                                  *m2 = CTtab + (long long)cdyn[c + 2] * nxu * nx + k, *m3 = CTtab + (long long)cdyn[c + 3] * nxu * nx + k;
                     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
                     if constexpr (NX > 0) {
+                        constexpr int CH = Chunk<NX + NU>::value;
 #pragma unroll
-                        for (int l = 0; l < NX + NU; ++l) {
-                            const double vl = v[l];
-                            a0 = fma(m0[l * NX], vl, a0);
-                            a1 = fma(m1[l * NX], vl, a1);
-                            a2 = fma(m2[l * NX], vl, a2);
-                            a3 = fma(m3[l * NX], vl, a3);
+                        for (int l0 = 0; l0 < NX + NU; l0 += CH) {
+                            double m[4][CH], vl[CH];
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) {
+                                m[0][i] = m0[(l0 + i) * NX];
+                                m[1][i] = m1[(l0 + i) * NX];
+                                m[2][i] = m2[(l0 + i) * NX];
+                                m[3][i] = m3[(l0 + i) * NX];
+                                vl[i] = v[l0 + i];
+                            }
+                            schedule_fence();
+#pragma unroll
+                            for (int i = 0; i < CH; ++i) {
+                                a0 = fma(m[0][i], vl[i], a0);
+                                a1 = fma(m[1][i], vl[i], a1);
+                                a2 = fma(m[2][i], vl[i], a2);
+                                a3 = fma(m[3][i], vl[i], a3);
+                            }
                         }
                     } else {
                         for (int l = 0; l < nxu; ++l) {
@@ -303,10 +359,23 @@ __device__ __forceinline__ void tree_forward(const Layout &L, const Sub &s, cons
 }
 
 // stage the subtree descriptor, then everything the sweep needs
-__device__ __forceinline__ const int *stage_desc(const TreeLevel &lv, int sub, Carve &cv) {
+// The loads of the descriptor, of the loop's "done" flag and (fused kernel) of the hand-off flag are independent: they are
+// all issued before the first of them is waited for (one global round trip instead of three at the head of the kernel).
+// Returns null if the loop has already stopped (uniform over the launch).
+__device__ __forceinline__ const int *stage_desc(const TreeLevel &lv, int sub, Carve &cv, const Ctrl *ctrl,
+                                                 const int *flag = nullptr, int *flag0 = nullptr) {
     int *desc = reinterpret_cast<int *>(cv.take((lv.desc_stride + 1) / 2));
     const int *src = lv.desc + (long long)sub * lv.desc_stride;
-    for (int i = threadIdx.x; i < lv.desc_stride; i += blockDim.x) desc[i] = __ldg(src + i);
+    int mine[2] = {0, 0};
+    const int i0 = threadIdx.x, i1 = threadIdx.x + blockDim.x;
+    if (i0 < lv.desc_stride) mine[0] = __ldg(src + i0);
+    if (i1 < lv.desc_stride) mine[1] = __ldg(src + i1);
+    const int done = ctrl ? *reinterpret_cast<const volatile int *>(&ctrl->done) : 0;
+    if (flag && threadIdx.x == 0) *flag0 = *reinterpret_cast<const volatile int *>(flag);
+    for (int i = threadIdx.x + 2 * blockDim.x; i < lv.desc_stride; i += blockDim.x) desc[i] = __ldg(src + i);
+    if (i0 < lv.desc_stride) desc[i0] = mine[0];
+    if (i1 < lv.desc_stride) desc[i1] = mine[1];
+    if (done) return nullptr;
     __syncthreads();
     return desc;
 }
@@ -317,13 +386,14 @@ template <int NX, int NU, bool RES>
 __global__ void __launch_bounds__(512) k_tree_bwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, TreeLevel lv,
                                                  const double *__restrict__ prim, double *__restrict__ q,
                                                  double *__restrict__ r) {
-    if (ctrl && ctrl->done) return;
     extern __shared__ __align__(16) double tree_smem[];
     const Layout &L = P.L;
     const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
     const bool vx = (nx & 1) == 0, vu = (nu & 1) == 0;
     Carve cv{tree_smem};
-    const Sub s = sub_view(stage_desc(lv, blockIdx.x, cv), lv);
+    const int *desc = stage_desc(lv, blockIdx.x, cv, ctrl);
+    if (!desc) return;
+    const Sub s = sub_view(desc, lv);
     const double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
     double *Q = q + (long long)blockIdx.y * L.n * nx, *R = r + (long long)blockIdx.y * L.m * nu;
     double *xb = cv.take((long long)lv.max_nodes * nx), *ub = cv.take((long long)lv.max_nodes * nu);
@@ -349,13 +419,14 @@ __global__ void __launch_bounds__(512) k_tree_bwd(const __grid_constant__ Params
 template <int NX, int NU, bool RES>
 __global__ void __launch_bounds__(512) k_tree_fwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, TreeLevel lv,
                                                  double *__restrict__ prim, const double *__restrict__ r) {
-    if (ctrl && ctrl->done) return;
     extern __shared__ __align__(16) double tree_smem[];
     const Layout &L = P.L;
     const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
     const bool vx = (nx & 1) == 0, vu = (nu & 1) == 0;
     Carve cv{tree_smem};
-    const Sub s = sub_view(stage_desc(lv, blockIdx.x, cv), lv);
+    const int *desc = stage_desc(lv, blockIdx.x, cv, ctrl);
+    if (!desc) return;
+    const Sub s = sub_view(desc, lv);
     double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
     const double *R = r + (long long)blockIdx.y * L.m * nu;
     double *rbuf = cv.take((long long)lv.max_nodes * nu);
@@ -381,13 +452,14 @@ template <int NX, int NU, bool RES>
 __global__ void __launch_bounds__(512) k_tree_top(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, TreeLevel lv,
                                                  double *__restrict__ prim, double *__restrict__ q, double *__restrict__ r,
                                                  const double *__restrict__ x0) {
-    if (ctrl && ctrl->done) return;
     extern __shared__ __align__(16) double tree_smem[];
     const Layout &L = P.L;
     const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
     const bool vx = (nx & 1) == 0, vu = (nu & 1) == 0;
     Carve cv{tree_smem};
-    const Sub s = sub_view(stage_desc(lv, 0, cv), lv);
+    const int *desc = stage_desc(lv, 0, cv, ctrl);
+    if (!desc) return;
+    const Sub s = sub_view(desc, lv);
     double *X = prim + (long long)blockIdx.x * L.np_pad + L.px, *U = prim + (long long)blockIdx.x * L.np_pad + L.pu;
     double *Q = q + (long long)blockIdx.x * L.n * nx, *R = r + (long long)blockIdx.x * L.m * nu;
     double *xb = cv.take((long long)lv.max_nodes * nx), *ub = cv.take((long long)lv.max_nodes * nu);
@@ -447,18 +519,26 @@ template <int NX, int NU, bool RES>
 __global__ void __launch_bounds__(512) k_tree_fused(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, TreeLevel lvs,
                                                    TreeLevel lvt, double *__restrict__ prim, double *__restrict__ q,
                                                    double *__restrict__ r, const double *__restrict__ x0, int *__restrict__ sync) {
-    if (ctrl && ctrl->done) return;
     extern __shared__ __align__(16) double tree_smem[];
+#ifdef RB_TRACE
+    long long tr[10];
+    int ntr = 0;
+#define RB_STAMP() do { long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); tr[ntr++] = t_; } while (0)
+#else
+#define RB_STAMP() do {} while (0)
+#endif
+    RB_STAMP();
     const Layout &L = P.L;
     const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
     const bool vx = (nx & 1) == 0, vu = (nu & 1) == 0;
     const bool is_top = blockIdx.x == (unsigned)lvs.num_sub;
     const TreeLevel &lv = is_top ? lvt : lvs;
     int *counter = sync + 2 * blockIdx.y, *flag = counter + 1;
-    int flag0 = 0;
-    if (!is_top && threadIdx.x == 0) flag0 = ld_acquire(flag);   // before this launch's top CTA can have flipped it
+    int flag0 = 0;   // the flag's value before this launch's top CTA can have flipped it (thread 0 of the subtree CTAs)
     Carve cv{tree_smem};
-    const Sub s = sub_view(stage_desc(lv, is_top ? 0 : blockIdx.x, cv), lv);
+    const int *desc = stage_desc(lv, is_top ? 0 : blockIdx.x, cv, ctrl, is_top ? nullptr : flag, &flag0);
+    if (!desc) return;
+    const Sub s = sub_view(desc, lv);
     double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
     double *Q = q + (long long)blockIdx.y * L.n * nx, *R = r + (long long)blockIdx.y * L.m * nu;
     double *xb = cv.take((long long)lv.max_nodes * nx), *ub = cv.take((long long)lv.max_nodes * nu);
@@ -483,27 +563,40 @@ __global__ void __launch_bounds__(512) k_tree_fused(const __grid_constant__ Para
         kt = knode;
         krt = krnode;
     }
+    RB_STAMP();
     stage_wait();
+    RB_STAMP();
     if (!is_top) {
         tree_backward<NX, NU, RES>(L, s, lv, xb, ub, qa, qb, scratch, rbuf, ct, kt, Q, R);
         __syncthreads();   // the root's q is written
+        RB_STAMP();
         if (threadIdx.x == 0) {
             __threadfence();
             atomicAdd(counter, 1);
-            while (ld_acquire(flag) == flag0) __nanosleep(64);
+            while (ld_acquire(flag) == flag0) {}
         }
         __syncthreads();
+        RB_STAMP();
         load_peer_rows(qa, X + (long long)s.lo[0] * nx, s.w[0] * nx);   // x of the root, from the top CTA
         __syncthreads();
         tree_forward<NX, NU, RES>(L, s, lv, qa, qb, scratch, rbuf, ctt, krt, X, U);
+        RB_STAMP();
+#ifdef RB_TRACE
+        if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 63) && ctrl && ctrl->iters == 40)
+            printf("sub %d: desc+issue %lld wait %lld bwd %lld spin %lld fwd %lld ns\n", blockIdx.x, tr[1] - tr[0], tr[2] - tr[1],
+                   tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4]);
+#endif
     } else {
         if (threadIdx.x == 0)
-            while (ld_acquire(counter) < lvs.num_sub) __nanosleep(64);
+            while (ld_acquire(counter) < lvs.num_sub) {}
         __syncthreads();
+        RB_STAMP();
         load_peer_rows(qa, Q + (long long)s.ext_first * nx, s.ne * nx);
         __syncthreads();
+        RB_STAMP();
         tree_backward<NX, NU, RES>(L, s, lv, xb, ub, qa, qb, scratch, rbuf, ct, kt, Q, R);
         __syncthreads();
+        RB_STAMP();
         for (int k = threadIdx.x; k < nx; k += blockDim.x) {
             const double v = x0[(long long)blockIdx.y * nx + k];
             qa[k] = v;
@@ -512,11 +605,17 @@ __global__ void __launch_bounds__(512) k_tree_fused(const __grid_constant__ Para
         __syncthreads();
         tree_forward<NX, NU, RES>(L, s, lv, qa, qb, scratch, rbuf, ctt, krt, X, U);
         __syncthreads();   // x of the cut stage is written
+        RB_STAMP();
         if (threadIdx.x == 0) {
             __threadfence();
             atomicExch(counter, 0);
             st_release(flag, ld_acquire(flag) + 1);
         }
+#ifdef RB_TRACE
+        if (threadIdx.x == 0 && ctrl && ctrl->iters == 40)
+            printf("top: desc+issue %lld wait %lld spin %lld loadq %lld bwd %lld fwd %lld ns\n", tr[1] - tr[0], tr[2] - tr[1],
+                   tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4], tr[6] - tr[5]);
+#endif
     }
 }
 
