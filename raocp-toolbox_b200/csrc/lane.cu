@@ -72,6 +72,9 @@ __device__ __forceinline__ int warp_octets_max(int v) {
 __device__ __forceinline__ double2 ld2(const double *__restrict__ p, int k2) {
     return __ldg(reinterpret_cast<const double2 *>(p + 2 * k2));
 }
+// L1 prefetch of the line holding *p: the later phases of a pass (tau / d5 / d6 of the children, the risk rows) then hit
+// L1 instead of paying a full memory round trip each, one after the other
+__device__ __forceinline__ void pf(const double *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void st2(double *__restrict__ p, int k2, double a, double b) {
     *reinterpret_cast<double2 *>(p + 2 * k2) = make_double2(a, b);
 }
@@ -115,6 +118,27 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_primal_lane(const __grid_co
         }
     }
     const int c0 = nonleaf ? T.child_first[node] : 0, cc = nonleaf ? T.child_count[node] : 0;
+    if (nonleaf) {   // lines of the kernel-projection phase at the end of the pass, fetched while the row phase runs
+        const int yo_pf = T.yoff[node];
+        if (g == 0) {
+            pf(Po + L.py + yo_pf);
+            pf(D + L.d1 + yo_pf);
+            pf(D + L.d2 + node);
+        } else if (g == 1) {
+            pf(Po + L.ptau + c0);
+            pf(Po + L.ps + c0);
+            pf(T.cond_prob + c0);
+        } else if (g == 2) {
+            pf(D + L.d5 + c0 - 1);
+            pf(D + L.d6 + c0 - 1);
+        } else if (g == 3) {
+            if (c0 < L.m) pf(D + L.d2 + c0);
+            else {
+                pf(D + L.d12 + c0 - L.m);
+                pf(D + L.d13 + c0 - L.m);
+            }
+        }
+    }
     if (nonleaf) {   // [xbar; ubar] = [x; u] - alpha (Gamma' d7 + sum_j sqrt(Q_j, R_j) [d3_j; d4_j])   (operators.py:74-87)
         const double *d7 = D + L.d7 + (long long)node * nxu;
         for (int part = 0; part < 2; ++part) {
@@ -226,6 +250,26 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_cons
     const int max_cc = warp_octets_max<kOct>(cc);
     const double *xo = Po + L.px + (long long)(node < L.n ? node : 0) * nx, *xn = Pn + L.px + (long long)(node < L.n ? node : 0) * nx;
     const double *uo = Po + L.pu + (long long)(nonleaf ? node : 0) * nu, *un = Pn + L.pu + (long long)(nonleaf ? node : 0) * nu;
+    if (nonleaf) {   // one lane of the group per line family; neighbouring nodes share most of these lines
+        const int yo_pf = T.yoff[node];
+        if (g == 0) {
+            pf(Po + L.py + yo_pf);
+            pf(Pn + L.py + yo_pf);
+            pf(Do + L.d1 + yo_pf);
+        } else if (g == 1) {
+            pf(Po + L.ps + node);
+            pf(Pn + L.ps + node);
+            pf(Do + L.d2 + node);
+        } else if (g == 2) {
+            pf(Po + L.ptau + c0);
+            pf(Pn + L.ptau + c0);
+            pf(T.cond_prob + c0);
+        } else if (g == 3) {
+            pf(Do + L.d5 + c0 - 1);
+            pf(Do + L.d6 + c0 - 1);
+            pf(Do + L.d7 + (long long)node * nxu);
+        }
+    }
 
     // ---- phase 1: classify the second-order-cone block of every child edge (cones.py:113-132) -------------------------
     for (int jj = 0; jj < max_cc; ++jj) {
