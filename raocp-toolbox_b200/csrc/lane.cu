@@ -30,7 +30,8 @@ struct ResidLane {
         for (int i = 0; i < 6; ++i) v[i] = 0ull;
     }
     __device__ __forceinline__ void put(int slot, double x) {
-        const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(x));
+        // |x| by clearing the sign bit with an integer AND (fabs would go through the FP64 pipe as DADD -RZ, |x|)
+        const unsigned long long b = (unsigned long long)__double_as_longlong(x) & 0x7fffffffffffffffull;
         v[slot] = b > v[slot] ? b : v[slot];
     }
     __device__ __forceinline__ double dual(double dd, double lpp, double inv_alpha) {   // dd = d - d+

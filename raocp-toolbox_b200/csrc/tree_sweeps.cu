@@ -568,7 +568,8 @@ __global__ void __launch_bounds__(512) k_tree_fused(const __grid_constant__ Para
     RB_STAMP();
     if (!is_top) {
         tree_backward<NX, NU, RES>(L, s, lv, xb, ub, qa, qb, scratch, rbuf, ct, kt, Q, R);
-        __syncthreads();   // the root's q is written
+        __threadfence();   // every thread publishes its part of the root's q before the CTA signals
+        __syncthreads();
         RB_STAMP();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -604,7 +605,8 @@ __global__ void __launch_bounds__(512) k_tree_fused(const __grid_constant__ Para
         }
         __syncthreads();
         tree_forward<NX, NU, RES>(L, s, lv, qa, qb, scratch, rbuf, ctt, krt, X, U);
-        __syncthreads();   // x of the cut stage is written
+        __threadfence();   // every thread publishes its rows of the cut stage's x before the flag flips
+        __syncthreads();
         RB_STAMP();
         if (threadIdx.x == 0) {
             __threadfence();
