@@ -24,16 +24,19 @@ namespace {
 constexpr int kMaxNodesPerCta = kLaneThreads / 4;   // nodes per CTA with the narrowest lane group
 
 struct ResidLane {
-    unsigned long long v[6];   // bit patterns of non-negative doubles order like the doubles; NaN sits above +inf
+    // Running maxima of |x| per residual norm, kept as the (signed) entry that attained them: one DSETP and two selects
+    // per update instead of five integer instructions on the bit pattern (sm_100a has no 64-bit or FP64 max).  A
+    // comparison with a NaN is false, so NaNs are caught separately: every dual entry feeds some primal entry's xi0
+    // through L*, and primal() ORs "xi0 is NaN" into `nan`; bits() then reports a NaN maximum, like the bit-pattern
+    // maxima of fused.cu do.
+    double v[6];
+    int nan;
     __device__ __forceinline__ void init() {
 #pragma unroll
-        for (int i = 0; i < 6; ++i) v[i] = 0ull;
+        for (int i = 0; i < 6; ++i) v[i] = 0.0;
+        nan = 0;
     }
-    __device__ __forceinline__ void put(int slot, double x) {
-        // |x| by clearing the sign bit with an integer AND (fabs would go through the FP64 pipe as DADD -RZ, |x|)
-        const unsigned long long b = (unsigned long long)__double_as_longlong(x) & 0x7fffffffffffffffull;
-        v[slot] = b > v[slot] ? b : v[slot];
-    }
+    __device__ __forceinline__ void put(int slot, double x) { v[slot] = fabs(x) > fabs(v[slot]) ? x : v[slot]; }
     __device__ __forceinline__ double dual(double dd, double lpp, double inv_alpha) {   // dd = d - d+
         const double xi2 = fma(dd, inv_alpha, lpp);
         put(2, xi2);
@@ -42,10 +45,17 @@ struct ResidLane {
     }
     __device__ __forceinline__ void primal(double dp, double g1, double g2, double inv_alpha) {   // dp = p+ - p
         const double xi1 = -fma(dp, inv_alpha, g1);
+        const double xi0 = xi1 + g2;
         put(1, xi1);
-        put(0, xi1 + g2);
+        put(0, xi0);
         put(4, dp);
         put(3, dp + g1);
+        nan |= xi0 != xi0;
+    }
+    // bit pattern of the maximum (non-negative doubles order like their bit patterns; a NaN pattern sits above +inf)
+    __device__ __forceinline__ unsigned long long bits(int slot) const {
+        if (nan) return 0x7ff8000000000000ull;
+        return (unsigned long long)__double_as_longlong(v[slot]) & 0x7fffffffffffffffull;
     }
 };
 
@@ -527,7 +537,7 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_cons
     // block-level reduction of the six maxima (as bit patterns), one atomic per slot per block
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-        unsigned long long mval = R.v[i];
+        unsigned long long mval = R.bits(i);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const unsigned long long other = __shfl_xor_sync(0xffffffffu, mval, o);

@@ -193,3 +193,21 @@ def test_calculate_chock_errors_lists(case):
     assert np.max(np.abs(np.array(norms) - want) / want) < 1e-9
     p_len, d_len = len(solver.cache.get_primal()[0]), len(solver.cache.get_dual()[0])
     assert [len(lst) for lst in lists] == [p_len, p_len, d_len, p_len, p_len, d_len]
+
+
+@pytest.mark.parametrize("rectangles", [True, False])
+def test_nan_in_the_initial_state_is_reported(rectangles):
+    """a NaN must not be lost by the running maxima of the residual norms: with rectangles the reference raises
+    ValueError in the projection (rectangle.py:58-59); without, the loop stops on a non-finite residual"""
+    import raocp_b200 as r
+    from oracle import problems
+    s = dict(problems.spec("mini2"))
+    s["rectangles"] = rectangles
+    problem = problems.build(s, r.core)
+    for lane_kernels in (True, False):
+        solver = r.core.Solver(problem, verbose=False)
+        solver.cache.device_solver.use_lane_kernels(lane_kernels)
+        x0 = s["x0"][:, :1].copy()
+        x0[0, 0] = np.nan
+        with pytest.raises(ValueError if rectangles else Exception):
+            solver.chock(x0, max_iters=5, tol=1e-3)
