@@ -41,6 +41,11 @@ METRIC = "CP iterations/sec"
 CPU_SAMPLE = {"cfg1": None, "cfg2": (3, 7, 4), "cfg3": (4, 8, 4), "cfg4": None, "cfg5": (3, 6, 4)}  # (modes, N, tau)
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel, from the committed `ncu --set full`
+# capture of the same command (profiles/): (workload, batch, dedup) -> bytes
+TRAFFIC = {}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
@@ -175,6 +180,7 @@ def run_ours(args, rank, world, local_rank):
     solver = r.core.Solver(problem, batch=batch, dedup=not args.no_dedup, device=local_rank, verbose=False)
     solver.cache.device_solver.use_tree_kernels(args.tree_mode)
     solver.cache.device_solver.use_mma_sweeps(not args.no_mma)
+    solver.cache.device_solver.use_pipeline(not args.no_pipeline)
     dev = solver.cache.device_solver
     dev.synchronize()
     t_setup = time.perf_counter() - t0
@@ -196,7 +202,9 @@ def run_ours(args, rank, world, local_rank):
         # ---- warm-up ---------------------------------------------------------------------------------------------
         dev.loop_begin(alpha, 1 << 30, -1.0, 0)
         dev.loop_enqueue(W)
-        phases = np.array([dev.profile_iteration() for _ in range(5)])[2:].mean(axis=0)
+        prof = [dev.profile_iteration_full() for _ in range(5)][2:]
+        phases = np.array([q[0] for q in prof]).mean(axis=0)
+        parts = np.array([q[1] for q in prof]).mean(axis=0)
         barrier()
         launches0 = dev.launch_count()
         sampler = ClockSampler(local_rank)
@@ -223,11 +231,14 @@ def run_ours(args, rank, world, local_rank):
         launches = dev.launch_count() - launches0
         # ---- per-launch durations (roofline of the dominant kernel): the same iteration as plain launches with a CUDA event
         #      after each one (rb_profile_iteration, on this stream), L2 flushed before every iteration like the timed region
-        cold_phases = []
+        cold_phases, cold_parts = [], []
         for _ in range(min(K, 50)):
             flush.zero_()
-            cold_phases.append(dev.profile_iteration())
+            ph, pt = dev.profile_iteration_full()
+            cold_phases.append(ph)
+            cold_parts.append(pt)
         cold_phases = np.array(cold_phases).mean(axis=0)
+        cold_parts = np.array(cold_parts).mean(axis=0)
         clocks = sampler.stop()
         # ---- end to end through the host API: pinned x0 -> device, one iteration, norms -> host, per step ----------------
         barrier()
@@ -288,25 +299,47 @@ def run_ours(args, rank, world, local_rank):
     b_alg = algorithmic_bytes(flat, batch, not args.no_dedup)
     ms_iter = cold_total / K
     achieved = b_alg / (ms_iter * 1e-3) / 1e9
-    b_dual = 8 * batch * (2 * flat.np_ + 2 * flat.nd_)
-    # dominant kernel = the dual pass (last launch of the iteration; the stopping test rides on its event interval)
-    t_dual = float(cold_phases[-1]) * 1e-3
-    # DRAM traffic of that kernel from the committed ncu --set full capture of this command (profiles/r1_final_raw.csv:
-    # dram__bytes_read.sum + dram__bytes_write.sum of k_dual_lane<4>, one launch); only known for the default workload
-    traffic = 70.0e6 + 7.33e6 if (args.workload == "cfg3" and batch == 1 and not args.no_dedup) else None
+    # ---- roofline of the dominant HBM kernel -------------------------------------------------------------------------------
+    # Pipelined loop: the chain dual pass k_dual_chain (nonleaf nodes with one child: L, dual half step, prox of g*, the
+    # six residual norms, and pbar of the next iteration).  Algorithmic bytes per launch = SURVEY 8(d)'s figure -- every
+    # iterate entry read once and written once -- restricted to the nodes of the launch: 16 B x (primal + dual doubles
+    # of a chain node and of the edge to its child).  What the kernel has to move is more (it reads p, p+, d and writes d+
+    # and pbar: 3 primal + 2 dual rows), reported as `bytes_moved_model`.
+    n_chain = dev.chain_dual_nodes()
+    pipelined = len(cold_parts) == 3 and n_chain > 0
+    if pipelined:
+        p_node = flat.nx + flat.nu + 3 + 2            # x_i, u_i, y_i (2c+1 = 3), tau_j, s_i
+        d_node = 3 + 1 + 2 * (flat.nx + flat.nu) + 2  # d1_i, d2_i, d3_j, d4_j, d5_j, d6_j, d7_i
+        b_kernel = 16 * batch * n_chain * (p_node + d_node)
+        b_moved = 8 * batch * n_chain * (3 * p_node + 2 * d_node)
+        t_kernel = float(cold_parts[1]) * 1e-3
+        kname = (f"chain dual pass k_dual_chain<{flat.nx},{flat.nu}> over {n_chain} of {flat.n} nodes (L, dual half step, "
+                 "prox of g*, six residual norms, pbar of the next iteration)")
+        traffic = TRAFFIC.get((args.workload, batch, not args.no_dedup))
+    else:
+        b_kernel = b_moved = 8 * batch * (2 * flat.np_ + 2 * flat.nd_)
+        t_kernel = float(cold_phases[-1]) * 1e-3
+        kname = "dual pass (L, dual half step, prox of g*, six residual norms), all nodes"
+        traffic = None
+    serial_ms = float(cold_phases.sum())
     roofline = {
-        "bound": "hbm", "kernel": "dual pass k_dual_lane (L, dual half step, prox of g*, six residual norms)",
-        "achieved": b_dual / t_dual / 1e9, "peak": peak, "unit": "GB/s", "frac": b_dual / t_dual / 1e9 / peak,
-        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": b_dual, "launch_ms": t_dual * 1e3,
-        "share_of_step": float(cold_phases[-1] / cold_phases.sum()),
+        "bound": "hbm", "kernel": kname,
+        "achieved": b_kernel / t_kernel / 1e9, "peak": peak, "unit": "GB/s", "frac": b_kernel / t_kernel / 1e9 / peak,
+        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": b_kernel, "bytes_moved_model": b_moved,
+        "launch_ms": t_kernel * 1e3, "share_of_step": float(t_kernel * 1e3 / serial_ms),
         "timing": "CUDA events around the plain launch on the bench stream, L2 flushed before every iteration, mean of "
-                  f"{min(K, 50)} iterations (includes ~2 us of launch gap; ncu duration in profiles/r1_final_launches.csv)",
+                  f"{min(K, 50)} iterations (includes ~2 us of launch gap); share_of_step = launch_ms / sum of all launches "
+                  "of the iteration run one after the other (the ncu launch list is serialised the same way)",
         "iteration": {"algorithmic_bytes": b_alg, "achieved": achieved, "frac": achieved / peak,
                       "note": "all launches of one CP iteration inside the CUDA graph, the timed region of `value`"},
-        "launch_ms_all": {"primal": float(cold_phases[0]), "sweeps_in_launch_order": [float(v) for v in cold_phases[1:-1]],
-                          "dual_and_check": float(cold_phases[-1])},
-        "launch_ms_all_warm": {"primal": float(phases[0]), "sweeps_in_launch_order": [float(v) for v in phases[1:-1]],
-                               "dual_and_check": float(phases[-1])},
+        "launch_ms_all": {"primal_or_kernel_projection": float(cold_phases[0]),
+                          "sweeps_in_launch_order": [float(v) for v in cold_phases[1:-1]],
+                          "dual_and_check": float(cold_phases[-1]),
+                          "dual_kernels_branching_chain_leaves": [float(v) for v in cold_parts]},
+        "launch_ms_all_warm": {"primal_or_kernel_projection": float(phases[0]),
+                               "sweeps_in_launch_order": [float(v) for v in phases[1:-1]],
+                               "dual_and_check": float(phases[-1]),
+                               "dual_kernels_branching_chain_leaves": [float(v) for v in parts]},
     }
     line = {
         "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -316,7 +349,8 @@ def run_ours(args, rank, world, local_rank):
                                f"nu={flat.nu}, AVaR(0.5), rectangles, seed 0", "instances_per_gpu": batch,
                    "parallelism": "single GPU" if world == 1 else f"{world} x independent instances (no collective)",
                    "l2": "flushed (256 MiB overwrite) before every timed iteration", "dedup_operators": not args.no_dedup,
-                   "residuals": "all six norms + stopping test every iteration", "alpha": alpha},
+                   "residuals": "all six norms + stopping test every iteration", "alpha": alpha,
+                   "loop": "pipelined (dual pass writes pbar of the next iteration)" if not args.no_pipeline else "primal pass + dual pass"},
         "warm": {"value": units * K / (warm_ms * 1e-3), "unit": "it/s", "ms_per_step": warm_ms / K,
                  "note": "same K iterations back to back, no L2 flush (iterates L2-resident when they fit)"},
         "e2e": {"value": units * K / e2e_t, "unit": "it/s", "h2d_bytes_per_step": int(x0_host.numel() * 8),
@@ -357,6 +391,8 @@ def main():
     ap.add_argument("--tree-mode", type=int, default=2, choices=[0, 1, 2],
                     help="ablation: branching sweep levels with sweeps.cu (0), tree_sweeps.cu per level (1), fused with the top (2)")
     ap.add_argument("--no-mma", action="store_true", help="ablation: chains with one warp per chain instead of chain_mma.cu")
+    ap.add_argument("--no-pipeline", action="store_true",
+                    help="ablation: primal pass + one dual pass per iteration (the loop before the pbar hand-over)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

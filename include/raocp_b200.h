@@ -167,10 +167,21 @@ int rb_loop_enqueue(rb_solver *s, int32_t count);
 int rb_loop_poll(rb_solver *s, int32_t *iters, int32_t *done, double *last_norms);
 int rb_step(rb_solver *s, const double *x0, double *norms);
 int rb_loop_end(rb_solver *s, double *xi_hist, double *delta_hist, int32_t *iters, int32_t *status);
-/* measurement hook: one iteration with a CUDA event after every launch; ms[8] = primal pass, the sweep launches in order
- * (backward levels bottom-up, top, forward levels top-down), dual pass (+ stopping test); unused entries -1.  Advances
- * the loop by one iteration. */
+/* measurement hook: one iteration as plain launches on one stream with a CUDA event after every launch; ms[12]:
+ * ms[0] primal pass (pipelined loop: the in-place kernel projection), then the sweep launches in order (backward levels
+ * bottom-up, top, forward levels top-down), then the dual pass (+ stopping test) as a whole; ms[8..10]: the kernels of
+ * the pipelined dual pass on their own (branching nodes, chain nodes, leaves; or ms[8] alone: all nodes); unused
+ * entries -1.  Advances the loop by one iteration. */
 int rb_profile_iteration(rb_solver *s, float *ms);
+/* test / ablation hook: 0 = the loop of round-1 v11 (primal pass, sweeps, one dual pass per iteration); 1 (default) = the
+ * pipelined loop: the dual pass of iteration k also writes pbar = p+ - alpha L* d+ (solver.py:27-39 of iteration k+1), so
+ * iteration k+1 only runs the kernel projection (cache.py:290-317) next to the backward sweep, and the dual pass is split
+ * into branching nodes (next to the forward chain sweep), chain nodes (k_dual_chain) and leaves.  Needs the lane
+ * passes; ignored otherwise and under subtree sharding. */
+int rb_use_pipeline(rb_solver *s, int32_t enable);
+/* how the pipelined dual pass is split: nodes [0, early) run next to the forward chain sweep, [chain_first, chain_first +
+ * chain_nodes) through k_dual_chain; chain_nodes = 0 when the loop is not pipelined or has no chain kernel for (nx, nu) */
+int rb_pipeline_info(const rb_solver *s, int32_t *early_nodes, int32_t *chain_first, int32_t *chain_nodes);
 int rb_use_graphs(rb_solver *s, int32_t enable);
 /* subtree sharding: rank 0 calls rb_shard_unique_id and distributes the 128 bytes (e.g. torch.distributed broadcast),
  * every rank then calls rb_shard_init (collective: ncclCommInitRank).  Afterwards rb_iterate / rb_loop_* run the

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <string>
 #include <vector>
@@ -89,6 +90,16 @@ struct rb_solver {
     double *xchg_send = nullptr, *xchg_recv = nullptr;
     size_t xchg_count = 0;
     bool shard_pending = false;   // an executed iteration whose residuals have not been gathered / tested yet
+    // pipelined loop (lane passes only): the dual pass of iteration k also writes pbar of iteration k+1 into the old
+    // primal buffer, so iteration k+1 has no primal pass -- only the kernel projection, in place, next to the backward
+    // sweep -- and the dual pass is split into the branching part (runs next to the forward chain sweep), the chain part
+    // (k_dual_chain) and the leaves
+    bool allow_pipe = true;
+    bool pbar_ready = false;        // prim[cur_i] holds pbar of the next iteration
+    int chain_first = 0;            // nodes [chain_first, m) are nonleaf nodes with exactly one child
+    int4 *chain_recs = nullptr;     // their packed topology records (launch_dual_chain)
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t pev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // fused loop
     cudaGraphExec_t graph[2] = {nullptr, nullptr};  // graph[src]: one iteration reading buffer src, writing 1-src
     bool use_graphs = true;
@@ -229,12 +240,14 @@ void launch_primal(rb_solver *s, cudaStream_t st, int src, int dst, const int *n
     }
 }
 
+bool use_pipe(const rb_solver *s) { return use_lane(s) && s->allow_pipe && !s->sharded; }
+
 void launch_dual(rb_solver *s, cudaStream_t st, int src, int dst, const int *nodes = nullptr, int count = -1) {
     const Layout &L = s->P.L;
     if (count < 0) count = L.n;
     if (use_lane(s)) {
         launch_dual_lane(dim3(1, L.batch), st, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
-                         nodes, count);
+                         nodes, 0, count, nullptr);
     } else {
         launch_dual_tile(s->diag_costs, dim3(s->tiles.num_tiles, L.batch), s->dual_smem, st, s->P, s->ctrl, s->tiles,
                          s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots);
@@ -242,15 +255,41 @@ void launch_dual(rb_solver *s, cudaStream_t st, int src, int dst, const int *nod
 }
 
 // kernels launched per iteration of the fused loop: primal pass, sweeps, dual pass, stopping test
+struct PipeSplit {
+    int early;   // nodes [0, early): final once the top of the tree is done (dual pass runs next to the forward levels)
+    int cf;      // nodes [early, cf): general lane pass after the sweeps; [cf, m): chain pass; [m, n): leaves
+};
+bool sweeps_fused(const rb_solver *s) {
+    const SweepPlan &pl = s->plan;
+    return s->tree_mode > 1 && s->fuse_ok && !(s->allow_mma && pl.lv[0].num_tiles > 0) && !s->sharded;
+}
+PipeSplit pipe_split(const rb_solver *s) {
+    const Layout &L = s->P.L;
+    const SweepPlan &pl = s->plan;
+    PipeSplit ps;
+    ps.cf = dual_chain_supported(L.nx, L.nu) ? std::max(1, std::min(s->chain_first, L.m)) : L.m;
+    const int v0 = sweeps_fused(s) ? 1 : 0;   // first forward level launched after the top
+    ps.early = v0 < pl.num_levels ? std::min(ps.cf, s->stage_off[pl.lv[v0].t_lo]) : 0;
+    return ps;
+}
+// kernels of the dual pass of the pipelined loop
+int pipe_dual_launches(const rb_solver *s) {
+    const Layout &L = s->P.L;
+    const PipeSplit ps = pipe_split(s);
+    if (ps.cf >= L.m) return (ps.early > 0 ? 1 : 0) + 1;
+    return (ps.early > 0 ? 1 : 0) + 1 + (ps.cf > ps.early ? 1 : 0) + 1;
+}
 int iter_launches(const rb_solver *s) {
     const SweepPlan &pl = s->plan;
-    const bool fused = s->tree_mode > 1 && s->fuse_ok && !(s->allow_mma && pl.lv[0].num_tiles > 0) && !s->sharded;
-    return 1 + (1 + 2 * pl.num_levels - (fused ? 2 : 0)) + 1 + 1;
+    const int sweeps = 1 + 2 * pl.num_levels - (sweeps_fused(s) ? 2 : 0);
+    if (use_pipe(s)) return 1 + sweeps + pipe_dual_launches(s) + 1;
+    return 1 + sweeps + 1 + 1;
 }
 
 // the launches of the DP sweeps on `prim` (x, u rows hold xbar, ubar on entry and the projection on exit); evs / nev:
 // optional event after every launch
-int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st, cudaEvent_t *evs = nullptr, int *nev = nullptr) {
+int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st, cudaEvent_t *evs = nullptr, int *nev = nullptr,
+                  const std::function<void()> &after_top = nullptr) {
     int ne = 0;
     const SweepPlan &pl = s->plan;
     const Layout &L = s->P.L;
@@ -295,6 +334,7 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
                          s->P, ctrl, pl, prim, s->q, s->r, s->x0);
     }
     if (evs) cudaEventRecord(evs[ne++], st);
+    if (after_top) after_top();
     for (int v = fused ? 1 : 0; v < pl.num_levels; ++v) fwd(v);
     if (nev) *nev = ne;
     return launch_ok(s, "DP sweeps");
@@ -493,6 +533,8 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
 
     TRYC(cudaSetDevice(s->device));
     TRYC(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (auto &q : s->side) TRYC(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+    for (auto &e : s->pev) TRYC(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const int n = pb->n, m = pb->m, nx = pb->nx, nu = pb->nu, nl = n - m;
     s->stage_off.assign(pb->stage_off, pb->stage_off + pb->num_stages + 1);
     s->parent.assign(pb->parent, pb->parent + n);
@@ -550,6 +592,8 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
     for (int i = 0; i < m; ++i) yoff[i + 1] = yoff[i] + 2 * s->child_count[i] + 1;
     L.ysz = yoff[m];
     for (int i = 0; i < m; ++i) s->max_children = std::max(s->max_children, s->child_count[i]);
+    s->chain_first = m;   // trailing run of nonleaf nodes with one child: the chain part of the tree (k_dual_chain)
+    while (s->chain_first > 1 && s->child_count[s->chain_first - 1] == 1) --s->chain_first;
     {
         int64_t pc = 0, pp = 0;  // compact / padded cursors
         auto addp = [&](long long &field, int64_t len) {
@@ -584,6 +628,14 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
     TRY(upload(s, pb->cost_idx, n, &tmp_i)); T.cost_idx = tmp_i;
     TRY(upload(s, pb->leafcost_idx, nl, &tmp_i)); T.leafcost_idx = tmp_i;
     TRY(upload(s, L.has_nl_rect ? pb->nl_rect_idx : nullptr, m, &tmp_i)); T.nl_rect_idx = tmp_i;
+    {   // packed topology records of the chain nodes (k_dual_chain): child, cost row of the child, y offset, rectangle row
+        std::vector<int4> recs(std::max(1, m - s->chain_first));
+        for (int i = s->chain_first; i < m; ++i) {
+            const int j = s->child_first[i];
+            recs[i - s->chain_first] = make_int4(j, s->cost_idx[j], yoff[i], L.has_nl_rect ? pb->nl_rect_idx[i] : 0);
+        }
+        TRY(upload(s, recs.data(), recs.size(), &s->chain_recs));
+    }
     TRY(upload(s, L.has_leaf_rect ? pb->leaf_rect_idx : nullptr, nl, &tmp_i)); T.leaf_rect_idx = tmp_i;
     TRY(upload(s, pb->cls, m, &tmp_i)); T.cls = tmp_i;
     TRY(upload(s, pb->cond_prob, n, &tmp_d)); T.cond_prob = tmp_d;
@@ -960,6 +1012,10 @@ void rb_destroy(rb_solver *s) {
     if (s->hist) cudaFree(s->hist);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    for (auto q : s->side)
+        if (q) cudaStreamDestroy(q);
+    for (auto e : s->pev)
+        if (e) cudaEventDestroy(e);
     delete s;
 }
 
@@ -1307,17 +1363,67 @@ int rb_residuals(rb_solver *s, double alpha, double *norms, double *vectors) {
 // ---- fused loop -------------------------------------------------------------------------------------------------------
 namespace {
 
-// the kernels of one iteration reading buffer src and writing buffer 1-src
-int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st) {
+// the kernels of one iteration reading buffer src and writing buffer 1-src.  have_pbar: prim[1-src] already holds
+// pbar = p - alpha L* d of this iteration (written by the previous dual pass)
+int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_pbar) {
     const Layout &L = s->P.L;
     const int dst = 1 - src;
-    (void)L;
-    launch_primal(s, st, src, dst);
-    int rc = launch_sweeps(s, s->ctrl, s->prim[dst], st);
+    if (!use_pipe(s)) {
+        launch_primal(s, st, src, dst);
+        int rc = launch_sweeps(s, s->ctrl, s->prim[dst], st);
+        if (rc != RB_OK) return rc;
+        launch_dual(s, st, src, dst);
+        k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
+        return launch_ok(s, "fused iteration");
+    }
+    const PipeSplit ps = pipe_split(s);
+    const dim3 nb(1, L.batch);
+    cudaStream_t s0 = s->side[0], s1 = s->side[1];
+    cudaEvent_t *ev = s->pev;
+    auto dual_lane = [&](cudaStream_t q, int first, int count) {
+        launch_dual_lane(nb, q, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, nullptr, first,
+                         count, s->prim[src]);
+    };
+    if (have_pbar) {   // kernel projection in place, next to the backward sweeps
+        RB_CUDA(s, cudaEventRecord(ev[0], st));
+        RB_CUDA(s, cudaStreamWaitEvent(s0, ev[0], 0));
+        launch_kproj(L.batch, s0, s->P, s->ctrl, s->prim[dst]);
+        RB_CUDA(s, cudaEventRecord(ev[1], s0));
+    } else {
+        launch_primal(s, st, src, dst);
+    }
+    bool early_done = false;
+    cudaError_t herr = cudaSuccess;
+    auto after_top = [&]() {   // the top of the tree is final: its dual pass runs next to the forward levels
+        if (ps.early <= 0) return;
+        if ((herr = cudaEventRecord(ev[2], st)) != cudaSuccess) return;
+        if ((herr = cudaStreamWaitEvent(s1, ev[2], 0)) != cudaSuccess) return;
+        if (have_pbar && (herr = cudaStreamWaitEvent(s1, ev[1], 0)) != cudaSuccess) return;
+        dual_lane(s1, 0, ps.early);
+        early_done = true;
+    };
+    int rc = launch_sweeps(s, s->ctrl, s->prim[dst], st, nullptr, nullptr, after_top);
     if (rc != RB_OK) return rc;
-    launch_dual(s, st, src, dst);
+    if (herr != cudaSuccess) return fail(s, RB_ERR_CUDA, std::string("pipelined iteration: ") + cudaGetErrorString(herr));
+    if (have_pbar) RB_CUDA(s, cudaStreamWaitEvent(st, ev[1], 0));
+    const int early = early_done ? ps.early : 0;
+    if (ps.cf >= L.m) {   // no chain pass: one general pass over the rest
+        dual_lane(st, early, L.n - early);
+    } else {
+        RB_CUDA(s, cudaEventRecord(ev[3], st));
+        RB_CUDA(s, cudaStreamWaitEvent(s1, ev[3], 0));
+        dual_lane(s1, early, ps.cf - early);
+        dual_lane(s1, L.m, L.n - L.m);
+        launch_dual_chain(L.batch, st, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
+                          s->chain_recs, ps.cf, L.m - ps.cf, s->prim[src]);
+        early_done = true;   // s1 carries work that st has to wait for
+    }
+    if (early_done) {
+        RB_CUDA(s, cudaEventRecord(ev[4], s1));
+        RB_CUDA(s, cudaStreamWaitEvent(st, ev[4], 0));
+    }
     k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
-    return launch_ok(s, "fused iteration");
+    return launch_ok(s, "pipelined iteration");
 }
 
 // the gather step of the sharded loop: q_j and d2_j of the cut nodes and the residual maxima of the previous iteration
@@ -1388,7 +1494,7 @@ int build_graphs(rb_solver *s) {
         cudaStream_t cap = nullptr;
         RB_CUDA(s, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
         RB_CUDA(s, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_iteration_kernels(s, src, cap);
+        int rc = enqueue_iteration_kernels(s, src, cap, true);
         cudaGraph_t g = nullptr;
         cudaError_t e = cudaStreamEndCapture(cap, &g);
         cudaStreamDestroy(cap);
@@ -1415,6 +1521,7 @@ int rb_loop_begin(rb_solver *s, double alpha, int32_t max_iters, double tol, int
         if (rc != RB_OK) return rc;
     }
     s->shard_pending = false;
+    s->pbar_ready = false;
     if (s->hist && s->hist_capacity < hist_capacity) {
         RB_CUDA(s, cudaStreamSynchronize(st));
         cudaFree(s->hist);
@@ -1449,12 +1556,13 @@ int rb_loop_enqueue(rb_solver *s, int32_t count) {
         if (s->sharded) {
             int rc = enqueue_iteration_sharded(s, src, s->stream);
             if (rc != RB_OK) return rc;
-        } else if (s->use_graphs) {
+        } else if (s->use_graphs && (s->pbar_ready || !use_pipe(s))) {
             RB_CUDA(s, cudaGraphLaunch(s->graph[src], s->stream));
-        } else {
-            int rc = enqueue_iteration_kernels(s, src, s->stream);
+        } else {   // plain launches; the first iteration of a pipelined loop has no pbar yet
+            int rc = enqueue_iteration_kernels(s, src, s->stream, s->pbar_ready);
             if (rc != RB_OK) return rc;
         }
+        s->pbar_ready = use_pipe(s);
         // the buffer just written holds the newest iterate: it is the next iteration's "old"
         std::swap(s->cur_i, s->old_i);
     }
@@ -1588,27 +1696,79 @@ int rb_step(rb_solver *s, const double *x0, double *norms) {
 int rb_profile_iteration(rb_solver *s, float *ms) {
     if (!s || !ms) return RB_ERR_INVALID;
     if (!s->in_loop) return fail(s, RB_ERR_STATE, "rb_loop_begin() has not been called");
+    const Layout &L = s->P.L;
     cudaStream_t st = s->stream;
     int nsweep = 0;
-    cudaEvent_t ev[9];
+    cudaEvent_t ev[12];
     for (auto &e : ev) RB_CUDA(s, cudaEventCreate(&e));
     const int src = s->old_i, dst = 1 - src;
+    const bool pipe = use_pipe(s);
     RB_CUDA(s, cudaEventRecord(ev[0], st));
-    launch_primal(s, st, src, dst);
+    if (pipe && s->pbar_ready) launch_kproj(L.batch, st, s->P, s->ctrl, s->prim[dst]);
+    else launch_primal(s, st, src, dst);
     RB_CUDA(s, cudaEventRecord(ev[1], st));
     int rcs = launch_sweeps(s, s->ctrl, s->prim[dst], st, ev + 2, &nsweep);
     if (rcs != RB_OK) return rcs;
-    launch_dual(s, st, src, dst);
+    for (int i = 0; i < 12; ++i) ms[i] = -1.0f;
+    int nd = 0;   // events ev[8..11] bracket the three kernels of the pipelined dual pass
+    if (pipe) {
+        const PipeSplit ps = pipe_split(s);
+        const dim3 nb(1, L.batch);
+        auto dual_lane = [&](int first, int count) {
+            launch_dual_lane(nb, st, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, nullptr,
+                             first, count, s->prim[src]);
+        };
+        RB_CUDA(s, cudaEventRecord(ev[8], st));
+        if (ps.cf >= L.m) {
+            dual_lane(0, L.n);
+            RB_CUDA(s, cudaEventRecord(ev[9], st));
+            nd = 1;
+        } else {
+            dual_lane(0, ps.cf);
+            RB_CUDA(s, cudaEventRecord(ev[9], st));
+            launch_dual_chain(L.batch, st, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
+                              s->chain_recs, ps.cf, L.m - ps.cf, s->prim[src]);
+            RB_CUDA(s, cudaEventRecord(ev[10], st));
+            dual_lane(L.m, L.n - L.m);
+            RB_CUDA(s, cudaEventRecord(ev[11], st));
+            nd = 3;
+        }
+    } else {
+        launch_dual(s, st, src, dst);
+    }
     k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
     RB_CUDA(s, cudaEventRecord(ev[2 + nsweep], st));
     RB_CUDA(s, cudaStreamSynchronize(st));
     int rc = launch_ok(s, "profiled iteration");
-    for (int i = 0; i < 8; ++i) ms[i] = -1.0f;
     for (int i = 0; i < 2 + nsweep; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    for (int i = 0; i < nd; ++i) cudaEventElapsedTime(&ms[8 + i], ev[8 + i], ev[9 + i]);
     for (auto &e : ev) cudaEventDestroy(e);
     std::swap(s->cur_i, s->old_i);
+    s->pbar_ready = pipe;
     s->launches += iter_launches(s);
     return rc;
+}
+
+int rb_pipeline_info(const rb_solver *s, int32_t *early_nodes, int32_t *chain_first, int32_t *chain_nodes) {
+    if (!s) return RB_ERR_INVALID;
+    const bool pipe = use_pipe(s);
+    const PipeSplit ps = pipe ? pipe_split(s) : PipeSplit{0, s->P.L.m};
+    if (early_nodes) *early_nodes = ps.early;
+    if (chain_first) *chain_first = ps.cf;
+    if (chain_nodes) *chain_nodes = pipe ? s->P.L.m - ps.cf : 0;
+    return RB_OK;
+}
+
+int rb_use_pipeline(rb_solver *s, int32_t enable) {
+    if (!s) return RB_ERR_INVALID;
+    if (s->in_loop) return fail(s, RB_ERR_STATE, "rb_use_pipeline() inside a loop");
+    s->allow_pipe = enable != 0;
+    for (int i = 0; i < 2; ++i)
+        if (s->graph[i]) {
+            cudaGraphExecDestroy(s->graph[i]);
+            s->graph[i] = nullptr;
+        }
+    return RB_OK;
 }
 
 int rb_force_dense_costs(rb_solver *s, int32_t enable) {

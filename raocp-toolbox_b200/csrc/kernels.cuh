@@ -61,9 +61,19 @@ constexpr int kLaneMaxChildren = 8;
 // templates on the number of lanes per node (4 or 8); nodes_batch.y = batch
 void launch_primal_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, const double *p_old,
                         const double *d_old, double *p_new, const int *node_list, int count);
+// first: node of lane group 0 when node_list is null.  pbar (may be null) = the p_old buffer: the pass also leaves
+// there the half step pbar = p+ - alpha L* d+ of the NEXT iteration (then the next iteration needs no primal pass, only
+// the kernel projection k_kproj_node in place)
 void launch_dual_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old,
                       const double *p_new, const double *d_old, double *d_new, double *slots, const int *node_list,
-                      int count);
+                      int first, int count, double *pbar);
+// the same pass specialised for a run of nonleaf nodes with ONE child each (the chain part of the tree)
+bool dual_chain_supported(int nx, int nu);
+// recs[i]: packed topology of node first + i = (child, cost-table row of the child, offset of y_i, rectangle row)
+void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
+                       const double *d_old, double *d_new, double *slots, const int4 *recs, int first, int count,
+                       double *pbar);
+void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim);
 __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, double *__restrict__ slots,
                         double *__restrict__ last);
 

@@ -15,6 +15,8 @@
 //                   (cache.py:290-317)
 //   k_dual_lane   : dbar = d + alpha L(2 p+ - p) (solver.py:44-58), prox of g* (cache.py:321-393), all six residual
 //                   inf-norms (solver.py:63-95,137-141)
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace rb {
@@ -22,6 +24,7 @@ namespace rb {
 namespace {
 
 constexpr int kMaxNodesPerCta = kLaneThreads / 4;   // nodes per CTA with the narrowest lane group
+constexpr int kChainDualThreads = 128;
 
 struct ResidLane {
     // Running maxima of |x| per residual norm, kept as the (signed) entry that attained them: one DSETP and two selects
@@ -58,6 +61,15 @@ struct ResidLane {
         return (unsigned long long)__double_as_longlong(v[slot]) & 0x7fffffffffffffffull;
     }
 };
+
+// Rectangle._constrain (rectangle.py:50-59) without branches: v if lo <= v <= hi, else lo if v <= lo, else hi if
+// v >= hi -- the two selects below give exactly that, also for lo > hi -- else (NaN) v itself with `bad` set
+__device__ __forceinline__ double box_clip_select(double v, double lo, double hi, int &bad) {
+    double r = v >= hi ? hi : v;
+    r = v <= lo ? lo : r;
+    bad |= v != v;
+    return r;
+}
 
 __device__ __forceinline__ double dual_w(double d_old, double lz, double alpha, double inv_alpha) {
     return fma(lz, alpha, d_old) * inv_alpha;
@@ -226,12 +238,16 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_primal_lane(const __grid_co
 }
 
 // ====================================================================================================================
-template <int kOct>
-__global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
+template <int kOct, int MINB>
+__global__ void __launch_bounds__(kLaneThreads, MINB) k_dual_lane(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
                                                            const double *__restrict__ p_old, const double *__restrict__ p_new,
                                                            const double *__restrict__ d_old, double *__restrict__ d_new,
                                                            double *__restrict__ slots, const int *__restrict__ node_list,
-                                                           int count) {
+                                                           int first, int count, double *pbar) {
+    // pbar (may be null): the buffer of p_old; when given, the pass also leaves there pbar = p+ - alpha L* d+, the
+    // half step of the NEXT iteration (solver.py:27-39), from the d+ it has in registers.  Every entry of p_old is
+    // read and overwritten by the same lane (s_i: all lanes of the group read it, so it is written after the block
+    // barrier), and it is never read again afterwards.
     if (ctrl->done) return;
     const double alpha = ctrl->alpha, inv_alpha = 1.0 / alpha;
     const Layout &L = P.L;
@@ -247,11 +263,14 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_cons
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = tid & (kOct - 1), ns = tid / kOct;
     if (tid == 0) blockflags = 0;
     const int slot = (blockIdx.x * blockDim.x + tid) / kOct;
-    const int node = slot < count ? (node_list ? node_list[slot] : slot) : L.n;   // L.n = idle octet
+    const int node = slot < count ? (node_list ? node_list[slot] : first + slot) : L.n;   // L.n = idle octet
     const double *Po = p_old + (long long)blockIdx.y * L.np_pad;
     const double *Pn = p_new + (long long)blockIdx.y * L.np_pad;
     const double *Do = d_old + (long long)blockIdx.y * L.nd_pad;
     double *Dn = d_new + (long long)blockIdx.y * L.nd_pad;
+    double *Pb = pbar ? pbar + (long long)blockIdx.y * L.np_pad : nullptr;
+    double sbar = 0.0;          // s-bar of this node, stored by lane 0 of the group after the block barrier
+    bool sbar_set = false;
     const int nx = L.nx, nu = L.nu, nxu = L.nxu;
     ResidLane R;
     R.init();
@@ -278,7 +297,35 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_cons
         } else if (g == 3) {
             pf(Do + L.d5 + c0 - 1);
             pf(Do + L.d6 + c0 - 1);
-            pf(Do + L.d7 + (long long)node * nxu);
+        }
+        // every row the two phases walk (the node's x / u / d7 rows, the contiguous d3 / d4 rows of its children), one
+        // line per lane and round: the phases below then meet L1 hits (or merge into the miss in flight) instead of
+        // one full memory round trip per loop iteration -- what bounds the pass when only a few nodes are in flight
+        for (int off = g * 16; off < nx; off += kOct * 16) {
+            pf(xo + off);
+            pf(xn + off);
+        }
+        for (int off = g * 16; off < nu; off += kOct * 16) {
+            pf(uo + off);
+            pf(un + off);
+        }
+        if (L.has_nl_rect)
+            for (int off = g * 16; off < nxu; off += kOct * 16) pf(Do + L.d7 + (long long)node * nxu + off);
+        for (int off = g * 16; off < cc * nx; off += kOct * 16) pf(Do + L.d3 + (long long)(c0 - 1) * nx + off);
+        for (int off = g * 16; off < cc * nu; off += kOct * 16) pf(Do + L.d4 + (long long)(c0 - 1) * nu + off);
+    } else if (leaf) {
+        const long long lo_ = (long long)(node - L.m) * nx;
+        for (int off = g * 16; off < nx; off += kOct * 16) {
+            pf(xo + off);
+            pf(xn + off);
+            pf(Do + L.d11 + lo_ + off);
+            if (L.has_leaf_rect) pf(Do + L.d14 + lo_ + off);
+        }
+        if (g == 0) {
+            pf(Po + L.ps + node);
+            pf(Pn + L.ps + node);
+            pf(Do + L.d12 + node - L.m);
+            pf(Do + L.d13 + node - L.m);
         }
     }
 
@@ -373,7 +420,7 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_cons
                     hi2 = ld2(M.nl_hi + ri + off7, k2);
                 }
                 const double z0 = 2 * n2.x - o2.x, z1 = 2 * n2.y - o2.y, dl0 = n2.x - o2.x, dl1 = n2.y - o2.y;
-                double g10 = 0.0, g20 = 0.0, g11 = 0.0, g21 = 0.0;
+                double g10 = 0.0, g20 = 0.0, g11 = 0.0, g21 = 0.0, lt0 = 0.0, lt1 = 0.0;
                 for (int jj = 0; jj < cc; ++jj) {
                     const int j = c0 + jj;
                     const double2 m2 = ld2(mtab + child_cost[jj][ns] * w, k2);
@@ -383,11 +430,17 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_cons
                     edge(m2.x, z0, dl0, dol2.x, scale, dn0, g10, g20);
                     edge(m2.y, z1, dl1, dol2.y, scale, dn1, g11, g21);
                     st2(seg_n + (long long)(j - 1) * w, k2, dn0, dn1);
+                    lt0 = fma(m2.x, dn0, lt0);
+                    lt1 = fma(m2.y, dn1, lt1);
                 }
                 double dn70 = 0.0, dn71 = 0.0;
                 entry(o2.x, n2.x, d7v.x, lo2.x, hi2.x, g10, g20, dn70);
                 entry(o2.y, n2.y, d7v.y, lo2.y, hi2.y, g11, g21, dn71);
                 if (L.has_nl_rect) st2(d7n + off7, k2, dn70, dn71);
+                if (Pb) {   // [xbar; ubar] of the next iteration (operators.py:74-87); dn7 is 0 without rectangles
+                    double *pb_row = Pb + (part == 0 ? L.px + (long long)node * nx : L.pu + (long long)node * nu);
+                    st2(pb_row, k2, n2.x - alpha * (lt0 + dn70), n2.y - alpha * (lt1 + dn71));
+                }
             }
         }
         // ---- d5, d6 and the tau_j residual rows: children spread over the lanes of the octet ----------------------------
@@ -403,6 +456,7 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_cons
             const double dn6 = alpha * (w6 - soc_last[jj][ns]);
             Dn[L.d5 + e0] = dn5;
             Dn[L.d6 + e0] = dn6;
+            if (Pb) Pb[L.ptau + j] = tn - alpha * (0.5 * (dn5 + dn6));   // taubar_j (operators.py:88)
             const double dd5 = do5 - dn5, dd6 = do6 - dn6;
             const double x5 = R.dual(dd5, hdt, inv_alpha), x6 = R.dual(dd6, hdt, inv_alpha);
             R.primal(tn - to, 0.5 * (dd5 + dd6), 0.5 * (x5 + x6), inv_alpha);
@@ -439,6 +493,9 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_cons
                 R.put(5, dd2);
                 R.primal(sn - so, dd2, xi22, inv_alpha);   // s_i of a nonleaf node: its L* row is d2_i
             }
+            sbar = sn - alpha * dn2;                 // operators.py:73; the root also takes the prox of alpha * identity
+            if (node == 0) sbar -= alpha;            // (cache.py:253-257)
+            sbar_set = true;
             for (int e = g; e < ny; e += kOct) {
                 const double b = e < cc ? T.cond_prob[c0 + e] : (e == 2 * cc ? 1.0 : 0.0);
                 const double dy = ynew[e] - yold[e];
@@ -450,7 +507,9 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_cons
                 const double dd = do1 - dnew;
                 const double xi2 = R.dual(dd, dy, inv_alpha);
                 R.primal(dy, dd - b * dd2, xi2 - b * xi22, inv_alpha);
+                if (Pb) Pb[L.py + yo + e] = ynew[e] - alpha * (dnew - b * dn2);   // ybar_i (operators.py:72)
             }
+            if (Pb && node == 0 && g == 0) Pb[L.ptau] = Pn[L.ptau] - alpha * Pn[L.ptau];   // tau_0 (always 0)
         }
     }
     // ---- leaf: SOC on [d11; d12; d13] (cache.py:375-386), rectangle on d14, x_i and s_i residual rows ---------------------
@@ -494,7 +553,7 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_cons
             }
             const long long ri = L.has_leaf_rect ? (long long)T.leaf_rect_idx[li] * nx : 0;
             auto leaf_entry = [&](double o, double nw, double mm, double dol, double dol14, double lo_b, double hi_b,
-                                  double &dnew, double &dn14) {
+                                  double &dnew, double &dn14, double &xb) {
                 const double z = 2 * nw - o, dlt = nw - o;
                 const double wv = dual_w(dol, mm * z, alpha, inv_alpha);
                 dnew = alpha * (wv - scale * wv);
@@ -509,6 +568,7 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_cons
                     g2 += R.dual(dd14, dlt, inv_alpha);
                 }
                 R.primal(dlt, g1, g2, inv_alpha);
+                xb = nw - alpha * (mm * dnew + dn14);   // xbar of the leaf (operators.py:89-92); dn14 is 0 without rectangles
             };
             for (int k2 = g; k2 < nx / 2; k2 += kOct) {
                 const double2 o2 = ld2(xo, k2), n2 = ld2(xn, k2), m2 = ld2(sq, k2), dol2 = ld2(d11o, k2);
@@ -518,11 +578,17 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_cons
                     lo2 = ld2(M.leaf_lo + ri, k2);
                     hi2 = ld2(M.leaf_hi + ri, k2);
                 }
-                double dn0, dn1, q0 = 0.0, q1 = 0.0;
-                leaf_entry(o2.x, n2.x, m2.x, dol2.x, d14v.x, lo2.x, hi2.x, dn0, q0);
-                leaf_entry(o2.y, n2.y, m2.y, dol2.y, d14v.y, lo2.y, hi2.y, dn1, q1);
+                double dn0, dn1, q0 = 0.0, q1 = 0.0, xb0, xb1;
+                leaf_entry(o2.x, n2.x, m2.x, dol2.x, d14v.x, lo2.x, hi2.x, dn0, q0, xb0);
+                leaf_entry(o2.y, n2.y, m2.y, dol2.y, d14v.y, lo2.y, hi2.y, dn1, q1, xb1);
                 st2(d11n, k2, dn0, dn1);
                 if (L.has_leaf_rect) st2(d14n, k2, q0, q1);
+                if (Pb) st2(Pb + L.px + (long long)node * nx, k2, xb0, xb1);
+            }
+            {
+                const double dn12 = alpha * (w12 - scale * w12), dn13 = alpha * (w13 - last);
+                sbar = sn - alpha * (0.5 * (dn12 + dn13));   // operators.py:93
+                sbar_set = true;
             }
             if (g == 0) {
                 const double dn12 = alpha * (w12 - scale * w12), dn13 = alpha * (w13 - last);
@@ -555,6 +621,253 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_dual_lane(const __grid_cons
         atomicMax(reinterpret_cast<unsigned long long *>(slots + (long long)blockIdx.y * 6 + tid), mval);
     }
     if (tid == 0 && blockflags) atomicOr(&ctrl->status, blockflags);
+    if (Pb && sbar_set && g == 0) Pb[L.ps + node] = sbar;
+}
+
+// ====================================================================================================================
+// Dual pass of the CHAIN part of the tree: nonleaf nodes with exactly one child (every stage past the stopping time,
+// 91 % of the nodes of cfg3).  Same arithmetic as k_dual_lane, specialised so that the pass is bound by memory rather
+// than by dependent loads and index arithmetic:
+//   * templated on <NX, NU, G lanes per node>: [x; u] is walked as ONE row of (NX+NU)/2 pairs, pair k = g + G r in
+//     round r (15 pairs over 4 lanes = 4 rounds for cfg3 instead of 3 + 2), all trip counts are compile-time;
+//   * every HBM row of the node (x, x+, u, u+, d3/d4 of the edge, d7) is requested at the top of the kernel, before
+//     anything is consumed (16 independent 16-byte loads per lane in flight), and is used from registers by both the
+//     cone classification and the update -- no second walk over the rows, no shared memory, no block barrier before
+//     the final reduction;
+//   * one child: the SOC scale is a per-group register, the child->parent sums of L* have one term.
+// Writes d+ of the node and of the edge to its child, and pbar = p+ - alpha L* d+ of the next iteration (see k_dual_lane).
+// ====================================================================================================================
+template <int NX, int NU, int G, int MINB>
+__global__ void __launch_bounds__(kChainDualThreads, MINB)
+    k_dual_chain(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, const double *__restrict__ p_old,
+                 const double *__restrict__ p_new, const double *__restrict__ d_old, double *__restrict__ d_new,
+                 double *__restrict__ slots, const int4 *__restrict__ recs, int first, int count, double *pbar) {
+    constexpr int HX = NX / 2, K = (NX + NU) / 2, R = (K + G - 1) / G, NXU = NX + NU;
+    const Layout &L = P.L;
+    const Topo &T = P.t;
+    const Tabs &M = P.m;
+    __shared__ unsigned long long blockmax[kChainDualThreads / 32][6];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = tid & (G - 1);
+    const int slot = (blockIdx.x * blockDim.x + tid) / G;
+    const bool active = slot < count;
+    const int node = first + (active ? slot : 0);   // idle groups of the last CTA repeat the first node, stores masked
+    // one global round trip for everything the row loads depend on: the control block and the node's packed topology
+    // record (child, cost-table row of the child, offset of y_i, rectangle row), both requested before `done` is tested
+    const int done = ctrl->done;
+    const double alpha = ctrl->alpha;
+    const int4 rec = __ldg(recs + (node - first));
+    if (done) return;
+    const double inv_alpha = 1.0 / alpha;
+    const double *Po = p_old + (long long)blockIdx.y * L.np_pad;
+    const double *Pn = p_new + (long long)blockIdx.y * L.np_pad;
+    const double *Do = d_old + (long long)blockIdx.y * L.nd_pad;
+    double *Dn = d_new + (long long)blockIdx.y * L.nd_pad;
+    double *Pb = pbar + (long long)blockIdx.y * L.np_pad;
+    const int j = rec.x;
+    const long long e0 = j - 1;
+    const int ci = rec.y, yo = rec.z;
+    const bool rect = L.has_nl_rect;
+    const long long ri = (long long)rec.w * NXU;
+    const double prob = T.cond_prob[j];
+
+    // ---- all row loads of the node, issued back to back ----------------------------------------------------------------
+    double2 o[R], n[R], de[R], mm[R], d7v[R];
+    // offsets of pair k of the [x; u] row in the primal buffers / in the d3 | d4 segments
+    const long long px_row = L.px + (long long)node * NX, pu_row = L.pu + (long long)node * NU - 2 * HX;
+    const long long d3_row = L.d3 + e0 * NX, d4_row = L.d4 + e0 * NU - 2 * HX;
+    auto off_p = [&](int kk) { return (kk < HX ? px_row : pu_row) + 2 * kk; };
+    auto off_e = [&](int kk) { return (kk < HX ? d3_row : d4_row) + 2 * kk; };
+    bool valid[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int k = g + G * r;
+        valid[r] = k < K;
+        const int kk = valid[r] ? k : 0;
+        const bool isx = kk < HX;
+        o[r] = __ldg(reinterpret_cast<const double2 *>(Po + off_p(kk)));
+        n[r] = __ldg(reinterpret_cast<const double2 *>(Pn + off_p(kk)));
+        de[r] = __ldg(reinterpret_cast<const double2 *>(Do + off_e(kk)));
+        d7v[r] = rect ? __ldg(reinterpret_cast<const double2 *>(Do + L.d7 + (long long)node * NXU + 2 * kk))
+                      : make_double2(0.0, 0.0);
+        mm[r] = __ldg(reinterpret_cast<const double2 *>(isx ? M.sq_d + ci * NX + 2 * kk : M.sr_d + ci * NU + 2 * (kk - HX)));
+    }
+    // scalars of the node and of the edge (same addresses for the lanes of a group: one request)
+    const double to = Po[L.ptau + j], tn = Pn[L.ptau + j], do5 = Do[L.d5 + e0], do6 = Do[L.d6 + e0];
+    const double so = Po[L.ps + node], sn = Pn[L.ps + node], do2 = Do[L.d2 + node];
+    const int ey = g < 2 ? g : 2;   // y_i = [y_a; y_b; y_last]: lanes 0, 1, 2 take one entry each
+    const double yold = Po[L.py + yo + ey], ynew = Pn[L.py + yo + ey], do1 = Do[L.d1 + yo + ey];
+
+    ResidLane Rs;
+    Rs.init();
+    int bad = 0;
+    // ---- second-order cone of the edge: [d3; d4; d5; d6] (cones.py:113-132) ---------------------------------------------
+    double2 w[R];
+    double ss = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        w[r].x = dual_w(de[r].x, mm[r].x * (2 * n[r].x - o[r].x), alpha, inv_alpha);
+        w[r].y = dual_w(de[r].y, mm[r].y * (2 * n[r].y - o[r].y), alpha, inv_alpha);
+        if (valid[r]) {
+            ss = fma(w[r].x, w[r].x, ss);
+            ss = fma(w[r].y, w[r].y, ss);
+        }
+    }
+    const double ht = 0.5 * (2 * tn - to), hdt = 0.5 * (tn - to);
+    const double w5 = dual_w(do5, ht, alpha, inv_alpha) - 0.5;
+    const double w6 = dual_w(do6, ht, alpha, inv_alpha) + 0.5;
+    if (g == 0) ss = fma(w5, w5, ss);
+    ss = oct_sum<G>(ss);
+    double scale, last;
+    {
+        const double rr = sqrt(ss);
+        if (rr <= w6) {          // inside the cone: projection = w
+            scale = 1.0;
+            last = w6;
+        } else if (rr <= -w6) {  // inside the polar cone: projection = 0
+            scale = 0.0;
+            last = 0.0;
+        } else {
+            last = (rr + w6) / 2;
+            scale = last / rr;
+        }
+    }
+    // ---- the [x; u] row: d3 / d4 of the edge, d7 of the node, residual rows, [xbar; ubar] ---------------------------------
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        double2 lo2 = make_double2(0.0, 0.0), hi2 = lo2;
+        if (rect) {
+            const int kk = valid[r] ? g + G * r : 0;
+            lo2 = __ldg(reinterpret_cast<const double2 *>(M.nl_lo + ri + 2 * kk));
+            hi2 = __ldg(reinterpret_cast<const double2 *>(M.nl_hi + ri + 2 * kk));
+        }
+        auto elem = [&](double ov, double nv, double dol, double mv, double wv, double d7old, double lo_b, double hi_b,
+                        double &dnew, double &d7new, double &pb) {
+            const double z = 2 * nv - ov, dlt = nv - ov;
+            dnew = alpha * (wv - scale * wv);
+            const double dd = dol - dnew;
+            const double xi2 = Rs.dual(dd, mv * dlt, inv_alpha);
+            double g1 = mv * dd, g2 = mv * xi2;
+            d7new = 0.0;
+            if (rect) {   // rectangle on [x; u] (cache.py:367-371)
+                const double w7 = dual_w(d7old, z, alpha, inv_alpha);
+                d7new = alpha * (w7 - box_clip_select(w7, lo_b, hi_b, bad));
+                const double dd7 = d7old - d7new;
+                g1 += dd7;
+                g2 += Rs.dual(dd7, dlt, inv_alpha);
+            }
+            Rs.primal(dlt, g1, g2, inv_alpha);
+            pb = nv - alpha * (mv * dnew + d7new);   // operators.py:74-87 applied to d+
+        };
+        double dn0, dn1, s0, s1, b0, b1;
+        elem(o[r].x, n[r].x, de[r].x, mm[r].x, w[r].x, d7v[r].x, lo2.x, hi2.x, dn0, s0, b0);
+        elem(o[r].y, n[r].y, de[r].y, mm[r].y, w[r].y, d7v[r].y, lo2.y, hi2.y, dn1, s1, b1);
+        if (valid[r] && active) {
+            const int kk = g + G * r;
+            *reinterpret_cast<double2 *>(Dn + off_e(kk)) = make_double2(dn0, dn1);
+            if (rect) *reinterpret_cast<double2 *>(Dn + L.d7 + (long long)node * NXU + 2 * kk) = make_double2(s0, s1);
+            *reinterpret_cast<double2 *>(Pb + off_p(kk)) = make_double2(b0, b1);
+        }
+    }
+    // ---- d5, d6 and the tau_j residual row (every lane computes, lane 0 stores) ---------------------------------------------
+    {
+        const double dn5 = alpha * (w5 - scale * w5), dn6 = alpha * (w6 - last);
+        const double dd5 = do5 - dn5, dd6 = do6 - dn6;
+        const double x5 = Rs.dual(dd5, hdt, inv_alpha), x6 = Rs.dual(dd6, hdt, inv_alpha);
+        Rs.primal(tn - to, 0.5 * (dd5 + dd6), 0.5 * (x5 + x6), inv_alpha);
+        if (g == 0 && active) {
+            Dn[L.d5 + e0] = dn5;
+            Dn[L.d6 + e0] = dn6;
+            Pb[L.ptau + j] = tn - alpha * (0.5 * (dn5 + dn6));
+        }
+    }
+    // ---- d1, d2 (risk block) and the y_i, s_i residual rows ----------------------------------------------------------------
+    {
+        const double b = g == 0 ? prob : (g == 2 ? 1.0 : 0.0);   // b_i = [pi; 0; 1] (risks.py:34-35); lanes >= 3 idle
+        const bool own = g < 3;
+        const double dot_z = oct_sum<G>(own ? b * (2 * ynew - yold) : 0.0);
+        const double dot_d = oct_sum<G>(own ? b * (ynew - yold) : 0.0);
+        const double w2 = dual_w(do2, (2 * sn - so) - dot_z, alpha, inv_alpha);
+        const double dn2 = alpha * (w2 - fmax(0.0, w2));
+        const double dd2 = do2 - dn2;
+        const double xi22 = fma(dd2, inv_alpha, (sn - so) - dot_d);
+        Rs.put(2, xi22);
+        Rs.put(5, dd2);
+        Rs.primal(sn - so, dd2, xi22, inv_alpha);
+        if (own) {
+            const double dy = ynew - yold;
+            const double wv = dual_w(do1, 2 * ynew - yold, alpha, inv_alpha);
+            const double zv = g < 2 ? fmax(0.0, wv) : wv;   // dual of R_+^{2c} x {0} (risks.py:32-33)
+            const double dnew = alpha * (wv - zv);
+            const double dd = do1 - dnew;
+            const double xi2 = Rs.dual(dd, dy, inv_alpha);
+            Rs.primal(dy, dd - b * dd2, xi2 - b * xi22, inv_alpha);
+            if (active) {
+                Dn[L.d1 + yo + g] = dnew;
+                Pb[L.py + yo + g] = ynew - alpha * (dnew - b * dn2);
+            }
+        }
+        __syncwarp();   // every lane of the group has consumed s_i before lane 0 replaces it
+        if (g == 0 && active) {
+            Dn[L.d2 + node] = dn2;
+            Pb[L.ps + node] = sn - alpha * dn2;
+        }
+    }
+    // block-level reduction of the six maxima (as bit patterns), one atomic per slot per block.  Warp level: two
+    // 32-bit redux.sync per slot (the high words, then the low words of the lanes that hold the maximal high word)
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const unsigned long long mine = Rs.bits(i);
+        const unsigned hi = (unsigned)(mine >> 32), lo = (unsigned)mine;
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+        if (lane == 0) blockmax[warp][i] = ((unsigned long long)mhi << 32) | mlo;
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(&ctrl->status, 1);
+    __syncthreads();
+    if (tid < 6) {
+        unsigned long long mval = blockmax[0][tid];
+#pragma unroll
+        for (int wv = 1; wv < kChainDualThreads / 32; ++wv) mval = blockmax[wv][tid] > mval ? blockmax[wv][tid] : mval;
+        atomicMax(reinterpret_cast<unsigned long long *>(slots + (long long)blockIdx.y * 6 + tid), mval);
+    }
+}
+
+// ====================================================================================================================
+// Projection onto ker [E' -I -I] of every nonleaf node (cache.py:290-317), IN PLACE on a buffer that holds
+// (ybar_i, taubar_j, sbar_j) -- the part of prox_f that does not depend on the DP sweeps; it runs next to them on its
+// own stream.  One thread per node; the sums follow the association of k_primal_lane's lane-group reductions.
+// ====================================================================================================================
+__global__ void __launch_bounds__(256) k_kproj_node(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
+                                                     double *__restrict__ prim) {
+    if (ctrl->done) return;
+    const Layout &L = P.L;
+    const Topo &T = P.t;
+    const int node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node >= L.m) return;
+    double *Pb = prim + (long long)blockIdx.y * L.np_pad;
+    const int c0 = T.child_first[node], cc = T.child_count[node];
+    const double a = T.risk_alpha[node], den = a * a + 3.0;
+    double *y = Pb + L.py + T.yoff[node], *tau = Pb + L.ptau + c0, *sv = Pb + L.ps + c0;
+    const double ylast = y[2 * cc];
+    double res[kLaneMaxChildren];
+#pragma unroll
+    for (int e = 0; e < kLaneMaxChildren; ++e) res[e] = e < cc ? a * y[e] - y[cc + e] + ylast - tau[e] - sv[e] : 0.0;
+    const double rsum = ((res[0] + res[1]) + (res[2] + res[3])) + ((res[4] + res[5]) + (res[6] + res[7]));
+    const double shift = rsum / (den + (double)cc);
+    double wv[kLaneMaxChildren];
+#pragma unroll
+    for (int e = 0; e < kLaneMaxChildren; ++e) {
+        wv[e] = 0.0;
+        if (e < cc) {
+            wv[e] = (res[e] - shift) / den;
+            y[e] = y[e] - a * wv[e];
+            y[cc + e] = y[cc + e] + wv[e];
+            tau[e] = tau[e] + wv[e];
+            sv[e] = sv[e] + wv[e];
+        }
+    }
+    const double wsum = ((wv[0] + wv[1]) + (wv[2] + wv[3])) + ((wv[4] + wv[5]) + (wv[6] + wv[7]));
+    y[2 * cc] = ylast - wsum;
 }
 
 // ---- host launchers: lanes per node chosen from the row length (pairs of doubles per lane and round) ----------------------
@@ -570,11 +883,59 @@ void launch_primal_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, cons
 
 void launch_dual_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old,
                       const double *p_new, const double *d_old, double *d_new, double *slots, const int *node_list,
-                      int count) {
+                      int first, int count, double *pbar) {
+    if (count <= 0) return;
     const int G = lane_group_width(P.L.nx);
     const dim3 grid((count * G + kLaneThreads - 1) / kLaneThreads, nodes_batch.y);
-    if (G == 4) k_dual_lane<4><<<grid, kLaneThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, node_list, count);
-    else k_dual_lane<8><<<grid, kLaneThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, node_list, count);
+    // a grid that fits the GPU at two CTAs per SM runs the 128-register build (no spills); a bigger one the 80-register
+    // build with three CTAs per SM
+    const bool roomy = (long long)grid.x * grid.y <= 2 * 148;
+#define RB_GO(G_, B_) \
+    k_dual_lane<G_, B_><<<grid, kLaneThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, node_list, first, count, pbar)
+    if (G == 4 && roomy) RB_GO(4, 2);
+    else if (G == 4) RB_GO(4, 3);
+    else if (roomy) RB_GO(8, 2);
+    else RB_GO(8, 3);
+#undef RB_GO
+}
+
+// sizes with an instantiation of the chain dual pass (lanes per node as lane_group_width picks them)
+#define RB_CHAIN_DUAL_DIMS(X) X(4, 2, 4) X(8, 4, 4) X(16, 8, 4) X(20, 10, 4)
+
+bool dual_chain_supported(int nx, int nu) {
+#define RB_HAS(NX, NU, G) \
+    if (nx == NX && nu == NU) return true;
+    RB_CHAIN_DUAL_DIMS(RB_HAS)
+#undef RB_HAS
+    return false;
+}
+
+void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
+                       const double *d_old, double *d_new, double *slots, const int4 *recs, int first, int count,
+                       double *pbar) {
+    if (count <= 0) return;
+    // resident CTAs per SM the kernel is compiled for: 3 (168 registers, no spills) or 4 (128 registers, ~40 words
+    // spilled to L1); RB_CHAIN_DUAL_MINB overrides for ablation runs
+    static const int minb = [] {
+        const char *e = getenv("RB_CHAIN_DUAL_MINB");
+        return e && atoi(e) == 4 ? 4 : 3;
+    }();
+#define RB_GO(NX, NU, G)                                                                                             \
+    if (P.L.nx == NX && P.L.nu == NU) {                                                                              \
+        const dim3 grid((count * G + kChainDualThreads - 1) / kChainDualThreads, batch);                             \
+        if (minb == 4)                                                                                               \
+            k_dual_chain<NX, NU, G, 4><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, pbar); \
+        else                                                                                                         \
+            k_dual_chain<NX, NU, G, 3><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, pbar); \
+        return;                                                                                                      \
+    }
+    RB_CHAIN_DUAL_DIMS(RB_GO)
+#undef RB_GO
+}
+
+void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim) {
+    const dim3 grid((P.L.m + 255) / 256, batch);
+    k_kproj_node<<<grid, 256, 0, st>>>(P, ctrl, prim);
 }
 
 }  // namespace rb

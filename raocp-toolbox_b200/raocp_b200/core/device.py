@@ -216,6 +216,18 @@ class DeviceSolver:
     def use_graphs(self, enable=True):
         self._call("rb_use_graphs", 1 if enable else 0)
 
+    def use_pipeline(self, enable=True):
+        self._call("rb_use_pipeline", 1 if enable else 0)
+
+    def pipeline_info(self):
+        """(early, chain_first, chain_nodes): the node ranges of the pipelined dual pass (rb_pipeline_info)"""
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._call("rb_pipeline_info", C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def chain_dual_nodes(self):
+        return self.pipeline_info()[2]
+
     def force_dense_costs(self, enable=True):
         self._call("rb_force_dense_costs", 1 if enable else 0)
 
@@ -251,10 +263,16 @@ class DeviceSolver:
         return iters.value, status.value
 
     def profile_iteration(self):
-        """ms per launch of one iteration (CUDA events): primal, sweep launches in order, dual + stopping test"""
-        ms = (C.c_float * 8)()
+        """ms per launch of one iteration (CUDA events): primal (or kernel projection), sweep launches in order, dual +
+        stopping test"""
+        return self.profile_iteration_full()[0]
+
+    def profile_iteration_full(self):
+        """(phases, dual_parts): phases as profile_iteration(); dual_parts = the kernels of the pipelined dual pass on
+        their own (branching nodes, chain nodes, leaves -- or one entry: all nodes); empty for the unpipelined loop"""
+        ms = (C.c_float * 12)()
         self._call("rb_profile_iteration", ms)
-        return [v for v in ms if v >= 0.0]
+        return [v for v in ms[:8] if v >= 0.0], [v for v in ms[8:] if v >= 0.0]
 
     # ---- subtree sharding over GPUs (one process per GPU) ------------------------------------------------------------------
     def shard_init(self, unique_id=None):

@@ -111,7 +111,8 @@ def test_prox_g_piecewise_equals_fused(case):
     assert seg_rel_err(flat, dev.get_dual(0)[0], g["proxg"][gather], dual=True) < 1e-12
 
 
-@pytest.mark.parametrize("mode", ["fused", "fused_tile_kernels", "fused_dense_costs", "fused_no_graph", "stepwise"])
+@pytest.mark.parametrize("mode", ["fused", "fused_unpipelined", "fused_tile_kernels", "fused_dense_costs", "fused_no_graph",
+                                  "stepwise"])
 def test_iterates_match_reference(case, mode):
     """first 100 iterates against the unmodified reference (same alpha, same x0), 1e-9 relative per segment"""
     g = golden(f"{case['name']}_iterates.npz")
@@ -131,6 +132,8 @@ def test_iterates_match_reference(case, mode):
                 fresh.cache.device_solver.use_lane_kernels(False)
             if mode == "fused_no_graph":
                 fresh.cache.device_solver.use_graphs(False)
+            if mode == "fused_unpipelined":   # primal pass + one dual pass per iteration (no pbar hand-over)
+                fresh.cache.device_solver.use_pipeline(False)
             status = fresh.chock(g["x0"], max_iters=k - 1, tol=0.0, alpha=alpha)
             assert status == 1 and fresh.iterations == k
             d2 = fresh.cache.device_solver

@@ -94,3 +94,88 @@ def test_batched_instances_through_chain_tiles():
             oracle.iterate()
         assert seg_rel_err(flat, dev.get_primal(0)[b], oracle.flat_primal(oracle.p), dual=False) < 1e-9
         assert seg_rel_err(flat, dev.get_dual(0)[b], oracle.flat_dual(oracle.d), dual=True) < 1e-9
+
+
+@pytest.mark.parametrize("graphs", [True, False])
+@pytest.mark.parametrize("name", ["chain2010", "shard", "mini2", "wide", "cfg1"])
+def test_pipelined_loop_equals_unpipelined(name, graphs):
+    """the pipelined loop (dual pass hands pbar to the next iteration; branching / chain / leaf dual kernels) against
+    the loop with a primal pass per iteration: same iterates to rounding, same residual history, and both 1e-9 from
+    the oracle; a stopping tolerance is met at the same iteration"""
+    import raocp_b200 as r
+    from oracle import problems
+    from oracle.cp_flat_oracle import FlatOracle
+    s = problems.spec(name)
+    problem = problems.build(s, r.core)
+    x0 = s["x0"][:, :1]
+    oracle = FlatOracle(problem)
+    alpha = oracle.step_size()
+    out = {}
+    for pipe in (True, False):
+        solver = r.core.Solver(problem, verbose=False)
+        dev = solver.cache.device_solver
+        dev.use_pipeline(pipe)
+        dev.use_graphs(graphs)
+        assert solver.chock(x0, max_iters=40, tol=0.0, alpha=alpha) == 1 and solver.iterations == 41
+        out[pipe] = (dev.get_primal(0)[0], dev.get_dual(0)[0], solver.residual_history[0].copy(), solver)
+    flat = out[True][3].cache.flat_problem
+    assert seg_rel_err(flat, out[True][0], out[False][0], dual=False) < 1e-12
+    assert seg_rel_err(flat, out[True][1], out[False][1], dual=True) < 1e-12
+    assert np.max(np.abs(out[True][2] - out[False][2]) / out[False][2]) < 1e-9
+    oracle.cache_initial_state(x0)
+    oracle.alpha = alpha
+    for _ in range(41):
+        oracle.iterate()
+    assert seg_rel_err(flat, out[True][0], oracle.flat_primal(oracle.p), dual=False) < 1e-9
+    assert seg_rel_err(flat, out[True][1], oracle.flat_dual(oracle.d), dual=True) < 1e-9
+    # stopping test: a tolerance first met inside the recorded history stops both loops at the same iteration
+    tol = float(np.sort(out[False][2].max(axis=1))[3]) * (1 + 1e-9)
+    its = []
+    for pipe in (True, False):
+        solver = r.core.Solver(problem, verbose=False)
+        solver.cache.device_solver.use_pipeline(pipe)
+        solver.cache.device_solver.use_graphs(graphs)
+        assert solver.chock(x0, max_iters=200, tol=tol, alpha=alpha) == 0
+        its.append(solver.iterations)
+    assert its[0] == its[1]
+
+
+def test_pipelined_batch_and_second_solve():
+    """batch > 1 through the pipelined kernels, and a second chock() on the same solver (the pbar hand-over must not
+    leak from one loop into the next)"""
+    from oracle.cp_flat_oracle import FlatOracle
+    s, solver, oracle = _pair("chain2010", None, "mma", batch=2)
+    flat, dev = solver.cache.flat_problem, solver.cache.device_solver
+    alpha = oracle.step_size()
+    oracles = [FlatOracle(flat.problem) for _ in range(2)]
+    for x0 in (s["x0"][:, :2], 0.5 - s["x0"][:, :2]):   # the second solve warm-starts from the first one's iterate
+        assert solver.chock(x0, max_iters=11, tol=0.0, alpha=alpha) == 1
+        for b in range(2):
+            oracles[b].cache_initial_state(x0[:, b:b + 1])
+            oracles[b].alpha = alpha
+            for _ in range(12):
+                oracles[b].iterate()
+            assert seg_rel_err(flat, dev.get_primal(0)[b], oracles[b].flat_primal(oracles[b].p), dual=False) < 1e-9
+            assert seg_rel_err(flat, dev.get_dual(0)[b], oracles[b].flat_dual(oracles[b].d), dual=True) < 1e-9
+
+
+def test_profile_hook_advances_like_an_iteration():
+    """rb_profile_iteration (plain launches with events) is one ordinary iteration of the loop"""
+    s, solver, oracle = _pair("chain2010", None, "mma")
+    flat, dev = solver.cache.flat_problem, solver.cache.device_solver
+    alpha = oracle.step_size()
+    x0 = s["x0"][:, :1]
+    solver.cache.cache_initial_state(x0)
+    dev.loop_begin(alpha, 1 << 30, -1.0, 0)
+    dev.loop_enqueue(3)
+    phases, parts = dev.profile_iteration_full()
+    assert len(phases) >= 3 and len(parts) in (1, 3) and all(v > 0 for v in phases + parts)
+    dev.loop_enqueue(2)
+    dev.profile_iteration()
+    dev.loop_end()
+    oracle.cache_initial_state(x0)
+    oracle.alpha = alpha
+    for _ in range(7):
+        oracle.iterate()
+    assert seg_rel_err(flat, dev.get_primal(0)[0], oracle.flat_primal(oracle.p), dual=False) < 1e-9
+    assert seg_rel_err(flat, dev.get_dual(0)[0], oracle.flat_dual(oracle.d), dual=True) < 1e-9
