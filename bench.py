@@ -180,7 +180,7 @@ def run_ours(args, rank, world, local_rank):
     solver = r.core.Solver(problem, batch=batch, dedup=not args.no_dedup, device=local_rank, verbose=False)
     solver.cache.device_solver.use_tree_kernels(args.tree_mode)
     solver.cache.device_solver.use_mma_sweeps(not args.no_mma)
-    solver.cache.device_solver.use_pipeline(not args.no_pipeline)
+    solver.cache.device_solver.use_pipeline(0 if args.no_pipeline else (3 if args.fwd_split else 1))
     dev = solver.cache.device_solver
     dev.synchronize()
     t_setup = time.perf_counter() - t0
@@ -391,6 +391,8 @@ def main():
     ap.add_argument("--tree-mode", type=int, default=2, choices=[0, 1, 2],
                     help="ablation: branching sweep levels with sweeps.cu (0), tree_sweeps.cu per level (1), fused with the top (2)")
     ap.add_argument("--no-mma", action="store_true", help="ablation: chains with one warp per chain instead of chain_mma.cu")
+    ap.add_argument("--fwd-split", action="store_true",
+                    help="ablation: forward chain walk in two pieces, the second overlapped with the dual pass of the first")
     ap.add_argument("--no-pipeline", action="store_true",
                     help="ablation: primal pass + one dual pass per iteration (the loop before the pbar hand-over)")
     args = ap.parse_args()

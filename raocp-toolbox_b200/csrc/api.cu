@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -95,9 +96,12 @@ struct rb_solver {
     // sweep -- and the dual pass is split into the branching part (runs next to the forward chain sweep), the chain part
     // (k_dual_chain) and the leaves
     bool allow_pipe = true;
+    bool pipe_fwd_split = false;    // cut the forward chain walk in two and overlap the second piece with the dual pass of the first
     bool pbar_ready = false;        // prim[cur_i] holds pbar of the next iteration
     int chain_first = 0;            // nodes [chain_first, m) are nonleaf nodes with exactly one child
     int4 *chain_recs = nullptr;     // their packed topology records (launch_dual_chain)
+    int chain_stride = -1;          // > 0: child_first[i] = i + chain_stride on the whole run
+    int chain_yo0 = 0;              // offset of y of node chain_first
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t pev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // fused loop
@@ -258,6 +262,8 @@ void launch_dual(rb_solver *s, cudaStream_t st, int src, int dst, const int *nod
 struct PipeSplit {
     int early;   // nodes [0, early): final once the top of the tree is done (dual pass runs next to the forward levels)
     int cf;      // nodes [early, cf): general lane pass after the sweeps; [cf, m): chain pass; [m, n): leaves
+    int split;   // > 0: the last forward level (chain walker) runs as steps [0, split) and [split, depth), and the chain
+    int mid;     //      dual pass of the nodes [cf, mid) -- final after the first piece -- runs next to the second piece
 };
 bool sweeps_fused(const rb_solver *s) {
     const SweepPlan &pl = s->plan;
@@ -270,6 +276,18 @@ PipeSplit pipe_split(const rb_solver *s) {
     ps.cf = dual_chain_supported(L.nx, L.nu) ? std::max(1, std::min(s->chain_first, L.m)) : L.m;
     const int v0 = sweeps_fused(s) ? 1 : 0;   // first forward level launched after the top
     ps.early = v0 < pl.num_levels ? std::min(ps.cf, s->stage_off[pl.lv[v0].t_lo]) : 0;
+    static const bool no_early = getenv("RB_NO_EARLY") != nullptr;   // ablation knob
+    if (no_early) ps.early = 0;
+    ps.split = 0;
+    ps.mid = ps.cf;
+    if (s->pipe_fwd_split && pl.num_levels > v0 && ps.cf < L.m) {
+        const SweepLevel &lv = pl.lv[pl.num_levels - 1];
+        if (s->allow_mma && lv.num_tiles > 0 && lv.depth >= 6 && s->stage_off[lv.t_lo] >= ps.cf) {
+            ps.split = lv.depth / 2;
+            ps.mid = std::min(L.m, s->stage_off[lv.t_lo + ps.split]);
+            if (ps.mid <= ps.cf) ps.split = 0, ps.mid = ps.cf;
+        }
+    }
     return ps;
 }
 // kernels of the dual pass of the pipelined loop
@@ -277,7 +295,7 @@ int pipe_dual_launches(const rb_solver *s) {
     const Layout &L = s->P.L;
     const PipeSplit ps = pipe_split(s);
     if (ps.cf >= L.m) return (ps.early > 0 ? 1 : 0) + 1;
-    return (ps.early > 0 ? 1 : 0) + 1 + (ps.cf > ps.early ? 1 : 0) + 1;
+    return (ps.early > 0 ? 1 : 0) + 1 + (ps.cf > ps.early ? 1 : 0) + 1 + (ps.split > 0 ? 2 : 0);   // split: + walker piece + dual piece
 }
 int iter_launches(const rb_solver *s) {
     const SweepPlan &pl = s->plan;
@@ -289,7 +307,8 @@ int iter_launches(const rb_solver *s) {
 // the launches of the DP sweeps on `prim` (x, u rows hold xbar, ubar on entry and the projection on exit); evs / nev:
 // optional event after every launch
 int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st, cudaEvent_t *evs = nullptr, int *nev = nullptr,
-                  const std::function<void()> &after_top = nullptr) {
+                  const std::function<void()> &after_top = nullptr, int fwd_split = 0,
+                  const std::function<void()> &after_piece = nullptr) {
     int ne = 0;
     const SweepPlan &pl = s->plan;
     const Layout &L = s->P.L;
@@ -313,7 +332,11 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
         if (evs) cudaEventRecord(evs[ne++], st);
     };
     auto fwd = [&](int v) {
-        if (s->allow_mma && pl.lv[v].num_tiles > 0)
+        if (s->allow_mma && pl.lv[v].num_tiles > 0 && fwd_split > 0 && v == pl.num_levels - 1) {
+            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, 0, fwd_split);
+            if (after_piece) after_piece();
+            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, fwd_split, -1);
+        } else if (s->allow_mma && pl.lv[v].num_tiles > 0)
             launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r);
         else if (tree && s->tree_lv[v].desc)
             launch_tree_fwd(dim3(s->tree_lv[v].num_sub, batch), 32 * s->tree_lv[v].warps, s->tree_smem[1 + v], st, s->P, ctrl,
@@ -635,6 +658,10 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
             recs[i - s->chain_first] = make_int4(j, s->cost_idx[j], yoff[i], L.has_nl_rect ? pb->nl_rect_idx[i] : 0);
         }
         TRY(upload(s, recs.data(), recs.size(), &s->chain_recs));
+        s->chain_yo0 = yoff[std::min(s->chain_first, m)];
+        s->chain_stride = s->chain_first < m ? s->child_first[s->chain_first] - s->chain_first : -1;
+        for (int i = s->chain_first; i < m; ++i)
+            if (s->child_first[i] - i != s->chain_stride) s->chain_stride = -1;
     }
     TRY(upload(s, L.has_leaf_rect ? pb->leaf_rect_idx : nullptr, nl, &tmp_i)); T.leaf_rect_idx = tmp_i;
     TRY(upload(s, pb->cls, m, &tmp_i)); T.cls = tmp_i;
@@ -1380,9 +1407,9 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
     const dim3 nb(1, L.batch);
     cudaStream_t s0 = s->side[0], s1 = s->side[1];
     cudaEvent_t *ev = s->pev;
-    auto dual_lane = [&](cudaStream_t q, int first, int count) {
+    auto dual_lane = [&](cudaStream_t q, int first, int count, bool narrow = false) {
         launch_dual_lane(nb, q, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, nullptr, first,
-                         count, s->prim[src]);
+                         count, s->prim[src], narrow);
     };
     if (have_pbar) {   // kernel projection in place, next to the backward sweeps
         RB_CUDA(s, cudaEventRecord(ev[0], st));
@@ -1399,14 +1426,29 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
         if ((herr = cudaEventRecord(ev[2], st)) != cudaSuccess) return;
         if ((herr = cudaStreamWaitEvent(s1, ev[2], 0)) != cudaSuccess) return;
         if (have_pbar && (herr = cudaStreamWaitEvent(s1, ev[1], 0)) != cudaSuccess) return;
-        dual_lane(s1, 0, ps.early);
+        dual_lane(s1, 0, ps.early, true);   // next to the forward chain walker: as few CTAs as possible
         early_done = true;
     };
-    int rc = launch_sweeps(s, s->ctrl, s->prim[dst], st, nullptr, nullptr, after_top);
+    auto dual_chain = [&](cudaStream_t q, int first, int count) {
+        launch_dual_chain(L.batch, q, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
+                          s->chain_recs + (first - ps.cf), first, count, s->chain_stride, s->chain_yo0 + 3 * (first - ps.cf),
+                          s->prim[src]);
+    };
+    bool piece_done = false;
+    auto after_piece = [&]() {   // the first piece of the forward chain walk is done: its nodes' dual pass starts
+        if (herr != cudaSuccess) return;
+        if ((herr = cudaEventRecord(ev[5], st)) != cudaSuccess) return;
+        if ((herr = cudaStreamWaitEvent(s1, ev[5], 0)) != cudaSuccess) return;
+        if (have_pbar && (herr = cudaStreamWaitEvent(s1, ev[1], 0)) != cudaSuccess) return;
+        dual_chain(s1, ps.cf, ps.mid - ps.cf);
+        piece_done = true;
+    };
+    int rc = launch_sweeps(s, s->ctrl, s->prim[dst], st, nullptr, nullptr, after_top, ps.split, after_piece);
     if (rc != RB_OK) return rc;
     if (herr != cudaSuccess) return fail(s, RB_ERR_CUDA, std::string("pipelined iteration: ") + cudaGetErrorString(herr));
     if (have_pbar) RB_CUDA(s, cudaStreamWaitEvent(st, ev[1], 0));
     const int early = early_done ? ps.early : 0;
+    const int chain_lo = piece_done ? ps.mid : ps.cf;
     if (ps.cf >= L.m) {   // no chain pass: one general pass over the rest
         dual_lane(st, early, L.n - early);
     } else {
@@ -1414,8 +1456,7 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
         RB_CUDA(s, cudaStreamWaitEvent(s1, ev[3], 0));
         dual_lane(s1, early, ps.cf - early);
         dual_lane(s1, L.m, L.n - L.m);
-        launch_dual_chain(L.batch, st, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
-                          s->chain_recs, ps.cf, L.m - ps.cf, s->prim[src]);
+        dual_chain(st, chain_lo, L.m - chain_lo);
         early_done = true;   // s1 carries work that st has to wait for
     }
     if (early_done) {
@@ -1727,7 +1768,7 @@ int rb_profile_iteration(rb_solver *s, float *ms) {
             dual_lane(0, ps.cf);
             RB_CUDA(s, cudaEventRecord(ev[9], st));
             launch_dual_chain(L.batch, st, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
-                              s->chain_recs, ps.cf, L.m - ps.cf, s->prim[src]);
+                              s->chain_recs, ps.cf, L.m - ps.cf, s->chain_stride, s->chain_yo0, s->prim[src]);
             RB_CUDA(s, cudaEventRecord(ev[10], st));
             dual_lane(L.m, L.n - L.m);
             RB_CUDA(s, cudaEventRecord(ev[11], st));
@@ -1745,7 +1786,7 @@ int rb_profile_iteration(rb_solver *s, float *ms) {
     for (auto &e : ev) cudaEventDestroy(e);
     std::swap(s->cur_i, s->old_i);
     s->pbar_ready = pipe;
-    s->launches += iter_launches(s);
+    s->launches += iter_launches(s) - (pipe && pipe_split(s).split > 0 ? 2 : 0);   // profiled: the chain walk in one piece
     return rc;
 }
 
@@ -1763,6 +1804,7 @@ int rb_use_pipeline(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
     if (s->in_loop) return fail(s, RB_ERR_STATE, "rb_use_pipeline() inside a loop");
     s->allow_pipe = enable != 0;
+    s->pipe_fwd_split = enable == 3;   // 3: additionally the forward chain walk in two pieces (measured slower: kept as an ablation)
     for (int i = 0; i < 2; ++i)
         if (s->graph[i]) {
             cudaGraphExecDestroy(s->graph[i]);

@@ -342,7 +342,11 @@ __global__ void __launch_bounds__(128) k_chain_mma_bwd(const __grid_constant__ P
 // ---- forward:  u = K x + R~^-1 r,  x_child = A x + B u -------------------------------------------------------------------
 template <int NX, int NU>
 __global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
-                                                      SweepLevel lv, double *__restrict__ prim, const double *__restrict__ r) {
+                                                      SweepLevel lv, double *__restrict__ prim, const double *__restrict__ r,
+                                                      int d_begin, int d_end) {
+    // steps d_begin <= d < d_end of the walk (d = depth below the head of the chain): a launch starts from the x of depth
+    // d_begin, which the level above (d_begin = 0) or the previous launch has written, so the walk can be cut into
+    // pieces whose nodes' dual pass runs while the next piece walks on
     using D = ChainDims<NX, NU>;
     extern __shared__ __align__(16) double mma_smem[];
     const Layout &L = P.L;
@@ -374,14 +378,14 @@ __global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ P
         }
         cp_async_commit();
     };
-    prefetch(0);
-    prefetch(1);
+    prefetch(d_begin);
+    prefetch(d_begin + 1);
     double w4[F4];   // [A ; B]' of the chain's dynamics row, fragment (2 kb + j) * QT + ob
     if (lv.depth > 1) ld_frags<F4>(w4, P.m.fragABT, tm.dyns[1], lane);
     double xs[D::QT][2];
-    ld_state<NX, NU, false>(X + (long long)tm.nodes[g] * NX, t, xs);   // x of the head was written by the level above
+    ld_state<NX, NU, false>(X + (long long)tm.nodes[d_begin * 8 + g] * NX, t, xs);   // written by the level above / the previous piece
 
-    for (int d = 0; d + 1 < lv.depth && tm.clss[d] >= 0; ++d) {
+    for (int d = d_begin; d < d_end && d + 1 < lv.depth && tm.clss[d] >= 0; ++d) {
         prefetch(d + 2);
         cp_async_wait<2>();
         const double *src = ring + (d % kStages) * 32 * kLaneWords;
@@ -500,10 +504,11 @@ void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, co
 }
 
 void launch_chain_mma_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, double *prim,
-                          const double *r) {
+                          const double *r, int d_begin, int d_end) {
+    if (d_end < 0) d_end = lv.depth;
 #define RB_GO(NX, NU)                                                                                             \
     if (P.L.nx == NX && P.L.nu == NU) {                                                                           \
-        k_chain_mma_fwd<NX, NU><<<mma_grid(lv, P.L.batch), 128, chain_mma_smem_bytes(NX, NU, lv.depth, false), st>>>(P, ctrl, lv, prim, r);        \
+        k_chain_mma_fwd<NX, NU><<<mma_grid(lv, P.L.batch), 128, chain_mma_smem_bytes(NX, NU, lv.depth, false), st>>>(P, ctrl, lv, prim, r, d_begin, d_end);        \
         return;                                                                                                   \
     }
     RB_MMA_DIMS(RB_GO)

@@ -66,13 +66,15 @@ void launch_primal_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, cons
 // the kernel projection k_kproj_node in place)
 void launch_dual_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old,
                       const double *p_new, const double *d_old, double *d_new, double *slots, const int *node_list,
-                      int first, int count, double *pbar);
+                      int first, int count, double *pbar, bool narrow = false);
+// narrow: keep the default lanes per node for a small launch (fewest CTAs: it runs next to a latency-critical kernel)
 // the same pass specialised for a run of nonleaf nodes with ONE child each (the chain part of the tree)
 bool dual_chain_supported(int nx, int nu);
-// recs[i]: packed topology of node first + i = (child, cost-table row of the child, offset of y_i, rectangle row)
+// recs[i]: packed topology of node first + i = (child, cost-table row of the child, offset of y_i, rectangle row);
+// stride > 0: the child of node i is i + stride for the whole run; yo0 = offset of y_first
 void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
                        const double *d_old, double *d_new, double *slots, const int4 *recs, int first, int count,
-                       double *pbar);
+                       int stride, int yo0, double *pbar);
 void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim);
 __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, double *__restrict__ slots,
                         double *__restrict__ last);
@@ -139,8 +141,9 @@ void launch_chain_mma_frags(cudaStream_t st, const Tabs &M, int nx, int nu, int 
                             bool classes);
 void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, const double *prim,
                           double *q, double *r);
+// d_begin, d_end: the steps of the walk to run (depth below the chain heads); d_end < 0 = to the leaves
 void launch_chain_mma_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, double *prim,
-                          const double *r);
+                          const double *r, int d_begin = 0, int d_end = -1);
 
 // ---- shard.cu: one tree sharded by subtree over the GPUs of a box ----------------------------------------------------------
 struct ShardPlan {

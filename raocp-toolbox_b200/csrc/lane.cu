@@ -15,6 +15,7 @@
 //                   (cache.py:290-317)
 //   k_dual_lane   : dbar = d + alpha L(2 p+ - p) (solver.py:44-58), prox of g* (cache.py:321-393), all six residual
 //                   inf-norms (solver.py:63-95,137-141)
+#include <algorithm>
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -641,7 +642,8 @@ template <int NX, int NU, int G, int MINB>
 __global__ void __launch_bounds__(kChainDualThreads, MINB)
     k_dual_chain(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, const double *__restrict__ p_old,
                  const double *__restrict__ p_new, const double *__restrict__ d_old, double *__restrict__ d_new,
-                 double *__restrict__ slots, const int4 *__restrict__ recs, int first, int count, double *pbar) {
+                 double *__restrict__ slots, const int4 *__restrict__ recs, int first, int count, int stride, int yo0,
+                 double *pbar) {
     constexpr int HX = NX / 2, K = (NX + NU) / 2, R = (K + G - 1) / G, NXU = NX + NU;
     const Layout &L = P.L;
     const Topo &T = P.t;
@@ -651,24 +653,22 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
     const int slot = (blockIdx.x * blockDim.x + tid) / G;
     const bool active = slot < count;
     const int node = first + (active ? slot : 0);   // idle groups of the last CTA repeat the first node, stores masked
-    // one global round trip for everything the row loads depend on: the control block and the node's packed topology
-    // record (child, cost-table row of the child, offset of y_i, rectangle row), both requested before `done` is tested
+    // ONE global round trip before the arithmetic starts: the control block, the node's packed topology record (child,
+    // cost-table row of the child, -, rectangle row) and the rows themselves are all requested before `done` is tested.
+    // In a breadth-first numbering every stage of the chain part has the same width, so the child of node i is
+    // i + stride (rb_create checks it; stride <= 0: take it from the record) and y_i starts at yo0 + 3 (i - first).
     const int done = ctrl->done;
     const double alpha = ctrl->alpha;
     const int4 rec = __ldg(recs + (node - first));
-    if (done) return;
-    const double inv_alpha = 1.0 / alpha;
     const double *Po = p_old + (long long)blockIdx.y * L.np_pad;
     const double *Pn = p_new + (long long)blockIdx.y * L.np_pad;
     const double *Do = d_old + (long long)blockIdx.y * L.nd_pad;
     double *Dn = d_new + (long long)blockIdx.y * L.nd_pad;
     double *Pb = pbar + (long long)blockIdx.y * L.np_pad;
-    const int j = rec.x;
+    const int j = stride > 0 ? node + stride : rec.x;
     const long long e0 = j - 1;
-    const int ci = rec.y, yo = rec.z;
+    const int yo = yo0 + 3 * (node - first);
     const bool rect = L.has_nl_rect;
-    const long long ri = (long long)rec.w * NXU;
-    const double prob = T.cond_prob[j];
 
     // ---- all row loads of the node, issued back to back ----------------------------------------------------------------
     double2 o[R], n[R], de[R], mm[R], d7v[R];
@@ -689,13 +689,22 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
         de[r] = __ldg(reinterpret_cast<const double2 *>(Do + off_e(kk)));
         d7v[r] = rect ? __ldg(reinterpret_cast<const double2 *>(Do + L.d7 + (long long)node * NXU + 2 * kk))
                       : make_double2(0.0, 0.0);
-        mm[r] = __ldg(reinterpret_cast<const double2 *>(isx ? M.sq_d + ci * NX + 2 * kk : M.sr_d + ci * NU + 2 * (kk - HX)));
     }
     // scalars of the node and of the edge (same addresses for the lanes of a group: one request)
     const double to = Po[L.ptau + j], tn = Pn[L.ptau + j], do5 = Do[L.d5 + e0], do6 = Do[L.d6 + e0];
     const double so = Po[L.ps + node], sn = Pn[L.ps + node], do2 = Do[L.d2 + node];
     const int ey = g < 2 ? g : 2;   // y_i = [y_a; y_b; y_last]: lanes 0, 1, 2 take one entry each
     const double yold = Po[L.py + yo + ey], ynew = Pn[L.py + yo + ey], do1 = Do[L.d1 + yo + ey];
+    const double prob = T.cond_prob[j];
+    if (done) return;
+    const double inv_alpha = 1.0 / alpha;
+    const int ci = rec.y;
+    const long long ri = (long long)rec.w * NXU;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {   // cost-table rows of the edge (a handful of rows per tree: L1 hits)
+        const int kk = valid[r] ? g + G * r : 0;
+        mm[r] = __ldg(reinterpret_cast<const double2 *>(kk < HX ? M.sq_d + ci * NX + 2 * kk : M.sr_d + ci * NU + 2 * (kk - HX)));
+    }
 
     ResidLane Rs;
     Rs.init();
@@ -837,14 +846,13 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
 // (ybar_i, taubar_j, sbar_j) -- the part of prox_f that does not depend on the DP sweeps; it runs next to them on its
 // own stream.  One thread per node; the sums follow the association of k_primal_lane's lane-group reductions.
 // ====================================================================================================================
-__global__ void __launch_bounds__(256) k_kproj_node(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
-                                                     double *__restrict__ prim) {
+__global__ void __launch_bounds__(1024) k_kproj_node(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
+                                                      double *__restrict__ prim) {
     if (ctrl->done) return;
     const Layout &L = P.L;
     const Topo &T = P.t;
-    const int node = blockIdx.x * blockDim.x + threadIdx.x;
-    if (node >= L.m) return;
     double *Pb = prim + (long long)blockIdx.y * L.np_pad;
+    for (int node = blockIdx.x * blockDim.x + threadIdx.x; node < L.m; node += gridDim.x * blockDim.x) {
     const int c0 = T.child_first[node], cc = T.child_count[node];
     const double a = T.risk_alpha[node], den = a * a + 3.0;
     double *y = Pb + L.py + T.yoff[node], *tau = Pb + L.ptau + c0, *sv = Pb + L.ps + c0;
@@ -868,6 +876,7 @@ __global__ void __launch_bounds__(256) k_kproj_node(const __grid_constant__ Para
     }
     const double wsum = ((wv[0] + wv[1]) + (wv[2] + wv[3])) + ((wv[4] + wv[5]) + (wv[6] + wv[7]));
     y[2 * cc] = ylast - wsum;
+    }
 }
 
 // ---- host launchers: lanes per node chosen from the row length (pairs of doubles per lane and round) ----------------------
@@ -883,19 +892,29 @@ void launch_primal_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, cons
 
 void launch_dual_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old,
                       const double *p_new, const double *d_old, double *d_new, double *slots, const int *node_list,
-                      int first, int count, double *pbar) {
+                      int first, int count, double *pbar, bool narrow) {
     if (count <= 0) return;
     const int G = lane_group_width(P.L.nx);
     const dim3 grid((count * G + kLaneThreads - 1) / kLaneThreads, nodes_batch.y);
-    // a grid that fits the GPU at two CTAs per SM runs the 128-register build (no spills); a bigger one the 80-register
-    // build with three CTAs per SM
-    const bool roomy = (long long)grid.x * grid.y <= 2 * 148;
-#define RB_GO(G_, B_) \
-    k_dual_lane<G_, B_><<<grid, kLaneThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, node_list, first, count, pbar)
-    if (G == 4 && roomy) RB_GO(4, 2);
-    else if (G == 4) RB_GO(4, 3);
-    else if (roomy) RB_GO(8, 2);
-    else RB_GO(8, 3);
+    // A launch over a few thousand nodes (the branching top of the tree, the leaves) is a handful of warps per SM, each
+    // a long serial instruction stream: such launches get more lanes per node (16: a row is one round per lane, and
+    // there are four times as many warps to spread over the SMs) and the 128-register build (no spills); a launch that
+    // fills the GPU runs the 80-register build with three CTAs per SM
+    const long long threads4 = (long long)count * 4 * nodes_batch.y;
+    static const int force_g = getenv("RB_SMALL_G") ? atoi(getenv("RB_SMALL_G")) : 0;   // ablation knob
+    int Gs = threads4 <= 148LL * kLaneThreads / 2 ? 16 : (threads4 <= 148LL * kLaneThreads ? 8 : G);
+    if (force_g == 4 || narrow) Gs = G;
+    if (force_g == 8 && Gs == 16) Gs = 8;
+    const dim3 grid_s((count * Gs + kLaneThreads - 1) / kLaneThreads, nodes_batch.y);
+    const bool roomy = (long long)grid_s.x * grid_s.y <= 2 * 148;
+#define RB_GO(G_, B_, GRID_) \
+    k_dual_lane<G_, B_><<<GRID_, kLaneThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, node_list, first, count, pbar)
+    if (roomy && Gs == 16) RB_GO(16, 2, grid_s);
+    else if (roomy && Gs == 8) RB_GO(8, 2, grid_s);
+    else if (G == 4 && roomy) RB_GO(4, 2, grid);
+    else if (G == 4) RB_GO(4, 3, grid);
+    else if (roomy) RB_GO(8, 2, grid);
+    else RB_GO(8, 3, grid);
 #undef RB_GO
 }
 
@@ -912,7 +931,7 @@ bool dual_chain_supported(int nx, int nu) {
 
 void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
                        const double *d_old, double *d_new, double *slots, const int4 *recs, int first, int count,
-                       double *pbar) {
+                       int stride, int yo0, double *pbar) {
     if (count <= 0) return;
     // resident CTAs per SM the kernel is compiled for: 3 (168 registers, no spills) or 4 (128 registers, ~40 words
     // spilled to L1); RB_CHAIN_DUAL_MINB overrides for ablation runs
@@ -920,22 +939,38 @@ void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, 
         const char *e = getenv("RB_CHAIN_DUAL_MINB");
         return e && atoi(e) == 4 ? 4 : 3;
     }();
-#define RB_GO(NX, NU, G)                                                                                             \
-    if (P.L.nx == NX && P.L.nu == NU) {                                                                              \
+    static const bool wide = [] {   // ablation: 8 lanes per node where 4 is the default
+        const char *e = getenv("RB_CHAIN_DUAL_G");
+        return e && atoi(e) == 8;
+    }();
+#define RB_GO_G(NX, NU, G)                                                                                           \
+    {                                                                                                                \
         const dim3 grid((count * G + kChainDualThreads - 1) / kChainDualThreads, batch);                             \
         if (minb == 4)                                                                                               \
-            k_dual_chain<NX, NU, G, 4><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, pbar); \
+            k_dual_chain<NX, NU, G, 4><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, stride, yo0, pbar); \
         else                                                                                                         \
-            k_dual_chain<NX, NU, G, 3><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, pbar); \
+            k_dual_chain<NX, NU, G, 3><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, stride, yo0, pbar); \
         return;                                                                                                      \
+    }
+#define RB_GO(NX, NU, G)                                                                                             \
+    if (P.L.nx == NX && P.L.nu == NU) {                                                                              \
+        if (wide && G == 4) RB_GO_G(NX, NU, 8)                                                                       \
+        RB_GO_G(NX, NU, G)                                                                                           \
     }
     RB_CHAIN_DUAL_DIMS(RB_GO)
 #undef RB_GO
 }
 
 void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim) {
-    const dim3 grid((P.L.m + 255) / 256, batch);
-    k_kproj_node<<<grid, 256, 0, st>>>(P, ctrl, prim);
+    // The pass runs next to the backward chain walker, which keeps one latency-critical warp per SM sub-partition on
+    // ~128 SMs: a few fat CTAs (they land on the SMs the walker leaves idle) disturb it less than a grid spread over all
+    // SMs (cfg3, L2 flushed before every iteration: 9086 it/s with 16 CTAs of 1024 threads against 7702 with 230 CTAs of
+    // 256).  RB_KPROJ_CTAS: ablation knob.
+    static const int cap = getenv("RB_KPROJ_CTAS") ? atoi(getenv("RB_KPROJ_CTAS")) : 16;   // 0: one thread per node, 256-thread CTAs
+    const int threads = cap > 0 ? 1024 : 256;
+    int ctas = (P.L.m + threads - 1) / threads;
+    if (cap > 0) ctas = std::min(ctas, std::max(1, cap / batch));
+    k_kproj_node<<<dim3(ctas, batch), threads, 0, st>>>(P, ctrl, prim);
 }
 
 }  // namespace rb

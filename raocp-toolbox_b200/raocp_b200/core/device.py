@@ -217,7 +217,9 @@ class DeviceSolver:
         self._call("rb_use_graphs", 1 if enable else 0)
 
     def use_pipeline(self, enable=True):
-        self._call("rb_use_pipeline", 1 if enable else 0)
+        """True / 1: pipelined loop (default); 3: additionally the forward chain walk in two pieces, overlapped with the
+        dual pass (ablation); False / 0: primal pass + one dual pass per iteration"""
+        self._call("rb_use_pipeline", int(enable))
 
     def pipeline_info(self):
         """(early, chain_first, chain_nodes): the node ranges of the pipelined dual pass (rb_pipeline_info)"""
