@@ -618,6 +618,7 @@ __global__ void __launch_bounds__(256, 2) k_dual_tile(const __grid_constant__ Pa
         atomicMax(reinterpret_cast<unsigned long long *>(slots + (long long)blockIdx.y * 6 + threadIdx.x), mval);
     }
     if (threadIdx.x == 0 && blockflags) atomicOr(&ctrl->status, blockflags);
+    if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0) ctrl->pending = 1;
 }
 
 cudaError_t tile_kernels_set_smem(size_t primal_bytes, size_t dual_bytes) {
@@ -646,28 +647,38 @@ void launch_dual_tile(bool diag, dim3 grid, size_t smem, cudaStream_t st, const 
 // max(xi0, xi1, xi2) <= tol.
 __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, double *__restrict__ slots,
                         double *__restrict__ last) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (ctrl->done) return;
-    const int it = ctrl->iters;
-    double *hist = ctrl->hist;
-    const int hist_capacity = ctrl->hist_capacity, max_iters = ctrl->max_iters;
-    const double tol = ctrl->tol;
-    bool all_ok = true;
-    for (int b = 0; b < P.L.batch; ++b) {
-        double *s = slots + (long long)b * 6;
-        const double err = fmax(s[0], fmax(s[1], s[2]));
-        if (!(err <= tol)) all_ok = false;
-        for (int i = 0; i < 6; ++i)
-            if (s[i] != s[i]) ctrl->status |= 2;   // a NaN maximum: some iterate entry is not finite
-        if (hist && it < hist_capacity)
-            for (int i = 0; i < 6; ++i) hist[((long long)it * P.L.batch + b) * 6 + i] = s[i];
-        for (int i = 0; i < 6; ++i) {
-            last[b * 6 + i] = s[i];
-            s[i] = 0.0;
+    // One warp.  The control block and the first instances' slots are requested together (the kernel is a chain of
+    // dependent global round trips otherwise, and it sits on the critical path of every iteration); a launch with
+    // nothing pending -- the loop tests iteration k at the head of iteration k + 1 and again before the host reads the
+    // norms -- is a no-op.
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const int batch = P.L.batch;
+    const Ctrl c = *ctrl;
+    const int total = batch * 6;
+    double mine = lane < total ? slots[lane] : 0.0;
+    if (c.done || !c.pending) return;
+    const int it = c.iters;
+    bool ok = true, nan = false;
+    for (int base = 0; base < total; base += 32) {
+        const int i = base + lane;
+        if (base > 0) mine = i < total ? slots[i] : 0.0;
+        if (i < total) {
+            if (mine != mine) nan = true;
+            if (i % 6 < 3 && !(mine <= c.tol)) ok = false;   // max(xi0, xi1, xi2) <= tol  <=>  each of them is
+            if (c.hist && it < c.hist_capacity) c.hist[(long long)it * total + i] = mine;
+            last[i] = mine;
+            slots[i] = 0.0;
         }
     }
-    ctrl->iters = it + 1;
-    if (it >= max_iters || all_ok) ctrl->done = 1;
+    const bool all_ok = __all_sync(0xffffffffu, ok);
+    const bool any_nan = __any_sync(0xffffffffu, nan);
+    if (lane == 0) {
+        if (any_nan) ctrl->status |= 2;   // a NaN maximum: some iterate entry is not finite
+        ctrl->iters = it + 1;
+        ctrl->pending = 0;
+        if (it >= c.max_iters || all_ok) ctrl->done = 1;
+    }
 }
 
 }  // namespace rb

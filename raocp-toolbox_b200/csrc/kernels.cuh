@@ -35,7 +35,7 @@ struct Ctrl {
     double alpha;    // step size alpha_1 = alpha_2 (solver.py:116-118)
     double *hist;    // [hist_capacity][batch][6] residual history or null
     int hist_capacity;
-    int pad;
+    int pending;     // set by the dual pass: `slots` hold the residual maxima of an iteration k_check has not tested yet
 };
 // tiles of consecutive nodes for the node-parallel passes (fused.cu): tiles[t] = (first node, one past the last);
 // a tile is either all nonleaf or all leaf nodes

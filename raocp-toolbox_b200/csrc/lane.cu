@@ -622,6 +622,7 @@ __global__ void __launch_bounds__(kLaneThreads, MINB) k_dual_lane(const __grid_c
         atomicMax(reinterpret_cast<unsigned long long *>(slots + (long long)blockIdx.y * 6 + tid), mval);
     }
     if (tid == 0 && blockflags) atomicOr(&ctrl->status, blockflags);
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) ctrl->pending = 1;
     if (Pb && sbar_set && g == 0) Pb[L.ps + node] = sbar;
 }
 
@@ -839,6 +840,7 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
         for (int wv = 1; wv < kChainDualThreads / 32; ++wv) mval = blockmax[wv][tid] > mval ? blockmax[wv][tid] : mval;
         atomicMax(reinterpret_cast<unsigned long long *>(slots + (long long)blockIdx.y * 6 + tid), mval);
     }
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) ctrl->pending = 1;
 }
 
 // ====================================================================================================================
@@ -903,8 +905,10 @@ void launch_dual_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, Ctrl *
     const long long threads4 = (long long)count * 4 * nodes_batch.y;
     static const int force_g = getenv("RB_SMALL_G") ? atoi(getenv("RB_SMALL_G")) : 0;   // ablation knob
     int Gs = threads4 <= 148LL * kLaneThreads / 2 ? 16 : (threads4 <= 148LL * kLaneThreads ? 8 : G);
-    if (force_g == 4 || narrow) Gs = G;
-    if (force_g == 8 && Gs == 16) Gs = 8;
+    static const int early_g = getenv("RB_EARLY_G") ? atoi(getenv("RB_EARLY_G")) : 0;   // ablation knob
+    if (narrow) Gs = early_g == 8 || early_g == 16 ? early_g : G;
+    else if (force_g == 4) Gs = G;
+    else if (force_g == 8 && Gs == 16) Gs = 8;
     const dim3 grid_s((count * Gs + kLaneThreads - 1) / kLaneThreads, nodes_batch.y);
     const bool roomy = (long long)grid_s.x * grid_s.y <= 2 * 148;
 #define RB_GO(G_, B_, GRID_) \
