@@ -239,8 +239,8 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_primal_lane(const __grid_co
 }
 
 // ====================================================================================================================
-template <int kOct, int MINB>
-__global__ void __launch_bounds__(kLaneThreads, MINB) k_dual_lane(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
+template <int kOct, int MINB, int BT = kLaneThreads>
+__global__ void __launch_bounds__(BT, MINB) k_dual_lane(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
                                                            const double *__restrict__ p_old, const double *__restrict__ p_new,
                                                            const double *__restrict__ d_old, double *__restrict__ d_new,
                                                            double *__restrict__ slots, const int *__restrict__ node_list,
@@ -259,7 +259,8 @@ __global__ void __launch_bounds__(kLaneThreads, MINB) k_dual_lane(const __grid_c
     __shared__ double soc_scale[kLaneMaxChildren][kMaxNodesPerCta];
     __shared__ double soc_last[kLaneMaxChildren][kMaxNodesPerCta];
     __shared__ int child_cost[kLaneMaxChildren][kMaxNodesPerCta];
-    __shared__ unsigned long long blockmax[kLaneThreads / 32][6];
+    static_assert(BT / kOct <= kMaxNodesPerCta, "per-node shared arrays are sized for kMaxNodesPerCta nodes");
+    __shared__ unsigned long long blockmax[BT / 32][6];
     __shared__ int blockflags;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = tid & (kOct - 1), ns = tid / kOct;
     if (tid == 0) blockflags = 0;
@@ -618,7 +619,7 @@ __global__ void __launch_bounds__(kLaneThreads, MINB) k_dual_lane(const __grid_c
     __syncthreads();
     if (tid < 6) {
         unsigned long long mval = blockmax[0][tid];
-        for (int wv = 1; wv < kLaneThreads / 32; ++wv) mval = blockmax[wv][tid] > mval ? blockmax[wv][tid] : mval;
+        for (int wv = 1; wv < BT / 32; ++wv) mval = blockmax[wv][tid] > mval ? blockmax[wv][tid] : mval;
         atomicMax(reinterpret_cast<unsigned long long *>(slots + (long long)blockIdx.y * 6 + tid), mval);
     }
     if (tid == 0 && blockflags) atomicOr(&ctrl->status, blockflags);
@@ -906,6 +907,11 @@ void launch_dual_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, Ctrl *
     static const int force_g = getenv("RB_SMALL_G") ? atoi(getenv("RB_SMALL_G")) : 0;   // ablation knob
     int Gs = threads4 <= 148LL * kLaneThreads / 2 ? 16 : (threads4 <= 148LL * kLaneThreads ? 8 : G);
     static const int early_g = getenv("RB_EARLY_G") ? atoi(getenv("RB_EARLY_G")) : 0;   // ablation knob
+    if (narrow && early_g == 85 && G == 4) {   // 8 lanes per node, 512-thread CTAs: the same few SMs, shorter warps
+        const dim3 grid_w((count * 8 + 511) / 512, nodes_batch.y);
+        k_dual_lane<8, 1, 512><<<grid_w, 512, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, node_list, first, count, pbar);
+        return;
+    }
     if (narrow) Gs = early_g == 8 || early_g == 16 ? early_g : G;
     else if (force_g == 4) Gs = G;
     else if (force_g == 8 && Gs == 16) Gs = 8;
