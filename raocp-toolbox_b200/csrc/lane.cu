@@ -654,7 +654,7 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = tid & (G - 1);
     const int slot = (blockIdx.x * blockDim.x + tid) / G;
     const bool active = slot < count;
-    const int node = first + (active ? slot : 0);   // idle groups of the last CTA repeat the first node, stores masked
+    const int node = first + (active ? slot : 0);   // idle groups of the last CTA repeat the first node: stores and maxima masked
     // ONE global round trip before the arithmetic starts: the control block, the node's packed topology record (child,
     // cost-table row of the child, -, rectangle row) and the rows themselves are all requested before `done` is tested.
     // In a breadth-first numbering every stage of the chain part has the same width, so the child of node i is
@@ -689,9 +689,11 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
         o[r] = __ldg(reinterpret_cast<const double2 *>(Po + off_p(kk)));
         n[r] = __ldg(reinterpret_cast<const double2 *>(Pn + off_p(kk)));
         de[r] = __ldg(reinterpret_cast<const double2 *>(Do + off_e(kk)));
-        d7v[r] = rect ? __ldg(reinterpret_cast<const double2 *>(Do + L.d7 + (long long)node * NXU + 2 * kk))
-                      : make_double2(0.0, 0.0);
-    }
+        if (MINB <= 3)
+            d7v[r] = rect ? __ldg(reinterpret_cast<const double2 *>(Do + L.d7 + (long long)node * NXU + 2 * kk))
+                          : make_double2(0.0, 0.0);
+        else if (rect) pf(Do + L.d7 + (long long)node * NXU + 2 * kk);   // 128-register build: d7 is fetched into L1 now and
+    }                                                                    // read in the update phase
     // scalars of the node and of the edge (same addresses for the lanes of a group: one request)
     const double to = Po[L.ptau + j], tn = Pn[L.ptau + j], do5 = Do[L.d5 + e0], do6 = Do[L.d6 + e0];
     const double so = Po[L.ps + node], sn = Pn[L.ps + node], do2 = Do[L.d2 + node];
@@ -711,87 +713,8 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
     ResidLane Rs;
     Rs.init();
     int bad = 0;
-    // ---- second-order cone of the edge: [d3; d4; d5; d6] (cones.py:113-132) ---------------------------------------------
-    double2 w[R];
-    double ss = 0.0;
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        w[r].x = dual_w(de[r].x, mm[r].x * (2 * n[r].x - o[r].x), alpha, inv_alpha);
-        w[r].y = dual_w(de[r].y, mm[r].y * (2 * n[r].y - o[r].y), alpha, inv_alpha);
-        if (valid[r]) {
-            ss = fma(w[r].x, w[r].x, ss);
-            ss = fma(w[r].y, w[r].y, ss);
-        }
-    }
-    const double ht = 0.5 * (2 * tn - to), hdt = 0.5 * (tn - to);
-    const double w5 = dual_w(do5, ht, alpha, inv_alpha) - 0.5;
-    const double w6 = dual_w(do6, ht, alpha, inv_alpha) + 0.5;
-    if (g == 0) ss = fma(w5, w5, ss);
-    ss = oct_sum<G>(ss);
-    double scale, last;
-    {
-        const double rr = sqrt(ss);
-        if (rr <= w6) {          // inside the cone: projection = w
-            scale = 1.0;
-            last = w6;
-        } else if (rr <= -w6) {  // inside the polar cone: projection = 0
-            scale = 0.0;
-            last = 0.0;
-        } else {
-            last = (rr + w6) / 2;
-            scale = last / rr;
-        }
-    }
-    // ---- the [x; u] row: d3 / d4 of the edge, d7 of the node, residual rows, [xbar; ubar] ---------------------------------
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        double2 lo2 = make_double2(0.0, 0.0), hi2 = lo2;
-        if (rect) {
-            const int kk = valid[r] ? g + G * r : 0;
-            lo2 = __ldg(reinterpret_cast<const double2 *>(M.nl_lo + ri + 2 * kk));
-            hi2 = __ldg(reinterpret_cast<const double2 *>(M.nl_hi + ri + 2 * kk));
-        }
-        auto elem = [&](double ov, double nv, double dol, double mv, double wv, double d7old, double lo_b, double hi_b,
-                        double &dnew, double &d7new, double &pb) {
-            const double z = 2 * nv - ov, dlt = nv - ov;
-            dnew = alpha * (wv - scale * wv);
-            const double dd = dol - dnew;
-            const double xi2 = Rs.dual(dd, mv * dlt, inv_alpha);
-            double g1 = mv * dd, g2 = mv * xi2;
-            d7new = 0.0;
-            if (rect) {   // rectangle on [x; u] (cache.py:367-371)
-                const double w7 = dual_w(d7old, z, alpha, inv_alpha);
-                d7new = alpha * (w7 - box_clip_select(w7, lo_b, hi_b, bad));
-                const double dd7 = d7old - d7new;
-                g1 += dd7;
-                g2 += Rs.dual(dd7, dlt, inv_alpha);
-            }
-            Rs.primal(dlt, g1, g2, inv_alpha);
-            pb = nv - alpha * (mv * dnew + d7new);   // operators.py:74-87 applied to d+
-        };
-        double dn0, dn1, s0, s1, b0, b1;
-        elem(o[r].x, n[r].x, de[r].x, mm[r].x, w[r].x, d7v[r].x, lo2.x, hi2.x, dn0, s0, b0);
-        elem(o[r].y, n[r].y, de[r].y, mm[r].y, w[r].y, d7v[r].y, lo2.y, hi2.y, dn1, s1, b1);
-        if (valid[r] && active) {
-            const int kk = g + G * r;
-            *reinterpret_cast<double2 *>(Dn + off_e(kk)) = make_double2(dn0, dn1);
-            if (rect) *reinterpret_cast<double2 *>(Dn + L.d7 + (long long)node * NXU + 2 * kk) = make_double2(s0, s1);
-            *reinterpret_cast<double2 *>(Pb + off_p(kk)) = make_double2(b0, b1);
-        }
-    }
-    // ---- d5, d6 and the tau_j residual row (every lane computes, lane 0 stores) ---------------------------------------------
-    {
-        const double dn5 = alpha * (w5 - scale * w5), dn6 = alpha * (w6 - last);
-        const double dd5 = do5 - dn5, dd6 = do6 - dn6;
-        const double x5 = Rs.dual(dd5, hdt, inv_alpha), x6 = Rs.dual(dd6, hdt, inv_alpha);
-        Rs.primal(tn - to, 0.5 * (dd5 + dd6), 0.5 * (x5 + x6), inv_alpha);
-        if (g == 0 && active) {
-            Dn[L.d5 + e0] = dn5;
-            Dn[L.d6 + e0] = dn6;
-            Pb[L.ptau + j] = tn - alpha * (0.5 * (dn5 + dn6));
-        }
-    }
-    // ---- d1, d2 (risk block) and the y_i, s_i residual rows ----------------------------------------------------------------
+    // ---- d1, d2 (risk block) and the y_i, s_i residual rows: first, while the rows are still in flight -- it only needs
+    //      the scalars, and they are dead (registers free) before the row phases start -----------------------------------------
     {
         const double b = g == 0 ? prob : (g == 2 ? 1.0 : 0.0);   // b_i = [pi; 0; 1] (risks.py:34-35); lanes >= 3 idle
         const bool own = g < 3;
@@ -822,6 +745,102 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
             Dn[L.d2 + node] = dn2;
             Pb[L.ps + node] = sn - alpha * dn2;
         }
+    }
+    // ---- second-order cone of the edge: [d3; d4; d5; d6] (cones.py:113-132) ---------------------------------------------
+    double ss = 0.0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double wx = dual_w(de[r].x, mm[r].x * (2 * n[r].x - o[r].x), alpha, inv_alpha);
+        const double wy = dual_w(de[r].y, mm[r].y * (2 * n[r].y - o[r].y), alpha, inv_alpha);
+        if (valid[r]) {
+            ss = fma(wx, wx, ss);
+            ss = fma(wy, wy, ss);
+        }
+    }
+    const double ht = 0.5 * (2 * tn - to), hdt = 0.5 * (tn - to);
+    const double w5 = dual_w(do5, ht, alpha, inv_alpha) - 0.5;
+    const double w6 = dual_w(do6, ht, alpha, inv_alpha) + 0.5;
+    if (g == 0) ss = fma(w5, w5, ss);
+    ss = oct_sum<G>(ss);
+    double scale, last;
+    {
+        const double rr = sqrt(ss);
+        if (rr <= w6) {          // inside the cone: projection = w
+            scale = 1.0;
+            last = w6;
+        } else if (rr <= -w6) {  // inside the polar cone: projection = 0
+            scale = 0.0;
+            last = 0.0;
+        } else {
+            last = (rr + w6) / 2;
+            scale = last / rr;
+        }
+    }
+    // ---- the [x; u] row: d3 / d4 of the edge, d7 of the node, residual rows, [xbar; ubar] ---------------------------------
+    // `dep` is 0 (scale >= 0) but only known once the cone is classified: the loads of this phase carry it in their
+    // index, so that the compiler cannot hoist them above the reduction and keep their registers busy across it
+    const int dep = MINB > 3 ? (__double2hiint(scale) >> 31) : 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        double2 lo2 = make_double2(0.0, 0.0), hi2 = lo2;
+        if (rect) {
+            const int kk = (valid[r] ? g + G * r : 0) + dep;
+            lo2 = __ldg(reinterpret_cast<const double2 *>(M.nl_lo + ri + 2 * kk));
+            hi2 = __ldg(reinterpret_cast<const double2 *>(M.nl_hi + ri + 2 * kk));
+            if (MINB > 3) d7v[r] = __ldg(reinterpret_cast<const double2 *>(Do + L.d7 + (long long)node * NXU + 2 * kk));
+        } else if (MINB > 3) {
+            d7v[r] = make_double2(0.0, 0.0);
+        }
+        if (MINB > 3) {   // cost-table row again (L1) instead of 16 registers across the cone phase
+            const int kk = (valid[r] ? g + G * r : 0) + dep;
+            mm[r] = __ldg(reinterpret_cast<const double2 *>(kk < HX ? M.sq_d + ci * NX + 2 * kk : M.sr_d + ci * NU + 2 * (kk - HX)));
+        }
+        auto elem = [&](double ov, double nv, double dol, double mv, double d7old, double lo_b, double hi_b, double &dnew,
+                        double &d7new, double &pb) {
+            const double z = 2 * nv - ov, dlt = nv - ov;
+            const double wv = dual_w(dol, mv * z, alpha, inv_alpha);   // as in the cone phase, bit for bit (not kept: registers)
+            dnew = alpha * (wv - scale * wv);
+            const double dd = dol - dnew;
+            const double xi2 = Rs.dual(dd, mv * dlt, inv_alpha);
+            double g1 = mv * dd, g2 = mv * xi2;
+            d7new = 0.0;
+            if (rect) {   // rectangle on [x; u] (cache.py:367-371)
+                const double w7 = dual_w(d7old, z, alpha, inv_alpha);
+                d7new = alpha * (w7 - box_clip_select(w7, lo_b, hi_b, bad));
+                const double dd7 = d7old - d7new;
+                g1 += dd7;
+                g2 += Rs.dual(dd7, dlt, inv_alpha);
+            }
+            Rs.primal(dlt, g1, g2, inv_alpha);
+            pb = nv - alpha * (mv * dnew + d7new);   // operators.py:74-87 applied to d+
+        };
+        double dn0, dn1, s0, s1, b0, b1;
+        elem(o[r].x, n[r].x, de[r].x, mm[r].x, d7v[r].x, lo2.x, hi2.x, dn0, s0, b0);
+        elem(o[r].y, n[r].y, de[r].y, mm[r].y, d7v[r].y, lo2.y, hi2.y, dn1, s1, b1);
+        if (valid[r] && active) {
+            const int kk = g + G * r;
+            *reinterpret_cast<double2 *>(Dn + off_e(kk)) = make_double2(dn0, dn1);
+            if (rect) *reinterpret_cast<double2 *>(Dn + L.d7 + (long long)node * NXU + 2 * kk) = make_double2(s0, s1);
+            *reinterpret_cast<double2 *>(Pb + off_p(kk)) = make_double2(b0, b1);
+        }
+    }
+    // ---- d5, d6 and the tau_j residual row (every lane computes, lane 0 stores) ---------------------------------------------
+    {
+        const double dn5 = alpha * (w5 - scale * w5), dn6 = alpha * (w6 - last);
+        const double dd5 = do5 - dn5, dd6 = do6 - dn6;
+        const double x5 = Rs.dual(dd5, hdt, inv_alpha), x6 = Rs.dual(dd6, hdt, inv_alpha);
+        Rs.primal(tn - to, 0.5 * (dd5 + dd6), 0.5 * (x5 + x6), inv_alpha);
+        if (g == 0 && active) {
+            Dn[L.d5 + e0] = dn5;
+            Dn[L.d6 + e0] = dn6;
+            Pb[L.ptau + j] = tn - alpha * (0.5 * (dn5 + dn6));
+        }
+    }
+    // The idle groups of the last CTA walked node `first` a second time -- possibly AFTER its own group had replaced p
+    // by pbar: whatever they computed must not reach the maxima
+    if (!active) {
+        Rs.init();
+        bad = 0;
     }
     // block-level reduction of the six maxima (as bit patterns), one atomic per slot per block.  Warp level: two
     // 32-bit redux.sync per slot (the high words, then the low words of the lanes that hold the maximal high word)
