@@ -180,7 +180,7 @@ def run_ours(args, rank, world, local_rank):
     solver = r.core.Solver(problem, batch=batch, dedup=not args.no_dedup, device=local_rank, verbose=False)
     solver.cache.device_solver.use_tree_kernels(args.tree_mode)
     solver.cache.device_solver.use_mma_sweeps(not args.no_mma)
-    solver.cache.device_solver.use_pipeline(0 if args.no_pipeline else (3 if args.fwd_split else 1))
+    solver.cache.device_solver.use_pipeline(0 if args.no_pipeline else (3 if args.fwd_split else (4 if args.no_risk_split else 1)))
     dev = solver.cache.device_solver
     dev.synchronize()
     t_setup = time.perf_counter() - t0
@@ -310,11 +310,15 @@ def run_ours(args, rank, world, local_rank):
     if pipelined:
         p_node = flat.nx + flat.nu + 3 + 2            # x_i, u_i, y_i (2c+1 = 3), tau_j, s_i
         d_node = 3 + 1 + 2 * (flat.nx + flat.nu) + 2  # d1_i, d2_i, d3_j, d4_j, d5_j, d6_j, d7_i
+        if not args.no_risk_split:                    # y_i, s_i, d1_i, d2_i are k_dual_risk_chain's (under the sweeps)
+            p_node -= 4
+            d_node -= 4
         b_kernel = 16 * batch * n_chain * (p_node + d_node)
         b_moved = 8 * batch * n_chain * (3 * p_node + 2 * d_node)
         t_kernel = float(cold_parts[1]) * 1e-3
         kname = (f"chain dual pass k_dual_chain<{flat.nx},{flat.nu}> over {n_chain} of {flat.n} nodes (L, dual half step, "
-                 "prox of g*, six residual norms, pbar of the next iteration)")
+                 "prox of g*, six residual norms, pbar of the next iteration"
+                 + ("" if args.no_risk_split else "; the risk block d1, d2 of these nodes runs under the sweeps") + ")")
         traffic = TRAFFIC.get((args.workload, batch, not args.no_dedup))
     else:
         b_kernel = b_moved = 8 * batch * (2 * flat.np_ + 2 * flat.nd_)
@@ -391,6 +395,8 @@ def main():
     ap.add_argument("--tree-mode", type=int, default=2, choices=[0, 1, 2],
                     help="ablation: branching sweep levels with sweeps.cu (0), tree_sweeps.cu per level (1), fused with the top (2)")
     ap.add_argument("--no-mma", action="store_true", help="ablation: chains with one warp per chain instead of chain_mma.cu")
+    ap.add_argument("--no-risk-split", action="store_true",
+                    help="ablation: risk block of the chain nodes inside the chain dual pass, not under the sweeps")
     ap.add_argument("--fwd-split", action="store_true",
                     help="ablation: forward chain walk in two pieces, the second overlapped with the dual pass of the first")
     ap.add_argument("--no-pipeline", action="store_true",

@@ -179,7 +179,8 @@ int rb_profile_iteration(rb_solver *s, float *ms);
  * into branching nodes (next to the forward chain sweep), chain nodes (k_dual_chain) and leaves; the forward chain walk
  * 3 = additionally the forward chain walk is cut in two pieces and the dual pass of the first piece's nodes runs next to
  * the second piece (measured slower on cfg3: the walker is latency-bound and loses more to the co-resident dual warps
- * than the overlap gains; kept as an ablation).  Needs the lane passes; ignored otherwise and under subtree sharding. */
+ * than the overlap gains; kept as an ablation).  4 = the risk block (d1, d2) of the chain nodes inside the chain dual pass
+ * instead of a kernel of its own under the sweeps (ablation).  Needs the lane passes; ignored otherwise and under subtree sharding. */
 int rb_use_pipeline(rb_solver *s, int32_t enable);
 /* how the pipelined dual pass is split: nodes [0, early) run next to the forward chain sweep, [chain_first, chain_first +
  * chain_nodes) through k_dual_chain; chain_nodes = 0 when the loop is not pipelined or has no chain kernel for (nx, nu) */

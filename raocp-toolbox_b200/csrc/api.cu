@@ -96,7 +96,8 @@ struct rb_solver {
     // sweep -- and the dual pass is split into the branching part (runs next to the forward chain sweep), the chain part
     // (k_dual_chain) and the leaves
     bool allow_pipe = true;
-    bool pipe_fwd_split = false;    // cut the forward chain walk in two and overlap the second piece with the dual pass of the first
+    bool pipe_fwd_split = false;
+    bool risk_split = true;         // the risk block of the chain nodes' dual pass as a kernel of its own under the sweeps    // cut the forward chain walk in two and overlap the second piece with the dual pass of the first
     bool pbar_ready = false;        // prim[cur_i] holds pbar of the next iteration
     int chain_first = 0;            // nodes [chain_first, m) are nonleaf nodes with exactly one child
     int4 *chain_recs = nullptr;     // their packed topology records (launch_dual_chain)
@@ -300,7 +301,7 @@ int pipe_dual_launches(const rb_solver *s) {
 int iter_launches(const rb_solver *s) {
     const SweepPlan &pl = s->plan;
     const int sweeps = 1 + 2 * pl.num_levels - (sweeps_fused(s) ? 2 : 0);
-    if (use_pipe(s)) return 1 + sweeps + pipe_dual_launches(s) + 1;
+    if (use_pipe(s)) return 1 + sweeps + pipe_dual_launches(s) + 1 + (s->risk_split && pipe_split(s).cf < s->P.L.m ? 1 : 0);
     return 1 + sweeps + 1 + 1;
 }
 
@@ -1411,13 +1412,19 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
         launch_dual_lane(nb, q, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, nullptr, first,
                          count, s->prim[src], narrow);
     };
-    if (have_pbar) {   // kernel projection in place, next to the backward sweeps
+    // side stream 0, under the backward sweeps: the kernel projection in place (or, in the first iteration of a loop, after
+    // the stand-alone primal pass on the main stream), then the risk block of the chain nodes' dual pass, which needs y, s only
+    const bool risk_split = ps.cf < L.m && s->risk_split;
+    if (!have_pbar) launch_primal(s, st, src, dst);
+    const bool side0 = have_pbar || risk_split;
+    if (side0) {
         RB_CUDA(s, cudaEventRecord(ev[0], st));
         RB_CUDA(s, cudaStreamWaitEvent(s0, ev[0], 0));
-        launch_kproj(L.batch, s0, s->P, s->ctrl, s->prim[dst]);
+        if (have_pbar) launch_kproj(L.batch, s0, s->P, s->ctrl, s->prim[dst]);
+        if (risk_split)
+            launch_dual_risk_chain(L.batch, s0, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
+                                   ps.cf, L.m - ps.cf, s->chain_stride, s->chain_yo0, s->prim[src]);
         RB_CUDA(s, cudaEventRecord(ev[1], s0));
-    } else {
-        launch_primal(s, st, src, dst);
     }
     bool early_done = false;
     cudaError_t herr = cudaSuccess;
@@ -1425,28 +1432,28 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
         if (ps.early <= 0) return;
         if ((herr = cudaEventRecord(ev[2], st)) != cudaSuccess) return;
         if ((herr = cudaStreamWaitEvent(s1, ev[2], 0)) != cudaSuccess) return;
-        if (have_pbar && (herr = cudaStreamWaitEvent(s1, ev[1], 0)) != cudaSuccess) return;
+        if (side0 && (herr = cudaStreamWaitEvent(s1, ev[1], 0)) != cudaSuccess) return;
         dual_lane(s1, 0, ps.early, true);   // next to the forward chain walker: as few CTAs as possible
         early_done = true;
     };
     auto dual_chain = [&](cudaStream_t q, int first, int count) {
         launch_dual_chain(L.batch, q, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
                           s->chain_recs + (first - ps.cf), first, count, s->chain_stride, s->chain_yo0 + 3 * (first - ps.cf),
-                          s->prim[src]);
+                          s->prim[src], risk_split ? 0 : 1);
     };
     bool piece_done = false;
     auto after_piece = [&]() {   // the first piece of the forward chain walk is done: its nodes' dual pass starts
         if (herr != cudaSuccess) return;
         if ((herr = cudaEventRecord(ev[5], st)) != cudaSuccess) return;
         if ((herr = cudaStreamWaitEvent(s1, ev[5], 0)) != cudaSuccess) return;
-        if (have_pbar && (herr = cudaStreamWaitEvent(s1, ev[1], 0)) != cudaSuccess) return;
+        if (side0 && (herr = cudaStreamWaitEvent(s1, ev[1], 0)) != cudaSuccess) return;
         dual_chain(s1, ps.cf, ps.mid - ps.cf);
         piece_done = true;
     };
     int rc = launch_sweeps(s, s->ctrl, s->prim[dst], st, nullptr, nullptr, after_top, ps.split, after_piece);
     if (rc != RB_OK) return rc;
     if (herr != cudaSuccess) return fail(s, RB_ERR_CUDA, std::string("pipelined iteration: ") + cudaGetErrorString(herr));
-    if (have_pbar) RB_CUDA(s, cudaStreamWaitEvent(st, ev[1], 0));
+    if (side0) RB_CUDA(s, cudaStreamWaitEvent(st, ev[1], 0));
     const int early = early_done ? ps.early : 0;
     const int chain_lo = piece_done ? ps.mid : ps.cf;
     if (ps.cf >= L.m) {   // no chain pass: one general pass over the rest
@@ -1747,6 +1754,12 @@ int rb_profile_iteration(rb_solver *s, float *ms) {
     RB_CUDA(s, cudaEventRecord(ev[0], st));
     if (pipe && s->pbar_ready) launch_kproj(L.batch, st, s->P, s->ctrl, s->prim[dst]);
     else launch_primal(s, st, src, dst);
+    const bool risk_split = pipe && s->risk_split && pipe_split(s).cf < L.m;
+    if (risk_split) {
+        const PipeSplit ps = pipe_split(s);
+        launch_dual_risk_chain(L.batch, st, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, ps.cf,
+                               L.m - ps.cf, s->chain_stride, s->chain_yo0, s->prim[src]);
+    }
     RB_CUDA(s, cudaEventRecord(ev[1], st));
     int rcs = launch_sweeps(s, s->ctrl, s->prim[dst], st, ev + 2, &nsweep);
     if (rcs != RB_OK) return rcs;
@@ -1768,7 +1781,7 @@ int rb_profile_iteration(rb_solver *s, float *ms) {
             dual_lane(0, ps.cf);
             RB_CUDA(s, cudaEventRecord(ev[9], st));
             launch_dual_chain(L.batch, st, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
-                              s->chain_recs, ps.cf, L.m - ps.cf, s->chain_stride, s->chain_yo0, s->prim[src]);
+                              s->chain_recs, ps.cf, L.m - ps.cf, s->chain_stride, s->chain_yo0, s->prim[src], risk_split ? 0 : 1);
             RB_CUDA(s, cudaEventRecord(ev[10], st));
             dual_lane(L.m, L.n - L.m);
             RB_CUDA(s, cudaEventRecord(ev[11], st));
@@ -1804,6 +1817,7 @@ int rb_use_pipeline(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
     if (s->in_loop) return fail(s, RB_ERR_STATE, "rb_use_pipeline() inside a loop");
     s->allow_pipe = enable != 0;
+    s->risk_split = enable != 4;       // 4: pipelined, the risk block inside the chain dual pass (ablation)
     s->pipe_fwd_split = enable == 3;   // 3: additionally the forward chain walk in two pieces (measured slower: kept as an ablation)
     for (int i = 0; i < 2; ++i)
         if (s->graph[i]) {

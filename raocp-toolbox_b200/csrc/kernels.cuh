@@ -74,7 +74,12 @@ bool dual_chain_supported(int nx, int nu);
 // stride > 0: the child of node i is i + stride for the whole run; yo0 = offset of y_first
 void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
                        const double *d_old, double *d_new, double *slots, const int4 *recs, int first, int count,
-                       int stride, int yo0, double *pbar);
+                       int stride, int yo0, double *pbar, int with_risk = 1);
+// the risk block (d1, d2, ybar, sbar, y / s residual rows) of the same run of nodes on its own: needs y, s only, runs
+// under the sweeps; the chain pass is then launched with with_risk = 0
+void launch_dual_risk_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
+                            const double *d_old, double *d_new, double *slots, int first, int count, int stride, int yo0,
+                            double *pbar);
 void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim);
 __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, double *__restrict__ slots,
                         double *__restrict__ last);

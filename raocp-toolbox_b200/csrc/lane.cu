@@ -645,7 +645,8 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
     k_dual_chain(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, const double *__restrict__ p_old,
                  const double *__restrict__ p_new, const double *__restrict__ d_old, double *__restrict__ d_new,
                  double *__restrict__ slots, const int4 *__restrict__ recs, int first, int count, int stride, int yo0,
-                 double *pbar) {
+                 double *pbar, int with_risk) {
+    // with_risk = 0: the risk block (d1, d2, ybar, sbar) of these nodes has been done by k_dual_risk_chain
     constexpr int HX = NX / 2, K = (NX + NU) / 2, R = (K + G - 1) / G, NXU = NX + NU;
     const Layout &L = P.L;
     const Topo &T = P.t;
@@ -696,10 +697,13 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
     }                                                                    // read in the update phase
     // scalars of the node and of the edge (same addresses for the lanes of a group: one request)
     const double to = Po[L.ptau + j], tn = Pn[L.ptau + j], do5 = Do[L.d5 + e0], do6 = Do[L.d6 + e0];
-    const double so = Po[L.ps + node], sn = Pn[L.ps + node], do2 = Do[L.d2 + node];
-    const int ey = g < 2 ? g : 2;   // y_i = [y_a; y_b; y_last]: lanes 0, 1, 2 take one entry each
-    const double yold = Po[L.py + yo + ey], ynew = Pn[L.py + yo + ey], do1 = Do[L.d1 + yo + ey];
-    const double prob = T.cond_prob[j];
+    double so = 0.0, sn = 0.0, do2 = 0.0, yold = 0.0, ynew = 0.0, do1 = 0.0, prob = 0.0;
+    if (with_risk) {
+        so = Po[L.ps + node], sn = Pn[L.ps + node], do2 = Do[L.d2 + node];
+        const int ey = g < 2 ? g : 2;   // y_i = [y_a; y_b; y_last]: lanes 0, 1, 2 take one entry each
+        yold = Po[L.py + yo + ey], ynew = Pn[L.py + yo + ey], do1 = Do[L.d1 + yo + ey];
+        prob = T.cond_prob[j];
+    }
     if (done) return;
     const double inv_alpha = 1.0 / alpha;
     const int ci = rec.y;
@@ -715,7 +719,7 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
     int bad = 0;
     // ---- d1, d2 (risk block) and the y_i, s_i residual rows: first, while the rows are still in flight -- it only needs
     //      the scalars, and they are dead (registers free) before the row phases start -----------------------------------------
-    {
+    if (with_risk) {
         const double b = g == 0 ? prob : (g == 2 ? 1.0 : 0.0);   // b_i = [pi; 0; 1] (risks.py:34-35); lanes >= 3 idle
         const bool own = g < 3;
         const double dot_z = oct_sum<G>(own ? b * (2 * ynew - yold) : 0.0);
@@ -864,6 +868,86 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
 }
 
 // ====================================================================================================================
+// The risk block of the chain nodes on its own: d1_i, d2_i (dual of R_+^{2c} x {0} and of R_+; risks.py:32-35,
+// cache.py:349-352), the y_i / s_i residual rows, and ybar_i, sbar_i of the next iteration.  It needs y, s only -- final
+// once the kernel projection is done -- so it runs right after it on the side stream, under the DP sweeps, and the chain
+// dual pass on the critical path is 15 % shorter.  One thread per node (three y entries), a few fat CTAs like
+// k_kproj_node (it runs next to the chain walkers).  Same arithmetic, in the same order, as the block in k_dual_chain.
+// ====================================================================================================================
+__global__ void __launch_bounds__(1024) k_dual_risk_chain(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
+                                                           const double *__restrict__ p_old, const double *__restrict__ p_new,
+                                                           const double *__restrict__ d_old, double *__restrict__ d_new,
+                                                           double *__restrict__ slots, int first, int count, int stride,
+                                                           int yo0, double *pbar) {
+    if (ctrl->done) return;
+    const double alpha = ctrl->alpha, inv_alpha = 1.0 / alpha;
+    const Layout &L = P.L;
+    const Topo &T = P.t;
+    __shared__ unsigned long long blockmax[32][6];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const double *Po = p_old + (long long)blockIdx.y * L.np_pad;
+    const double *Pn = p_new + (long long)blockIdx.y * L.np_pad;
+    const double *Do = d_old + (long long)blockIdx.y * L.nd_pad;
+    double *Dn = d_new + (long long)blockIdx.y * L.nd_pad;
+    double *Pb = pbar + (long long)blockIdx.y * L.np_pad;
+    ResidLane Rs;
+    Rs.init();
+    for (int i = blockIdx.x * blockDim.x + tid; i < count; i += gridDim.x * blockDim.x) {
+        const int node = first + i, yo = yo0 + 3 * i;
+        const int j = stride > 0 ? node + stride : T.child_first[node];
+        const double prob = T.cond_prob[j];
+        double yo_[3], yn_[3], d1_[3];
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            yo_[e] = Po[L.py + yo + e];
+            yn_[e] = Pn[L.py + yo + e];
+            d1_[e] = Do[L.d1 + yo + e];
+        }
+        const double so = Po[L.ps + node], sn = Pn[L.ps + node], do2 = Do[L.d2 + node];
+        const double b[3] = {prob, 0.0, 1.0};   // b_i = [pi; 0; 1] (risks.py:34-35)
+        // b' (2 y+ - y) and b' (y+ - y), summed like the lane-group reduction of k_dual_chain: (e0 + e1) + (e2 + 0)
+        const double dot_z = (b[0] * (2 * yn_[0] - yo_[0]) + b[1] * (2 * yn_[1] - yo_[1])) + (b[2] * (2 * yn_[2] - yo_[2]) + 0.0);
+        const double dot_d = (b[0] * (yn_[0] - yo_[0]) + b[1] * (yn_[1] - yo_[1])) + (b[2] * (yn_[2] - yo_[2]) + 0.0);
+        const double w2 = dual_w(do2, (2 * sn - so) - dot_z, alpha, inv_alpha);
+        const double dn2 = alpha * (w2 - fmax(0.0, w2));
+        const double dd2 = do2 - dn2;
+        const double xi22 = fma(dd2, inv_alpha, (sn - so) - dot_d);
+        Rs.put(2, xi22);
+        Rs.put(5, dd2);
+        Rs.primal(sn - so, dd2, xi22, inv_alpha);
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const double dy = yn_[e] - yo_[e];
+            const double wv = dual_w(d1_[e], 2 * yn_[e] - yo_[e], alpha, inv_alpha);
+            const double zv = e < 2 ? fmax(0.0, wv) : wv;   // dual of R_+^{2c} x {0} (risks.py:32-33)
+            const double dnew = alpha * (wv - zv);
+            const double dd = d1_[e] - dnew;
+            const double xi2 = Rs.dual(dd, dy, inv_alpha);
+            Rs.primal(dy, dd - b[e] * dd2, xi2 - b[e] * xi22, inv_alpha);
+            Dn[L.d1 + yo + e] = dnew;
+            Pb[L.py + yo + e] = yn_[e] - alpha * (dnew - b[e] * dn2);
+        }
+        Dn[L.d2 + node] = dn2;
+        Pb[L.ps + node] = sn - alpha * dn2;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const unsigned long long mine = Rs.bits(i);
+        const unsigned hi = (unsigned)(mine >> 32), lo = (unsigned)mine;
+        const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+        if (lane == 0) blockmax[warp][i] = ((unsigned long long)mhi << 32) | mlo;
+    }
+    __syncthreads();
+    if (tid < 6) {
+        unsigned long long mval = blockmax[0][tid];
+        for (int wv = 1; wv < (int)(blockDim.x >> 5); ++wv) mval = blockmax[wv][tid] > mval ? blockmax[wv][tid] : mval;
+        atomicMax(reinterpret_cast<unsigned long long *>(slots + (long long)blockIdx.y * 6 + tid), mval);
+    }
+    if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) ctrl->pending = 1;
+}
+
+// ====================================================================================================================
 // Projection onto ker [E' -I -I] of every nonleaf node (cache.py:290-317), IN PLACE on a buffer that holds
 // (ybar_i, taubar_j, sbar_j) -- the part of prox_f that does not depend on the DP sweeps; it runs next to them on its
 // own stream.  One thread per node; the sums follow the association of k_primal_lane's lane-group reductions.
@@ -960,7 +1044,7 @@ bool dual_chain_supported(int nx, int nu) {
 
 void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
                        const double *d_old, double *d_new, double *slots, const int4 *recs, int first, int count,
-                       int stride, int yo0, double *pbar) {
+                       int stride, int yo0, double *pbar, int with_risk) {
     if (count <= 0) return;
     // resident CTAs per SM the kernel is compiled for: 3 (168 registers, no spills) or 4 (128 registers, ~40 words
     // spilled to L1); RB_CHAIN_DUAL_MINB overrides for ablation runs
@@ -976,9 +1060,9 @@ void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, 
     {                                                                                                                \
         const dim3 grid((count * G + kChainDualThreads - 1) / kChainDualThreads, batch);                             \
         if (minb == 4)                                                                                               \
-            k_dual_chain<NX, NU, G, 4><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, stride, yo0, pbar); \
+            k_dual_chain<NX, NU, G, 4><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, stride, yo0, pbar, with_risk); \
         else                                                                                                         \
-            k_dual_chain<NX, NU, G, 3><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, stride, yo0, pbar); \
+            k_dual_chain<NX, NU, G, 3><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, stride, yo0, pbar, with_risk); \
         return;                                                                                                      \
     }
 #define RB_GO(NX, NU, G)                                                                                             \
@@ -988,6 +1072,14 @@ void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, 
     }
     RB_CHAIN_DUAL_DIMS(RB_GO)
 #undef RB_GO
+}
+
+void launch_dual_risk_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
+                            const double *d_old, double *d_new, double *slots, int first, int count, int stride, int yo0,
+                            double *pbar) {
+    if (count <= 0) return;
+    const int ctas = std::max(1, std::min((count + 1023) / 1024, std::max(1, 16 / batch)));
+    k_dual_risk_chain<<<dim3(ctas, batch), 1024, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, first, count, stride, yo0, pbar);
 }
 
 void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim) {

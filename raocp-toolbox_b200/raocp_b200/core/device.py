@@ -218,7 +218,8 @@ class DeviceSolver:
 
     def use_pipeline(self, enable=True):
         """True / 1: pipelined loop (default); 3: additionally the forward chain walk in two pieces, overlapped with the
-        dual pass (ablation); False / 0: primal pass + one dual pass per iteration"""
+        dual pass (ablation); 4: the risk block of the chain nodes inside the chain dual pass instead of a kernel of its own
+        under the sweeps (ablation); False / 0: primal pass + one dual pass per iteration"""
         self._call("rb_use_pipeline", int(enable))
 
     def pipeline_info(self):

@@ -111,7 +111,7 @@ def test_pipelined_loop_equals_unpipelined(name, graphs):
     oracle = FlatOracle(problem)
     alpha = oracle.step_size()
     out = {}
-    for pipe in (True, False, 3):   # 3: pipelined with the forward chain walk in two pieces
+    for pipe in (True, False, 3, 4):   # 3: forward chain walk in two pieces; 4: risk block inside the chain dual pass
         solver = r.core.Solver(problem, verbose=False)
         dev = solver.cache.device_solver
         dev.use_pipeline(pipe)
@@ -119,7 +119,7 @@ def test_pipelined_loop_equals_unpipelined(name, graphs):
         assert solver.chock(x0, max_iters=40, tol=0.0, alpha=alpha) == 1 and solver.iterations == 41
         out[pipe] = (dev.get_primal(0)[0], dev.get_dual(0)[0], solver.residual_history[0].copy(), solver)
     flat = out[True][3].cache.flat_problem
-    for other in (False, 3):
+    for other in (False, 3, 4):
         assert seg_rel_err(flat, out[True][0], out[other][0], dual=False) < 1e-12
         assert seg_rel_err(flat, out[True][1], out[other][1], dual=True) < 1e-12
         assert np.max(np.abs(out[True][2] - out[other][2]) / out[other][2]) < 1e-9
