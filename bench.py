@@ -33,6 +33,8 @@ for p in (os.path.join(ROOT, "raocp-toolbox_b200"), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line (NCCL prints its version banner there)
+
 import numpy as np  # noqa: E402
 
 METRIC = "CP iterations/sec"
