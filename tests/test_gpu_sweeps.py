@@ -180,3 +180,33 @@ def test_profile_hook_advances_like_an_iteration():
         oracle.iterate()
     assert seg_rel_err(flat, dev.get_primal(0)[0], oracle.flat_primal(oracle.p), dual=False) < 1e-9
     assert seg_rel_err(flat, dev.get_dual(0)[0], oracle.flat_dual(oracle.d), dual=True) < 1e-9
+
+
+@pytest.mark.parametrize("pipe", [True, False])
+def test_step_with_a_new_initial_state_mid_loop(pipe):
+    """rb_step (the end-to-end call of bench.py: x0 from host memory, one iteration, six norms back) with x0 CHANGED in the
+    middle of a running loop -- the receding-horizon use.  In the pipelined loop the half step of the next iteration has
+    already been written when the new x0 arrives; it must not matter (xbar_0 is never used by the projection)."""
+    import torch
+    s, solver, oracle = _pair("chain2010", None, "mma")
+    flat, dev = solver.cache.flat_problem, solver.cache.device_solver
+    dev.use_pipeline(pipe)
+    alpha = oracle.step_size()
+    xa = s["x0"][:, :1]
+    xb = 0.25 - 0.5 * xa
+    solver.cache.cache_initial_state(xa)
+    dev.loop_begin(alpha, 1 << 30, -1.0, 0)
+    x_host = torch.zeros(1, flat.nx, dtype=torch.float64).pin_memory()
+    n_host = torch.zeros(1, 6, dtype=torch.float64).pin_memory()
+    oracle.alpha = alpha
+    for x0, steps in ((xa, 4), (xb, 5), (xa, 3)):
+        x_host[0] = torch.from_numpy(x0[:, 0].copy())
+        oracle.cache_initial_state(x0)
+        for _ in range(steps):
+            dev.step(x_host.data_ptr(), n_host.data_ptr())
+            xi, delta = oracle.iterate()
+            want = np.concatenate((np.array(xi), np.array(delta)))
+            assert np.max(np.abs(n_host.numpy()[0] - want) / want) < 1e-6
+    dev.loop_end()
+    assert seg_rel_err(flat, dev.get_primal(0)[0], oracle.flat_primal(oracle.p), dual=False) < 1e-9
+    assert seg_rel_err(flat, dev.get_dual(0)[0], oracle.flat_dual(oracle.d), dual=True) < 1e-9
