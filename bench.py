@@ -45,7 +45,7 @@ CPU_SAMPLE = {"cfg1": None, "cfg2": (3, 7, 4), "cfg3": (4, 8, 4), "cfg4": None, 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel, from the committed `ncu --set full`
 # capture of the same command (profiles/): (workload, batch, dedup) -> bytes
-TRAFFIC = {}
+TRAFFIC = {("cfg3", 1, True): 57.84e6 + 4.56e6}   # profiles/r1c_iter_raw.csv, k_dual_chain<20,10,4,3>
 
 
 def peaks():
