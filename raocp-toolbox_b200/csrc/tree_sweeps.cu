@@ -212,6 +212,58 @@ __device__ __forceinline__ void tree_backward(const Layout &L, const Sub &s, con
         } else {
             const bool bottom = d == s.depth - 1;
             const int *cdyn = bottom ? s.xdyn : s.dyn + s.off[d + 1];
+            // A stage with a handful of parents leaves most warps idle while each busy warp is one long serial stream
+            // (four children x nx multiply-adds per lane).  With four children per parent and room for four warps per
+            // parent, every child goes to a warp of its own and the parent's first warp adds the four partial sums -- in
+            // the order child_sum adds them, so the result does not change by a bit.  In-kernel timestamps (RB_TRACE):
+            // 4-parent stage 1.5 -> 1.28 us, 1-parent stage 1.1 -> 0.8 us.  (Blocking a 16-parent stage by child index, so
+            // that a table word is read once for four parents, was measured too: 2.88 -> 2.56 us for that stage but
+            // slower small stages and a slower kernel overall; not kept.)
+            bool split = false;
+            if constexpr (NX > 0 && NX + NU <= 32) {
+                split = w * 4 <= warps;
+                for (int p = 0; p < w && split; ++p) split = s.ccount[off + p] == 4;
+            }
+            if (split) {
+                if constexpr (NX > 0 && NX + NU <= 32) {
+                    double *part = scratch + (long long)warp * 2 * nxu;
+                    if (warp < w * 4 && lane < nxu) {
+                        const int c = s.cfirst[off + (warp >> 2)] + (warp & 3);
+                        const double *m = Ctab + (long long)cdyn[c] * nx * nxu + lane, *v = qchild + (long long)c * nx;
+                        double a = 0.0;
+                        constexpr int CH = Chunk<NX>::value;
+#pragma unroll
+                        for (int l0 = 0; l0 < NX; l0 += CH) {
+                            double mm[CH], vv[CH];
+#pragma unroll
+                            for (int t = 0; t < CH; ++t) {
+                                mm[t] = m[(l0 + t) * nxu];
+                                vv[t] = v[l0 + t];
+                            }
+                            schedule_fence();
+#pragma unroll
+                            for (int t = 0; t < CH; ++t) a = fma(mm[t], vv[t], a);
+                        }
+                        part[lane] = a;
+                    }
+                    __syncthreads();
+                    if (warp < w * 4 && (warp & 3) == 0) {
+                        const int p = warp >> 2, i = off + p;
+                        const double *K = Ktab + (long long)(RES ? i : s.cls[i]) * nu * nx;
+                        double a = 0.0;
+                        if (lane < nxu) a = (part[lane] + part[2 * nxu + lane]) + (part[4 * nxu + lane] + part[6 * nxu + lane]);
+                        __syncwarp();   // the partial sums of this warp are consumed: rv (same scratch row) may be written
+                        if (lane >= nx && lane < nxu) {
+                            const double rk = ub[i * nu + lane - nx] - a;
+                            rv[lane - nx] = rk;
+                            if (rbuf) rbuf[i * nu + lane - nx] = rk;
+                            Rglob[(long long)(lo + p) * nu + lane - nx] = rk;
+                        }
+                        __syncwarp();
+                        if (lane < nx) qcur[p * nx + lane] = a - xb[i * nx + lane] - dot_col<NU>(K, nx, rv, lane, nu);
+                    }
+                }
+            } else
             for (int p = warp; p < w; p += warps) {
                 const int i = off + p, c0 = s.cfirst[i], cc = s.ccount[i];
                 const double *K = Ktab + (long long)(RES ? i : s.cls[i]) * nu * nx;
@@ -277,6 +329,51 @@ __device__ __forceinline__ void tree_forward(const Layout &L, const Sub &s, cons
         const bool bottom = d == s.depth - 1;
         const int *cdyn = bottom ? s.xdyn : s.dyn + s.off[d + 1];
         const long long cglob = bottom ? s.ext_first : s.lo[d + 1];
+        bool split = false;   // as in tree_backward: one warp per child when the stage has only a few parents
+        if constexpr (NX > 0 && NX + NU <= 32) {
+            split = w * 4 <= warps;
+            for (int p = 0; p < w && split; ++p) split = s.ccount[off + p] == 4;
+        }
+        if (split) {
+            if constexpr (NX > 0 && NX + NU <= 32) {
+                if (warp < w * 4 && (warp & 3) == 0) {   // the parent's first warp: u = K x + R~^-1 r, [x; u] into its scratch row
+                    const int p = warp >> 2, i = off + p;
+                    if (lane < nx) v[lane] = xcur[p * nx + lane];
+                    if (lane < nu) v[nx + lane] = rbuf[i * nu + lane];
+                    __syncwarp();
+                    const double *KR = KRtab + (long long)(RES ? i : s.cls[i]) * nxu * nu;
+                    double ua = 0.0;
+                    if (lane < nu) ua = dot_col<NX + NU>(KR, nu, v, lane, nxu);
+                    __syncwarp();
+                    if (lane < nu) {
+                        v[nx + lane] = ua;
+                        Uglob[(long long)(lo + p) * nu + lane] = ua;
+                    }
+                }
+                __syncthreads();
+                if (warp < w * 4 && lane < nx) {   // one child per warp: x_child = [A B] [x; u]
+                    const int p = warp >> 2, c = s.cfirst[off + p] + (warp & 3);
+                    const double *vp = scratch + (long long)(warp & ~3) * 2 * nxu;
+                    const double *m = CTtab + (long long)cdyn[c] * nxu * nx + lane;
+                    double a = 0.0;
+                    constexpr int CH = Chunk<NX + NU>::value;
+#pragma unroll
+                    for (int l0 = 0; l0 < NX + NU; l0 += CH) {
+                        double mm[CH], vl[CH];
+#pragma unroll
+                        for (int t = 0; t < CH; ++t) {
+                            mm[t] = m[(l0 + t) * NX];
+                            vl[t] = vp[l0 + t];
+                        }
+                        schedule_fence();
+#pragma unroll
+                        for (int t = 0; t < CH; ++t) a = fma(mm[t], vl[t], a);
+                    }
+                    if (!bottom) xnext[c * nx + lane] = a;
+                    Xglob[(cglob + c) * nx + lane] = a;
+                }
+            }
+        } else
         for (int p = warp; p < w; p += warps) {
             const int i = off + p, c0 = s.cfirst[i], cc = s.ccount[i];
             for (int k = lane; k < nx; k += 32) v[k] = xcur[p * nx + k];
