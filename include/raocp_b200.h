@@ -160,7 +160,9 @@ int rb_iterate_fixed(rb_solver *s, double alpha, int32_t iters, double *norms);
  *                   the stopping test fired are no-ops.
  *   rb_loop_poll    synchronises and reports iterations executed, the stop flag and the last residual norms [batch][6].
  *   rb_step         one end-to-end step for a host caller: x0 (host, may be NULL = unchanged) -> device, one
- *                   iteration, the six residual norms -> host, synchronised.
+ *                   iteration, the six residual norms -> host, synchronised.  In the pipelined loop this is ONE upload
+ *                   (the kernel projection copies x0 into x_0 of the old iterate, cache.py:79-82), one graph launch and
+ *                   no download: the stopping test writes the norms to mapped host memory as well.
  *   rb_loop_end     closes the loop: current == old == newest iterate (no copy), history to the host. */
 int rb_loop_begin(rb_solver *s, double alpha, int32_t max_iters, double tol, int32_t hist_capacity);
 int rb_loop_enqueue(rb_solver *s, int32_t count);

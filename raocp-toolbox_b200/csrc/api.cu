@@ -48,6 +48,7 @@ struct rb_solver {
     bool in_loop = false;
     int loop_old0 = 1;  // which buffer was "old" when the fused loop began
     double *h_pinned = nullptr;  // pinned staging for control block / residual read-back
+    double *h_last = nullptr, *h_last_dev = nullptr;   // mapped pinned mirror of `last` (k_check writes it; rb_step reads it)
     double *q = nullptr, *r = nullptr, *x0 = nullptr;
     Ctrl *ctrl = nullptr;
     double *slots = nullptr, *last = nullptr, *hist = nullptr;
@@ -769,6 +770,16 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
     TRY(dev_zero(s, 1, &s->ctrl));
     TRY(dev_zero(s, B * 6, &s->slots));
     TRY(dev_zero(s, B * 6, &s->last));
+    if (B * 6 <= 1024 && L.nx <= 1024 &&
+        cudaHostAlloc((void **)&s->h_last, B * 6 * sizeof(double), cudaHostAllocMapped) == cudaSuccess) {
+        if (cudaHostGetDevicePointer((void **)&s->h_last_dev, s->h_last, 0) != cudaSuccess) {
+            cudaFreeHost(s->h_last);
+            s->h_last = s->h_last_dev = nullptr;
+        }
+    } else {
+        cudaGetLastError();
+        s->h_last = s->h_last_dev = nullptr;
+    }
     TRY(dev_zero(s, 1, &s->status));
     // ---- sweep plan (sweeps.cu): first cut at the first stage with >= 64 nodes; second cut where the tree turns into
     //      chains (below the stopping time of a Markov tree) if there are >= 256 of them, else -- if the tree keeps
@@ -1039,6 +1050,7 @@ void rb_destroy(rb_solver *s) {
     if (s->nccl_comm) nccl_comm_destroy(s->nccl_comm);
     if (s->hist) cudaFree(s->hist);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
+    if (s->h_last) cudaFreeHost(s->h_last);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     for (auto q : s->side)
         if (q) cudaStreamDestroy(q);
@@ -1401,7 +1413,7 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
         int rc = launch_sweeps(s, s->ctrl, s->prim[dst], st);
         if (rc != RB_OK) return rc;
         launch_dual(s, st, src, dst);
-        k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
+        k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
         return launch_ok(s, "fused iteration");
     }
     const PipeSplit ps = pipe_split(s);
@@ -1420,7 +1432,7 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
     if (side0) {
         RB_CUDA(s, cudaEventRecord(ev[0], st));
         RB_CUDA(s, cudaStreamWaitEvent(s0, ev[0], 0));
-        if (have_pbar) launch_kproj(L.batch, s0, s->P, s->ctrl, s->prim[dst]);
+        if (have_pbar) launch_kproj(L.batch, s0, s->P, s->ctrl, s->prim[dst], s->h_last_dev ? s->x0 : nullptr, s->prim[src]);
         if (risk_split)
             launch_dual_risk_chain(L.batch, s0, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
                                    ps.cf, L.m - ps.cf, s->chain_stride, s->chain_yo0, s->prim[src]);
@@ -1470,7 +1482,7 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
         RB_CUDA(s, cudaEventRecord(ev[4], s1));
         RB_CUDA(s, cudaStreamWaitEvent(st, ev[4], 0));
     }
-    k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
+    k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
     return launch_ok(s, "pipelined iteration");
 }
 
@@ -1481,7 +1493,7 @@ int shard_exchange(rb_solver *s, int src, cudaStream_t st) {
     const int rc = nccl_all_gather_f64(s->xchg_send, s->xchg_recv, s->xchg_count, s->nccl_comm, st);
     if (rc != 0) return fail(s, RB_ERR_CUDA, std::string("ncclAllGather: ") + nccl_error(rc));
     k_shard_unpack<<<8, 256, 0, st>>>(s->P, s->ctrl, s->shard, s->xchg_recv, s->q, s->dual[src], s->slots);
-    if (s->shard_pending) k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
+    if (s->shard_pending) k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
     s->shard_pending = false;
     return launch_ok(s, "shard exchange");
 }
@@ -1726,15 +1738,24 @@ int rb_step(rb_solver *s, const double *x0, double *norms) {
     if (!s || !norms) return RB_ERR_INVALID;
     if (!s->in_loop) return fail(s, RB_ERR_STATE, "rb_loop_begin() has not been called");
     const Layout &L = s->P.L;
+    // pipelined loop with the mapped mirror: ONE upload (the kernel projection copies x0 into x_0 of the old iterate)
+    // and no download (k_check has written the norms to host memory when the stream is idle)
+    const bool lean = s->h_last_dev && use_pipe(s) && s->pbar_ready;
     if (x0) {
         RB_CUDA(s, cudaMemcpyAsync(s->x0, x0, (size_t)L.batch * L.nx * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-        RB_CUDA(s, cudaMemcpy2DAsync(s->prim[s->old_i] + L.px, L.np_pad * sizeof(double), x0, L.nx * sizeof(double),
-                                     L.nx * sizeof(double), L.batch, cudaMemcpyHostToDevice, s->stream));
+        if (!lean)
+            RB_CUDA(s, cudaMemcpy2DAsync(s->prim[s->old_i] + L.px, L.np_pad * sizeof(double), x0, L.nx * sizeof(double),
+                                         L.nx * sizeof(double), L.batch, cudaMemcpyHostToDevice, s->stream));
     }
     int rc = rb_loop_enqueue(s, 1);
     if (rc != RB_OK) return rc;
-    RB_CUDA(s, cudaMemcpyAsync(norms, s->last, (size_t)L.batch * 6 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
-    RB_CUDA(s, cudaStreamSynchronize(s->stream));
+    if (s->h_last_dev) {
+        RB_CUDA(s, cudaStreamSynchronize(s->stream));
+        std::memcpy(norms, s->h_last, (size_t)L.batch * 6 * sizeof(double));
+    } else {
+        RB_CUDA(s, cudaMemcpyAsync(norms, s->last, (size_t)L.batch * 6 * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+        RB_CUDA(s, cudaStreamSynchronize(s->stream));
+    }
     return RB_OK;
 }
 
@@ -1752,7 +1773,7 @@ int rb_profile_iteration(rb_solver *s, float *ms) {
     const int src = s->old_i, dst = 1 - src;
     const bool pipe = use_pipe(s);
     RB_CUDA(s, cudaEventRecord(ev[0], st));
-    if (pipe && s->pbar_ready) launch_kproj(L.batch, st, s->P, s->ctrl, s->prim[dst]);
+    if (pipe && s->pbar_ready) launch_kproj(L.batch, st, s->P, s->ctrl, s->prim[dst], s->h_last_dev ? s->x0 : nullptr, s->prim[src]);
     else launch_primal(s, st, src, dst);
     const bool risk_split = pipe && s->risk_split && pipe_split(s).cf < L.m;
     if (risk_split) {
@@ -1790,7 +1811,7 @@ int rb_profile_iteration(rb_solver *s, float *ms) {
     } else {
         launch_dual(s, st, src, dst);
     }
-    k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last);
+    k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
     RB_CUDA(s, cudaEventRecord(ev[2 + nsweep], st));
     RB_CUDA(s, cudaStreamSynchronize(st));
     int rc = launch_ok(s, "profiled iteration");

@@ -646,7 +646,9 @@ void launch_dual_tile(bool diag, dim3 grid, size_t smem, cudaStream_t st, const 
 // into the history and reset.  The loop stops when the iteration index reaches max_iters or every instance has
 // max(xi0, xi1, xi2) <= tol.
 __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, double *__restrict__ slots,
-                        double *__restrict__ last) {
+                        double *__restrict__ last, double *__restrict__ host_last) {
+    // host_last (may be null): mapped pinned host memory; the norms land there as well, so that a host caller that
+    // synchronises after every iteration (rb_step) needs no device-to-host copy of its own
     // One warp.  The control block and the first instances' slots are requested together (the kernel is a chain of
     // dependent global round trips otherwise, and it sits on the critical path of every iteration); a launch with
     // nothing pending -- the loop tests iteration k at the head of iteration k + 1 and again before the host reads the
@@ -668,6 +670,7 @@ __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctr
             if (i % 6 < 3 && !(mine <= c.tol)) ok = false;   // max(xi0, xi1, xi2) <= tol  <=>  each of them is
             if (c.hist && it < c.hist_capacity) c.hist[(long long)it * total + i] = mine;
             last[i] = mine;
+            if (host_last) host_last[i] = mine;
             slots[i] = 0.0;
         }
     }

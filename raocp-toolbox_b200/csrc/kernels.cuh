@@ -80,9 +80,12 @@ void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, 
 void launch_dual_risk_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
                             const double *d_old, double *d_new, double *slots, int first, int count, int stride, int yo0,
                             double *pbar);
-void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim);
+// x0 / p_old (may be null): also copy the initial state x0 [batch][nx] into x_0 of the OLD iterate (what
+// cache_initial_state does, cache.py:79-82) -- rb_step then uploads x0 once
+void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim, const double *x0 = nullptr,
+                  double *p_old = nullptr);
 __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, double *__restrict__ slots,
-                        double *__restrict__ last);
+                        double *__restrict__ last, double *__restrict__ host_last);
 
 // ---- sweeps.cu: the DP sweeps in a handful of launches ---------------------------------------------------------------
 struct SweepLevel {

@@ -953,11 +953,14 @@ __global__ void __launch_bounds__(1024) k_dual_risk_chain(const __grid_constant_
 // own stream.  One thread per node; the sums follow the association of k_primal_lane's lane-group reductions.
 // ====================================================================================================================
 __global__ void __launch_bounds__(1024) k_kproj_node(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
-                                                      double *__restrict__ prim) {
+                                                      double *__restrict__ prim, const double *__restrict__ x0,
+                                                      double *__restrict__ p_old) {
     if (ctrl->done) return;
     const Layout &L = P.L;
     const Topo &T = P.t;
     double *Pb = prim + (long long)blockIdx.y * L.np_pad;
+    if (x0 && blockIdx.x == 0 && threadIdx.x < L.nx)   // x_0 of the old iterate = the initial state (cache.py:79-82)
+        p_old[(long long)blockIdx.y * L.np_pad + L.px + threadIdx.x] = x0[(long long)blockIdx.y * L.nx + threadIdx.x];
     for (int node = blockIdx.x * blockDim.x + threadIdx.x; node < L.m; node += gridDim.x * blockDim.x) {
     const int c0 = T.child_first[node], cc = T.child_count[node];
     const double a = T.risk_alpha[node], den = a * a + 3.0;
@@ -1082,7 +1085,7 @@ void launch_dual_risk_chain(int batch, cudaStream_t st, const Params &P, Ctrl *c
     k_dual_risk_chain<<<dim3(ctas, batch), 1024, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, first, count, stride, yo0, pbar);
 }
 
-void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim) {
+void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim, const double *x0, double *p_old) {
     // The pass runs next to the backward chain walker, which keeps one latency-critical warp per SM sub-partition on
     // ~128 SMs: a few fat CTAs (they land on the SMs the walker leaves idle) disturb it less than a grid spread over all
     // SMs (cfg3, L2 flushed before every iteration: 9086 it/s with 16 CTAs of 1024 threads against 7702 with 230 CTAs of
@@ -1091,7 +1094,7 @@ void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl,
     const int threads = cap > 0 ? 1024 : 256;
     int ctas = (P.L.m + threads - 1) / threads;
     if (cap > 0) ctas = std::min(ctas, std::max(1, cap / batch));
-    k_kproj_node<<<dim3(ctas, batch), threads, 0, st>>>(P, ctrl, prim);
+    k_kproj_node<<<dim3(ctas, batch), threads, 0, st>>>(P, ctrl, prim, x0, p_old);
 }
 
 }  // namespace rb
