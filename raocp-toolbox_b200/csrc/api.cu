@@ -49,6 +49,7 @@ struct rb_solver {
     int loop_old0 = 1;  // which buffer was "old" when the fused loop began
     double *h_pinned = nullptr;  // pinned staging for control block / residual read-back
     double *h_last = nullptr, *h_last_dev = nullptr;   // mapped pinned mirror of `last` (k_check writes it; rb_step reads it)
+    bool mirror_on = false;                            // Ctrl::mirror has been switched on in the running loop
     double *q = nullptr, *r = nullptr, *x0 = nullptr;
     Ctrl *ctrl = nullptr;
     double *slots = nullptr, *last = nullptr, *hist = nullptr;
@@ -1581,6 +1582,7 @@ int rb_loop_begin(rb_solver *s, double alpha, int32_t max_iters, double tol, int
         if (rc != RB_OK) return rc;
     }
     s->shard_pending = false;
+    s->mirror_on = false;
     s->pbar_ready = false;
     if (s->hist && s->hist_capacity < hist_capacity) {
         RB_CUDA(s, cudaStreamSynchronize(st));
@@ -1741,6 +1743,12 @@ int rb_step(rb_solver *s, const double *x0, double *norms) {
     // pipelined loop with the mapped mirror: ONE upload (the kernel projection copies x0 into x_0 of the old iterate)
     // and no download (k_check has written the norms to host memory when the stream is idle)
     const bool lean = s->h_last_dev && use_pipe(s) && s->pbar_ready;
+    if (s->h_last_dev && !s->mirror_on) {   // from now on the stopping test mirrors the norms into host memory
+        int *one = reinterpret_cast<int *>(s->h_pinned + 256);
+        *one = 1;
+        RB_CUDA(s, cudaMemcpyAsync(&s->ctrl->mirror, one, sizeof(int), cudaMemcpyHostToDevice, s->stream));
+        s->mirror_on = true;
+    }
     if (x0) {
         RB_CUDA(s, cudaMemcpyAsync(s->x0, x0, (size_t)L.batch * L.nx * sizeof(double), cudaMemcpyHostToDevice, s->stream));
         if (!lean)

@@ -670,7 +670,7 @@ __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctr
             if (i % 6 < 3 && !(mine <= c.tol)) ok = false;   // max(xi0, xi1, xi2) <= tol  <=>  each of them is
             if (c.hist && it < c.hist_capacity) c.hist[(long long)it * total + i] = mine;
             last[i] = mine;
-            if (host_last) host_last[i] = mine;
+            if (host_last && c.mirror) host_last[i] = mine;
             slots[i] = 0.0;
         }
     }

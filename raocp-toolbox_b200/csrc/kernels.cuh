@@ -36,6 +36,8 @@ struct Ctrl {
     double *hist;    // [hist_capacity][batch][6] residual history or null
     int hist_capacity;
     int pending;     // set by the dual pass: `slots` hold the residual maxima of an iteration k_check has not tested yet
+    int mirror;      // k_check also writes the norms to mapped host memory (switched on by the first rb_step of a loop: the
+    int pad;         // posted write to system memory costs the kernel ~1 us, which a loop that never reads them need not pay)
 };
 // tiles of consecutive nodes for the node-parallel passes (fused.cu): tiles[t] = (first node, one past the last);
 // a tile is either all nonleaf or all leaf nodes
