@@ -27,6 +27,7 @@ SHAPES = {
     "chain63": (4, 7, 3, 6, 3),
     "chain105": (3, 9, 5, 10, 5),
     "chain2010": (4, 9, 4, 20, 10),  # 1 621 nodes, 256 chains of 6 nodes: a small cfg3
+    "chain6432": (3, 6, 3, 64, 32),  # 121 nodes, 27 chains of 4 nodes, cfg5's sizes: fragments in shared memory (chain_mma BIG)
 }
 
 

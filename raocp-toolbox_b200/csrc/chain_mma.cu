@@ -240,8 +240,11 @@ __device__ __forceinline__ void lds_vec(double (&v)[N], const double *src) {
 }
 
 // ---- backward:  r = ubar - B'q_child,  q = A'q_child - xbar - K'r    -------------------------------
-template <int NX, int NU>
-__global__ void __launch_bounds__(128) k_chain_mma_bwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
+// BIG (nx + nu > 32): the fragments do not fit into registers.  One warp per CTA; the [A | B] fragments of the tile's
+// dynamics row are copied once into shared memory (lane-major, every lane reads only its own words: no barrier), the class
+// fragments are read straight out of the ring stage -- one 16-byte shared-memory load per two MMAs.
+template <int NX, int NU, bool BIG>
+__global__ void __launch_bounds__(BIG ? 32 : 128) k_chain_mma_bwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
                                                       SweepLevel lv, const double *__restrict__ prim,
                                                       double *__restrict__ q, double *__restrict__ r) {
     using D = ChainDims<NX, NU>;
@@ -252,10 +255,18 @@ __global__ void __launch_bounds__(128) k_chain_mma_bwd(const __grid_constant__ P
     if (tile >= lv.num_tiles) return;
     constexpr int F1 = 2 * D::QT * D::NT, F2 = 2 * D::RN * D::QT;
     constexpr int kLaneWords = ring_lane_words(2 * D::QT + 2 * D::RN + F2);   // per lane and stage: xbar | ubar | K fragments
+    constexpr int kAbWords = BIG ? ring_lane_words(F1) : 0;                   // per lane: the [A | B] fragments (BIG)
+    static_assert(!BIG || (D::NT % 2 == 0 && D::QT % 2 == 0 && D::RN % 2 == 0), "BIG reads fragment pairs");
     double *ring = mma_smem + ((size_t)warp * kStages * 32 + lane) * kLaneWords;   // stage s: ring + s * 32 * kLaneWords
     TileMeta tm;
-    if (!stage_meta(lv, ctrl, tile, warp, lane, reinterpret_cast<int *>(mma_smem + (size_t)warps * kStages * 32 * kLaneWords), tm))
+    if (!stage_meta(lv, ctrl, tile, warp, lane,
+                    reinterpret_cast<int *>(mma_smem + (size_t)warps * kStages * 32 * kLaneWords + (size_t)warps * 32 * kAbWords), tm))
         return;
+    const double *w1s = mma_smem + (size_t)warps * kStages * 32 * kLaneWords + ((size_t)warp * 32 + lane) * kAbWords;
+    if constexpr (BIG) {   // the oldest commit group: complete before the first step's wait returns
+        if (lv.depth > 1) cp_frags<F1>(const_cast<double *>(w1s), P.m.fragAB, tm.dyns[1], lane);
+        cp_async_commit();
+    }
     const int t = tm.t, g = tm.g;
     const double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
     double *Q = q + (long long)blockIdx.y * L.n * NX, *R = r + (long long)blockIdx.y * L.m * NU;
@@ -279,8 +290,10 @@ __global__ void __launch_bounds__(128) k_chain_mma_bwd(const __grid_constant__ P
     int d = lv.depth - 1;
     prefetch(d);
     prefetch(d - 1);
-    double w1[F1];   // [A | B] of the chain's dynamics row (one row per tile: build_chain_tiles), fragment (2 kb + j) * NT + ob
-    if (lv.depth > 1) ld_frags<F1>(w1, P.m.fragAB, tm.dyns[1], lane);
+    double w1[BIG ? 2 : F1];   // [A | B] of the chain's dynamics row (one row per tile: build_chain_tiles), fragment (2 kb + j) * NT + ob
+    if constexpr (!BIG) {
+        if (lv.depth > 1) ld_frags<F1>(w1, P.m.fragAB, tm.dyns[1], lane);
+    }
     double qs[D::QT][2];
 #pragma unroll
     for (int b = 0; b < D::QT; ++b) qs[b][0] = qs[b][1] = 0.0;
@@ -299,9 +312,10 @@ __global__ void __launch_bounds__(128) k_chain_mma_bwd(const __grid_constant__ P
                 qs[b][1] = -xb[2 * b + 1];
             }
         } else {
-            double ub[2 * D::RN], w2[F2];
+            double ub[2 * D::RN], w2[BIG ? 2 : F2];
             lds_vec(ub, src + 2 * D::QT);
-            lds_vec(w2, src + 2 * D::QT + 2 * D::RN);
+            const double *w2s = src + 2 * D::QT + 2 * D::RN;
+            if constexpr (!BIG) lds_vec(w2, w2s);
             // E = [A'q ; B'q]
             double E[D::NT][2];
 #pragma unroll
@@ -309,9 +323,19 @@ __global__ void __launch_bounds__(128) k_chain_mma_bwd(const __grid_constant__ P
 #pragma unroll
             for (int kb = 0; kb < D::QT; ++kb)
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < 2; ++j) {
+                    if constexpr (BIG) {
 #pragma unroll
-                    for (int ob = 0; ob < D::NT; ++ob) dmma(E[ob], qs[kb][j], w1[(2 * kb + j) * D::NT + ob]);
+                        for (int ob = 0; ob < D::NT; ob += 2) {
+                            const double2 w = *reinterpret_cast<const double2 *>(w1s + (2 * kb + j) * D::NT + ob);
+                            dmma(E[ob], qs[kb][j], w.x);
+                            dmma(E[ob + 1], qs[kb][j], w.y);
+                        }
+                    } else {
+#pragma unroll
+                        for (int ob = 0; ob < D::NT; ++ob) dmma(E[ob], qs[kb][j], w1[(2 * kb + j) * D::NT + ob]);
+                    }
+                }
             // r = ubar - B'q  on the input slots (nr = -r feeds the second product)
             double rr[D::RN][2], nr[D::RN][2];
 #pragma unroll
@@ -331,17 +355,27 @@ __global__ void __launch_bounds__(128) k_chain_mma_bwd(const __grid_constant__ P
 #pragma unroll
             for (int i = 0; i < D::RN; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j)
+                for (int j = 0; j < 2; ++j) {
+                    if constexpr (BIG) {
 #pragma unroll
-                    for (int ob = 0; ob < D::QT; ++ob) dmma(qs[ob], nr[i][j], w2[(2 * i + j) * D::QT + ob]);
+                        for (int ob = 0; ob < D::QT; ob += 2) {
+                            const double2 w = *reinterpret_cast<const double2 *>(w2s + (2 * i + j) * D::QT + ob);
+                            dmma(qs[ob], nr[i][j], w.x);
+                            dmma(qs[ob + 1], nr[i][j], w.y);
+                        }
+                    } else {
+#pragma unroll
+                        for (int ob = 0; ob < D::QT; ++ob) dmma(qs[ob], nr[i][j], w2[(2 * i + j) * D::QT + ob]);
+                    }
+                }
         }
         if (d == 0 && tm.valid) st_state<NX, NU>(Q + (long long)node * NX, t, qs);   // only the head's q leaves the chain
     }
 }
 
 // ---- forward:  u = K x + R~^-1 r,  x_child = A x + B u -------------------------------------------------------------------
-template <int NX, int NU>
-__global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
+template <int NX, int NU, bool BIG>
+__global__ void __launch_bounds__(BIG ? 32 : 128) k_chain_mma_fwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
                                                       SweepLevel lv, double *__restrict__ prim, const double *__restrict__ r,
                                                       int d_begin, int d_end) {
     // steps d_begin <= d < d_end of the walk (d = depth below the head of the chain): a launch starts from the x of depth
@@ -355,10 +389,18 @@ __global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ P
     if (tile >= lv.num_tiles) return;
     constexpr int F4 = 2 * D::NT * D::QT, F3 = 2 * D::NT * D::RN;
     constexpr int kLaneWords = ring_lane_words(2 * D::RN + F3);                // per lane and stage: r | [K R~^-1] fragments
+    constexpr int kAbWords = BIG ? ring_lane_words(F4) : 0;                    // per lane: the [A ; B]' fragments (BIG)
+    static_assert(!BIG || (D::NT % 2 == 0 && D::QT % 2 == 0 && D::RN % 2 == 0), "BIG reads fragment pairs");
     double *ring = mma_smem + ((size_t)warp * kStages * 32 + lane) * kLaneWords;
     TileMeta tm;
-    if (!stage_meta(lv, ctrl, tile, warp, lane, reinterpret_cast<int *>(mma_smem + (size_t)warps * kStages * 32 * kLaneWords), tm))
+    if (!stage_meta(lv, ctrl, tile, warp, lane,
+                    reinterpret_cast<int *>(mma_smem + (size_t)warps * kStages * 32 * kLaneWords + (size_t)warps * 32 * kAbWords), tm))
         return;
+    const double *w4s = mma_smem + (size_t)warps * kStages * 32 * kLaneWords + ((size_t)warp * 32 + lane) * kAbWords;
+    if constexpr (BIG) {
+        if (lv.depth > 1) cp_frags<F4>(const_cast<double *>(w4s), P.m.fragABT, tm.dyns[1], lane);
+        cp_async_commit();
+    }
     const int t = tm.t, g = tm.g;
     double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
     const double *R = r + (long long)blockIdx.y * L.m * NU;
@@ -380,8 +422,10 @@ __global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ P
     };
     prefetch(d_begin);
     prefetch(d_begin + 1);
-    double w4[F4];   // [A ; B]' of the chain's dynamics row, fragment (2 kb + j) * QT + ob
-    if (lv.depth > 1) ld_frags<F4>(w4, P.m.fragABT, tm.dyns[1], lane);
+    double w4[BIG ? 2 : F4];   // [A ; B]' of the chain's dynamics row, fragment (2 kb + j) * QT + ob
+    if constexpr (!BIG) {
+        if (lv.depth > 1) ld_frags<F4>(w4, P.m.fragABT, tm.dyns[1], lane);
+    }
     double xs[D::QT][2];
     ld_state<NX, NU, false>(X + (long long)tm.nodes[d_begin * 8 + g] * NX, t, xs);   // written by the level above / the previous piece
 
@@ -390,9 +434,10 @@ __global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ P
         cp_async_wait<2>();
         const double *src = ring + (d % kStages) * 32 * kLaneWords;
         const int node = tm.nodes[d * 8 + g], child = tm.nodes[(d + 1) * 8 + g];
-        double rr[2 * D::RN], w3[F3];
+        double rr[2 * D::RN], w3[BIG ? 2 : F3];
         lds_vec(rr, src);
-        lds_vec(w3, src + 2 * D::RN);
+        const double *w3s = src + 2 * D::RN;
+        if constexpr (!BIG) lds_vec(w3, w3s);
         // u = [K R~^-1] [x ; r]  (lands on the input slots)
         double ua[D::RN][2];
 #pragma unroll
@@ -405,8 +450,17 @@ __global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ P
                 double v = 0.0;
                 if (kb < D::QT) v = xs[kb < D::QT ? kb : 0][j];
                 if (kb >= D::RT0 && !is_x) v = rr[2 * (kb >= D::RT0 ? kb - D::RT0 : 0) + j];
+                if constexpr (BIG) {
 #pragma unroll
-                for (int i = 0; i < D::RN; ++i) dmma(ua[i], v, w3[(2 * kb + j) * D::RN + i]);
+                    for (int i = 0; i < D::RN; i += 2) {
+                        const double2 w = *reinterpret_cast<const double2 *>(w3s + (2 * kb + j) * D::RN + i);
+                        dmma(ua[i], v, w.x);
+                        dmma(ua[i + 1], v, w.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < D::RN; ++i) dmma(ua[i], v, w3[(2 * kb + j) * D::RN + i]);
+                }
             }
         if (tm.valid) st_input<NX, NU>(U + (long long)node * NU, t, ua);
         // x_child = [A B] [x ; u]
@@ -421,8 +475,17 @@ __global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ P
                 double v = 0.0;
                 if (kb < D::QT) v = xs[kb < D::QT ? kb : 0][j];
                 if (kb >= D::RT0 && !is_x) v = ua[kb >= D::RT0 ? kb - D::RT0 : 0][j];
+                if constexpr (BIG) {
 #pragma unroll
-                for (int ob = 0; ob < D::QT; ++ob) dmma(xn[ob], v, w4[(2 * kb + j) * D::QT + ob]);
+                    for (int ob = 0; ob < D::QT; ob += 2) {
+                        const double2 w = *reinterpret_cast<const double2 *>(w4s + (2 * kb + j) * D::QT + ob);
+                        dmma(xn[ob], v, w.x);
+                        dmma(xn[ob + 1], v, w.y);
+                    }
+                } else {
+#pragma unroll
+                    for (int ob = 0; ob < D::QT; ++ob) dmma(xn[ob], v, w4[(2 * kb + j) * D::QT + ob]);
+                }
             }
         if (tm.valid) st_state<NX, NU>(X + (long long)child * NX, t, xn);
 #pragma unroll
@@ -436,11 +499,19 @@ __global__ void __launch_bounds__(128) k_chain_mma_fwd(const __grid_constant__ P
 }  // namespace
 
 // ---- host side --------------------------------------------------------------------------------------------------------------
-#define RB_MMA_DIMS(X) X(2, 1) X(3, 2) X(4, 2) X(8, 4) X(10, 5) X(20, 10)
+// (nx, nu, BIG): BIG = fragments in shared memory, one warp per CTA (nx + nu > 32)
+#define RB_MMA_DIMS(X) X(2, 1, false) X(3, 2, false) X(4, 2, false) X(8, 4, false) X(10, 5, false) X(20, 10, false) X(64, 32, true)
 
 bool chain_mma_supported(int nx, int nu) {
-#define RB_HAS(NX, NU) \
+#define RB_HAS(NX, NU, BIG) \
     if (nx == NX && nu == NU) return true;
+    RB_MMA_DIMS(RB_HAS)
+#undef RB_HAS
+    return false;
+}
+static bool chain_mma_big(int nx, int nu) {
+#define RB_HAS(NX, NU, BIG) \
+    if (nx == NX && nu == NU) return BIG;
     RB_MMA_DIMS(RB_HAS)
 #undef RB_HAS
     return false;
@@ -475,18 +546,22 @@ void launch_chain_mma_frags(cudaStream_t st, const Tabs &M, int nx, int nu, int 
     }
 }
 
-static dim3 mma_grid(const SweepLevel &lv, int batch) { return dim3((lv.num_tiles + 3) / 4, batch); }
-// dynamic shared memory of a 4-warp CTA: the cp.async rings + the tile metadata
+static dim3 mma_grid(const SweepLevel &lv, int batch, bool big) {
+    return big ? dim3(lv.num_tiles, batch) : dim3((lv.num_tiles + 3) / 4, batch);
+}
+// dynamic shared memory of a CTA (4 warps, or 1 if BIG): the cp.async rings (+ the dynamics fragments if BIG) + the tile metadata
 size_t chain_mma_smem_bytes(int nx, int nu, int depth, bool backward) {
     const int NT = (nx + nu + 7) / 8, QT = (nx + 7) / 8, RT0 = nx / 8, RN = NT - RT0;
     const int lane_words = ring_lane_words(backward ? 2 * QT + 2 * RN + 2 * RN * QT : 2 * RN + 2 * NT * RN);
-    return (size_t)4 * kStages * 32 * lane_words * sizeof(double) + (size_t)4 * (depth * 10 + 8) * sizeof(int);
+    const bool big = chain_mma_big(nx, nu);
+    const int warps = big ? 1 : 4, ab_words = big ? ring_lane_words(2 * QT * NT) : 0;
+    return (size_t)warps * 32 * (kStages * lane_words + ab_words) * sizeof(double) + (size_t)warps * (depth * 10 + 8) * sizeof(int);
 }
 cudaError_t chain_mma_set_smem(int bytes) {
     cudaError_t e = cudaSuccess;
-#define RB_SET(NX, NU)                                                                                                       \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_bwd<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_fwd<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+#define RB_SET(NX, NU, BIG)                                                                                                       \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_bwd<NX, NU, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_fwd<NX, NU, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     RB_MMA_DIMS(RB_SET)
 #undef RB_SET
     return e;
@@ -494,9 +569,9 @@ cudaError_t chain_mma_set_smem(int bytes) {
 
 void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, const double *prim,
                           double *q, double *r) {
-#define RB_GO(NX, NU)                                                                                             \
+#define RB_GO(NX, NU, BIG)                                                                                             \
     if (P.L.nx == NX && P.L.nu == NU) {                                                                           \
-        k_chain_mma_bwd<NX, NU><<<mma_grid(lv, P.L.batch), 128, chain_mma_smem_bytes(NX, NU, lv.depth, true), st>>>(P, ctrl, lv, prim, q, r);     \
+        k_chain_mma_bwd<NX, NU, BIG><<<mma_grid(lv, P.L.batch, BIG), BIG ? 32 : 128, chain_mma_smem_bytes(NX, NU, lv.depth, true), st>>>(P, ctrl, lv, prim, q, r);     \
         return;                                                                                                   \
     }
     RB_MMA_DIMS(RB_GO)
@@ -506,9 +581,9 @@ void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, co
 void launch_chain_mma_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, double *prim,
                           const double *r, int d_begin, int d_end) {
     if (d_end < 0) d_end = lv.depth;
-#define RB_GO(NX, NU)                                                                                             \
+#define RB_GO(NX, NU, BIG)                                                                                             \
     if (P.L.nx == NX && P.L.nu == NU) {                                                                           \
-        k_chain_mma_fwd<NX, NU><<<mma_grid(lv, P.L.batch), 128, chain_mma_smem_bytes(NX, NU, lv.depth, false), st>>>(P, ctrl, lv, prim, r, d_begin, d_end);        \
+        k_chain_mma_fwd<NX, NU, BIG><<<mma_grid(lv, P.L.batch, BIG), BIG ? 32 : 128, chain_mma_smem_bytes(NX, NU, lv.depth, false), st>>>(P, ctrl, lv, prim, r, d_begin, d_end);        \
         return;                                                                                                   \
     }
     RB_MMA_DIMS(RB_GO)
