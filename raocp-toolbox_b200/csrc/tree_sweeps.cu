@@ -62,17 +62,23 @@ __device__ __forceinline__ void stage_wait() {
 template <int COLS>
 __device__ __forceinline__ double dot_col(const double *MT, int stride, const double *v, int k, int cols) {
     if constexpr (COLS > 0) {
-        double m[COLS];
-#pragma unroll
-        for (int l = 0; l < COLS; ++l) m[l] = MT[l * stride + k];
-        asm volatile("" ::: "memory");   // loads first (see schedule_fence)
+        constexpr int CH = COLS > 32 ? 32 : COLS;   // at most 32 loads in flight per lane (wide rows: nx + nu > 32)
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-        for (int l = 0; l < COLS; ++l) {
-            if ((l & 3) == 0) a0 = fma(m[l], v[l], a0);
-            else if ((l & 3) == 1) a1 = fma(m[l], v[l], a1);
-            else if ((l & 3) == 2) a2 = fma(m[l], v[l], a2);
-            else a3 = fma(m[l], v[l], a3);
+        for (int l0 = 0; l0 < COLS; l0 += CH) {
+            double m[CH];
+#pragma unroll
+            for (int l = 0; l < CH; ++l)
+                if (l0 + l < COLS) m[l] = MT[(l0 + l) * stride + k];
+            asm volatile("" ::: "memory");   // loads first (see schedule_fence)
+#pragma unroll
+            for (int l = 0; l < CH; ++l)
+                if (l0 + l < COLS) {
+                    if ((l & 3) == 0) a0 = fma(m[l], v[l0 + l], a0);
+                    else if ((l & 3) == 1) a1 = fma(m[l], v[l0 + l], a1);
+                    else if ((l & 3) == 2) a2 = fma(m[l], v[l0 + l], a2);
+                    else a3 = fma(m[l], v[l0 + l], a3);
+                }
         }
         return (a0 + a1) + (a2 + a3);
     } else {
@@ -719,7 +725,7 @@ __global__ void __launch_bounds__(512) k_tree_fused(const __grid_constant__ Para
 }
 
 // ---- host side ----------------------------------------------------------------------------------------------------------------
-#define RB_TREE_DIMS(X) X(2, 1) X(3, 2) X(4, 2) X(8, 4) X(10, 5) X(20, 10)
+#define RB_TREE_DIMS(X) X(2, 1) X(3, 2) X(4, 2) X(8, 4) X(10, 5) X(20, 10) X(64, 32)
 
 // bytes of dynamic shared memory of the three kernels for a level (the maximum: one attribute for all)
 size_t tree_smem_bytes(const TreeLevel &lv, int nx, int nu, int warps, bool top) {
