@@ -809,6 +809,15 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
         }
         if (c_chain > c1 && c_chain < L.num_stages - 1 && L.num_stages - c_chain <= 64 && width(c_chain) >= cut2_min) {
             c2 = c_chain;
+            // The top is ONE CTA and every level-0 subtree is one CTA; a stage of either costs what its parents cost.
+            // Balance them: the first cut goes where the widest parent stage of the top, width(c - 1), and the widest
+            // parent stage of a subtree, width(c2 - 1) / width(c), are closest (cfg3: stage 3 either way; cfg5, 3 modes:
+            // stage 3 with 27 subtrees of 1 + 3 + 9 nodes instead of stage 4 with a 27-parent stage in the top).
+            if (pb->sweep_cut1_min == 0) {
+                auto cost = [&](int c) { return std::max(width(c - 1), width(c2 - 1) / std::max(1, width(c))); };
+                for (int c = c1 - 1; c >= 1 && width(c) >= 8; --c)
+                    if (cost(c) < cost(c1)) c1 = c;
+            }
         } else {
             for (int t = c1 + 1; t < L.num_stages; ++t)
                 if (width(t) >= std::max(2048, cut2_min) && width(t) >= 8 * width(c1)) {
