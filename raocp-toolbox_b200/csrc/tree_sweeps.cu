@@ -190,6 +190,52 @@ __device__ __forceinline__ double child_sum(const double *tab, long long len, in
     return (a0 + a1) + (a2 + a3);
 }
 
+// Wide rows (nx + nu > 32, operator tables in global memory): a stage whose parents all have the same children pattern
+// (same count, same dynamics rows -- every stage of a Markov tree) is BLOCKED over its parents: a warp owns one
+// (child position, 32 output entries) pair, loads a table word once (16 loads in flight per lane) and uses it for up to PB
+// parents, whose vectors it reads from shared memory (broadcast).  A 9-parent stage then moves the three tables from L2
+// once instead of nine times -- a CTA's L2 bandwidth (~64 B/clk) is what bounded these stages.
+// acc[p] = sum_l M[l * stride] * v[p * vstride + l], p < PB (rows of parents >= np shadow the last one; results unused)
+template <int ROWS, int PB>
+__device__ __forceinline__ void blocked_dots(const double *M, int stride, const double *v, int vstride, int np, double (&acc)[9]) {
+    const double *vp[PB];
+#pragma unroll
+    for (int p = 0; p < PB; ++p) {
+        vp[p] = v + (long long)(p < np ? p : np - 1) * vstride;
+        acc[p] = 0.0;
+    }
+#pragma unroll
+    for (int l0 = 0; l0 < ROWS; l0 += 16) {
+        double m[16];
+#pragma unroll
+        for (int l = 0; l < 16; ++l)
+            if (l0 + l < ROWS) m[l] = M[(long long)(l0 + l) * stride];
+        schedule_fence();
+#pragma unroll
+        for (int l = 0; l < 16; ++l)
+            if (l0 + l < ROWS) {
+#pragma unroll
+                for (int p = 0; p < PB; ++p) acc[p] = fma(m[l], vp[p][l0 + l], acc[p]);
+            }
+    }
+}
+template <int ROWS>
+__device__ __forceinline__ void blocked_dots_np(const double *M, int stride, const double *v, int vstride, int np, double (&acc)[9]) {
+    if (np <= 1) blocked_dots<ROWS, 1>(M, stride, v, vstride, np, acc);
+    else if (np <= 3) blocked_dots<ROWS, 3>(M, stride, v, vstride, np, acc);
+    else blocked_dots<ROWS, 9>(M, stride, v, vstride, np, acc);
+}
+// is the stage uniform (see above)?  children of consecutive parents are consecutive (breadth-first numbering)
+__device__ __forceinline__ bool stage_uniform(const Sub &s, int off, int w, const int *cdyn, int cc) {
+    const int cf0 = s.cfirst[off];
+    bool ok = cc >= 1;
+    for (int p = 0; p < w && ok; ++p) {
+        ok = s.ccount[off + p] == cc && s.cfirst[off + p] == cf0 + p * cc;
+        for (int j = 0; j < cc && ok; ++j) ok = cdyn[cf0 + p * cc + j] == cdyn[cf0 + j];
+    }
+    return ok;
+}
+
 // ---- backward over the subtree --------------------------------------------------------------------------------------------
 // One warp per parent, one block barrier per stage.  xb, ub: staged rows (local node order); qa holds the q of the
 // external children on entry; rbuf (optional) keeps r for a forward pass in the same kernel.  The root stage's q is
@@ -230,7 +276,59 @@ __device__ __forceinline__ void tree_backward(const Layout &L, const Sub &s, con
                 split = w * 4 <= warps;
                 for (int p = 0; p < w && split; ++p) split = s.ccount[off + p] == 4;
             }
-            if (split) {
+            bool blocked = false;
+            if constexpr (NX > 0 && NX + NU > 32)
+                blocked = s.ccount[off] * w <= 2 * warps && stage_uniform(s, off, w, cdyn, s.ccount[off]);
+            if (blocked) {
+                if constexpr (NX > 0 && NX + NU > 32) {
+                    constexpr int PASSES = (NX + NU + 31) / 32;
+                    const int cc = s.ccount[off], cf0 = s.cfirst[off], nblk = (w + 8) / 9, nt = cc * PASSES * nblk;
+                    // partial[j][p][k] = entry k of [A'q ; B'q] of child j of parent p  (scratch: cc * w * nxu doubles)
+                    for (int task = warp; task < nt; task += warps) {
+                        const int j = task % cc, t = (task / cc) % PASSES, p0 = 9 * (task / (cc * PASSES));
+                        const int k = lane + 32 * t, np = min(9, w - p0);
+                        if (k < nxu) {
+                            double a[9];
+                            blocked_dots_np<NX>(Ctab + (long long)cdyn[cf0 + j] * nx * nxu + k, nxu,
+                                                qchild + (long long)(cf0 + p0 * cc + j) * nx, cc * nx, np, a);
+#pragma unroll
+                            for (int p = 0; p < 9; ++p)
+                                if (p < np) scratch[((long long)j * w + p0 + p) * nxu + k] = a[p];
+                        }
+                    }
+                    __syncthreads();
+                    for (int p = warp; p < w; p += warps) {
+                        const int i = off + p;
+                        const double *K = Ktab + (long long)(RES ? i : s.cls[i]) * nu * nx;
+                        double a[PASSES];
+#pragma unroll
+                        for (int t = 0; t < PASSES; ++t) {
+                            const int k = lane + 32 * t;
+                            a[t] = 0.0;
+                            if (k < nxu)
+                                for (int j = 0; j < cc; ++j) a[t] += scratch[((long long)j * w + p) * nxu + k];
+                        }
+                        __syncwarp();   // the partial sums of parent p are consumed: r goes where partial[0][p][nx..) was
+                        double *rvp = scratch + (long long)p * nxu + nx;
+#pragma unroll
+                        for (int t = 0; t < PASSES; ++t) {
+                            const int k = lane + 32 * t;
+                            if (k >= nx && k < nxu) {
+                                const double rk = ub[i * nu + k - nx] - a[t];
+                                rvp[k - nx] = rk;
+                                if (rbuf) rbuf[i * nu + k - nx] = rk;
+                                Rglob[(long long)(lo + p) * nu + k - nx] = rk;
+                            }
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int t = 0; t < PASSES; ++t) {
+                            const int k = lane + 32 * t;
+                            if (k < nx) qcur[p * nx + k] = a[t] - xb[i * nx + k] - dot_col<NU>(K, nx, rvp, k, nu);
+                        }
+                    }
+                }
+            } else if (split) {
                 if constexpr (NX > 0 && NX + NU <= 32) {
                     double *part = scratch + (long long)warp * 2 * nxu;
                     if (warp < w * 4 && lane < nxu) {
@@ -340,7 +438,54 @@ __device__ __forceinline__ void tree_forward(const Layout &L, const Sub &s, cons
             split = w * 4 <= warps;
             for (int p = 0; p < w && split; ++p) split = s.ccount[off + p] == 4;
         }
-        if (split) {
+        bool blocked = false;   // as in tree_backward: wide rows, uniform stage
+        if constexpr (NX > 0 && NX + NU > 32) blocked = w <= 2 * warps && stage_uniform(s, off, w, cdyn, s.ccount[off]);
+        if (blocked) {
+            if constexpr (NX > 0 && NX + NU > 32) {
+                for (int p = warp; p < w; p += warps) {   // u = K x + R~^-1 r; [x ; u] of parent p into scratch row p
+                    const int i = off + p;
+                    double *vp = scratch + (long long)p * nxu;
+                    for (int k = lane; k < nx; k += 32) vp[k] = xcur[p * nx + k];
+                    for (int a = lane; a < nu; a += 32) vp[nx + a] = rbuf[i * nu + a];
+                    __syncwarp();
+                    const double *KR = KRtab + (long long)(RES ? i : s.cls[i]) * nxu * nu;
+                    double ua[(NU + 31) / 32];
+#pragma unroll
+                    for (int t = 0; t < (NU + 31) / 32; ++t) {
+                        const int a = lane + 32 * t;
+                        ua[t] = a < nu ? dot_col<NX + NU>(KR, nu, vp, a, nxu) : 0.0;
+                    }
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 0; t < (NU + 31) / 32; ++t) {
+                        const int a = lane + 32 * t;
+                        if (a < nu) {
+                            vp[nx + a] = ua[t];
+                            Uglob[(long long)(lo + p) * nu + a] = ua[t];
+                        }
+                    }
+                }
+                __syncthreads();
+                constexpr int PASSES = (NX + 31) / 32;
+                const int cc = s.ccount[off], cf0 = s.cfirst[off], nblk = (w + 8) / 9, nt = cc * PASSES * nblk;
+                for (int task = warp; task < nt; task += warps) {   // x of child j of up to 9 parents = [A B]_j [x ; u]
+                    const int j = task % cc, t = (task / cc) % PASSES, p0 = 9 * (task / (cc * PASSES));
+                    const int k = lane + 32 * t, np = min(9, w - p0);
+                    if (k < nx) {
+                        double a[9];
+                        blocked_dots_np<NX + NU>(CTtab + (long long)cdyn[cf0 + j] * nxu * nx + k, nx,
+                                                 scratch + (long long)p0 * nxu, nxu, np, a);
+#pragma unroll
+                        for (int p = 0; p < 9; ++p)
+                            if (p < np) {
+                                const int c = cf0 + (p0 + p) * cc + j;
+                                if (!bottom) xnext[c * nx + k] = a[p];
+                                Xglob[(cglob + c) * nx + k] = a[p];
+                            }
+                    }
+                }
+            }
+        } else if (split) {
             if constexpr (NX > 0 && NX + NU <= 32) {
                 if (warp < w * 4 && (warp & 3) == 0) {   // the parent's first warp: u = K x + R~^-1 r, [x; u] into its scratch row
                     const int p = warp >> 2, i = off + p;
