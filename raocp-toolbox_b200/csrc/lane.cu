@@ -1035,7 +1035,7 @@ void launch_dual_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, Ctrl *
 }
 
 // sizes with an instantiation of the chain dual pass (lanes per node as lane_group_width picks them)
-#define RB_CHAIN_DUAL_DIMS(X) X(4, 2, 4) X(8, 4, 4) X(16, 8, 4) X(20, 10, 4)
+#define RB_CHAIN_DUAL_DIMS(X) X(4, 2, 4) X(8, 4, 4) X(16, 8, 4) X(20, 10, 4) X(64, 32, 8)
 
 bool dual_chain_supported(int nx, int nu) {
 #define RB_HAS(NX, NU, G) \
