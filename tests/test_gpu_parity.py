@@ -172,6 +172,25 @@ def test_demo_reproduces_golden_residual_history():
     assert np.max(np.abs(xi[:k] - gold[:k]) / gold[:k]) < 1e-6
 
 
+# iterations of the NumPy oracle (oracle/cp_flat_oracle.py, pinned to the reference) until max(xi) <= tol on cfg1, seed 0,
+# alpha = 0.24574029027120411 -- recorded with the loop in the docstring below (21 s of CPU for the full 12 229 iterations)
+CFG1_ITERATIONS_TO_TOL = {1e-3: 5133, 1e-4: 7011, 1e-5: 9672, 1e-6: 12229}
+
+
+@pytest.mark.parametrize("tol", [1e-3, 1e-6])
+def test_cfg1_converges_at_the_oracle_iteration(tol):
+    """north star: convergence at the same iteration count +-1.  Recorded with
+    `o = FlatOracle(problem); o.cache_initial_state(x0); o.alpha = o.step_size(); k = first k with max(o.iterate()[0]) <= tol`;
+    the second solve checks that Solver.chock continues from the current iterate like the reference's (cache.py:79-82)."""
+    s, problem, r = _build("cfg1")
+    solver = r.core.Solver(problem, verbose=False)
+    assert solver.chock(s["x0"][:, :1], max_iters=20000, tol=tol, alpha=0.24574029027120411) == 0
+    assert abs(solver.iterations - CFG1_ITERATIONS_TO_TOL[tol]) <= 1
+    assert np.max(solver.residual_history[0][-1]) <= tol < np.max(solver.residual_history[0][-2])
+    assert solver.chock(s["x0"][:, :1], max_iters=20000, tol=tol, alpha=0.24574029027120411) == 0
+    assert solver.iterations <= 50   # already converged: warm start
+
+
 def test_step_size_matches_oracle(case):
     from oracle.cp_flat_oracle import FlatOracle
     lam = case["dev"].lambda_max()
