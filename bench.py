@@ -33,7 +33,16 @@ for p in (os.path.join(ROOT, "raocp-toolbox_b200"), ROOT):
     if p not in sys.path:
         sys.path.insert(0, p)
 
-os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line (NCCL prints its version banner there)
+# stdout carries exactly ONE JSON line: libraries that write to file descriptor 1 (NCCL prints its version banner there) are
+# sent to stderr for the whole run, and the line itself goes to a duplicate of the original stdout
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 
 import numpy as np  # noqa: E402
 
@@ -157,7 +166,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "wall_s": time.perf_counter() - t0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, rank, world, local_rank):
@@ -179,7 +188,8 @@ def run_ours(args, rank, world, local_rank):
     problem = problems.build(spec, r.core)
     t_build = time.perf_counter() - t0
     t0 = time.perf_counter()
-    solver = r.core.Solver(problem, batch=batch, dedup=not args.no_dedup, device=local_rank, verbose=False)
+    cuts = tuple(int(v) for v in args.sweep_cuts.split(",")) if args.sweep_cuts else None
+    solver = r.core.Solver(problem, batch=batch, dedup=not args.no_dedup, device=local_rank, verbose=False, sweep_cuts=cuts)
     solver.cache.device_solver.use_tree_kernels(args.tree_mode)
     solver.cache.device_solver.use_mma_sweeps(not args.no_mma)
     solver.cache.device_solver.use_pipeline(0 if args.no_pipeline else (3 if args.fwd_split else (4 if args.no_risk_split else 1)))
@@ -401,7 +411,7 @@ def run_ours(args, rank, world, local_rank):
         if "cpu_baseline" in line and line["cpu_baseline"].get("value"):
             ttt["cpu_seconds_extrapolated"] = ttt["iterations"] / line["cpu_baseline"]["value"]
         line["time_to_1e-6"] = ttt
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -417,6 +427,7 @@ def main():
     ap.add_argument("--no-dedup", action="store_true", help="stream per-node K / R~ (one factorisation class per node)")
     ap.add_argument("--ttt-iters", type=int, default=50000,
                     help="iteration cap of the time-to-1e-6-residual leg (0: skip it)")
+    ap.add_argument("--sweep-cuts", default="", help="ablation: 'a,b' = rb_problem.sweep_cut1_min, sweep_cut2_min")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--tree-mode", type=int, default=2, choices=[0, 1, 2],
                     help="ablation: branching sweep levels with sweeps.cu (0), tree_sweeps.cu per level (1), fused with the top (2)")
