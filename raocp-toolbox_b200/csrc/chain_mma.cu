@@ -239,6 +239,24 @@ __device__ __forceinline__ void lds_vec(double (&v)[N], const double *src) {
     }
 }
 
+// BIG: acc[o] += a(r) * W[r][o] over the ROWS rows of a lane's fragment block in shared memory (LEN words per row), the
+// row r + 1 loaded while the MMAs of row r issue (ptxas otherwise puts every LDS.128 right in front of the two DMMAs that
+// use it).  Measured neutral on cfg5 (45 / 50 us either way): ncu has the lone warp of an SM at ~27 cycles per DMMA with a
+// third of its samples on the NOP ptxas puts between two DMMAs -- the walker is bound by the DMMA rate of a single warp.
+template <int ROWS, int LEN, typename AF>
+__device__ __forceinline__ void mma_rows(const double *w, AF a_of_row, double (&acc)[LEN][2]) {
+    double wr[2][LEN];
+    lds_vec(wr[0], w);
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        if (r + 1 < ROWS) lds_vec(wr[(r + 1) & 1], w + (r + 1) * LEN);
+        asm volatile("" ::: "memory");
+        const double a = a_of_row(r);
+#pragma unroll
+        for (int o = 0; o < LEN; ++o) dmma(acc[o], a, wr[r & 1][o]);
+    }
+}
+
 // ---- backward:  r = ubar - B'q_child,  q = A'q_child - xbar - K'r    -------------------------------
 // BIG (nx + nu > 32): the fragments do not fit into registers.  One warp per CTA; the [A | B] fragments of the tile's
 // dynamics row are copied once into shared memory (lane-major, every lane reads only its own words: no barrier), the class
@@ -320,22 +338,16 @@ __global__ void __launch_bounds__(BIG ? 32 : 128) k_chain_mma_bwd(const __grid_c
             double E[D::NT][2];
 #pragma unroll
             for (int ob = 0; ob < D::NT; ++ob) E[ob][0] = E[ob][1] = 0.0;
+            if constexpr (BIG) {
+                mma_rows<2 * D::QT, D::NT>(w1s, [&](int r) { return qs[r >> 1][r & 1]; }, E);
+            } else {
 #pragma unroll
-            for (int kb = 0; kb < D::QT; ++kb)
+                for (int kb = 0; kb < D::QT; ++kb)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if constexpr (BIG) {
-#pragma unroll
-                        for (int ob = 0; ob < D::NT; ob += 2) {
-                            const double2 w = *reinterpret_cast<const double2 *>(w1s + (2 * kb + j) * D::NT + ob);
-                            dmma(E[ob], qs[kb][j], w.x);
-                            dmma(E[ob + 1], qs[kb][j], w.y);
-                        }
-                    } else {
+                    for (int j = 0; j < 2; ++j)
 #pragma unroll
                         for (int ob = 0; ob < D::NT; ++ob) dmma(E[ob], qs[kb][j], w1[(2 * kb + j) * D::NT + ob]);
-                    }
-                }
+            }
             // r = ubar - B'q  on the input slots (nr = -r feeds the second product)
             double rr[D::RN][2], nr[D::RN][2];
 #pragma unroll
@@ -352,22 +364,16 @@ __global__ void __launch_bounds__(BIG ? 32 : 128) k_chain_mma_bwd(const __grid_c
             for (int b = 0; b < D::QT; ++b)
 #pragma unroll
                 for (int j = 0; j < 2; ++j) qs[b][j] = (8 * b + 2 * t + j < NX) ? E[b][j] - xb[2 * b + j] : 0.0;
+            if constexpr (BIG) {
+                mma_rows<2 * D::RN, D::QT>(w2s, [&](int r) { return nr[r >> 1][r & 1]; }, qs);
+            } else {
 #pragma unroll
-            for (int i = 0; i < D::RN; ++i)
+                for (int i = 0; i < D::RN; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    if constexpr (BIG) {
-#pragma unroll
-                        for (int ob = 0; ob < D::QT; ob += 2) {
-                            const double2 w = *reinterpret_cast<const double2 *>(w2s + (2 * i + j) * D::QT + ob);
-                            dmma(qs[ob], nr[i][j], w.x);
-                            dmma(qs[ob + 1], nr[i][j], w.y);
-                        }
-                    } else {
+                    for (int j = 0; j < 2; ++j)
 #pragma unroll
                         for (int ob = 0; ob < D::QT; ++ob) dmma(qs[ob], nr[i][j], w2[(2 * i + j) * D::QT + ob]);
-                    }
-                }
+            }
         }
         if (d == 0 && tm.valid) st_state<NX, NU>(Q + (long long)node * NX, t, qs);   // only the head's q leaves the chain
     }
@@ -442,51 +448,55 @@ __global__ void __launch_bounds__(BIG ? 32 : 128) k_chain_mma_fwd(const __grid_c
         double ua[D::RN][2];
 #pragma unroll
         for (int i = 0; i < D::RN; ++i) ua[i][0] = ua[i][1] = 0.0;
-#pragma unroll
-        for (int kb = 0; kb < D::NT; ++kb)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
+        if constexpr (BIG) {
+            mma_rows<2 * D::NT, D::RN>(w3s, [&](int r) {
+                const int kb = r >> 1, j = r & 1;
                 const bool is_x = 8 * kb + 2 * t + j < NX;
                 double v = 0.0;
                 if (kb < D::QT) v = xs[kb < D::QT ? kb : 0][j];
                 if (kb >= D::RT0 && !is_x) v = rr[2 * (kb >= D::RT0 ? kb - D::RT0 : 0) + j];
-                if constexpr (BIG) {
+                return v;
+            }, ua);
+        } else {
 #pragma unroll
-                    for (int i = 0; i < D::RN; i += 2) {
-                        const double2 w = *reinterpret_cast<const double2 *>(w3s + (2 * kb + j) * D::RN + i);
-                        dmma(ua[i], v, w.x);
-                        dmma(ua[i + 1], v, w.y);
-                    }
-                } else {
+            for (int kb = 0; kb < D::NT; ++kb)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const bool is_x = 8 * kb + 2 * t + j < NX;
+                    double v = 0.0;
+                    if (kb < D::QT) v = xs[kb < D::QT ? kb : 0][j];
+                    if (kb >= D::RT0 && !is_x) v = rr[2 * (kb >= D::RT0 ? kb - D::RT0 : 0) + j];
 #pragma unroll
                     for (int i = 0; i < D::RN; ++i) dmma(ua[i], v, w3[(2 * kb + j) * D::RN + i]);
                 }
-            }
+        }
         if (tm.valid) st_input<NX, NU>(U + (long long)node * NU, t, ua);
         // x_child = [A B] [x ; u]
         double xn[D::QT][2];
 #pragma unroll
         for (int b = 0; b < D::QT; ++b) xn[b][0] = xn[b][1] = 0.0;
-#pragma unroll
-        for (int kb = 0; kb < D::NT; ++kb)
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
+        if constexpr (BIG) {
+            mma_rows<2 * D::NT, D::QT>(w4s, [&](int r) {
+                const int kb = r >> 1, j = r & 1;
                 const bool is_x = 8 * kb + 2 * t + j < NX;
                 double v = 0.0;
                 if (kb < D::QT) v = xs[kb < D::QT ? kb : 0][j];
                 if (kb >= D::RT0 && !is_x) v = ua[kb >= D::RT0 ? kb - D::RT0 : 0][j];
-                if constexpr (BIG) {
+                return v;
+            }, xn);
+        } else {
 #pragma unroll
-                    for (int ob = 0; ob < D::QT; ob += 2) {
-                        const double2 w = *reinterpret_cast<const double2 *>(w4s + (2 * kb + j) * D::QT + ob);
-                        dmma(xn[ob], v, w.x);
-                        dmma(xn[ob + 1], v, w.y);
-                    }
-                } else {
+            for (int kb = 0; kb < D::NT; ++kb)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const bool is_x = 8 * kb + 2 * t + j < NX;
+                    double v = 0.0;
+                    if (kb < D::QT) v = xs[kb < D::QT ? kb : 0][j];
+                    if (kb >= D::RT0 && !is_x) v = ua[kb >= D::RT0 ? kb - D::RT0 : 0][j];
 #pragma unroll
                     for (int ob = 0; ob < D::QT; ++ob) dmma(xn[ob], v, w4[(2 * kb + j) * D::QT + ob]);
                 }
-            }
+        }
         if (tm.valid) st_state<NX, NU>(X + (long long)child * NX, t, xn);
 #pragma unroll
         for (int b = 0; b < D::QT; ++b) {
