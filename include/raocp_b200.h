@@ -85,7 +85,7 @@ typedef struct {
      * (rank, world); world <= 1 = not sharded.  Rank r owns a contiguous block of the subtrees below the first stage
      * with >= 64 nodes and replicates the nodes above it; rb_shard_init must follow rb_create. */
     int32_t shard_rank, shard_world;
-    /* tuning / test hook for the cut stages of the DP sweeps (sweeps.cu); 0 = defaults (64 and 256 nodes): the first cut
+    /* tuning / test hook for the cut stages of the DP sweeps (sweeps.cu); 0 = defaults (64 nodes, 200 chains): the first cut
      * is the first stage with >= sweep_cut1_min nodes, the second the stage where the tree turns into chains if it has
      * >= sweep_cut2_min of them.  Must be 0 when shard_world > 1. */
     int32_t sweep_cut1_min, sweep_cut2_min;

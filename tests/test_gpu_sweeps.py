@@ -19,7 +19,7 @@ CASES = [
     ("chain105", (64, 200)),    # nx=10, nu=5 (odd nu)
     ("chain2010", None),        # default plan: cut at 64 nodes, 256 chains
     ("chain6432", (9, 27)),     # nx=64, nu=32 (cfg5's sizes): tensor-core walker with the fragments in shared memory
-    ("cfg2", None),             # default plan, no chain level (243 chains < 256)
+    ("cfg2", None),             # default plan: one tree level + 243 chains
     ("wide", (2, 4)),           # nx=40, nu=36: rows wider than a warp, run-time-size kernels
     ("cfg1", None),             # 31 nodes: the whole tree is the "top"
 ]
