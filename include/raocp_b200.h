@@ -187,13 +187,18 @@ int rb_use_pipeline(rb_solver *s, int32_t enable);
 /* how the pipelined dual pass is split: nodes [0, early) run next to the forward chain sweep, [chain_first, chain_first +
  * chain_nodes) through k_dual_chain; chain_nodes = 0 when the loop is not pipelined or has no chain kernel for (nx, nu) */
 int rb_pipeline_info(const rb_solver *s, int32_t *early_nodes, int32_t *chain_first, int32_t *chain_nodes);
-int rb_use_graphs(rb_solver *s, int32_t enable);
+int rb_use_graphs(rb_solver *s, int32_t enable); /* 1 (default): one CUDA graph per iteration; 0: plain launches */
 /* subtree sharding: rank 0 calls rb_shard_unique_id and distributes the 128 bytes (e.g. torch.distributed broadcast),
  * every rank then calls rb_shard_init (collective: ncclCommInitRank).  Afterwards rb_iterate / rb_loop_* run the
  * sharded loop: per iteration ONE all-gather of the cut-stage q_j, d2_j and the residual maxima; the iterates of a
  * rank are valid on its own nodes and on the replicated top of the tree. */
 int rb_shard_unique_id(char *id128);
 int rb_shard_init(rb_solver *s, const char *id128);
+/* the cut the device chose for the DP sweeps and for subtree sharding -- the ONE source of truth for it (the host
+ * never re-derives the rule): cut_stage = first stage below the replicated top, cut_first = its first node, num_cut =
+ * its width (rank r of W owns the cut nodes [r*num_cut/W, (r+1)*num_cut/W) and their descendants), chain_stage = the
+ * stage from which the chain walkers take over (-1: none).  Any pointer may be NULL.  Valid after rb_create. */
+int rb_shard_info(const rb_solver *s, int32_t *cut_stage, int32_t *cut_first, int32_t *num_cut, int32_t *chain_stage);
 /* test hook: 0 = never use the lanes-per-node passes (lane.cu), always the warp-per-node tile kernels */
 int rb_use_lane_kernels(rb_solver *s, int32_t enable);
 /* test hook: 0 = walk chains with one warp per chain (sweeps.cu) instead of eight chains per warp on the FP64 tensor
@@ -204,7 +209,7 @@ int rb_use_mma_sweeps(rb_solver *s, int32_t enable);
  * level and the top fused into one cooperative launch when all its CTAs can be co-resident */
 int rb_use_tree_kernels(rb_solver *s, int32_t mode);
 /* test hook: 1 = use the general dense-matrix cost path even if sqrtQ, sqrtR, sqrtQf are all diagonal */
-int rb_force_dense_costs(rb_solver *s, int32_t enable); /* 1 (default): one CUDA graph per iteration; 0: plain launches */
+int rb_force_dense_costs(rb_solver *s, int32_t enable);
 int rb_launch_count(const rb_solver *s, int64_t *kernels_launched); /* kernels launched by this handle so far */
 
 /* -- stand-alone projections (cones.py:30-132, rectangle.py:29-59): host vector in, host vector out ----------------

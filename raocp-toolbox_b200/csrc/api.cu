@@ -1242,26 +1242,40 @@ int rb_lambda_max(rb_solver *s, double *lambda_max) {
         }
     }
     const int ng = (int)groups.size();
-    int *d_ptr = nullptr, *d_idx = nullptr;
-    double *d_work = nullptr, *d_out = nullptr;
     const int dim = std::max(L.nx, L.nu);
-    RB_CUDA(s, cudaMalloc((void **)&d_ptr, grp_ptr.size() * sizeof(int)));
-    RB_CUDA(s, cudaMalloc((void **)&d_idx, std::max<size_t>(grp_idx.size(), 1) * sizeof(int)));
-    RB_CUDA(s, cudaMalloc((void **)&d_work, (size_t)std::max(ng, s->num_leafcost) * dim * dim * sizeof(double)));
-    RB_CUDA(s, cudaMalloc((void **)&d_out, sizeof(double)));
+    // temporaries in ONE allocation, released on every path
+    struct Scratch {
+        char *p = nullptr;
+        ~Scratch() { if (p) cudaFree(p); }
+    } scratch;
+    auto up8 = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t b_ptr = up8(grp_ptr.size() * sizeof(int)), b_idx = up8(std::max<size_t>(grp_idx.size(), 1) * sizeof(int)),
+                 b_work = up8((size_t)std::max(ng, s->num_leafcost) * dim * dim * sizeof(double)), b_out = 256;
+    RB_CUDA(s, cudaMalloc((void **)&scratch.p, b_ptr + b_idx + b_work + b_out));
+    int *d_ptr = reinterpret_cast<int *>(scratch.p), *d_idx = reinterpret_cast<int *>(scratch.p + b_ptr);
+    double *d_work = reinterpret_cast<double *>(scratch.p + b_ptr + b_idx);
+    double *d_out = reinterpret_cast<double *>(scratch.p + b_ptr + b_idx + b_work);
     RB_CUDA(s, cudaMemcpyAsync(d_ptr, grp_ptr.data(), grp_ptr.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
     RB_CUDA(s, cudaMemcpyAsync(d_idx, grp_idx.data(), grp_idx.size() * sizeof(int), cudaMemcpyHostToDevice, s->stream));
     RB_CUDA(s, cudaMemsetAsync(d_out, 0, sizeof(double), s->stream));
     for (int kind = 0; kind < 3; ++kind) {
         const int count = kind == 2 ? s->num_leafcost : ng;
-        k_gram_eig<<<count, 32, 0, s->stream>>>(s->P, d_ptr, d_idx, kind, count, d_work, d_out);
+        k_gram_eig<<<count, 32, 0, s->stream>>>(s->P, d_ptr, d_idx, kind, count, d_work, d_out, s->status);
         RB_LAUNCHED(s, "k_gram_eig");
     }
     k_risk_block_eig<<<(L.m + 3) / 4, 128, 0, s->stream>>>(s->P, d_out);
     RB_LAUNCHED(s, "k_risk_block_eig");
     RB_CUDA(s, cudaMemcpyAsync(lambda_max, d_out, sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    int st = 0;
+    RB_CUDA(s, cudaMemcpyAsync(&st, s->status, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     RB_CUDA(s, cudaStreamSynchronize(s->stream));
-    cudaFree(d_ptr); cudaFree(d_idx); cudaFree(d_work); cudaFree(d_out);
+    if (st & 8) {
+        RB_CUDA(s, cudaMemsetAsync(s->status, 0, sizeof(int), s->stream));
+        return fail(s, RB_ERR_NUMERIC, "step size: the Jacobi eigenvalue iteration did not converge (non-finite or "
+                                       "ill-conditioned cost matrices); lambda_max(L*L) would be under-estimated");
+    }
+    if (!(*lambda_max == *lambda_max) || *lambda_max <= 0.0)
+        return fail(s, RB_ERR_NUMERIC, "step size: lambda_max(L*L) is not a positive finite number");
     return RB_OK;
 }
 
@@ -1702,6 +1716,25 @@ int rb_loop_end(rb_solver *s, double *xi_hist, double *delta_hist, int32_t *iter
     return rc;
 }
 
+// a loop that failed half way: drain the stream, give the buffers back the roles they had at rb_loop_begin (the iterate of
+// that moment is still intact in the "old" buffer of the first iteration only if nothing ran; either way the handle is
+// usable again and rb_use_* / rb_loop_begin are accepted), keep the error message of the failing call
+static int abort_loop(rb_solver *s, int rc) {
+    const std::string msg = s->err;
+    cudaStreamSynchronize(s->stream);
+    for (auto q : s->side)
+        if (q) cudaStreamSynchronize(q);
+    cudaGetLastError();
+    s->in_loop = false;
+    s->pbar_ready = false;
+    s->shard_pending = false;
+    s->old_i = s->loop_old0;
+    s->cur_i = 1 - s->loop_old0;
+    s->collapsed = true;
+    s->err = msg;
+    return rc;
+}
+
 int rb_iterate(rb_solver *s, double alpha, int32_t max_iters, double tol, int32_t check_every, double *xi_hist,
                double *delta_hist, int32_t hist_capacity, int32_t *iters, int32_t *status) {
     if (!s || max_iters < 0) return RB_ERR_INVALID;
@@ -1716,14 +1749,11 @@ int rb_iterate(rb_solver *s, double alpha, int32_t max_iters, double tol, int32_
     while (launched < total) {
         const int todo = std::min(chunk, total - launched);
         rc = rb_loop_enqueue(s, todo);
-        if (rc != RB_OK) return rc;
+        if (rc != RB_OK) return abort_loop(s, rc);
         launched += todo;
         int32_t it = 0, done = 0;
         rc = rb_loop_poll(s, &it, &done, nullptr);
-        if (rc != RB_OK) {
-            s->in_loop = false;
-            return rc;
-        }
+        if (rc != RB_OK) return abort_loop(s, rc);
         if (done) break;
     }
     return rb_loop_end(s, xi_hist, delta_hist, iters, status);
@@ -1734,13 +1764,10 @@ int rb_iterate_fixed(rb_solver *s, double alpha, int32_t iters, double *norms) {
     int rc = rb_loop_begin(s, alpha, iters - 1, -1.0, 0);
     if (rc != RB_OK) return rc;
     rc = rb_loop_enqueue(s, iters);
-    if (rc != RB_OK) return rc;
+    if (rc != RB_OK) return abort_loop(s, rc);
     int32_t it = 0, done = 0;
     rc = rb_loop_poll(s, &it, &done, norms);
-    if (rc != RB_OK) {
-        s->in_loop = false;
-        return rc;
-    }
+    if (rc != RB_OK) return abort_loop(s, rc);
     return rb_loop_end(s, nullptr, nullptr, nullptr, nullptr);
 }
 
@@ -1899,6 +1926,16 @@ int rb_shard_init(rb_solver *s, const char *id128) {
     RB_CUDA(s, cudaSetDevice(s->device));
     const int rc = nccl_comm_init(&s->nccl_comm, s->shard.world, id, s->shard.rank);
     if (rc != 0) return fail(s, RB_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl_error(rc));
+    return RB_OK;
+}
+
+int rb_shard_info(const rb_solver *s, int32_t *cut_stage, int32_t *cut_first, int32_t *num_cut, int32_t *chain_stage) {
+    if (!s) return RB_ERR_INVALID;
+    const SweepPlan &pl = s->plan;
+    if (cut_stage) *cut_stage = pl.t_top;
+    if (cut_first) *cut_first = pl.t_top < s->P.L.num_stages ? s->stage_off[pl.t_top] : s->P.L.n;
+    if (num_cut) *num_cut = pl.num_levels > 0 ? pl.lv[0].num_sub : 0;
+    if (chain_stage) *chain_stage = pl.num_levels > 1 ? pl.lv[1].t_lo : -1;
     return RB_OK;
 }
 

@@ -193,7 +193,8 @@ size_t offline_smem_bytes(int nx, int nu);
 
 // lambda_max(L* L) pieces
 __global__ void k_gram_eig(const __grid_constant__ Params P, const int *__restrict__ grp_ptr, const int *__restrict__ grp_idx,
-                           int kind, int num_groups, double *__restrict__ work, double *__restrict__ out_max);
+                           int kind, int num_groups, double *__restrict__ work, double *__restrict__ out_max,
+                           int *__restrict__ status);
 __global__ void k_risk_block_eig(const __grid_constant__ Params P, double *__restrict__ out_max);
 
 }  // namespace rb

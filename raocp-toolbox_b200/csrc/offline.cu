@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kOffThreads) k_offline_level(const __grid_cons
 // work: [num_groups][dim*dim] scratch.
 __global__ void k_gram_eig(const __grid_constant__ Params P, const int *__restrict__ grp_ptr,
                            const int *__restrict__ grp_idx, int kind, int num_groups, double *__restrict__ work,
-                           double *__restrict__ out_max) {
+                           double *__restrict__ out_max, int *__restrict__ status) {
     const int g = blockIdx.x;
     if (g >= num_groups) return;
     const int lane = threadIdx.x;
@@ -192,6 +192,7 @@ __global__ void k_gram_eig(const __grid_constant__ Params P, const int *__restri
     }
     __syncwarp();
     // cyclic Jacobi (eigenvalues only): rotate rows/columns p, q until the off-diagonal mass vanishes
+    bool converged = false;
     for (int sweep = 0; sweep < 30; ++sweep) {
         double off = 0.0, diag = 0.0;
         for (int i = lane; i < dim * dim; i += 32) {
@@ -200,7 +201,11 @@ __global__ void k_gram_eig(const __grid_constant__ Params P, const int *__restri
         }
         off = warp_sum(off);
         diag = warp_sum(diag);
-        if (off <= 1e-34 * diag) break;   // off-diagonal mass below (1e-17)^2 of the diagonal: converged
+        if (off <= 1e-34 * diag) {   // off-diagonal mass below (1e-17)^2 of the diagonal: converged
+            converged = true;
+            break;
+        }
+        if (!(off == off) || !(diag == diag)) break;   // NaN in the cost matrices: reported below
         for (int p = 0; p < dim - 1; ++p) {
             for (int q = p + 1; q < dim; ++q) {
                 const double apq = G[p * dim + q];
@@ -225,6 +230,17 @@ __global__ void k_gram_eig(const __grid_constant__ Params P, const int *__restri
                 }
             }
         }
+    }
+    if (!converged) {   // the 30-sweep cap was hit (or NaN): one more look at the off-diagonal mass, with a usable tolerance
+        double off = 0.0, diag = 0.0;
+        for (int i = lane; i < dim * dim; i += 32) {
+            if (i / dim != i % dim) off = fma(G[i], G[i], off);
+            else diag = fma(G[i], G[i], diag);
+        }
+        off = warp_sum(off);
+        diag = warp_sum(diag);
+        // a diagonal maximum taken before convergence UNDER-estimates lambda_max -> alpha too large -> divergence: refuse
+        if (!(off <= 1e-26 * diag) && lane == 0) atomicOr(status, 8);
     }
     double best = 0.0;
     for (int k = lane; k < dim; k += 32) best = fmax(best, G[k * dim + k]);

@@ -54,6 +54,7 @@ class DeviceSolver:
         self._call("rb_sizes", C.byref(np_), C.byref(nd_))
         assert (np_.value, nd_.value) == (f.np_, f.nd_), "host / device layout mismatch"
         self.np_, self.nd_, self.batch = f.np_, f.nd_, f.batch
+        f.shard_cut = self.shard_info()[0]     # the device's cut stage is the only source of truth (flatten.shard_*)
 
     def _call(self, name, *args):
         _lib.check(getattr(self._lib, name)(self._h, *args), self._h)
@@ -278,6 +279,12 @@ class DeviceSolver:
         return [v for v in ms[:8] if v >= 0.0], [v for v in ms[8:] if v >= 0.0]
 
     # ---- subtree sharding over GPUs (one process per GPU) ------------------------------------------------------------------
+    def shard_info(self):
+        """(cut_stage, cut_first, num_cut, chain_stage) as chosen by rb_create (rb_shard_info)"""
+        v = [C.c_int32() for _ in range(4)]
+        self._call("rb_shard_info", *[C.byref(x) for x in v])
+        return tuple(x.value for x in v)
+
     def shard_init(self, unique_id=None):
         """collective: rank 0 creates the NCCL id, torch.distributed carries it, every rank joins the communicator"""
         import torch

@@ -215,15 +215,16 @@ class FlatProblem:
         st = mp["d_starts"]
         return [flat[st[k]: st[k + 1]].reshape(-1, 1).copy() for k in range(len(st) - 1)]
 
-    # ---- subtree sharding (mirrors rb_create / shard.cu) ------------------------------------------------------------------
-    SHARD_CUT_WIDTH = 64   # the cut stage is the first stage with at least this many nodes (= first sweep level)
+    # ---- subtree sharding: ownership of the compact entries, given the cut stage THE DEVICE chose ---------------------------
+    # The cut rule lives in rb_create only (csrc/api.cu: balanced first cut of the sweep plan); DeviceSolver stores the
+    # answer of rb_shard_info() in `shard_cut` right after rb_create.  Host-only tests pass a cut stage explicitly.
+    shard_cut = None
 
     def shard_cut_stage(self):
-        widths = np.diff(self.stage_off)
-        wide = np.flatnonzero(widths >= self.SHARD_CUT_WIDTH)
-        if wide.size == 0:
-            raise Exception("the tree has no stage with >= 64 nodes: nothing to shard")
-        return int(wide[0])
+        if self.shard_cut is None:
+            raise Exception("the cut stage is decided by the device (rb_shard_info): create the DeviceSolver first "
+                            "or set FlatProblem.shard_cut")
+        return int(self.shard_cut)
 
     def shard_owned_nodes(self, rank, world):
         """bool[n]: nodes whose node-indexed quantities rank `rank` owns (its subtrees below the cut stage; rank 0 also
