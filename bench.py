@@ -47,14 +47,21 @@ def emit(line):
 import numpy as np  # noqa: E402
 
 METRIC = "CP iterations/sec"
-# bounded CPU samples: same modes / nx / nu as the workload on a shorter tree, so the node-by-node CPU port (55 s per
-# iteration on the full cfg3 tree) finishes in seconds; scaled to the full tree by node count (cost is linear in nodes)
-CPU_SAMPLE = {"cfg1": None, "cfg2": (3, 7, 4), "cfg3": (4, 8, 4), "cfg4": None, "cfg5": (3, 6, 4)}  # (modes, N, tau)
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel, from the committed `ncu --set full`
-# capture of the same command (profiles/): (workload, batch, dedup) -> bytes
-TRAFFIC = {("cfg3", 1, True): 57.84e6 + 4.56e6}   # profiles/r1c_iter_raw.csv, k_dual_chain<20,10,4,3>
+def measured_traffic(workload, batch, dedup, kernel_tag):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel: profiles/traffic.json maps
+    "<workload>/<batch>/<dedup>/<kernel tag>" to the bytes of a committed `ncu --set full` capture (file and commit named
+    there).  No entry for the kernel this run timed -> null (never a stale literal)."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        table = json.load(open(path))
+    except Exception:
+        return None, None
+    ent = table.get(f"{workload}/{batch}/{'dedup' if dedup else 'nodedup'}/{kernel_tag}")
+    if not ent:
+        return None, None
+    return float(ent["dram_bytes_per_launch"]), f"{ent['capture']} @ {ent['commit']}"
 
 
 def peaks():
@@ -73,27 +80,65 @@ def algorithmic_bytes(flat, batch, dedup):
 
 
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  NVML is polled from a thread every millisecond (the default
+    driver run times 20 iterations = 2 ms: `nvidia-smi -lms` never gets a sample in); the recipe's nvidia-smi query
+    (B200_PROFILING.md) is the fallback when pynvml is missing."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
              "clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
-    def __init__(self, index):
-        self.index, self.proc, self.path = index, None, None
+    def __init__(self, index, pci_bus_id=None):
+        self.index, self.pci = index, pci_bus_id
+        self.proc = self.path = self.thread = None
+        self.sm, self.mask, self.stop_flag, self.max_mhz, self.power = [], 0, False, None, 0.0
+
+    def _poll(self, nv, h):
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                self.mask |= int(get(h))
+                self.power = max(self.power, nv.nvmlDeviceGetPowerUsage(h) / 1e3)
+            except Exception:
+                pass
+            time.sleep(0.001)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByPciBusId(self.pci.encode()) if self.pci else nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            if self.sm:
+                out.update(sm_mhz=float(np.median(self.sm)), sm_min_mhz=float(np.min(self.sm)), samples=len(self.sm),
+                           power_w_max=self.power, source="NVML polled every 1 ms during the timed region")
+            out["sm_max_mhz"] = self.max_mhz
+            out["reasons"] = sorted(name for bit, name in self.BITS.items() if self.mask & bit)
+            return out
         if self.proc is None:
             return out
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -116,57 +161,151 @@ class ClockSampler:
         if sm:
             out["sm_mhz"] = float(np.median(sm))
             out["samples"] = len(sm)
+            out["source"] = "nvidia-smi -lms 20"
         out["reasons"] = sorted(reasons)
         return out
 
 
-def cpu_baseline(workload, budget_iters=4):
-    """Times the node-by-node CPU port of the reference (oracle/cp_node_oracle.py, kind "port") on a bounded sample."""
+def _x0_of(spec):
+    return spec["x0"][:, :1]
+
+
+def reference_timing(workload, step_budget_s, max_steps, warmup_steps=0):
+    """The UNMODIFIED reference (oracle/ref_loader.py: /root/reference or baseline/_ref) on the ACTUAL workload, its own
+    Solver methods called in the order of Solver.chock's loop body with the iterate history pruned (oracle/ref_stepper.py;
+    BASELINE.md section 3).  Steps until `step_budget_s` seconds of stepping are used up (at least one timed iteration)."""
+    from oracle import problems, ref_loader
+    from oracle.cp_flat_oracle import FlatOracle
+    from oracle.ref_stepper import RefStepper
+    api = ref_loader.RefApi()
+    spec = problems.spec(workload)
+    t0 = time.perf_counter()
+    problem = problems.build(spec, api)
+    build_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    alpha = FlatOracle(problem).step_size()    # closed-form block lambda_max == ARPACK's to 1e-15 (SURVEY 8c); ARPACK itself
+    alpha_s = time.perf_counter() - t0         # needs ~65 L / L* pairs through Python callbacks, minutes at cfg3
+    st = RefStepper(api, problem, _x0_of(spec), alpha)
+    for _ in range(warmup_steps):
+        st.step()
+    times = []
+    while len(times) < max_steps and (not times or sum(times) + times[-1] <= step_budget_s):
+        t0 = time.perf_counter()
+        st.step()
+        times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    return {"value": 1.0 / sec, "unit": "it/s", "cores": 1, "kind": "reference", "extrapolated": False,
+            "seconds_per_iteration": sec, "iterations_timed": len(times), "warmup_iterations": warmup_steps,
+            "offline_s": st.setup_s, "problem_build_s": build_s, "nodes": int(problem.tree.num_nodes),
+            "residuals_last": [float(v) for v in st.xi[-1]],
+            "sample": f"{len(times)} full Chambolle-Pock iteration(s) of the unmodified reference Solver on the whole "
+                      f"{workload} problem ({int(problem.tree.num_nodes)} nodes; {ref_loader.source()}), manual stepping with "
+                      f"pruned history, residual norms every iteration: {sec:.2f} s/iteration; Solver() incl. Cache._offline "
+                      f"{st.setup_s:.1f} s, problem build {build_s:.1f} s; single Python process (NumPy on (k,1) blocks is "
+                      f"single-threaded: 1 core used of {os.cpu_count()})"}
+
+
+def port_timing(workload, step_budget_s, max_steps):
+    """fallback when the reference is not installed: the node-by-node NumPy port (oracle/cp_node_oracle.py) on the full tree"""
     from oracle import problems
     from oracle.cp_node_oracle import NodeOracle
+    from oracle.cp_flat_oracle import FlatOracle
     import raocp_b200 as r
-    full = problems.spec(workload)
-    sample_shape = CPU_SAMPLE.get(workload)
-    s = dict(full)
-    if sample_shape is not None:
-        modes, horizon, tau = sample_shape
-        s["horizon"], s["tau"] = horizon, tau
-    problem = problems.build(s, r.core)
-    n_sample = problem.tree.num_nodes
-    n_full = problems.build(full, r.core).tree.num_nodes if sample_shape is not None else n_sample
+    spec = problems.spec(workload)
+    problem = problems.build(spec, r.core)
     t0 = time.perf_counter()
     orc = NodeOracle(problem)
     t_setup = time.perf_counter() - t0
-    orc.cache_initial_state(full["x0"][:, :1])
-    from oracle.cp_flat_oracle import FlatOracle
+    orc.cache_initial_state(_x0_of(spec))
     orc.alpha = FlatOracle(problem).step_size()
-    orc.iterate()  # warm-up
-    t0 = time.perf_counter()
-    for _ in range(budget_iters):
+    times = []
+    while len(times) < max_steps and (not times or sum(times) + times[-1] <= step_budget_s):
+        t0 = time.perf_counter()
         orc.iterate()
-    dt = (time.perf_counter() - t0) / budget_iters
-    its_sample = 1.0 / dt
-    value = its_sample * n_sample / n_full
-    return {"value": value, "unit": "it/s", "cores": 1, "kind": "port",
-            "sample": f"{budget_iters} iterations of oracle/cp_node_oracle.py (NumPy, node-by-node like the reference) on "
-                      f"a {n_sample}-node tree with the workload's modes/nx/nu: {its_sample:.3f} it/s, scaled by "
-                      f"{n_sample}/{n_full} nodes to the full tree; setup (offline + null spaces) {t_setup:.1f} s; "
-                      f"host cores available: {os.cpu_count()}"}
+        times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    return {"value": 1.0 / sec, "unit": "it/s", "cores": 1, "kind": "port", "extrapolated": False,
+            "seconds_per_iteration": sec, "iterations_timed": len(times), "offline_s": t_setup,
+            "nodes": int(problem.tree.num_nodes),
+            "sample": f"{len(times)} iteration(s) of oracle/cp_node_oracle.py (NumPy, node by node like the reference) on the "
+                      f"whole {workload} tree: {sec:.2f} s/iteration; the reference itself is not installed on this box"}
+
+
+def cpu_baseline(workload, step_budget_s=20.0, max_steps=50, warmup_steps=0):
+    from oracle import ref_loader
+    if ref_loader.available():
+        try:
+            return reference_timing(workload, step_budget_s, max_steps, warmup_steps)
+        except Exception as exc:   # e.g. a scipy / numpy combination the reference cannot run on
+            why = f"{type(exc).__name__}: {exc}"
+            out = port_timing(workload, step_budget_s, max_steps)
+            out["sample"] += f" (reference failed: {why})"
+            return out
+    return port_timing(workload, step_budget_s, max_steps)
 
 
 def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores, on the SAME workload
+    (whole tree).  cfg3 costs ~40-55 s per iteration on the reference, so K and W are capped by a time budget; the line says
+    how many iterations were timed."""
     if rank != 0:
         return
     t0 = time.perf_counter()
-    base = cpu_baseline(args.workload, budget_iters=max(1, min(args.steps, 6)))
+    base = cpu_baseline(args.workload, step_budget_s=args.ref_budget_s, max_steps=max(1, args.steps),
+                        warmup_steps=1 if args.workload in ("cfg1", "cfg2", "cfg4") else 0)
     line = {"metric": METRIC, "value": base["value"], "unit": "it/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 / base["value"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload, "batch": 1, "note": "CPU port of the reference, bounded sample"},
+            "config": {"workload": f"{args.workload}: {base['nodes']}-node scenario tree, same seeded problem as the CUDA arm",
+                       "batch": 1, "steps_timed": base["iterations_timed"], "warmup_done": base.get("warmup_iterations", 0),
+                       "note": "the requested --steps / --warmup are capped by --ref-budget-s seconds of stepping"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "offline_s": base.get("offline_s"), "gpu_launches": 0,
             "wall_s": time.perf_counter() - t0}
     emit(line)
+
+
+def parity_check(workload, r, local_rank):
+    """pass / fail carried by every bench line (checker only, nothing here is timed): (1) 30 iterations of the default
+    pipelined loop on chain2010 (a 1 621-node sibling of cfg3: same kernels) against the NumPy oracle; (2) when the at-size
+    fixture of the workload is committed (tests/golden/<workload>_at_size.npz, recorded from the unmodified reference), 100
+    iterations of a fresh solver on the WORKLOAD ITSELF against the reference's residual history, sampled entries and
+    per-segment checksums."""
+    from oracle import problems
+    from oracle.cp_flat_oracle import FlatOracle
+    out = {}
+    s = problems.spec("chain2010")
+    problem = problems.build(s, r.core)
+    orc = FlatOracle(problem)
+    alpha = orc.step_size()
+    sol = r.core.Solver(problem, device=local_rank, verbose=False)
+    sol.chock(s["x0"][:, :1], max_iters=29, tol=0.0, alpha=alpha)
+    orc.cache_initial_state(s["x0"][:, :1])
+    orc.alpha = alpha
+    for _ in range(30):
+        xi, _ = orc.iterate()
+    dev = sol.cache.device_solver
+    p, d = dev.get_primal(0)[0], dev.get_dual(0)[0]
+    e_it = max(float(np.max(np.abs(p - orc.flat_primal(orc.p))) / max(1.0, np.max(np.abs(p)))),
+               float(np.max(np.abs(d - orc.flat_dual(orc.d))) / max(1.0, np.max(np.abs(d)))))
+    e_res = float(np.max(np.abs(sol.residual_history[0][-1] - np.array(xi)) / np.array(xi)))
+    out["sibling_chain2010_30_iterations_vs_oracle"] = {"iterate_rel_err": e_it, "residual_rel_err": e_res,
+                                                        "pass": bool(e_it < 1e-9 and e_res < 1e-6)}
+    fixture = os.path.join(ROOT, "tests", "golden", f"{workload}_at_size.npz")
+    if workload != "cfg4" and os.path.isfile(fixture):
+        from oracle.at_size_check import check_against_fixture
+        g = np.load(fixture)
+        s = problems.spec(workload)
+        sol = r.core.Solver(problems.build(s, r.core), device=local_rank, verbose=False)
+        sol.chock(g["x0"], max_iters=99, tol=0.0, alpha=float(g["alpha"]))
+        dev = sol.cache.device_solver
+        worst = check_against_fixture(sol.cache.flat_problem, g, "", 100, dev.get_primal(0)[0], dev.get_dual(0)[0])
+        e_res = float(np.max(np.abs(sol.residual_history[0] - g["xi"]) / g["xi"]))
+        out[f"{workload}_100_iterations_vs_reference_fixture"] = {"iterate_rel_err": float(worst), "residual_rel_err": e_res,
+                                                                   "pass": bool(worst < 1e-9 and e_res < 1e-6)}
+    out["pass"] = all(v["pass"] for v in out.values())
+    return out
 
 
 def run_ours(args, rank, world, local_rank):
@@ -196,6 +335,15 @@ def run_ours(args, rank, world, local_rank):
     dev = solver.cache.device_solver
     dev.synchronize()
     t_setup = time.perf_counter() - t0
+    # the offline factorisation on its own ("timed separately"): rb_offline re-run on the uploaded problem
+    # (Riccati-like recursion per factorisation class, level by level, + the tensor-core fragment tables), wall time incl. sync
+    off_times = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        dev.offline()
+        dev.synchronize()
+        off_times.append(time.perf_counter() - t0)
+    t_offline = float(min(off_times))
     flat = solver.cache.flat_problem
     alpha = solver.compute_step_size()
     stream = torch.cuda.Stream()
@@ -219,7 +367,11 @@ def run_ours(args, rank, world, local_rank):
         parts = np.array([q[1] for q in prof]).mean(axis=0)
         barrier()
         launches0 = dev.launch_count()
-        sampler = ClockSampler(local_rank)
+        props = torch.cuda.get_device_properties(local_rank)
+        pci = None
+        if all(hasattr(props, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            pci = f"{props.pci_domain_id:08x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        sampler = ClockSampler(local_rank, pci)
         sampler.start()
         # ---- cold: L2 flushed before every timed iteration --------------------------------------------------------
         starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
@@ -278,11 +430,21 @@ def run_ours(args, rank, world, local_rank):
             t0 = time.perf_counter()
             st_ttt = cold.chock(spec["x0"][:, :1], max_iters=args.ttt_iters, tol=1e-6, alpha=alpha)
             ttt_s = time.perf_counter() - t0
+            hist = np.max(cold.residual_history[0], axis=1)            # max(xi0, xi1, xi2) per iteration
+            per_it = ttt_s / max(1, int(cold.iterations))
+            levels = {}
+            for tol in (1e-3, 1e-4, 1e-5, 1e-6):
+                hit = np.flatnonzero(hist <= tol)
+                levels[f"{tol:.0e}"] = ({"converged": True, "iterations": int(hit[0]) + 1, "seconds": (int(hit[0]) + 1) * per_it}
+                                        if hit.size else {"converged": False, "iterations": None, "seconds": None})
             ttt = {"seconds": ttt_s, "iterations": int(cold.iterations), "converged": st_ttt == 0, "tol": 1e-6,
-                   "max_iters": args.ttt_iters, "final_residual": float(np.max(cold.residual_history[0][-1])),
+                   "max_iters": args.ttt_iters, "final_residual": float(hist[-1]), "by_tolerance": levels,
+                   "reference_demo_tolerance": "the reference's own main.py:80 stops at tol=1e-3",
                    "note": "fresh Solver, zero iterates: Solver.chock(x0, max_iters, tol=1e-6) -- x0 upload, device-side "
                            "stopping test after every iteration, host poll every 64 iterations, residual history download; "
-                           "`converged` false means the cap was reached first and `seconds` is the time to `final_residual`"}
+                           "`converged` false means the cap was reached first and `seconds` is the time to `final_residual`; "
+                           "by_tolerance: first iteration of THIS run whose max(xi) is below the tolerance, seconds = that "
+                           "iteration count x the run's mean wall time per iteration"}
             del cold
 
     # ---- N > 1: the same single tree sharded by subtree over all ranks (one all-gather per iteration) -------------------
@@ -349,21 +511,23 @@ def run_ours(args, rank, world, local_rank):
         kname = (f"chain dual pass k_dual_chain<{flat.nx},{flat.nu}> over {n_chain} of {flat.n} nodes (L, dual half step, "
                  "prox of g*, six residual norms, pbar of the next iteration"
                  + ("" if args.no_risk_split else "; the risk block d1, d2 of these nodes runs under the sweeps") + ")")
-        traffic = TRAFFIC.get((args.workload, batch, not args.no_dedup))
+        ktag = f"k_dual_chain<{flat.nx},{flat.nu}>" + ("" if not args.no_risk_split else "+risk")
+        traffic, traffic_src = measured_traffic(args.workload, batch, not args.no_dedup, ktag)
     else:
         b_kernel = b_moved = 8 * batch * (2 * flat.np_ + 2 * flat.nd_)
         t_kernel = float(cold_phases[-1]) * 1e-3
         kname = "dual pass (L, dual half step, prox of g*, six residual norms), all nodes"
-        traffic = None
+        traffic, traffic_src = None, None
     serial_ms = float(cold_phases.sum())
     roofline = {
         "bound": "hbm", "kernel": kname,
         "achieved": b_kernel / t_kernel / 1e9, "peak": peak, "unit": "GB/s", "frac": b_kernel / t_kernel / 1e9 / peak,
-        "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes": b_kernel, "bytes_moved_model": b_moved,
+        "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes": b_kernel, "bytes_moved_model": b_moved,
         "launch_ms": t_kernel * 1e3, "share_of_step": float(t_kernel * 1e3 / serial_ms),
         "timing": "CUDA events around the plain launch on the bench stream, L2 flushed before every iteration, mean of "
                   f"{min(K, 50)} iterations (includes ~2 us of launch gap); share_of_step = launch_ms / sum of all launches "
-                  "of the iteration run one after the other (the ncu launch list is serialised the same way)",
+                  "of the iteration run ONE AFTER THE OTHER (the ncu launch list is serialised the same way) -- not a share "
+                  "of the overlapped graph iteration, where several of these launches run side by side",
         "iteration": {"algorithmic_bytes": b_alg, "achieved": achieved, "frac": achieved / peak,
                       "note": "all launches of one CP iteration inside the CUDA graph, the timed region of `value`"},
         "launch_ms_all": {"primal_or_kernel_projection": float(cold_phases[0]),
@@ -396,6 +560,9 @@ def run_ours(args, rank, world, local_rank):
         "roofline": roofline,
         "clocks": clocks,
         "setup": {"problem_build_s": t_build, "flatten_upload_offline_s": t_setup, "factorisation_classes": flat.num_cls},
+        "offline_s": {"value": t_offline, "what": "rb_offline (Cache._offline, cache.py:200-242) on the device, wall time incl. "
+                      "synchronise, best of 3; the reference's time for the same call is cpu_baseline.offline_s",
+                      "classes": flat.num_cls, "per_node_classes": bool(args.no_dedup)},
         "residuals_last": [float(v) for v in last_norms[0]],
     }
     if world > 1:
@@ -405,11 +572,14 @@ def run_ours(args, rank, world, local_rank):
                      "q_j, d2_j and residual maxima per iteration, K iterations back to back (warm), max over ranks; "
                      "compare with warm.value / n_gpus of the N=1 run"}
             if shard_ms is not None else {"unavailable": locals().get("shard_err", "batch > 1")})
-    if not args.no_cpu:
+    if not args.no_parity:
+        try:
+            line["parity_check"] = parity_check(args.workload, r, local_rank)
+        except Exception as exc:
+            line["parity_check"] = {"pass": False, "error": f"{type(exc).__name__}: {exc}"}
+    if not args.no_cpu and world == 1:
         line["cpu_baseline"] = cpu_baseline(args.workload)
     if ttt is not None:
-        if "cpu_baseline" in line and line["cpu_baseline"].get("value"):
-            ttt["cpu_seconds_extrapolated"] = ttt["iterations"] / line["cpu_baseline"]["value"]
         line["time_to_1e-6"] = ttt
     emit(line)
     if dist is not None:
@@ -429,6 +599,9 @@ def main():
                     help="iteration cap of the time-to-1e-6-residual leg (0: skip it)")
     ap.add_argument("--sweep-cuts", default="", help="ablation: 'a,b' = rb_problem.sweep_cut1_min, sweep_cut2_min")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0,
+                    help="--impl reference: seconds of stepping the reference may use (at least one iteration is timed)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity_check leg")
     ap.add_argument("--tree-mode", type=int, default=2, choices=[0, 1, 2],
                     help="ablation: branching sweep levels with sweeps.cu (0), tree_sweeps.cu per level (1), fused with the top (2)")
     ap.add_argument("--no-mma", action="store_true", help="ablation: chains with one warp per chain instead of chain_mma.cu")

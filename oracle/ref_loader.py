@@ -1,19 +1,42 @@
-"""Import the UNMODIFIED reference package from /root/reference (this container only).
+"""Import the UNMODIFIED reference package: /root/reference (this container) or baseline/_ref (the offline pip install
+`python -m pip install --no-index --no-build-isolation --no-deps --target baseline/_ref <copy of /root/reference>`, git-ignored,
+travels to the GPU box with the snapshot; used by `bench.py --impl reference` and the cpu_baseline leg only).
 
 TEST INFRASTRUCTURE.  The reference imports turtle, matplotlib.pyplot and tikzplotlib at module level
 (reference raocp/core/scenario_tree.py:4, raocp/core/solver.py:8-9); none is installed here and none is used by
 the hot path, so empty stub modules are injected for those names before the import.  The GPU box has no
-/root/reference: `available()` is False there and every caller must skip.
+/root/reference; tests marked `reference` skip there, the bench takes baseline/_ref.
 """
 import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("RAOCP_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _has(root):
+    return bool(root) and os.path.isfile(os.path.join(root, "raocp", "core", "solver.py"))
+
+
+def _find():
+    for root in (os.environ.get("RAOCP_REFERENCE_ROOT"), "/root/reference",
+                 os.path.join(os.path.dirname(_HERE), "baseline", "_ref")):
+        if _has(root):
+            return root
+    return os.environ.get("RAOCP_REFERENCE_ROOT", "/root/reference")
+
+
+REFERENCE_ROOT = _find()
 
 
 def available():
-    return os.path.isfile(os.path.join(REFERENCE_ROOT, "raocp", "core", "solver.py"))
+    return _has(REFERENCE_ROOT)
+
+
+def source():
+    """where the reference was found: 'source tree' (/root/reference) or 'baseline/_ref' (pip --target install)"""
+    return "baseline/_ref (pip --target install of the unmodified reference)" if "baseline" in REFERENCE_ROOT \
+        else f"{REFERENCE_ROOT} (source tree)"
 
 
 def load():

@@ -2,7 +2,7 @@
 
 API parity with reference raocp/core/constraints/cones.py:4-230 (Real, Zero, NonnegativeOrthant, SecondOrderCone,
 Cartesian; `project` / `project_onto_dual`; same dimension checks and error messages).  The arithmetic runs on the
-device through the C-ABI entry rb_cone_project (kernel rb_k_cone in csrc/standalone.cu) -- these classes are the
+device through the C-ABI entry rb_cone_project (kernel k_cone in csrc/ops.cu) -- these classes are the
 host-side mirror only; inside the solver the same device functions are fused into the dual pass.
 """
 import numpy as np
@@ -22,7 +22,7 @@ def _check_dimension(cone_type, cone_dimension, vector):
 
 
 def _device_project(code, vector):
-    from .. import _lib
+    from ... import _lib
     return _lib.cone_project(code, vector)
 
 

@@ -1,7 +1,7 @@
 """Box constraint lo <= [x; u] <= hi (nonleaf) / lo <= x <= hi (leaf).
 
 API parity with reference raocp/core/constraints/rectangle.py:5-69.  `project` clips on the device
-(kernel rb_k_box in csrc/standalone.cu, via the C-ABI entry rb_box_project); a NaN entry raises ValueError like
+(kernel k_box in csrc/ops.cu, via the C-ABI entry rb_box_project); a NaN entry raises ValueError like
 the reference's `_constrain` (rectangle.py:50-59).
 """
 import numpy as np
@@ -35,7 +35,7 @@ class Rectangle(bc.Constraint):
 
     def project(self, vector):
         self._check_input(vector)
-        from .. import _lib
+        from ... import _lib
         return _lib.box_project(vector, self._lo, self._hi)
 
     @staticmethod
