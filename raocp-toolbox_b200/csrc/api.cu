@@ -83,6 +83,7 @@ struct rb_solver {
     SweepLevel shard_lv[2]{};
     std::vector<int> chain_lo[2];   // host copy of lv.lo of chain levels (tile building)
     bool allow_mma = true;
+    bool mma_w4 = false;     // rb_use_mma_sweeps(2): four warps per chain tile where instantiated (measured ablation, chain_mma.cu)
     int tree_mode = 2;       // 0: sweeps.cu stage kernels; 1: tree_sweeps.cu, one launch per level; 2: + level 0 fused with the top
     bool fuse_ok = false;    // the fused launch is possible (co-residency, same residency mode, one smem footprint)
     size_t fuse_smem = 0;
@@ -326,7 +327,7 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
     const bool fused = s->tree_mode > 1 && s->fuse_ok && !(s->allow_mma && pl.lv[0].num_tiles > 0);
     auto bwd = [&](int v) {
         if (s->allow_mma && pl.lv[v].num_tiles > 0)
-            launch_chain_mma_bwd(st, s->P, ctrl, pl.lv[v], prim, s->q, s->r);
+            launch_chain_mma_bwd(st, s->P, ctrl, pl.lv[v], prim, s->q, s->r, s->mma_w4 && chain_mma_w4(L.nx, L.nu));
         else if (tree && s->tree_lv[v].desc)
             launch_tree_bwd(dim3(s->tree_lv[v].num_sub, batch), 32 * s->tree_lv[v].warps, s->tree_smem[1 + v], st, s->P, ctrl,
                             s->tree_lv[v], prim, s->q, s->r);
@@ -336,11 +337,11 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
     };
     auto fwd = [&](int v) {
         if (s->allow_mma && pl.lv[v].num_tiles > 0 && fwd_split > 0 && v == pl.num_levels - 1) {
-            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, 0, fwd_split);
+            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, 0, fwd_split, s->mma_w4 && chain_mma_w4(L.nx, L.nu));
             if (after_piece) after_piece();
-            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, fwd_split, -1);
+            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, fwd_split, -1, s->mma_w4 && chain_mma_w4(L.nx, L.nu));
         } else if (s->allow_mma && pl.lv[v].num_tiles > 0)
-            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r);
+            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, 0, -1, s->mma_w4 && chain_mma_w4(L.nx, L.nu));
         else if (tree && s->tree_lv[v].desc)
             launch_tree_fwd(dim3(s->tree_lv[v].num_sub, batch), 32 * s->tree_lv[v].warps, s->tree_smem[1 + v], st, s->P, ctrl,
                             s->tree_lv[v], prim, s->r);
@@ -924,14 +925,19 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
             int f_ab, f_abt, f_k, f_kr;
             chain_mma_frag_counts(nx, nu, &f_ab, &f_abt, &f_k, &f_kr);
             double *t_ab = nullptr, *t_abt = nullptr, *t_k = nullptr, *t_kr = nullptr;
-            TRY(dev_zero(s, (size_t)s->num_dyn * f_ab * 32, &t_ab));
-            TRY(dev_zero(s, (size_t)s->num_dyn * f_abt * 32, &t_abt));
-            TRY(dev_zero(s, (size_t)s->num_cls * f_k * 32, &t_k));
-            TRY(dev_zero(s, (size_t)s->num_cls * f_kr * 32, &t_kr));
+            // two images of every table: k-major, then output-block-major (launch_chain_mma_frags)
+            TRY(dev_zero(s, (size_t)2 * s->num_dyn * f_ab * 32, &t_ab));
+            TRY(dev_zero(s, (size_t)2 * s->num_dyn * f_abt * 32, &t_abt));
+            TRY(dev_zero(s, (size_t)2 * s->num_cls * f_k * 32, &t_k));
+            TRY(dev_zero(s, (size_t)2 * s->num_cls * f_kr * 32, &t_kr));
             s->P.m.fragAB = t_ab;
             s->P.m.fragABT = t_abt;
             s->P.m.fragK = t_k;
             s->P.m.fragKR = t_kr;
+            s->P.m.fragAB4 = t_ab + (size_t)s->num_dyn * f_ab * 32;
+            s->P.m.fragABT4 = t_abt + (size_t)s->num_dyn * f_abt * 32;
+            s->P.m.fragK4 = t_k + (size_t)s->num_cls * f_k * 32;
+            s->P.m.fragKR4 = t_kr + (size_t)s->num_cls * f_kr * 32;
             size_t mma_need = 0;
             for (int v = 0; v < pl.num_levels; ++v)
                 if (pl.lv[v].num_tiles > 0)
@@ -1540,7 +1546,7 @@ int enqueue_iteration_sharded(rb_solver *s, int src, cudaStream_t st) {
     launch_primal(s, st, src, dst, s->owned_nodes, s->n_owned);
     for (int v = pl.num_levels - 1; v >= 0; --v)
         if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
-            launch_chain_mma_bwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->q, s->r);
+            launch_chain_mma_bwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->q, s->r, s->mma_w4 && chain_mma_w4(L.nx, L.nu));
         else if (s->tree_mode > 0 && s->shard_tree_lv[v].desc)
             launch_tree_bwd(dim3(s->shard_tree_lv[v].num_sub, 1), 32 * s->shard_tree_lv[v].warps, s->tree_smem[1 + v], st, s->P,
                             s->ctrl, s->shard_tree_lv[v], s->prim[dst], s->q, s->r);
@@ -1558,7 +1564,7 @@ int enqueue_iteration_sharded(rb_solver *s, int src, cudaStream_t st) {
                          s->ctrl, pl, s->prim[dst], s->q, s->r, s->x0);
     for (int v = 0; v < pl.num_levels; ++v)
         if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
-            launch_chain_mma_fwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->r);
+            launch_chain_mma_fwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->r, 0, -1, s->mma_w4 && chain_mma_w4(L.nx, L.nu));
         else if (s->tree_mode > 0 && s->shard_tree_lv[v].desc)
             launch_tree_fwd(dim3(s->shard_tree_lv[v].num_sub, 1), 32 * s->shard_tree_lv[v].warps, s->tree_smem[1 + v], st, s->P,
                             s->ctrl, s->shard_tree_lv[v], s->prim[dst], s->r);
@@ -1953,6 +1959,7 @@ int rb_use_lane_kernels(rb_solver *s, int32_t enable) {
 int rb_use_mma_sweeps(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
     s->allow_mma = enable != 0;
+    s->mma_w4 = enable == 2;   // 2: four warps per tile where instantiated (ablation); other non-zero values: one warp per tile
     for (int i = 0; i < 2; ++i)
         if (s->graph[i]) {
             cudaGraphExecDestroy(s->graph[i]);

@@ -18,6 +18,11 @@
 // Measured on B200 (profiles/microbench/fp64_pipes.cu): DMMA m8n8k4 issues every 16 cycles from a single warp per SM
 // sub-partition at the full 37 TFLOP/s, dependent latency 26 cycles -- one warp per sub-partition saturates the pipe, so
 // a step costs (#MMA x 16) cycles instead of the ~2000 cycles of the one-warp-per-chain walker.
+#include <algorithm>
+#ifdef RB_TRACE
+#include <cstdio>
+#endif
+
 #include "kernels.cuh"
 
 namespace rb {
@@ -115,23 +120,33 @@ __device__ __forceinline__ double frag(const double *__restrict__ tab, int ld, i
     return (l >= 0 && l < rows && o >= 0 && o < cols) ? tab[l * ld + o] : 0.0;
 }
 
-// The fragments are gathered ONCE per table (after the offline factorisation) into lane-major tables, so that a walker
-// fetches its F fragment words of table entry e as one contiguous, unpredicated run: out[(e * 32 + lane) * F + f], with
-// f = (2 * kbi + kj) * nob + obi for k-blocks kb0 + kbi and output blocks ob0 + obi.
+// The fragments are gathered ONCE per table (after the offline factorisation) into PAIR-MAJOR tables: fragment word f of lane
+// `lane` of table entry e sits at out[((e * F/2 + f/2) * 32 + lane) * 2 + (f & 1)], with f = (2 * kbi + kj) * nob + obi for
+// k-blocks kb0 + kbi and output blocks ob0 + obi.  A warp's 16-byte copy of one pair is then ONE contiguous 512-byte run (four
+// 128-byte lines) -- with the lane-major layout of round 1 (out[(e * 32 + lane) * F + f]) every lane of every copy touched a
+// line of its own, 32 L1 tag look-ups per instruction, which is what the walkers were actually bound by (ncu r2c: shared-memory
+// loads at ~400 cycles behind a queue of uncoalesced LDGSTS).
+// ob_major: the word goes to position g = obi * (F / nob) + (2 * kbi + kj) instead of f (tables of the four-warp walkers).
 __global__ void k_frag_table(const double *__restrict__ tab, long long entry_stride, int ld, int l_off, int rows, int o_off,
-                             int cols, int kb0, int ob0, int nob, double *__restrict__ out) {
+                             int cols, int kb0, int ob0, int nob, double *__restrict__ out, int ob_major) {
     const int e = blockIdx.x, f = blockIdx.y, F = gridDim.y, lane = threadIdx.x;
     const int obi = f % nob, kj = (f / nob) & 1, kbi = f / (2 * nob);
-    out[((long long)e * 32 + lane) * F + f] =
+    const int g = ob_major ? obi * (F / nob) + 2 * kbi + kj : f;
+    out[(((long long)e * (F / 2) + g / 2) * 32 + lane) * 2 + (g & 1)] =
         frag(tab + e * entry_stride, ld, l_off, rows, o_off, cols, kb0 + kbi, kj, ob0 + obi, lane);
 }
 
+// address of fragment word f of `lane` in a pair-major table of F words per lane and entry
+template <int F>
+__device__ __forceinline__ const double *frag_addr(const double *__restrict__ table, int entry, int lane, int f) {
+    return table + (((long long)entry * (F / 2) + f / 2) * 32 + lane) * 2 + (f & 1);
+}
 template <int F>
 __device__ __forceinline__ void ld_frags(double (&w)[F], const double *__restrict__ table, int entry, int lane) {
-    const double2 *b = reinterpret_cast<const double2 *>(table + ((long long)entry * 32 + lane) * F);
+    static_assert(F % 2 == 0, "pairs");
 #pragma unroll
     for (int f = 0; f < F; f += 2) {
-        const double2 v = __ldg(b + f / 2);
+        const double2 v = __ldg(reinterpret_cast<const double2 *>(frag_addr<F>(table, entry, lane, f)));
         w[f] = v.x;
         w[f + 1] = v.y;
     }
@@ -224,9 +239,9 @@ __device__ __forceinline__ void cp_input(double *dst, const double *__restrict__
 // the lane's F fragment words of one table entry (F is even: 16-byte copies)
 template <int F>
 __device__ __forceinline__ void cp_frags(double *dst, const double *__restrict__ table, int entry, int lane) {
-    const double *src = table + ((long long)entry * 32 + lane) * F;
+    static_assert(F % 2 == 0, "pairs");
 #pragma unroll
-    for (int f = 0; f < F; f += 2) cp_async<16>(dst + f, src + f);
+    for (int f = 0; f < F; f += 2) cp_async<16>(dst + f, frag_addr<F>(table, entry, lane, f));
 }
 template <int N>
 __device__ __forceinline__ void lds_vec(double (&v)[N], const double *src) {
@@ -506,11 +521,378 @@ __global__ void __launch_bounds__(BIG ? 32 : 128) k_chain_mma_fwd(const __grid_c
     }
 }
 
+
+// ---- four warps per tile (nx + nu in (24, 32]: four 8-wide slot blocks) ------------------------------------------------------
+// ncu of the one-warp-per-tile walkers on cfg3 (profiles/r2a_crit_*): 250 instructions per step of which 36 are DMMAs, a single
+// warp per SM sub-partition at IPC 0.12 -- the step is one long dependent stream (address arithmetic, copies, the DMMA chains one
+// after the other), 2 300 cycles of which the tensor pipe is busy 580.  Here a tile is walked by FOUR warps, warp w owning the
+// output block w of every product: its share of a step is one accumulator chain per product (6 + 4 dependent DMMAs backward,
+// 8 + 8 forward), one 16-byte row copy and 4-8 fragment words.  The state vector (and r / u) is exchanged through shared
+// memory in the accumulator layout -- every lane writes the pair it computed and reads the pairs of all blocks as the A
+// operands of the next product: two 128-thread named barriers per step, no shuffles.  The four warps of a tile sit on the
+// four sub-partitions of the SM and every sub-partition interleaves the warps of the CTA's four tiles.
+// Every reduction is split in two independent halves (see below): results differ from the one-warp kernels in the last bits.
+constexpr int kWpt = 4;
+constexpr int kStages4 = 4;   // ring stages of the four-warp walkers: copies are issued three steps ahead, two may be in flight
+__device__ __forceinline__ void tile_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(kWpt * 32) : "memory"); }
+
+template <int NX, int NU>
+struct Wide4 {
+    using D = ChainDims<NX, NU>;
+    static_assert(D::NT == kWpt && D::VEC && D::RT0 == 2 && D::RN == 2, "four slot blocks, the last two with input slots");
+    static constexpr int F1 = 2 * D::QT * D::NT, F2 = 2 * D::RN * D::QT, F3 = 2 * D::NT * D::RN, F4 = 2 * D::NT * D::QT;
+    static constexpr int LW_B = ring_lane_words(4 + 2 * D::RN);               // xbar pair | ubar pair | K fragments of the block
+    static constexpr int LW_F = ring_lane_words(2 * D::RN + 2 * D::NT);       // r (all input blocks) | [K R~^-1] fragments
+    static constexpr int XW = (D::RN + D::QT) * 64;                           // exchange doubles per tile: r / u blocks, state blocks
+    // backward: one ring per block and tile; forward: only the blocks with input slots consume copied inputs
+    __host__ __device__ static constexpr size_t ring_doubles(bool backward) {
+        return backward ? (size_t)4 * 4 * kStages4 * 32 * LW_B : (size_t)4 * D::RN * kStages4 * 32 * LW_F;
+    }
+    __host__ __device__ static constexpr size_t smem_bytes(int depth, bool backward) {
+        return ring_doubles(backward) * sizeof(double) + (size_t)4 * XW * sizeof(double) + (size_t)4 * (depth * 10 + 8) * sizeof(int);
+    }
+};
+
+#ifdef RB_TRACE
+#define RB_TK(i) do { if (d == trace_d) tk[i] = clock64(); } while (0)
+#else
+#define RB_TK(i) do {} while (0)
+#endif
+
+// Warp w of tile slot s owns block (w + s) % 4: every sub-partition (warp id % 4) then hosts all four blocks once, and the
+// DMMA load of a step (6 + 4 | 6 + 4 | 6 + 4 | 6 backward, 8 | 8 | 8 + 8 | 8 forward) is spread evenly over the four
+// tensor pipes -- with block = w all warps of one block share a pipe and every dependent DMMA queues behind three others
+// (in-kernel clocks: 70 cycles per dependent DMMA instead of 26).
+template <int NX, int NU>
+__global__ void __launch_bounds__(4 * kWpt * 32) k_chain_mma_bwd_w4(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
+                                                                SweepLevel lv, const double *__restrict__ prim,
+                                                                double *__restrict__ q, double *__restrict__ r) {
+    using D = ChainDims<NX, NU>;
+    using W = Wide4<NX, NU>;
+    extern __shared__ __align__(16) double mma_smem[];
+    const Layout &L = P.L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = warp >> 2, ob = (warp + slot) & 3;   // tile of the CTA, output block of this warp
+    const int tile = blockIdx.x * 4 + slot;
+    if (tile >= lv.num_tiles) return;            // all four warps of the tile leave together
+#ifdef RB_TRACE
+    const long long t_entry = clock64();
+    long long t_meta = 0, t_loop = 0;
+#endif
+    constexpr int LW = W::LW_B;
+    double *ring = mma_smem + ((size_t)(slot * 4 + ob) * kStages4 * 32 + lane) * LW;
+    double2 *xr = reinterpret_cast<double2 *>(mma_smem + W::ring_doubles(true) + (size_t)slot * W::XW);   // [RN][32]
+    double2 *xq = xr + D::RN * 32;                                                                                    // [QT][32]
+    TileMeta tm;   // the four warps write the same image: benign
+    const bool live = stage_meta(lv, ctrl, tile, slot, lane,
+                                 reinterpret_cast<int *>(mma_smem + W::ring_doubles(true) + (size_t)4 * W::XW), tm);
+    tile_bar(1 + slot);
+    if (!live) return;
+#ifdef RB_TRACE
+    t_meta = clock64();
+#endif
+    const int t = tm.t, g = tm.g;
+    const int s0 = 8 * ob + 2 * t, a0 = s0 - NX;
+    const bool has_state = s0 < NX, has_input = a0 >= 0 && a0 < NU;
+    const bool ob_state = 8 * ob < NX, ob_input = 8 * ob + 8 > NX;   // warp-uniform: the block holds state / input slots
+    const double *Xn = prim + (long long)blockIdx.y * L.np_pad + L.px, *Un = prim + (long long)blockIdx.y * L.np_pad + L.pu;
+    double *Q = q + (long long)blockIdx.y * L.n * NX, *R = r + (long long)blockIdx.y * L.m * NU;
+#pragma unroll
+    for (int s = 0; s < kStages4; ++s)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) ring[s * 32 * LW + k] = 0.0;   // pairs that are never copied stay zero (own ring: before the barrier below)
+    // The warp of block 3 (input slots only) has nothing to do while the others run their K'r chains: it is the PRODUCER of
+    // the step inputs of all four blocks (xbar / ubar pairs, K fragments), copying into the four rings two steps ahead and
+    // waiting for its copies before the step's second barrier.  Same lane -> same words in every ring.
+    const bool producer = ob == 3;
+    double *rings = mma_smem + ((size_t)(slot * 4) * kStages4 * 32 + lane) * LW;   // ring of block b: rings + b * kStages4 * 32 * LW
+    auto prefetch = [&](int d, int stage) {   // producer only; one commit group per step, possibly empty
+        if (d >= 0) {
+            const int node = tm.nodes[d * 8 + g], cls = tm.clss[d];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                double *dst = rings + ((size_t)b * kStages4 + stage) * 32 * LW;
+                const int sb = 8 * b + 2 * t, ab = sb - NX;
+                if (sb < NX) cp_async<16>(dst, Xn + (long long)node * NX + sb);
+                if (cls >= 0) {
+                    if (ab >= 0 && ab < NU) cp_async<16>(dst + 2, Un + (long long)node * NU + ab);
+                    if (8 * b < NX) {
+#pragma unroll
+                        for (int k = 0; k < 2 * D::RN; k += 2)
+                            cp_async<16>(dst + 4 + k, frag_addr<W::F2>(P.m.fragK4, cls, lane, b * 2 * D::RN + k));
+                    }
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    int d = lv.depth - 1;
+    int st_use = 0, st_fill = 3;   // ring stage read by this step / filled for the step three steps on
+    tile_bar(1 + slot);            // the rings are zeroed
+    if (producer) {
+        prefetch(d, 0);
+        prefetch(d - 1, 1);
+        prefetch(d - 2, 2);
+    }
+    double w1[2 * D::QT];   // column block `ob` of [A | B] of the tile's dynamics row
+#pragma unroll
+    for (int k = 0; k < 2 * D::QT; k += 2) {
+        const double2 v = lv.depth > 1 ? __ldg(reinterpret_cast<const double2 *>(frag_addr<W::F1>(P.m.fragAB4, tm.dyns[1], lane, ob * 2 * D::QT + k)))
+                                       : make_double2(0.0, 0.0);
+        w1[k] = v.x;
+        w1[k + 1] = v.y;
+    }
+    double qs[D::QT][2];
+#pragma unroll
+    for (int b = 0; b < D::QT; ++b) qs[b][0] = qs[b][1] = 0.0;
+#ifdef RB_TRACE
+    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int trace_d = 6;
+#endif
+    if (producer) cp_async_wait<2>();   // the inputs of the first step have landed
+    tile_bar(1 + slot);
+#ifdef RB_TRACE
+    t_loop = clock64();
+#endif
+    for (; d >= 0; --d) {
+        RB_TK(0);
+        const double *src = ring + st_use * 32 * LW;
+        const int node = tm.nodes[d * 8 + g];
+        const double2 xb = *reinterpret_cast<const double2 *>(src);
+        double qp[2];
+        RB_TK(1);
+        if (tm.clss[d] < 0) {   // leaf: q = -xbar
+            qp[0] = -xb.x;
+            qp[1] = -xb.y;
+        } else {
+            const double2 ub = *reinterpret_cast<const double2 *>(src + 2);
+            // block `ob` of [A'q ; B'q], the reduction in two independent halves (the warps of a sub-partition share one
+            // tensor pipe: a dependent DMMA comes back after ~64 cycles, two chains per warp keep the pipe full)
+            double E[2] = {0.0, 0.0}, E2[2] = {0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < D::QT; ++k) {
+                dmma(E, qs[k >> 1][k & 1], w1[k]);
+                dmma(E2, qs[(k + D::QT) >> 1][(k + D::QT) & 1], w1[k + D::QT]);
+            }
+            E[0] += E2[0];
+            E[1] += E2[1];
+            if (ob_input) {   // r = ubar - B'q on the input slots; -r feeds K'r
+                const double r0 = has_input ? ub.x - E[0] : 0.0, r1 = has_input ? ub.y - E[1] : 0.0;
+                if (has_input && tm.valid) *reinterpret_cast<double2 *>(R + (long long)node * NU + a0) = make_double2(r0, r1);
+                xr[(ob - D::RT0) * 32 + lane] = make_double2(-r0, -r1);
+            }
+            qp[0] = has_state ? E[0] - xb.x : 0.0;
+            qp[1] = has_state ? E[1] - xb.y : 0.0;
+            RB_TK(2);
+            tile_bar(1 + slot);
+            RB_TK(3);
+            if (ob_state) {   // q = A'q - xbar - K'r on the state slots
+                double w2[2 * D::RN];
+                lds_vec(w2, src + 4);
+                double q2[2] = {0.0, 0.0};
+                static_assert(D::RN == 2, "two input blocks: one chain each");
+                const double2 nr0 = xr[lane], nr1 = xr[32 + lane];
+                dmma(qp, nr0.x, w2[0]);
+                dmma(q2, nr1.x, w2[2]);
+                dmma(qp, nr0.y, w2[1]);
+                dmma(q2, nr1.y, w2[3]);
+                qp[0] += q2[0];
+                qp[1] += q2[1];
+            }
+        }
+        if (ob_state) xq[ob * 32 + lane] = make_double2(qp[0], qp[1]);
+        RB_TK(4);
+        if (producer) {   // off the critical path: the other warps are in their K'r chains
+            prefetch(d - 3, st_fill);
+            cp_async_wait<2>();   // the inputs of step d - 1 have landed: visible to the consumers after the barrier
+        }
+        RB_TK(5);
+        tile_bar(1 + slot);
+        RB_TK(6);
+#pragma unroll
+        for (int b = 0; b < D::QT; ++b) {
+            const double2 v = xq[b * 32 + lane];
+            qs[b][0] = v.x;
+            qs[b][1] = v.y;
+        }
+        if (d == 0 && has_state && tm.valid)   // only the head's q leaves the chain
+            *reinterpret_cast<double2 *>(Q + (long long)node * NX + s0) = make_double2(qp[0], qp[1]);
+        st_use = st_use == kStages4 - 1 ? 0 : st_use + 1;
+        st_fill = st_fill == kStages4 - 1 ? 0 : st_fill + 1;
+#ifdef RB_TRACE
+        if (d == trace_d) tk[7] = clock64() + (long long)(qs[0][0] == 12345.678);
+#endif
+    }
+#ifdef RB_TRACE
+    if (blockIdx.x == 5 && slot == 1 && lane == 0 && ctrl && ctrl->iters == 30)
+        printf("bwd_w4 ob %d: wait %lld E-phase %lld bar1 %lld Kr-phase %lld prefetch %lld bar2 %lld readback %lld cycles; meta %lld "
+               "prologue %lld loop %lld\n", ob, tk[1] - tk[0], tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4],
+               tk[6] - tk[5], tk[7] - tk[6], t_meta - t_entry, t_loop - t_meta, clock64() - t_loop);
+#endif
+}
+
+// Forward: u is computed by the warps of the blocks with input slots (2, 3), x_child by those of the blocks with state slots
+// (0, 1, 2).  The warps of blocks 0 and 1 are idle while u is computed: they are the PRODUCERS of the step inputs of blocks 2
+// and 3 (r rows, [K R~^-1] fragments), copying with cp.async into their partner's ring two steps ahead and waiting for their
+// own copies before the step's first barrier -- the consumers then never issue or wait for a copy.
+template <int NX, int NU>
+__global__ void __launch_bounds__(4 * kWpt * 32) k_chain_mma_fwd_w4(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
+                                                                SweepLevel lv, double *__restrict__ prim,
+                                                                const double *__restrict__ r, int d_begin, int d_end) {
+    using D = ChainDims<NX, NU>;
+    using W = Wide4<NX, NU>;
+    extern __shared__ __align__(16) double mma_smem[];
+    const Layout &L = P.L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int slot = warp >> 2, ob = (warp + slot) & 3;
+    const int tile = blockIdx.x * 4 + slot;
+    if (tile >= lv.num_tiles) return;
+    constexpr int LW = W::LW_F;
+    const bool ob_state = 8 * ob < NX, ob_input = 8 * ob + 8 > NX;
+    const int cons = ob_input ? ob : ob + 2;   // the consumer block whose ring this warp reads (consumer) or fills (producer)
+    double *ring = mma_smem + ((size_t)(slot * D::RN + cons - D::RT0) * kStages4 * 32 + lane) * LW;
+    double2 *xu = reinterpret_cast<double2 *>(mma_smem + W::ring_doubles(false) + (size_t)slot * W::XW);   // [RN][32]
+    double2 *xq = xu + D::RN * 32;                                                                                    // [QT][32]
+    TileMeta tm;
+    const bool live = stage_meta(lv, ctrl, tile, slot, lane,
+                                 reinterpret_cast<int *>(mma_smem + W::ring_doubles(false) + (size_t)4 * W::XW), tm);
+    tile_bar(1 + slot);
+    if (!live) return;
+    const int t = tm.t, g = tm.g;
+    const int s0 = 8 * ob + 2 * t, a0 = s0 - NX;
+    const bool has_state = s0 < NX, has_input = a0 >= 0 && a0 < NU;
+    double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
+    const double *R = r + (long long)blockIdx.y * L.m * NU;
+    const bool producer = !ob_input;
+    auto prefetch = [&](int d, int stage) {   // producers only; one commit group per step, possibly empty
+        if (d < lv.depth) {
+            const int cls = tm.clss[d];
+            if (cls >= 0) {
+                double *dst = ring + stage * 32 * LW;
+                cp_input<NX, NU>(dst, R + (long long)tm.nodes[d * 8 + g] * NU, t);
+#pragma unroll
+                for (int k = 0; k < 2 * D::NT; k += 2)
+                    cp_async<16>(dst + 2 * D::RN + k, frag_addr<W::F3>(P.m.fragKR4, cls, lane, (cons - D::RT0) * 2 * D::NT + k));
+            }
+        }
+        cp_async_commit();
+    };
+    if (producer) {
+#pragma unroll
+        for (int s = 0; s < kStages4; ++s)
+#pragma unroll
+            for (int k = 0; k < 2 * D::RN; ++k) ring[s * 32 * LW + k] = 0.0;
+        prefetch(d_begin, 0);
+        prefetch(d_begin + 1, 1);
+        prefetch(d_begin + 2, 2);
+    }
+    double w4[2 * D::NT];   // column block `ob` of [A ; B]' of the tile's dynamics row
+#pragma unroll
+    for (int k = 0; k < 2 * D::NT; k += 2) {
+        const double2 v = (ob_state && lv.depth > 1)
+                              ? __ldg(reinterpret_cast<const double2 *>(frag_addr<W::F4>(P.m.fragABT4, tm.dyns[1], lane, ob * 2 * D::NT + k)))
+                              : make_double2(0.0, 0.0);
+        w4[k] = v.x;
+        w4[k + 1] = v.y;
+    }
+    double xs[D::QT][2];
+    ld_state<NX, NU, false>(X + (long long)tm.nodes[d_begin * 8 + g] * NX, t, xs);   // written by the level above / the previous piece
+    if (producer) cp_async_wait<2>();   // the inputs of the first step are in the partner's ring
+    tile_bar(1 + slot);
+    int st_use = 0, st_fill = 3;
+#ifdef RB_TRACE
+    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int trace_d = d_begin + 6;
+#endif
+    for (int d = d_begin; d < d_end && d + 1 < lv.depth && tm.clss[d] >= 0; ++d) {
+        RB_TK(0);
+        const double *src = ring + st_use * 32 * LW;
+        const int node = tm.nodes[d * 8 + g], child = tm.nodes[(d + 1) * 8 + g];
+        if (ob_input) {   // block `ob` of u = [K R~^-1] [x ; r]
+            double rr[2 * D::RN], w3[2 * D::NT];
+            lds_vec(rr, src);
+            lds_vec(w3, src + 2 * D::RN);
+            double ua[2] = {0.0, 0.0}, ub2[2] = {0.0, 0.0};   // two independent halves of the reduction (see the backward kernel)
+#pragma unroll
+            for (int kb = 0; kb < D::NT; ++kb)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const bool is_x = 8 * kb + 2 * t + j < NX;
+                    double v = 0.0;
+                    if (kb < D::QT) v = xs[kb < D::QT ? kb : 0][j];
+                    if (kb >= D::RT0 && !is_x) v = rr[2 * (kb >= D::RT0 ? kb - D::RT0 : 0) + j];
+                    if (kb & 1) dmma(ub2, v, w3[2 * kb + j]);
+                    else dmma(ua, v, w3[2 * kb + j]);
+                }
+            ua[0] += ub2[0];
+            ua[1] += ub2[1];
+            if (has_input && tm.valid) *reinterpret_cast<double2 *>(U + (long long)node * NU + a0) = make_double2(ua[0], ua[1]);
+            xu[(ob - D::RT0) * 32 + lane] = make_double2(ua[0], ua[1]);
+        } else {   // producer: inputs of step d + 3 on their way, those of step d + 1 landed before the barrier
+            prefetch(d + 3, st_fill);
+            cp_async_wait<2>();
+        }
+        RB_TK(1);
+        tile_bar(1 + slot);
+        RB_TK(2);
+        if (ob_state) {   // block `ob` of x_child = [A B] [x ; u]
+            double2 uu[D::RN];
+#pragma unroll
+            for (int i = 0; i < D::RN; ++i) uu[i] = xu[i * 32 + lane];
+            double xn[2] = {0.0, 0.0}, xn2[2] = {0.0, 0.0};
+#pragma unroll
+            for (int kb = 0; kb < D::NT; ++kb)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const bool is_x = 8 * kb + 2 * t + j < NX;
+                    double v = 0.0;
+                    if (kb < D::QT) v = xs[kb < D::QT ? kb : 0][j];
+                    if (kb >= D::RT0 && !is_x) v = j == 0 ? uu[kb >= D::RT0 ? kb - D::RT0 : 0].x : uu[kb >= D::RT0 ? kb - D::RT0 : 0].y;
+                    if (kb & 1) dmma(xn2, v, w4[2 * kb + j]);
+                    else dmma(xn, v, w4[2 * kb + j]);
+                }
+            xn[0] += xn2[0];
+            xn[1] += xn2[1];
+            if (has_state && tm.valid) *reinterpret_cast<double2 *>(X + (long long)child * NX + s0) = make_double2(xn[0], xn[1]);
+            xq[ob * 32 + lane] = make_double2(xn[0], xn[1]);
+        }
+        RB_TK(3);
+        tile_bar(1 + slot);
+        RB_TK(4);
+#pragma unroll
+        for (int b = 0; b < D::QT; ++b) {
+            const double2 v = xq[b * 32 + lane];
+            xs[b][0] = v.x;
+            xs[b][1] = v.y;
+        }
+        st_use = st_use == kStages4 - 1 ? 0 : st_use + 1;
+        st_fill = st_fill == kStages4 - 1 ? 0 : st_fill + 1;
+#ifdef RB_TRACE
+        if (d == trace_d) tk[5] = clock64() + (long long)(xs[0][0] == 12345.678);
+#endif
+    }
+#ifdef RB_TRACE
+    if (blockIdx.x == 5 && slot == 1 && lane == 0 && ctrl && ctrl->iters == 30)
+        printf("fwd_w4 ob %d: u-phase / prefetch %lld bar1 %lld x-phase %lld bar2 %lld readback %lld cycles\n", ob, tk[1] - tk[0],
+               tk[2] - tk[1], tk[3] - tk[2], tk[4] - tk[3], tk[5] - tk[4]);
+#endif
+}
+
 }  // namespace
 
 // ---- host side --------------------------------------------------------------------------------------------------------------
 // (nx, nu, BIG): BIG = fragments in shared memory, one warp per CTA (nx + nu > 32)
 #define RB_MMA_DIMS(X) X(2, 1, false) X(3, 2, false) X(4, 2, false) X(8, 4, false) X(10, 5, false) X(20, 10, false) X(64, 32, true)
+
+// (nx, nu) walked by four warps per tile (k_chain_mma_*_w4): four slot blocks
+#define RB_MMA_W4_DIMS(X) X(20, 10)
+bool chain_mma_w4(int nx, int nu) {
+#define RB_HAS(NX, NU) \
+    if (nx == NX && nu == NU) return true;
+    RB_MMA_W4_DIMS(RB_HAS)
+#undef RB_HAS
+    return false;
+}
 
 bool chain_mma_supported(int nx, int nu) {
 #define RB_HAS(NX, NU, BIG) \
@@ -538,21 +920,23 @@ void chain_mma_frag_counts(int nx, int nu, int *f_ab, int *f_abt, int *f_k, int 
 void launch_chain_mma_frags(cudaStream_t st, const Tabs &M, int nx, int nu, int num_dyn, int num_cls, bool dynamics,
                             bool classes) {
     const int S = nx + nu, NT = (S + 7) / 8, QT = (nx + 7) / 8, RT0 = nx / 8, RN = NT - RT0;
-    if (dynamics) {
-        // [A'q ; B'q]: rows = state slots of q, columns = all slots
-        k_frag_table<<<dim3(num_dyn, 2 * QT * NT), 32, 0, st>>>(M.ABcat, (long long)nx * S, S, 0, nx, 0, S, 0, 0, NT,
-                                                                const_cast<double *>(M.fragAB));
-        // A x + B u: rows = all slots of [x ; u], columns = state slots
-        k_frag_table<<<dim3(num_dyn, 2 * NT * QT), 32, 0, st>>>(M.ABcatT, (long long)S * nx, nx, 0, S, 0, nx, 0, 0, QT,
-                                                                const_cast<double *>(M.fragABT));
-    }
-    if (classes) {
-        // K'r: rows = input slots (r), columns = state slots
-        k_frag_table<<<dim3(num_cls, 2 * RN * QT), 32, 0, st>>>(M.K, (long long)nu * nx, nx, nx, nu, 0, nx, RT0, 0, QT,
-                                                                const_cast<double *>(M.fragK));
-        // K x + R~^-1 r: rows = all slots of [x ; r], columns = input slots
-        k_frag_table<<<dim3(num_cls, 2 * NT * RN), 32, 0, st>>>(M.KRcatT, (long long)S * nu, nu, 0, S, nx, nu, 0, RT0, RN,
-                                                                const_cast<double *>(M.fragKR));
+    for (int obm = 0; obm < 2; ++obm) {   // k-major tables (one warp per tile, BIG), then output-block-major (four warps per tile)
+        if (dynamics) {
+            // [A'q ; B'q]: rows = state slots of q, columns = all slots
+            k_frag_table<<<dim3(num_dyn, 2 * QT * NT), 32, 0, st>>>(M.ABcat, (long long)nx * S, S, 0, nx, 0, S, 0, 0, NT,
+                                                                    const_cast<double *>(obm ? M.fragAB4 : M.fragAB), obm);
+            // A x + B u: rows = all slots of [x ; u], columns = state slots
+            k_frag_table<<<dim3(num_dyn, 2 * NT * QT), 32, 0, st>>>(M.ABcatT, (long long)S * nx, nx, 0, S, 0, nx, 0, 0, QT,
+                                                                    const_cast<double *>(obm ? M.fragABT4 : M.fragABT), obm);
+        }
+        if (classes) {
+            // K'r: rows = input slots (r), columns = state slots
+            k_frag_table<<<dim3(num_cls, 2 * RN * QT), 32, 0, st>>>(M.K, (long long)nu * nx, nx, nx, nu, 0, nx, RT0, 0, QT,
+                                                                    const_cast<double *>(obm ? M.fragK4 : M.fragK), obm);
+            // K x + R~^-1 r: rows = all slots of [x ; r], columns = input slots
+            k_frag_table<<<dim3(num_cls, 2 * NT * RN), 32, 0, st>>>(M.KRcatT, (long long)S * nu, nu, 0, S, nx, nu, 0, RT0, RN,
+                                                                    const_cast<double *>(obm ? M.fragKR4 : M.fragKR), obm);
+        }
     }
 }
 
@@ -560,7 +944,11 @@ static dim3 mma_grid(const SweepLevel &lv, int batch, bool big) {
     return big ? dim3(lv.num_tiles, batch) : dim3((lv.num_tiles + 3) / 4, batch);
 }
 // dynamic shared memory of a CTA (4 warps, or 1 if BIG): the cp.async rings (+ the dynamics fragments if BIG) + the tile metadata
-size_t chain_mma_smem_bytes(int nx, int nu, int depth, bool backward) {
+size_t chain_mma_smem_bytes(int nx, int nu, int depth, bool backward, bool w4) {
+#define RB_W4(NX, NU) \
+    if (w4 && nx == NX && nu == NU) return Wide4<NX, NU>::smem_bytes(depth, backward);
+    RB_MMA_W4_DIMS(RB_W4)
+#undef RB_W4
     const int NT = (nx + nu + 7) / 8, QT = (nx + 7) / 8, RT0 = nx / 8, RN = NT - RT0;
     const int lane_words = ring_lane_words(backward ? 2 * QT + 2 * RN + 2 * RN * QT : 2 * RN + 2 * NT * RN);
     const bool big = chain_mma_big(nx, nu);
@@ -574,14 +962,30 @@ cudaError_t chain_mma_set_smem(int bytes) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_fwd<NX, NU, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     RB_MMA_DIMS(RB_SET)
 #undef RB_SET
+#define RB_SET(NX, NU)                                                                                                         \
+    if (e == cudaSuccess) {                                                                                                    \
+        const int need = (int)std::max(Wide4<NX, NU>::smem_bytes(64, true), Wide4<NX, NU>::smem_bytes(64, false));             \
+        e = cudaFuncSetAttribute(k_chain_mma_bwd_w4<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);               \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_fwd_w4<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
+    }
+    RB_MMA_W4_DIMS(RB_SET)
+#undef RB_SET
     return e;
 }
 
 void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, const double *prim,
-                          double *q, double *r) {
+                          double *q, double *r, bool w4) {
+#define RB_GO4(NX, NU)                                                                                                         \
+    if (w4 && P.L.nx == NX && P.L.nu == NU) {                                                        \
+        k_chain_mma_bwd_w4<NX, NU><<<dim3((lv.num_tiles + 3) / 4, P.L.batch), 4 * kWpt * 32,                                   \
+                                     Wide4<NX, NU>::smem_bytes(lv.depth, true), st>>>(P, ctrl, lv, prim, q, r);               \
+        return;                                                                                                                \
+    }
+    RB_MMA_W4_DIMS(RB_GO4)
+#undef RB_GO4
 #define RB_GO(NX, NU, BIG)                                                                                             \
     if (P.L.nx == NX && P.L.nu == NU) {                                                                           \
-        k_chain_mma_bwd<NX, NU, BIG><<<mma_grid(lv, P.L.batch, BIG), BIG ? 32 : 128, chain_mma_smem_bytes(NX, NU, lv.depth, true), st>>>(P, ctrl, lv, prim, q, r);     \
+        k_chain_mma_bwd<NX, NU, BIG><<<mma_grid(lv, P.L.batch, BIG), BIG ? 32 : 128, chain_mma_smem_bytes(NX, NU, lv.depth, true, false), st>>>(P, ctrl, lv, prim, q, r);     \
         return;                                                                                                   \
     }
     RB_MMA_DIMS(RB_GO)
@@ -589,11 +993,19 @@ void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, co
 }
 
 void launch_chain_mma_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, double *prim,
-                          const double *r, int d_begin, int d_end) {
+                          const double *r, int d_begin, int d_end, bool w4) {
     if (d_end < 0) d_end = lv.depth;
+#define RB_GO4(NX, NU)                                                                                                         \
+    if (w4 && P.L.nx == NX && P.L.nu == NU) {                                                        \
+        k_chain_mma_fwd_w4<NX, NU><<<dim3((lv.num_tiles + 3) / 4, P.L.batch), 4 * kWpt * 32,                                   \
+                                     Wide4<NX, NU>::smem_bytes(lv.depth, false), st>>>(P, ctrl, lv, prim, r, d_begin, d_end);  \
+        return;                                                                                                                \
+    }
+    RB_MMA_W4_DIMS(RB_GO4)
+#undef RB_GO4
 #define RB_GO(NX, NU, BIG)                                                                                             \
     if (P.L.nx == NX && P.L.nu == NU) {                                                                           \
-        k_chain_mma_fwd<NX, NU, BIG><<<mma_grid(lv, P.L.batch, BIG), BIG ? 32 : 128, chain_mma_smem_bytes(NX, NU, lv.depth, false), st>>>(P, ctrl, lv, prim, r, d_begin, d_end);        \
+        k_chain_mma_fwd<NX, NU, BIG><<<mma_grid(lv, P.L.batch, BIG), BIG ? 32 : 128, chain_mma_smem_bytes(NX, NU, lv.depth, false, false), st>>>(P, ctrl, lv, prim, r, d_begin, d_end);        \
         return;                                                                                                   \
     }
     RB_MMA_DIMS(RB_GO)

@@ -49,6 +49,9 @@ struct Tabs {
     // MMA fragment images of ABcat / ABcatT ([num_dyn][F][32]) and K / KRcatT ([num_cls][F][32]) for chain_mma.cu; null
     // when no sweep level is tiled
     const double *fragAB, *fragABT, *fragK, *fragKR;
+    // the same fragments ordered output-block-major (f = obi * nk + k): the four-warps-per-tile walkers fetch the block of one
+    // warp as one contiguous run
+    const double *fragAB4, *fragABT4, *fragK4, *fragKR4;
 };
 
 struct Params {

@@ -144,16 +144,18 @@ void launch_tree_top(int grid, int threads, size_t smem, cudaStream_t st, const 
 
 // ---- chain_mma.cu: chain levels on the FP64 tensor cores, 8 chains per warp ---------------------------------------------------
 bool chain_mma_supported(int nx, int nu);
-size_t chain_mma_smem_bytes(int nx, int nu, int depth, bool backward);
+bool chain_mma_w4(int nx, int nu);   // four warps per tile are instantiated for these sizes (k_chain_mma_*_w4)
+size_t chain_mma_smem_bytes(int nx, int nu, int depth, bool backward, bool w4 = false);
 cudaError_t chain_mma_set_smem(int bytes);
 void chain_mma_frag_counts(int nx, int nu, int *f_ab, int *f_abt, int *f_k, int *f_kr);
 void launch_chain_mma_frags(cudaStream_t st, const Tabs &M, int nx, int nu, int num_dyn, int num_cls, bool dynamics,
                             bool classes);
+// w4: walk a tile with four warps (one output block each) -- only where chain_mma_w4(nx, nu)
 void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, const double *prim,
-                          double *q, double *r);
+                          double *q, double *r, bool w4 = false);
 // d_begin, d_end: the steps of the walk to run (depth below the chain heads); d_end < 0 = to the leaves
 void launch_chain_mma_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, double *prim,
-                          const double *r, int d_begin = 0, int d_end = -1);
+                          const double *r, int d_begin = 0, int d_end = -1, bool w4 = false);
 
 // ---- shard.cu: one tree sharded by subtree over the GPUs of a box ----------------------------------------------------------
 struct ShardPlan {

@@ -239,7 +239,9 @@ class DeviceSolver:
         self._call("rb_use_lane_kernels", 1 if enable else 0)
 
     def use_mma_sweeps(self, enable=True):
-        self._call("rb_use_mma_sweeps", 1 if enable else 0)
+        """False / 0: one warp per chain (sweeps.cu); True / 1 (default): tensor cores, one warp per tile; 2: tensor cores, four
+        warps per tile where instantiated (ablation)"""
+        self._call("rb_use_mma_sweeps", int(enable))
 
     def use_tree_kernels(self, mode=2):
         """0: sweeps.cu stage kernels; 1: tree_sweeps.cu per level; 2: level 0 + top fused (default)"""
