@@ -188,6 +188,10 @@ int rb_use_pipeline(rb_solver *s, int32_t enable);
  * chain_nodes) through k_dual_chain; chain_nodes = 0 when the loop is not pipelined or has no chain kernel for (nx, nu) */
 int rb_pipeline_info(const rb_solver *s, int32_t *early_nodes, int32_t *chain_first, int32_t *chain_nodes);
 int rb_use_graphs(rb_solver *s, int32_t enable); /* 1 (default): one CUDA graph per iteration; 0: plain launches */
+/* batch >= 64 instances of one tree (instance-parallel mode): 1 (default) = the fused loop runs in the
+ * batch-innermost "panel" layout (csrc/batch.cu: the 32 lanes of a warp are 32 instances; iterates are converted at
+ * rb_loop_begin / rb_loop_end); 0 = the instance-major kernels of batch == 1, one grid row per instance (ablation). */
+int rb_use_batch_panels(rb_solver *s, int32_t enable);
 /* subtree sharding: rank 0 calls rb_shard_unique_id and distributes the 128 bytes (e.g. torch.distributed broadcast),
  * every rank then calls rb_shard_init (collective: ncclCommInitRank).  Afterwards rb_iterate / rb_loop_* run the
  * sharded loop: per iteration ONE all-gather of the cut-stage q_j, d2_j and the residual maxima; the iterates of a

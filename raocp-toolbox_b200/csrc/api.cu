@@ -108,6 +108,11 @@ struct rb_solver {
     int chain_yo0 = 0;              // offset of y of node chain_first
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t pev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    // batch-innermost ("panel") path of the fused loop (batch.cu): buffers allocated on first use; panel_live = the loop's
+    // iterates are in the panel buffers (rb_loop_begin converted them, rb_loop_end converts the newest one back)
+    bool allow_panel = true;
+    bool panel_live = false;
+    double *pprim[2] = {nullptr, nullptr}, *pdual[2] = {nullptr, nullptr}, *pq = nullptr, *pr = nullptr, *pc2 = nullptr;
     // fused loop
     cudaGraphExec_t graph[2] = {nullptr, nullptr};  // graph[src]: one iteration reading buffer src, writing 1-src
     bool use_graphs = true;
@@ -250,6 +255,14 @@ void launch_primal(rb_solver *s, cudaStream_t st, int src, int dst, const int *n
 
 bool use_pipe(const rb_solver *s) { return use_lane(s) && s->allow_pipe && !s->sharded; }
 
+// many instances of a small tree: lanes = instances (batch.cu).  Needs diagonal cost square roots; the padding instances of
+// the last panel cost as much as real ones, so a batch has to fill at least a few panels to pay
+bool use_panel(const rb_solver *s) {
+    const Layout &L = s->P.L;
+    return s->allow_panel && !s->sharded && L.batch >= 64 && s->diag_costs && batch_panel_supported(L.nx, L.nu) &&
+           s->max_children <= batch_panel_max_children();
+}
+
 void launch_dual(rb_solver *s, cudaStream_t st, int src, int dst, const int *nodes = nullptr, int count = -1) {
     const Layout &L = s->P.L;
     if (count < 0) count = L.n;
@@ -301,8 +314,19 @@ int pipe_dual_launches(const rb_solver *s) {
     if (ps.cf >= L.m) return (ps.early > 0 ? 1 : 0) + 1;
     return (ps.early > 0 ? 1 : 0) + 1 + (ps.cf > ps.early ? 1 : 0) + 1 + (ps.split > 0 ? 2 : 0);   // split: + walker piece + dual piece
 }
+// stages [0, panel_top) of the sweeps run fused in one launch (k_bp_top): the leading stages with <= 32 parents
+int panel_top(const rb_solver *s) {
+    const int stages = s->P.L.num_stages - 1;   // nonleaf stages
+    int t = 0;
+    while (t < stages && s->stage_off[t + 1] - s->stage_off[t] <= 32) ++t;
+    return t >= 2 ? t : 0;
+}
 int iter_launches(const rb_solver *s) {
     const SweepPlan &pl = s->plan;
+    if (use_panel(s)) {   // kproj | stages backward, (fused top), forward | dual x 3 | check
+        const int top = panel_top(s);
+        return 1 + 2 * (s->P.L.num_stages - 1 - top) + (top > 0 ? 1 : 0) + 3 + 1;
+    }
     const int sweeps = 1 + 2 * pl.num_levels - (sweeps_fused(s) ? 2 : 0);
     if (use_pipe(s)) return 1 + sweeps + pipe_dual_launches(s) + 1 + (s->risk_split && pipe_split(s).cf < s->P.L.m ? 1 : 0);
     return 1 + sweeps + 1 + 1;
@@ -1435,15 +1459,39 @@ namespace {
 
 // the kernels of one iteration reading buffer src and writing buffer 1-src.  have_pbar: prim[1-src] already holds
 // pbar = p - alpha L* d of this iteration (written by the previous dual pass)
+void launch_panel_sweeps(rb_solver *s, cudaStream_t st, double *prim, cudaEvent_t mid = nullptr) {
+    const Layout &L = s->P.L;
+    const int top = panel_top(s);
+    for (int t = L.num_stages - 2; t >= top; --t)
+        launch_bp_bwd(st, s->P, s->ctrl, prim, s->pq, s->pr, s->stage_off[t], s->stage_off[t + 1] - s->stage_off[t]);
+    if (mid) cudaEventRecord(mid, st);
+    if (top > 0) launch_bp_top(st, s->P, s->ctrl, prim, s->pq, s->pr, s->x0, s->plan.stage_off, top);
+    for (int t = top; t <= L.num_stages - 2; ++t)
+        launch_bp_fwd(st, s->P, s->ctrl, prim, s->pr, s->x0, s->stage_off[t], s->stage_off[t + 1] - s->stage_off[t]);
+}
+
+// the batch-innermost path: always pipelined (the dual pass leaves pbar of the next iteration in the old primal buffer)
+int enqueue_iteration_panel(rb_solver *s, int src, cudaStream_t st, bool have_pbar) {
+    const Layout &L = s->P.L;
+    const int dst = 1 - src;
+    if (!have_pbar) launch_bp_primal(st, s->P, s->ctrl, s->pprim[src], s->pdual[src], s->pprim[dst]);
+    launch_bp_kproj(st, s->P, s->ctrl, s->pprim[dst], s->x0, s->pprim[src]);
+    launch_panel_sweeps(s, st, s->pprim[dst]);
+    launch_bp_dual(st, s->P, s->ctrl, s->pprim[src], s->pprim[dst], s->pdual[src], s->pdual[dst], s->slots, s->pprim[src], s->pc2);
+    launch_check(st, s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
+    return launch_ok(s, "panel iteration");
+}
+
 int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_pbar) {
     const Layout &L = s->P.L;
     const int dst = 1 - src;
+    if (s->panel_live) return enqueue_iteration_panel(s, src, st, have_pbar);
     if (!use_pipe(s)) {
         launch_primal(s, st, src, dst);
         int rc = launch_sweeps(s, s->ctrl, s->prim[dst], st);
         if (rc != RB_OK) return rc;
         launch_dual(s, st, src, dst);
-        k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
+        launch_check(st, s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
         return launch_ok(s, "fused iteration");
     }
     const PipeSplit ps = pipe_split(s);
@@ -1512,7 +1560,7 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
         RB_CUDA(s, cudaEventRecord(ev[4], s1));
         RB_CUDA(s, cudaStreamWaitEvent(st, ev[4], 0));
     }
-    k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
+    launch_check(st, s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
     return launch_ok(s, "pipelined iteration");
 }
 
@@ -1523,7 +1571,7 @@ int shard_exchange(rb_solver *s, int src, cudaStream_t st) {
     const int rc = nccl_all_gather_f64(s->xchg_send, s->xchg_recv, s->xchg_count, s->nccl_comm, st);
     if (rc != 0) return fail(s, RB_ERR_CUDA, std::string("ncclAllGather: ") + nccl_error(rc));
     k_shard_unpack<<<8, 256, 0, st>>>(s->P, s->ctrl, s->shard, s->xchg_recv, s->q, s->dual[src], s->slots);
-    if (s->shard_pending) k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
+    if (s->shard_pending) launch_check(st, s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
     s->shard_pending = false;
     return launch_ok(s, "shard exchange");
 }
@@ -1606,6 +1654,30 @@ int rb_loop_begin(rb_solver *s, double alpha, int32_t max_iters, double tol, int
     if (!s->have_x0) return fail(s, RB_ERR_STATE, "initial state not set (cache_initial_state)");
     const Layout &L = s->P.L;
     cudaStream_t st = s->stream;
+    const bool panel = use_panel(s);
+    if (panel != s->panel_live)   // the graphs were captured for the other layout
+        for (int i = 0; i < 2; ++i)
+            if (s->graph[i]) {
+                cudaGraphExecDestroy(s->graph[i]);
+                s->graph[i] = nullptr;
+            }
+    s->panel_live = panel;
+    if (panel && !s->pq) {
+        for (int w = 0; w < 2; ++w) {
+            rc = dev_zero(s, batch_panel_doubles(L.np_pad, L.batch), &s->pprim[w]);
+            if (rc != RB_OK) return rc;
+            rc = dev_zero(s, batch_panel_doubles(L.nd_pad, L.batch), &s->pdual[w]);
+            if (rc != RB_OK) return rc;
+        }
+        rc = dev_zero(s, batch_panel_doubles((long long)L.n * L.nx, L.batch), &s->pq);
+        if (rc != RB_OK) return rc;
+        rc = dev_zero(s, batch_panel_doubles((long long)L.m * L.nu, L.batch), &s->pr);
+        if (rc != RB_OK) return rc;
+        rc = dev_zero(s, (size_t)L.m * L.nxu, &s->pc2);
+        if (rc != RB_OK) return rc;
+        launch_bp_c2(st, s->P, s->pc2);
+        RB_LAUNCHED(s, "k_bp_c2");
+    }
     if (s->use_graphs && !s->sharded) {
         rc = build_graphs(s);
         if (rc != RB_OK) return rc;
@@ -1636,6 +1708,12 @@ int rb_loop_begin(rb_solver *s, double alpha, int32_t max_iters, double tol, int
     s->collapsed = false;
     s->in_loop = true;
     s->loop_old0 = s->old_i;
+    if (s->panel_live) {   // the old iterate into panels (32 instances per panel, the lanes of a warp)
+        launch_to_panels(st, s->prim[s->old_i], s->pprim[s->old_i], L.np_pad, L.batch);
+        launch_to_panels(st, s->dual[s->old_i], s->pdual[s->old_i], L.nd_pad, L.batch);
+        s->launches += 2;
+        return launch_ok(s, "panel conversion");
+    }
     return RB_OK;
 }
 
@@ -1647,13 +1725,13 @@ int rb_loop_enqueue(rb_solver *s, int32_t count) {
         if (s->sharded) {
             int rc = enqueue_iteration_sharded(s, src, s->stream);
             if (rc != RB_OK) return rc;
-        } else if (s->use_graphs && (s->pbar_ready || !use_pipe(s))) {
+        } else if (s->use_graphs && (s->pbar_ready || !(use_pipe(s) || s->panel_live))) {
             RB_CUDA(s, cudaGraphLaunch(s->graph[src], s->stream));
         } else {   // plain launches; the first iteration of a pipelined loop has no pbar yet
             int rc = enqueue_iteration_kernels(s, src, s->stream, s->pbar_ready);
             if (rc != RB_OK) return rc;
         }
-        s->pbar_ready = use_pipe(s);
+        s->pbar_ready = use_pipe(s) || s->panel_live;
         // the buffer just written holds the newest iterate: it is the next iteration's "old"
         std::swap(s->cur_i, s->old_i);
     }
@@ -1704,6 +1782,14 @@ int rb_loop_end(rb_solver *s, double *xi_hist, double *delta_hist, int32_t *iter
     s->old_i = newest;
     s->cur_i = 1 - newest;
     s->collapsed = true;
+    if (s->panel_live) {   // the newest iterate back into the instance-major buffers the rest of the API works on
+        launch_from_panels(s->stream, s->pprim[newest], s->prim[newest], L.np_pad, L.batch);
+        launch_from_panels(s->stream, s->pdual[newest], s->dual[newest], L.nd_pad, L.batch);
+        s->launches += 2;
+        RB_CUDA(s, cudaStreamSynchronize(s->stream));
+        int rcp = launch_ok(s, "panel conversion");
+        if (rcp != RB_OK) return rcp;
+    }
     Ctrl *hc = reinterpret_cast<Ctrl *>(s->h_pinned);
     if ((xi_hist || delta_hist) && hc->hist_capacity > 0) {
         const int rows = std::min(iters, hc->hist_capacity);
@@ -1734,6 +1820,7 @@ static int abort_loop(rb_solver *s, int rc) {
     s->in_loop = false;
     s->pbar_ready = false;
     s->shard_pending = false;
+    s->panel_live = false;
     s->old_i = s->loop_old0;
     s->cur_i = 1 - s->loop_old0;
     s->collapsed = true;
@@ -1784,7 +1871,7 @@ int rb_step(rb_solver *s, const double *x0, double *norms) {
     const Layout &L = s->P.L;
     // pipelined loop with the mapped mirror: ONE upload (the kernel projection copies x0 into x_0 of the old iterate)
     // and no download (k_check has written the norms to host memory when the stream is idle)
-    const bool lean = s->h_last_dev && use_pipe(s) && s->pbar_ready;
+    const bool lean = s->panel_live || (s->h_last_dev && use_pipe(s) && s->pbar_ready);   // the kernel projection copies x0 into x_0
     if (s->h_last_dev && !s->mirror_on) {   // from now on the stopping test mirrors the norms into host memory
         int *one = reinterpret_cast<int *>(s->h_pinned + 256);
         *one = 1;
@@ -1821,6 +1908,31 @@ int rb_profile_iteration(rb_solver *s, float *ms) {
     cudaEvent_t ev[12];
     for (auto &e : ev) RB_CUDA(s, cudaEventCreate(&e));
     const int src = s->old_i, dst = 1 - src;
+    if (s->panel_live) {   // ms[0] kernel projection (+ primal pass), ms[1] backward stages, ms[2] forward stages, ms[3] dual + check
+        for (int i = 0; i < 12; ++i) ms[i] = -1.0f;
+        RB_CUDA(s, cudaEventRecord(ev[0], st));
+        if (!s->pbar_ready) launch_bp_primal(st, s->P, s->ctrl, s->pprim[src], s->pdual[src], s->pprim[dst]);
+        launch_bp_kproj(st, s->P, s->ctrl, s->pprim[dst], s->x0, s->pprim[src]);
+        RB_CUDA(s, cudaEventRecord(ev[1], st));
+        launch_panel_sweeps(s, st, s->pprim[dst], ev[2]);   // ms[1]: backward stage launches; ms[2]: fused top + forward stage launches
+        RB_CUDA(s, cudaEventRecord(ev[3], st));
+        launch_bp_dual(st, s->P, s->ctrl, s->pprim[src], s->pprim[dst], s->pdual[src], s->pdual[dst], s->slots, s->pprim[src], s->pc2,
+                       ev + 5);
+        RB_CUDA(s, cudaEventRecord(ev[7], st));
+        launch_check(st, s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
+        RB_CUDA(s, cudaEventRecord(ev[4], st));
+        RB_CUDA(s, cudaStreamSynchronize(st));
+        int rcp = launch_ok(s, "profiled panel iteration");
+        for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+        cudaEventElapsedTime(&ms[8], ev[3], ev[5]);    // x / u block of the nonleaf nodes
+        cudaEventElapsedTime(&ms[9], ev[5], ev[6]);    // risk block
+        cudaEventElapsedTime(&ms[10], ev[6], ev[7]);   // leaves
+        for (auto &e : ev) cudaEventDestroy(e);
+        std::swap(s->cur_i, s->old_i);
+        s->pbar_ready = true;
+        s->launches += iter_launches(s);
+        return rcp;
+    }
     const bool pipe = use_pipe(s);
     RB_CUDA(s, cudaEventRecord(ev[0], st));
     if (pipe && s->pbar_ready) launch_kproj(L.batch, st, s->P, s->ctrl, s->prim[dst], s->h_last_dev ? s->x0 : nullptr, s->prim[src]);
@@ -1861,7 +1973,7 @@ int rb_profile_iteration(rb_solver *s, float *ms) {
     } else {
         launch_dual(s, st, src, dst);
     }
-    k_check<<<1, 32, 0, st>>>(s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
+    launch_check(st, s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
     RB_CUDA(s, cudaEventRecord(ev[2 + nsweep], st));
     RB_CUDA(s, cudaStreamSynchronize(st));
     int rc = launch_ok(s, "profiled iteration");
@@ -1976,6 +2088,13 @@ int rb_use_tree_kernels(rb_solver *s, int32_t enable) {
             cudaGraphExecDestroy(s->graph[i]);
             s->graph[i] = nullptr;
         }
+    return RB_OK;
+}
+
+int rb_use_batch_panels(rb_solver *s, int32_t enable) {
+    if (!s) return RB_ERR_INVALID;
+    if (s->in_loop) return fail(s, RB_ERR_STATE, "rb_use_batch_panels() inside a loop");
+    s->allow_panel = enable != 0;
     return RB_OK;
 }
 

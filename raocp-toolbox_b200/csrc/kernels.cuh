@@ -38,6 +38,7 @@ struct Ctrl {
     int pending;     // set by the dual pass: `slots` hold the residual maxima of an iteration k_check has not tested yet
     int mirror;      // k_check also writes the norms to mapped host memory (switched on by the first rb_step of a loop: the
     int pad;         // posted write to system memory costs the kernel ~1 us, which a loop that never reads them need not pay)
+    int chk_fail, chk_nan, chk_arrived;   // scratch of k_check_wide (many CTAs): some instance above tol / NaN seen / CTAs done
 };
 // tiles of consecutive nodes for the node-parallel passes (fused.cu): tiles[t] = (first node, one past the last);
 // a tile is either all nonleaf or all leaf nodes
@@ -88,6 +89,8 @@ void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl,
                   double *p_old = nullptr);
 __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, double *__restrict__ slots,
                         double *__restrict__ last, double *__restrict__ host_last);
+// the same stopping test for large batches (one thread per slot, the last CTA to finish closes the iteration); launch_check picks
+void launch_check(cudaStream_t st, const Params &P, Ctrl *ctrl, double *slots, double *last, double *host_last);
 
 // ---- sweeps.cu: the DP sweeps in a handful of launches ---------------------------------------------------------------
 struct SweepLevel {
@@ -156,6 +159,26 @@ void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, co
 // d_begin, d_end: the steps of the walk to run (depth below the chain heads); d_end < 0 = to the leaves
 void launch_chain_mma_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, double *prim,
                           const double *r, int d_begin = 0, int d_end = -1, bool w4 = false);
+
+// ---- batch.cu: many instances of one small tree, batch-innermost ("panel") layout: the lanes of a warp are 32 instances ------
+bool batch_panel_supported(int nx, int nu);
+size_t batch_panel_doubles(long long stride, int batch);   // doubles of a panel buffer with `stride` elements per instance
+void launch_to_panels(cudaStream_t st, const double *src, double *dst, long long stride, int batch);
+void launch_from_panels(cudaStream_t st, const double *src, double *dst, long long stride, int batch);
+void launch_bp_primal(cudaStream_t st, const Params &P, const Ctrl *ctrl, const double *p_old, const double *d_old, double *p_out);
+void launch_bp_kproj(cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim, const double *x0, double *p_old);
+void launch_bp_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const double *prim, double *q, double *r, int first, int count);
+void launch_bp_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim, const double *r, const double *x0, int first,
+                   int count);
+// the three dual kernels (x / u block and risk block of the nonleaf nodes, leaves); pbar = the p_old buffer; c2: [m][nx + nu]
+// diagonal of L* L on the x / u rows (launch_bp_c2, once)
+void launch_bp_dual(cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new, const double *d_old,
+                    double *d_new, double *slots, double *pbar, const double *c2, cudaEvent_t *evs = nullptr);   // evs: 2 events (after the first two kernels)
+void launch_bp_c2(cudaStream_t st, const Params &P, double *c2);
+// the stages [0, t_top) backward and forward in one launch (one CTA per panel, a warp per parent: stages of <= 32 parents)
+void launch_bp_top(cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim, double *q, double *r, const double *x0,
+                   const int *stage_off, int t_top);
+int batch_panel_max_children();
 
 // ---- shard.cu: one tree sharded by subtree over the GPUs of a box ----------------------------------------------------------
 struct ShardPlan {

@@ -217,6 +217,10 @@ class DeviceSolver:
     def use_graphs(self, enable=True):
         self._call("rb_use_graphs", 1 if enable else 0)
 
+    def use_batch_panels(self, enable=True):
+        """batch >= 64: fused loop in the batch-innermost panel layout (default) or with the instance-major kernels"""
+        self._call("rb_use_batch_panels", 1 if enable else 0)
+
     def use_pipeline(self, enable=True):
         """True / 1: pipelined loop (default); 3: additionally the forward chain walk in two pieces, overlapped with the
         dual pass (ablation); 4: the risk block of the chain nodes inside the chain dual pass instead of a kernel of its own
