@@ -447,39 +447,72 @@ def run_ours(args, rank, world, local_rank):
                            "iteration count x the run's mean wall time per iteration"}
             del cold
 
-    # ---- N > 1: the same single tree sharded by subtree over all ranks (one all-gather per iteration) -------------------
-    shard_ms = None
-    if dist is not None and batch == 1:
-        try:
-            sh = r.core.Solver(problem, device=local_rank, verbose=False, shard=(rank, world))
+    # ---- N > 1: ONE tree sharded by subtree over all ranks (one exchange of the cut-stage messages per iteration) -------------
+    #      strong: the cfg3 tree itself; weak: a tree ~N times wider (oracle/problems.py wide_spec), so that every GPU owns about
+    #      one cfg3 worth of nodes -- the headline at N > 1
+    sharded = {}
+    if dist is not None and batch == 1 and args.workload == "cfg3":
+        def sharded_leg(prob, x0_col):
+            sh = r.core.Solver(prob, device=local_rank, verbose=False, shard=(rank, world))
             sdev = sh.cache.device_solver
             sdev.shard_init()
+            sdev.use_pipeline(0 if args.no_pipeline else 1)
             sdev.set_stream(stream.cuda_stream)
-            sdev.set_initial_state(spec["x0"][:, :1].reshape(-1))
+            a = sh.compute_step_size()
+            sdev.set_initial_state(x0_col.reshape(-1))
             with torch.cuda.stream(stream):
-                sdev.loop_begin(alpha, 1 << 30, -1.0, 0)
+                sdev.loop_begin(a, 1 << 30, -1.0, 0)
                 sdev.loop_enqueue(W)
+                st_ = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+                en_ = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
                 barrier()
+                for k in range(K):
+                    flush.zero_()
+                    st_[k].record(stream)
+                    sdev.loop_enqueue(1)
+                    en_[k].record(stream)
+                barrier()
+                cold = float(sum(a_.elapsed_time(b_) for a_, b_ in zip(st_, en_)))
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                barrier()
                 e0.record(stream)
                 sdev.loop_enqueue(K)
                 e1.record(stream)
                 barrier()
-                shard_ms = e0.elapsed_time(e1)
+                warm = e0.elapsed_time(e1)
+                # end to end: x0 from pinned host memory and the six norms back, every step, on every rank
+                xh = torch.from_numpy(np.ascontiguousarray(x0_col.reshape(1, -1))).pin_memory()
+                nh = torch.zeros(1, 6, dtype=torch.float64).pin_memory()
+                barrier()
+                t0_ = time.perf_counter()
+                for _ in range(K):
+                    sdev.step(xh.data_ptr(), nh.data_ptr())
+                torch.cuda.synchronize()
+                e2e = time.perf_counter() - t0_
                 sdev.loop_end()
+            t_ = torch.tensor([cold, warm, e2e], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+            cold, warm, e2e = t_.tolist()
+            fl = sh.cache.flat_problem
+            return {"nodes": int(fl.n), "cut_stage": int(sdev.shard_info()[0]), "cut_subtrees": int(sdev.shard_info()[2]),
+                    "cold_ms_per_step": cold / K, "warm_ms_per_step": warm / K, "e2e_s_per_step": e2e / K,
+                    "np": int(fl.np_), "nd": int(fl.nd_), "exchange": "peer-memory push / pull kernels inside the CUDA graph"
+                    if os.environ.get("RAOCP_SHARD_P2P", "1") != "0" else "ncclAllGather between plain launches"}
+        try:
+            sharded["strong"] = sharded_leg(problem, spec["x0"][:, :1])
         except Exception as exc:   # e.g. the tree has fewer cut-stage subtrees than ranks
-            shard_ms = None
-            shard_err = str(exc)
+            sharded["strong"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
+        try:
+            wide = problems.wide_spec(world)
+            sharded["weak"] = sharded_leg(problems.build(wide, r.core), wide["x0"][:, :1])
+        except Exception as exc:
+            sharded["weak"] = {"unavailable": f"{type(exc).__name__}: {exc}"}
 
     cold_total, e2e_t = float(cold_ms.sum()), e2e_s
     if dist is not None:
         t = torch.tensor([cold_total, warm_ms, e2e_t, solve_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         cold_total, warm_ms, e2e_t, solve_s = t.tolist()
-        if shard_ms is not None:
-            t = torch.tensor([shard_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            shard_ms = float(t.item())
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -565,13 +598,48 @@ def run_ours(args, rank, world, local_rank):
                       "classes": flat.num_cls, "per_node_classes": bool(args.no_dedup)},
         "residuals_last": [float(v) for v in last_norms[0]],
     }
-    if world > 1:
-        line["sharded_single_tree"] = (
-            {"value": K / (shard_ms * 1e-3), "unit": "it/s", "ms_per_step": shard_ms / K, "scaling": "strong",
-             "note": f"ONE {flat.n}-node tree sharded by subtree over {world} GPUs, one NCCL all-gather of the cut-stage "
-                     "q_j, d2_j and residual maxima per iteration, K iterations back to back (warm), max over ranks; "
-                     "compare with warm.value / n_gpus of the N=1 run"}
-            if shard_ms is not None else {"unavailable": locals().get("shard_err", "batch > 1")})
+    if world > 1 and sharded:
+        # headline at N > 1 for the tree workload: the WIDE tree sharded by subtree (weak scaling: one cfg3 worth of nodes per
+        # GPU, one exchange per iteration).  value = cfg3-equivalents advanced by one iteration per second = (nodes / cfg3
+        # nodes) x iterations/s; the N independent replicas measured above move to `replicas`.
+        line["replicas"] = {"value": line["value"], "unit": "it/s", "ms_per_step": line["ms_per_step"],
+                            "warm": line["warm"], "e2e": line["e2e"],
+                            "note": f"{world} independent cfg3 instances, one per GPU, no collective (linear by construction)"}
+        wk, sg = sharded.get("weak", {}), sharded.get("strong", {})
+        if "cold_ms_per_step" in sg:
+            line["sharded_cfg3_strong"] = {
+                "value": 1e3 / sg["cold_ms_per_step"], "warm_value": 1e3 / sg["warm_ms_per_step"], "unit": "it/s", "scaling": "strong",
+                "ms_per_step": sg["cold_ms_per_step"], "cut_stage": sg["cut_stage"], "exchange": sg["exchange"],
+                "note": f"ONE {flat.n}-node cfg3 tree over {world} GPUs (latency-bound: sharding cuts the width of the sweeps, not "
+                        "their depth); compare with the N=1 value"}
+        else:
+            line["sharded_cfg3_strong"] = sg
+        if "cold_ms_per_step" in wk:
+            equiv = wk["nodes"] / flat.n
+            line.update({
+                "value": equiv * 1e3 / wk["cold_ms_per_step"], "ms_per_step": wk["cold_ms_per_step"], "scaling": "weak",
+                "warm": {"value": equiv * 1e3 / wk["warm_ms_per_step"], "unit": "it/s", "ms_per_step": wk["warm_ms_per_step"],
+                         "note": "back to back, no L2 flush"},
+                "e2e": {"value": equiv / wk["e2e_s_per_step"], "unit": "it/s", "h2d_bytes_per_step": int(world * flat.nx * 8),
+                        "d2h_bytes_per_step": int(world * 48),
+                        "note": "rb_step per iteration on every rank: x0 from pinned host memory, one sharded iteration, residual "
+                                "norms to the host (those of the previous iteration: the stopping test of iteration k rides on the "
+                                "exchange of iteration k + 1), synchronised every step"}})
+            line["config"].update({
+                "workload": f"cfg3 widened for {world} GPUs: ONE {wk['nodes']}-node scenario tree (= {equiv:.2f} x cfg3's {flat.n} nodes), "
+                            f"nx={flat.nx}, nu={flat.nu}, AVaR(0.5), rectangles, seed 0, sharded by subtree below stage "
+                            f"{wk['cut_stage']} ({wk['cut_subtrees']} subtrees), top of the tree replicated",
+                "parallelism": f"subtree sharding over {world} GPUs, one exchange of the cut-stage q_j, sbar_j and residual maxima per "
+                               f"iteration ({wk['exchange']})",
+                "value_definition": "cfg3-equivalents x iterations/s = (tree nodes / 62 805) x CP iterations per second of the "
+                                    "sharded tree; N = 1 is the plain cfg3 value"})
+            b_w = 8 * 2 * (wk["np"] + wk["nd"])
+            line["roofline"]["iteration"] = {"algorithmic_bytes": b_w, "achieved": b_w / (wk["cold_ms_per_step"] * 1e-3) / 1e9,
+                                             "frac": b_w / (wk["cold_ms_per_step"] * 1e-3) / 1e9 / (world * peak),
+                                             "note": f"sharded wide tree, all {world} GPUs: B_alg / t_iteration / (N x peak)"}
+            line["roofline"]["note"] = "the per-kernel figures above are rank 0's replica leg (one cfg3 instance on one GPU)"
+        else:
+            line["sharded_weak"] = wk
     if not args.no_parity:
         try:
             line["parity_check"] = parity_check(args.workload, r, local_rank)

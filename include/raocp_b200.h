@@ -198,6 +198,13 @@ int rb_use_batch_panels(rb_solver *s, int32_t enable);
  * rank are valid on its own nodes and on the replicated top of the tree. */
 int rb_shard_unique_id(char *id128);
 int rb_shard_init(rb_solver *s, const char *id128);
+/* Device-initiated exchange over NVLink peer memory (optional, after rb_shard_init): every rank calls rb_shard_p2p_export
+ * (128 bytes: two CUDA IPC handles), the host distributes them, every rank calls rb_shard_p2p_open with all world * 128 bytes.
+ * Afterwards the cut-stage messages are written straight into the peers' buffers by a kernel and awaited by a kernel, the
+ * whole sharded iteration is ONE CUDA graph, and the pipelined loop (rb_use_pipeline) runs under sharding as well.  Without
+ * it the exchange is a host-launched ncclAllGather between plain launches of the unpipelined loop. */
+int rb_shard_p2p_export(rb_solver *s, char *handles128);
+int rb_shard_p2p_open(rb_solver *s, const char *all_handles);
 /* the cut the device chose for the DP sweeps and for subtree sharding -- the ONE source of truth for it (the host
  * never re-derives the rule): cut_stage = first stage below the replicated top, cut_first = its first node, num_cut =
  * its width (rank r of W owns the cut nodes [r*num_cut/W, (r+1)*num_cut/W) and their descendants), chain_stage = the

@@ -64,6 +64,39 @@ def spec(name, seed=0, batch=1):
                 x_lim=5.0, u_lim=1.0, x0=x0, rectangles=True)
 
 
+def wide_spec(n_gpus, seed=0):
+    """cfg3 made ~n_gpus times WIDER (the weak-scaling tree of the subtree-sharded bench): same nx = 20, nu = 10, horizon 20,
+    AVaR(0.5), rectangles.  n_gpus = 2: eight modes in two blocks of four (block-diagonal transition matrix, so every node
+    still has four children but the root has eight) -> 8 192 chains; 4: four modes with stopping time 7 -> 16 384 chains;
+    8: both -> 32 768 chains.  At most 8 children per node (the limit of the lanes-per-node passes)."""
+    if n_gpus == 1:
+        return spec("cfg3", seed=seed)
+    blocks = 2 if n_gpus in (2, 8) else 1
+    tau = 7 if n_gpus in (4, 8) else 6
+    if n_gpus not in (2, 4, 8):
+        raise ValueError("wide_spec: n_gpus must be 1, 2, 4 or 8")
+    modes, nx, nu, horizon = 4 * blocks, 20, 10, 20
+    rng = np.random.default_rng(seed + 1000 * n_gpus)
+    p = np.zeros((modes, modes))
+    for b in range(blocks):
+        blk = rng.uniform(0.1, 1.0, size=(4, 4))
+        p[4 * b: 4 * b + 4, 4 * b: 4 * b + 4] = blk / blk.sum(axis=1, keepdims=True)
+    v = rng.uniform(0.1, 1.0, size=modes)
+    v /= v.sum()
+    a_list, b_list, q_list, r_list = [], [], [], []
+    for _ in range(modes):
+        a = rng.standard_normal((nx, nx))
+        a *= 0.9 / np.max(np.abs(np.linalg.eigvals(a)))
+        a_list.append(a)
+        b_list.append(rng.standard_normal((nx, nu)) / np.sqrt(nx))
+        q_list.append(np.diag(rng.uniform(0.5, 2.0, size=nx)))
+        r_list.append(np.diag(rng.uniform(0.5, 2.0, size=nu)))
+    qf = np.diag(rng.uniform(0.5, 2.0, size=nx))
+    x0 = rng.uniform(-1.0, 1.0, size=(nx, 1))
+    return dict(name=f"cfg3x{n_gpus}", seed=seed, p=p, v=v, horizon=horizon, tau=tau, nx=nx, nu=nu, a=a_list, b=b_list, q=q_list,
+                r=r_list, qf=qf, avar=0.5, x_lim=5.0, u_lim=1.0, x0=x0, rectangles=True)
+
+
 def demo_spec():
     """The reference's demo problem, numbers from reference main.py:11-80 (43 nodes, nx=3, nu=2, AVaR 0.95)."""
     p = np.array([[0.1, 0.8, 0.1], [0.4, 0.6, 0.0], [0.0, 0.3, 0.7]])

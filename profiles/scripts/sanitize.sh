@@ -18,17 +18,15 @@ run() {   # tool, label, args...
 for tool in memcheck racecheck synccheck initcheck; do
   # pipelined default: MMA chain walkers, fused tree kernel (cooperative, flag hand-off), chain / risk / lane dual passes
   run $tool chain2010_p1_t2_m1 chain2010 4 1 2 1
-  # per-level tree kernels, forward split, risk block inside the chain pass
-  run $tool chain2010_p3_t1_m1 chain2010 4 3 1 1
-  run $tool chain2010_p4_t2_m1 chain2010 4 4 2 1
+  # four warps per chain tile (named barriers, producer warps), per-level tree kernels, forward split
+  run $tool chain2010_p3_t1_m2 chain2010 4 3 1 2
   # unpipelined loop, global-memory stage kernels, warp-per-chain walker
   run $tool chain2010_p0_t0_m0 chain2010 4 0 0 0
   # cfg5's sizes: BIG chain walkers (fragments in shared memory), wide-row tree kernels
   run $tool chain6432_p1_t2_m1 chain6432 3 1 2 1
-  run $tool chain6432_p0_t1_m0 chain6432 3 0 1 0
-  # small trees: cfg1 (31 nodes), cfg2 (branching + 243 chains, nx=10), batch of 3 instances
+  # small trees: cfg1 (31 nodes), a batch of 3 instances (instance-major kernels), a batch of 70 (panel kernels, batch.cu)
   run $tool cfg1_p1_t2_m1 cfg1 6 1 2 1
-  run $tool cfg2_p1_t2_m1 cfg2 3 1 2 1
   run $tool mini3_b3_p1_t2_m1 mini3 4 1 2 1 3
+  run $tool mini3_b70_panels mini3 4 1 2 1 70
 done
 cat $O/summary.txt

@@ -93,6 +93,16 @@ struct rb_solver {
     size_t tree_smem[3]{};   // dynamic shared memory of the top / level launches   // chain levels on the FP64 tensor cores when the level carries tiles (rb_use_mma_sweeps)
     double *xchg_send = nullptr, *xchg_recv = nullptr;
     size_t xchg_count = 0;
+    // device-initiated exchange over peer memory (shard.cu k_shard_push / _pull) and the pipelined sharded loop it enables
+    bool p2p = false;
+    PeerXchg px{};
+    double *p2p_recv = nullptr;
+    unsigned long long *p2p_flag = nullptr;
+    void *p2p_opened[2 * kMaxPeers] = {};
+    int *own_nonleaf = nullptr, *top_nonleaf = nullptr, *own_lane = nullptr;   // node lists of the pipelined sharded loop
+    int n_own_nonleaf = 0, n_top_nonleaf = 0, n_own_lane = 0;
+    OwnMap own_chain{0, 0, 0};      // the rank's columns of the chain stages
+    int n_own_chain = 0;
     bool shard_pending = false;   // an executed iteration whose residuals have not been gathered / tested yet
     // pipelined loop (lane passes only): the dual pass of iteration k also writes pbar of iteration k+1 into the old
     // primal buffer, so iteration k+1 has no primal pass -- only the kernel projection, in place, next to the backward
@@ -1072,6 +1082,35 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
         s->xchg_count = (size_t)sp.cap * (nx + 1) + 6;
         TRY(dev_zero(s, s->xchg_count, &s->xchg_send));
         TRY(dev_zero(s, s->xchg_count * W, &s->xchg_recv));
+        {   // node lists of the pipelined sharded loop: the chain nodes [chain_first, m) go through k_dual_chain (the rank's
+            // columns of every chain stage: OwnMap), everything else the rank owns -- and the replicated top -- through the
+            // general lane pass; the kernel projection takes the nonleaf nodes of either set
+            std::vector<int> own_nl, top_nl, lane;
+            const int cf = s->chain_stride > 0 ? s->chain_first : m;
+            for (int i : top) {
+                if (i < m) top_nl.push_back(i);
+                lane.push_back(i);
+            }
+            for (int i : owned) {
+                if (i < m) own_nl.push_back(i);
+                if (i < cf || i >= m) lane.push_back(i);
+            }
+            TRY(upload(s, own_nl.data(), own_nl.size(), &s->own_nonleaf));
+            TRY(upload(s, top_nl.data(), top_nl.size(), &s->top_nonleaf));
+            TRY(upload(s, lane.data(), lane.size(), &s->own_lane));
+            s->n_own_nonleaf = (int)own_nl.size();
+            s->n_top_nonleaf = (int)top_nl.size();
+            s->n_own_lane = (int)lane.size();
+            if (cf < m) {   // stage of chain_first and the rank's columns there
+                int t = 0;
+                while (s->stage_off[t + 1] <= cf) ++t;
+                const int wdt = s->stage_off[t + 1] - s->stage_off[t];
+                if (s->stage_off[t] == cf && wdt == s->chain_stride && stage_range[t].second > stage_range[t].first) {
+                    s->own_chain = OwnMap{stage_range[t].second - stage_range[t].first, stage_range[t].first - cf, wdt};
+                    s->n_own_chain = (m - cf) / wdt * s->own_chain.w;
+                }
+            }
+        }
         s->sharded = true;
     }
     *out = s;
@@ -1087,6 +1126,8 @@ void rb_destroy(rb_solver *s) {
     for (int i = 0; i < 2; ++i)
         if (s->graph[i]) cudaGraphExecDestroy(s->graph[i]);
     for (void *p : s->allocs) cudaFree(p);
+    for (void *p : s->p2p_opened)
+        if (p) cudaIpcCloseMemHandle(p);
     if (s->nccl_comm) nccl_comm_destroy(s->nccl_comm);
     if (s->hist) cudaFree(s->hist);
     if (s->h_pinned) cudaFreeHost(s->h_pinned);
@@ -1566,11 +1607,20 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
 
 // the gather step of the sharded loop: q_j and d2_j of the cut nodes and the residual maxima of the previous iteration
 // cross NVLink, then the stopping test of the previous iteration runs (identically on every rank)
-int shard_exchange(rb_solver *s, int src, cudaStream_t st) {
-    k_shard_pack<<<8, 256, 0, st>>>(s->P, s->ctrl, s->shard, s->q, s->dual[src], s->slots, s->xchg_send);
-    const int rc = nccl_all_gather_f64(s->xchg_send, s->xchg_recv, s->xchg_count, s->nccl_comm, st);
-    if (rc != 0) return fail(s, RB_ERR_CUDA, std::string("ncclAllGather: ") + nccl_error(rc));
-    k_shard_unpack<<<8, 256, 0, st>>>(s->P, s->ctrl, s->shard, s->xchg_recv, s->q, s->dual[src], s->slots);
+int shard_exchange(rb_solver *s, int src, cudaStream_t st, double *aux = nullptr) {
+    // aux: the per-cut-node scalar that travels with q_j; default d2_j of the old dual (unpipelined loop), else sbar_j of pbar
+    if (!aux) aux = s->dual[src] + s->P.L.d2;
+    if (s->p2p) {
+        launch_shard_push(st, s->P, s->ctrl, s->shard, s->q, aux, s->slots, s->px);
+        launch_shard_pull(st, s->P, s->ctrl, s->shard, s->q, aux, s->slots, s->px);
+        s->launches += 3;
+    } else {
+        k_shard_pack<<<8, 256, 0, st>>>(s->P, s->ctrl, s->shard, s->q, aux, s->slots, s->xchg_send);
+        const int rc = nccl_all_gather_f64(s->xchg_send, s->xchg_recv, s->xchg_count, s->nccl_comm, st);
+        if (rc != 0) return fail(s, RB_ERR_CUDA, std::string("ncclAllGather: ") + nccl_error(rc));
+        k_shard_unpack<<<8, 256, 0, st>>>(s->P, s->ctrl, s->shard, s->xchg_recv, s->q, aux, s->slots);
+        s->launches += 2;
+    }
     if (s->shard_pending) launch_check(st, s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
     s->shard_pending = false;
     return launch_ok(s, "shard exchange");
@@ -1624,6 +1674,80 @@ int enqueue_iteration_sharded(rb_solver *s, int src, cudaStream_t st) {
     return launch_ok(s, "sharded iteration");
 }
 
+// The pipelined loop under subtree sharding (needs the peer-memory exchange, so that the whole iteration is kernels and fits a
+// CUDA graph): owned kernel projection next to the owned backward sweeps -> push / pull of q_j, sbar_j and the residual maxima
+// (+ the stopping test of the previous iteration) -> replicated top (kernel projection, sweep, dual pass) -> owned forward
+// sweeps -> owned dual passes, which leave pbar of the next iteration.  The risk block of the chain nodes adds to the residual
+// maxima of THIS iteration, so it may only start once the exchange has collected those of the previous one.
+bool shard_pipe(const rb_solver *s) {
+    return s->sharded && s->p2p && use_lane(s) && s->allow_pipe && s->tree_mode > 0 && s->tree_top.desc != nullptr;
+}
+int enqueue_iteration_sharded_pipe(rb_solver *s, int src, cudaStream_t st, bool have_pbar) {
+    const SweepPlan &pl = s->plan;
+    const Layout &L = s->P.L;
+    const int dst = 1 - src;
+    const bool w4 = s->mma_w4 && chain_mma_w4(L.nx, L.nu);
+    const size_t per_warp = (size_t)(2 * L.nxu + 32) * sizeof(double);
+    auto grid = [&](const SweepLevel &lv) { return dim3((lv.num_sub + lv.subs_per_cta - 1) / lv.subs_per_cta, 1); };
+    auto threads = [&](const SweepLevel &lv) { return 32 * lv.warps_per_sub * lv.subs_per_cta; };
+    auto smem = [&](const SweepLevel &lv) {
+        return per_warp * lv.warps_per_sub * lv.subs_per_cta + (size_t)lv.subs_per_cta * lv.stage_cap * L.nxu * sizeof(double);
+    };
+    cudaStream_t s0 = s->side[0], s1 = s->side[1];
+    cudaEvent_t *ev = s->pev;
+    const int cf = s->n_own_chain > 0 ? s->chain_first : L.m;
+    if (!have_pbar) launch_primal(s, st, src, dst, s->owned_nodes, s->n_owned);   // incl. the kernel projection of the owned nodes
+    RB_CUDA(s, cudaEventRecord(ev[0], st));
+    RB_CUDA(s, cudaStreamWaitEvent(s0, ev[0], 0));
+    if (have_pbar) launch_kproj(1, s0, s->P, s->ctrl, s->prim[dst], nullptr, nullptr, s->own_nonleaf, s->n_own_nonleaf);
+    for (int v = pl.num_levels - 1; v >= 0; --v)
+        if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
+            launch_chain_mma_bwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->q, s->r, w4);
+        else if (s->shard_tree_lv[v].desc)
+            launch_tree_bwd(dim3(s->shard_tree_lv[v].num_sub, 1), 32 * s->shard_tree_lv[v].warps, s->tree_smem[1 + v], st, s->P,
+                            s->ctrl, s->shard_tree_lv[v], s->prim[dst], s->q, s->r);
+        else
+            launch_sweep_sub_bwd(grid(s->shard_lv[v]), threads(s->shard_lv[v]), smem(s->shard_lv[v]), st, s->P, s->ctrl,
+                                 s->shard_lv[v], s->prim[dst], s->q, s->r);
+    int rc = shard_exchange(s, src, st, have_pbar ? s->prim[dst] + L.ps : nullptr);
+    if (rc != RB_OK) return rc;
+    RB_CUDA(s, cudaEventRecord(ev[1], st));          // the maxima of the previous iteration are collected and tested
+    RB_CUDA(s, cudaStreamWaitEvent(s0, ev[1], 0));
+    if (cf < L.m && s->risk_split)
+        launch_dual_risk_chain(1, s0, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, cf,
+                               s->n_own_chain, s->chain_stride, s->chain_yo0, s->prim[src], s->own_chain);
+    RB_CUDA(s, cudaEventRecord(ev[2], s0));
+    if (have_pbar) launch_kproj(1, st, s->P, s->ctrl, s->prim[dst], s->h_last_dev ? s->x0 : nullptr, s->prim[src], s->top_nonleaf,
+                                s->n_top_nonleaf);
+    else launch_primal(s, st, src, dst, s->top_nodes, s->n_top);
+    launch_tree_top(1, 32 * s->tree_top.warps, s->tree_smem[0], st, s->P, s->ctrl, s->tree_top, s->prim[dst], s->q, s->r, s->x0);
+    RB_CUDA(s, cudaEventRecord(ev[3], st));
+    RB_CUDA(s, cudaStreamWaitEvent(s1, ev[3], 0));   // the top is final: its dual pass runs next to the forward sweeps
+    launch_dual_lane(dim3(1, 1), s1, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, s->own_lane, 0,
+                     s->n_top, s->prim[src], true);
+    for (int v = 0; v < pl.num_levels; ++v)
+        if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
+            launch_chain_mma_fwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->r, 0, -1, w4);
+        else if (s->shard_tree_lv[v].desc)
+            launch_tree_fwd(dim3(s->shard_tree_lv[v].num_sub, 1), 32 * s->shard_tree_lv[v].warps, s->tree_smem[1 + v], st, s->P,
+                            s->ctrl, s->shard_tree_lv[v], s->prim[dst], s->r);
+        else
+            launch_sweep_sub_fwd(grid(s->shard_lv[v]), threads(s->shard_lv[v]), smem(s->shard_lv[v]), st, s->P, s->ctrl,
+                                 s->shard_lv[v], s->prim[dst], s->r);
+    RB_CUDA(s, cudaStreamWaitEvent(st, ev[2], 0));   // owned kernel projection (+ risk block) done
+    RB_CUDA(s, cudaEventRecord(ev[4], st));
+    RB_CUDA(s, cudaStreamWaitEvent(s1, ev[4], 0));
+    launch_dual_lane(dim3(1, 1), s1, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
+                     s->own_lane + s->n_top, 0, s->n_own_lane - s->n_top, s->prim[src]);
+    if (cf < L.m)
+        launch_dual_chain(1, st, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, s->chain_recs, cf,
+                          s->n_own_chain, s->chain_stride, s->chain_yo0, s->prim[src], s->risk_split ? 0 : 1, s->own_chain);
+    RB_CUDA(s, cudaEventRecord(ev[5], s1));
+    RB_CUDA(s, cudaStreamWaitEvent(st, ev[5], 0));
+    s->shard_pending = true;
+    return launch_ok(s, "pipelined sharded iteration");
+}
+
 // capture one iteration per buffer parity into a CUDA graph (the kernel arguments never change afterwards: step size
 // and stopping parameters live in the device control block)
 int build_graphs(rb_solver *s) {
@@ -1632,7 +1756,13 @@ int build_graphs(rb_solver *s) {
         cudaStream_t cap = nullptr;
         RB_CUDA(s, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
         RB_CUDA(s, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_iteration_kernels(s, src, cap, true);
+        int rc;
+        if (shard_pipe(s)) {   // steady state: pbar is there and the previous iteration is waiting for its stopping test
+            s->shard_pending = true;
+            rc = enqueue_iteration_sharded_pipe(s, src, cap, true);
+        } else {
+            rc = enqueue_iteration_kernels(s, src, cap, true);
+        }
         cudaGraph_t g = nullptr;
         cudaError_t e = cudaStreamEndCapture(cap, &g);
         cudaStreamDestroy(cap);
@@ -1678,8 +1808,10 @@ int rb_loop_begin(rb_solver *s, double alpha, int32_t max_iters, double tol, int
         launch_bp_c2(st, s->P, s->pc2);
         RB_LAUNCHED(s, "k_bp_c2");
     }
-    if (s->use_graphs && !s->sharded) {
+    if (s->use_graphs && (!s->sharded || shard_pipe(s))) {
+        const int64_t before = s->launches;
         rc = build_graphs(s);
+        s->launches = before;   // captured, not launched
         if (rc != RB_OK) return rc;
     }
     s->shard_pending = false;
@@ -1722,7 +1854,18 @@ int rb_loop_enqueue(rb_solver *s, int32_t count) {
     if (!s->in_loop) return fail(s, RB_ERR_STATE, "rb_loop_begin() has not been called");
     for (int k = 0; k < count; ++k) {
         const int src = s->old_i;
-        if (s->sharded) {
+        if (s->sharded && shard_pipe(s)) {
+            if (s->use_graphs && s->pbar_ready && s->shard_pending) {
+                RB_CUDA(s, cudaGraphLaunch(s->graph[src], s->stream));
+            } else {
+                int rc = enqueue_iteration_sharded_pipe(s, src, s->stream, s->pbar_ready);
+                if (rc != RB_OK) return rc;
+            }
+            s->pbar_ready = true;
+            s->shard_pending = true;
+            std::swap(s->cur_i, s->old_i);
+            continue;
+        } else if (s->sharded) {
             int rc = enqueue_iteration_sharded(s, src, s->stream);
             if (rc != RB_OK) return rc;
         } else if (s->use_graphs && (s->pbar_ready || !(use_pipe(s) || s->panel_live))) {
@@ -1731,7 +1874,7 @@ int rb_loop_enqueue(rb_solver *s, int32_t count) {
             int rc = enqueue_iteration_kernels(s, src, s->stream, s->pbar_ready);
             if (rc != RB_OK) return rc;
         }
-        s->pbar_ready = use_pipe(s) || s->panel_live;
+        s->pbar_ready = (use_pipe(s) || s->panel_live) && !s->sharded;
         // the buffer just written holds the newest iterate: it is the next iteration's "old"
         std::swap(s->cur_i, s->old_i);
     }
@@ -1761,6 +1904,7 @@ int rb_loop_poll(rb_solver *s, int32_t *iters, int32_t *done, double *last_norms
     if (done) *done = hc->done;
     if (hc->status) {
         RB_CUDA(s, cudaMemsetAsync(&s->ctrl->status, 0, sizeof(int), s->stream));
+        if (hc->status & 16) return fail(s, RB_ERR_CUDA, "subtree sharding: the peer-memory exchange timed out (a rank is gone)");
         if (hc->status & 1) return fail(s, RB_ERR_NUMERIC, "Rectangle constraint - 'nan' value cannot be constrained");
         return fail(s, RB_ERR_NUMERIC, "non-finite value in the residuals");
     }
@@ -2044,6 +2188,59 @@ int rb_shard_init(rb_solver *s, const char *id128) {
     RB_CUDA(s, cudaSetDevice(s->device));
     const int rc = nccl_comm_init(&s->nccl_comm, s->shard.world, id, s->shard.rank);
     if (rc != 0) return fail(s, RB_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl_error(rc));
+    return RB_OK;
+}
+
+// peer-memory exchange: every rank exports its receive buffer and flag array (two cudaIpcMemHandle_t, 64 bytes each), the host
+// side distributes them (torch.distributed), every rank opens the others'
+int rb_shard_p2p_export(rb_solver *s, char *handles128) {
+    if (!s || !handles128) return RB_ERR_INVALID;
+    if (!s->sharded) return fail(s, RB_ERR_STATE, "the problem was not created with shard_world > 1");
+    if (s->shard.world > kMaxPeers) return fail(s, RB_ERR_INVALID, "peer-memory exchange supports at most 8 ranks");
+    RB_CUDA(s, cudaSetDevice(s->device));
+    const int W = s->shard.world;
+    if (!s->p2p_recv) {
+        int rc = dev_zero(s, (size_t)2 * W * s->xchg_count, &s->p2p_recv);
+        if (rc != RB_OK) return rc;
+        rc = dev_zero(s, (size_t)2 * W, &s->p2p_flag);
+        if (rc != RB_OK) return rc;
+        unsigned long long *seq = nullptr;
+        rc = dev_zero(s, 1, &seq);
+        if (rc != RB_OK) return rc;
+        const unsigned long long one = 1ull;
+        RB_CUDA(s, cudaMemcpy(seq, &one, sizeof(one), cudaMemcpyHostToDevice));
+        s->px.seq = seq;
+    }
+    cudaIpcMemHandle_t h[2];
+    RB_CUDA(s, cudaIpcGetMemHandle(&h[0], s->p2p_recv));
+    RB_CUDA(s, cudaIpcGetMemHandle(&h[1], s->p2p_flag));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    std::memcpy(handles128, h, 128);
+    return RB_OK;
+}
+
+int rb_shard_p2p_open(rb_solver *s, const char *all_handles) {
+    if (!s || !all_handles) return RB_ERR_INVALID;
+    if (!s->sharded || !s->p2p_recv) return fail(s, RB_ERR_STATE, "rb_shard_p2p_export() first");
+    RB_CUDA(s, cudaSetDevice(s->device));
+    const int W = s->shard.world, R = s->shard.rank;
+    for (int r = 0; r < W; ++r) {
+        if (r == R) {
+            s->px.recv[r] = s->p2p_recv;
+            s->px.flag[r] = s->p2p_flag;
+            continue;
+        }
+        cudaIpcMemHandle_t h[2];
+        std::memcpy(h, all_handles + (size_t)r * 128, 128);
+        void *pr = nullptr, *pf = nullptr;
+        RB_CUDA(s, cudaIpcOpenMemHandle(&pr, h[0], cudaIpcMemLazyEnablePeerAccess));
+        RB_CUDA(s, cudaIpcOpenMemHandle(&pf, h[1], cudaIpcMemLazyEnablePeerAccess));
+        s->p2p_opened[2 * r] = pr;
+        s->p2p_opened[2 * r + 1] = pf;
+        s->px.recv[r] = static_cast<double *>(pr);
+        s->px.flag[r] = static_cast<unsigned long long *>(pf);
+    }
+    s->p2p = true;
     return RB_OK;
 }
 

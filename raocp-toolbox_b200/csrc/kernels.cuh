@@ -56,6 +56,13 @@ void launch_dual_tile(bool diag, dim3 grid, size_t smem, cudaStream_t st, const 
                       const double *p_old, const double *p_new, const double *d_old, double *d_new, double *slots);
 constexpr int kDualRowsHost = 15;
 
+// Subtree sharding: the nodes a rank owns in a run of equally wide stages (the chain part of the tree) are the columns
+// [lo, lo + w) of every stage.  at(i) maps the i-th owned node to its offset from the first node of the run; w = 0: identity.
+struct OwnMap {
+    int w, lo, full;
+    __host__ __device__ int at(int i) const { return w > 0 ? (i / w) * full + lo + i % w : i; }
+};
+
 // ---- lane.cu: eight lanes per node (diagonal cost square roots, even nx / nu, <= kLaneMaxChildren children per node) ---------------
 constexpr int kLaneThreads = 256;
 constexpr int kLaneOctet = 8;    // lanes that share one node
@@ -77,16 +84,16 @@ bool dual_chain_supported(int nx, int nu);
 // stride > 0: the child of node i is i + stride for the whole run; yo0 = offset of y_first
 void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
                        const double *d_old, double *d_new, double *slots, const int4 *recs, int first, int count,
-                       int stride, int yo0, double *pbar, int with_risk = 1);
+                       int stride, int yo0, double *pbar, int with_risk = 1, OwnMap own = OwnMap{0, 0, 0});
 // the risk block (d1, d2, ybar, sbar, y / s residual rows) of the same run of nodes on its own: needs y, s only, runs
 // under the sweeps; the chain pass is then launched with with_risk = 0
 void launch_dual_risk_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
                             const double *d_old, double *d_new, double *slots, int first, int count, int stride, int yo0,
-                            double *pbar);
+                            double *pbar, OwnMap own = OwnMap{0, 0, 0});
 // x0 / p_old (may be null): also copy the initial state x0 [batch][nx] into x_0 of the OLD iterate (what
 // cache_initial_state does, cache.py:79-82) -- rb_step then uploads x0 once
 void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim, const double *x0 = nullptr,
-                  double *p_old = nullptr);
+                  double *p_old = nullptr, const int *node_list = nullptr, int count = 0);
 __global__ void k_check(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, double *__restrict__ slots,
                         double *__restrict__ last, double *__restrict__ host_last);
 // the same stopping test for large batches (one thread per slot, the last CTA to finish closes the iteration); launch_check picks
@@ -191,11 +198,22 @@ struct ShardPlan {
 struct NcclId {
     char internal[128];
 };
+// peer-mapped exchange buffers (CUDA IPC; one box: <= 8 ranks)
+constexpr int kMaxPeers = 8;
+struct PeerXchg {
+    double *recv[kMaxPeers];               // receive buffer of every rank: [2 parities][world][cap * (nx + 1) + 6]
+    unsigned long long *flag[kMaxPeers];   // flags of every rank: [2 parities][world]
+    unsigned long long *seq;               // local: number of the next exchange (starts at 1)
+};
+void launch_shard_push(cudaStream_t st, const Params &P, const Ctrl *ctrl, const ShardPlan &sp, const double *q, const double *aux,
+                       const double *slots, const PeerXchg &px);
+void launch_shard_pull(cudaStream_t st, const Params &P, Ctrl *ctrl, const ShardPlan &sp, double *q, double *aux, double *slots,
+                       const PeerXchg &px);
 __global__ void k_shard_pack(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, ShardPlan sp,
-                             const double *__restrict__ q, const double *__restrict__ dual_src,
+                             const double *__restrict__ q, const double *__restrict__ aux,
                              const double *__restrict__ slots, double *__restrict__ send);
 __global__ void k_shard_unpack(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, ShardPlan sp,
-                               const double *__restrict__ recv, double *__restrict__ q, double *__restrict__ dual_src,
+                               const double *__restrict__ recv, double *__restrict__ q, double *__restrict__ aux,
                                double *__restrict__ slots);
 const char *nccl_load();   // nullptr on success, else the reason
 int nccl_unique_id(NcclId *id);

@@ -645,7 +645,7 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
     k_dual_chain(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, const double *__restrict__ p_old,
                  const double *__restrict__ p_new, const double *__restrict__ d_old, double *__restrict__ d_new,
                  double *__restrict__ slots, const int4 *__restrict__ recs, int first, int count, int stride, int yo0,
-                 double *pbar, int with_risk) {
+                 double *pbar, int with_risk, OwnMap own) {
     // with_risk = 0: the risk block (d1, d2, ybar, sbar) of these nodes has been done by k_dual_risk_chain
     constexpr int HX = NX / 2, K = (NX + NU) / 2, R = (K + G - 1) / G, NXU = NX + NU;
     const Layout &L = P.L;
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = tid & (G - 1);
     const int slot = (blockIdx.x * blockDim.x + tid) / G;
     const bool active = slot < count;
-    const int node = first + (active ? slot : 0);   // idle groups of the last CTA repeat the first node: stores and maxima masked
+    const int node = first + own.at(active ? slot : 0);   // idle groups of the last CTA repeat the first node: stores and maxima masked
     // ONE global round trip before the arithmetic starts: the control block, the node's packed topology record (child,
     // cost-table row of the child, -, rectangle row) and the rows themselves are all requested before `done` is tested.
     // In a breadth-first numbering every stage of the chain part has the same width, so the child of node i is
@@ -878,7 +878,7 @@ __global__ void __launch_bounds__(1024) k_dual_risk_chain(const __grid_constant_
                                                            const double *__restrict__ p_old, const double *__restrict__ p_new,
                                                            const double *__restrict__ d_old, double *__restrict__ d_new,
                                                            double *__restrict__ slots, int first, int count, int stride,
-                                                           int yo0, double *pbar) {
+                                                           int yo0, double *pbar, OwnMap own) {
     if (ctrl->done) return;
     const double alpha = ctrl->alpha, inv_alpha = 1.0 / alpha;
     const Layout &L = P.L;
@@ -892,7 +892,8 @@ __global__ void __launch_bounds__(1024) k_dual_risk_chain(const __grid_constant_
     double *Pb = pbar + (long long)blockIdx.y * L.np_pad;
     ResidLane Rs;
     Rs.init();
-    for (int i = blockIdx.x * blockDim.x + tid; i < count; i += gridDim.x * blockDim.x) {
+    for (int i0 = blockIdx.x * blockDim.x + tid; i0 < count; i0 += gridDim.x * blockDim.x) {
+        const int i = own.at(i0);
         const int node = first + i, yo = yo0 + 3 * i;
         const int j = stride > 0 ? node + stride : T.child_first[node];
         const double prob = T.cond_prob[j];
@@ -954,14 +955,17 @@ __global__ void __launch_bounds__(1024) k_dual_risk_chain(const __grid_constant_
 // ====================================================================================================================
 __global__ void __launch_bounds__(1024) k_kproj_node(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
                                                       double *__restrict__ prim, const double *__restrict__ x0,
-                                                      double *__restrict__ p_old) {
+                                                      double *__restrict__ p_old, const int *__restrict__ node_list, int count) {
+    // node_list / count: the nonleaf nodes to project (subtree sharding); null = all of them
     if (ctrl->done) return;
     const Layout &L = P.L;
     const Topo &T = P.t;
     double *Pb = prim + (long long)blockIdx.y * L.np_pad;
     if (x0 && blockIdx.x == 0 && threadIdx.x < L.nx)   // x_0 of the old iterate = the initial state (cache.py:79-82)
         p_old[(long long)blockIdx.y * L.np_pad + L.px + threadIdx.x] = x0[(long long)blockIdx.y * L.nx + threadIdx.x];
-    for (int node = blockIdx.x * blockDim.x + threadIdx.x; node < L.m; node += gridDim.x * blockDim.x) {
+    const int total = node_list ? count : L.m;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < total; slot += gridDim.x * blockDim.x) {
+    const int node = node_list ? node_list[slot] : slot;
     const int c0 = T.child_first[node], cc = T.child_count[node];
     const double a = T.risk_alpha[node], den = a * a + 3.0;
     double *y = Pb + L.py + T.yoff[node], *tau = Pb + L.ptau + c0, *sv = Pb + L.ps + c0;
@@ -1047,7 +1051,7 @@ bool dual_chain_supported(int nx, int nu) {
 
 void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
                        const double *d_old, double *d_new, double *slots, const int4 *recs, int first, int count,
-                       int stride, int yo0, double *pbar, int with_risk) {
+                       int stride, int yo0, double *pbar, int with_risk, OwnMap own) {
     if (count <= 0) return;
     // resident CTAs per SM the kernel is compiled for: 3 (168 registers, no spills) or 4 (128 registers, ~40 words
     // spilled to L1); RB_CHAIN_DUAL_MINB overrides for ablation runs
@@ -1063,9 +1067,9 @@ void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, 
     {                                                                                                                \
         const dim3 grid((count * G + kChainDualThreads - 1) / kChainDualThreads, batch);                             \
         if (minb == 4)                                                                                               \
-            k_dual_chain<NX, NU, G, 4><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, stride, yo0, pbar, with_risk); \
+            k_dual_chain<NX, NU, G, 4><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, stride, yo0, pbar, with_risk, own); \
         else                                                                                                         \
-            k_dual_chain<NX, NU, G, 3><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, stride, yo0, pbar, with_risk); \
+            k_dual_chain<NX, NU, G, 3><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, stride, yo0, pbar, with_risk, own); \
         return;                                                                                                      \
     }
 #define RB_GO(NX, NU, G)                                                                                             \
@@ -1079,22 +1083,25 @@ void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, 
 
 void launch_dual_risk_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
                             const double *d_old, double *d_new, double *slots, int first, int count, int stride, int yo0,
-                            double *pbar) {
+                            double *pbar, OwnMap own) {
     if (count <= 0) return;
     const int ctas = std::max(1, std::min((count + 1023) / 1024, std::max(1, 16 / batch)));
-    k_dual_risk_chain<<<dim3(ctas, batch), 1024, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, first, count, stride, yo0, pbar);
+    k_dual_risk_chain<<<dim3(ctas, batch), 1024, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, first, count, stride, yo0, pbar, own);
 }
 
-void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim, const double *x0, double *p_old) {
+void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim, const double *x0, double *p_old,
+                  const int *node_list, int count) {
     // The pass runs next to the backward chain walker, which keeps one latency-critical warp per SM sub-partition on
     // ~128 SMs: a few fat CTAs (they land on the SMs the walker leaves idle) disturb it less than a grid spread over all
     // SMs (cfg3, L2 flushed before every iteration: 9086 it/s with 16 CTAs of 1024 threads against 7702 with 230 CTAs of
     // 256).  RB_KPROJ_CTAS: ablation knob.
     static const int cap = getenv("RB_KPROJ_CTAS") ? atoi(getenv("RB_KPROJ_CTAS")) : 16;   // 0: one thread per node, 256-thread CTAs
     const int threads = cap > 0 ? 1024 : 256;
-    int ctas = (P.L.m + threads - 1) / threads;
+    const int total = node_list ? count : P.L.m;
+    if (total <= 0 && !x0) return;
+    int ctas = std::max(1, (total + threads - 1) / threads);
     if (cap > 0) ctas = std::min(ctas, std::max(1, cap / batch));
-    k_kproj_node<<<dim3(ctas, batch), threads, 0, st>>>(P, ctrl, prim, x0, p_old);
+    k_kproj_node<<<dim3(ctas, batch), threads, 0, st>>>(P, ctrl, prim, x0, p_old, node_list, count);
 }
 
 }  // namespace rb

@@ -17,20 +17,22 @@ namespace rb {
 
 // message of one rank: [cut nodes of the rank][nx + 1] then 6 residual maxima; stride = cap * (nx + 1) + 6
 __global__ void k_shard_pack(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, ShardPlan sp,
-                             const double *__restrict__ q, const double *__restrict__ dual_src,
+                             const double *__restrict__ q, const double *__restrict__ aux,
                              const double *__restrict__ slots, double *__restrict__ send) {
+    // aux[node]: the scalar that travels with q_j -- d2_j (aux = dual + L.d2: the top's primal pass forms sbar_j from it) or, in
+    // the pipelined loop, sbar_j itself (aux = pbar + L.ps, written by the owner's dual pass)
     if (ctrl->done) return;
     const int nx = P.L.nx, w = nx + 1;
     const int count = sp.cut_hi - sp.cut_lo;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count * w; i += gridDim.x * blockDim.x) {
         const int c = i / w, k = i - c * w, node = sp.cut_first + sp.cut_lo + c;
-        send[i] = k < nx ? q[(long long)node * nx + k] : dual_src[P.L.d2 + node];
+        send[i] = k < nx ? q[(long long)node * nx + k] : aux[node];
     }
     if (blockIdx.x == 0 && threadIdx.x < 6) send[(long long)sp.cap * w + threadIdx.x] = slots[threadIdx.x];
 }
 
 __global__ void k_shard_unpack(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, ShardPlan sp,
-                               const double *__restrict__ recv, double *__restrict__ q, double *__restrict__ dual_src,
+                               const double *__restrict__ recv, double *__restrict__ q, double *__restrict__ aux,
                                double *__restrict__ slots) {
     if (ctrl->done) return;
     const int nx = P.L.nx, w = nx + 1;
@@ -42,7 +44,7 @@ __global__ void k_shard_unpack(const __grid_constant__ Params P, const Ctrl *__r
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count * w; i += gridDim.x * blockDim.x) {
             const int c = i / w, k = i - c * w, node = sp.cut_first + lo + c;
             if (k < nx) q[(long long)node * nx + k] = msg[i];
-            else dual_src[P.L.d2 + node] = msg[i];
+            else aux[node] = msg[i];
         }
     }
     if (blockIdx.x == 0 && threadIdx.x < 6) {   // global residual maxima (bit patterns of non-negative doubles)
@@ -54,6 +56,97 @@ __global__ void k_shard_unpack(const __grid_constant__ Params P, const Ctrl *__r
         }
         slots[threadIdx.x] = __longlong_as_double((long long)best);
     }
+}
+
+// ---- device-initiated exchange over NVLink peer memory ("peer-mapped buffers + flags") ---------------------------------
+// Every rank's receive buffer and flag array are mapped into every other rank (CUDA IPC).  push: CTA r of rank R writes R's
+// message straight into rank r's receive slot [parity][R] (st.global over NVLink; r == R: the local copy), fences at system scope
+// and releases flag [parity][R] = seq.  pull: waits until the flags of all ranks carry seq, then unpacks like k_shard_unpack.
+// No host call, no NCCL kernel: the exchange is two small launches inside the iteration's CUDA graph.  seq (device counter,
+// bumped by k_shard_seq once per exchange) also selects the parity, so a slot is rewritten two exchanges later -- after its
+// reader has demonstrably passed the exchange in between.  A wait that exceeds ~2 s sets status bit 16 instead of hanging.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_shard_push(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, ShardPlan sp,
+                                                    const double *__restrict__ q, const double *__restrict__ aux,
+                                                    const double *__restrict__ slots, PeerXchg px) {
+    if (ctrl->done) return;
+    const int nx = P.L.nx, w = nx + 1, peer = blockIdx.x;
+    const unsigned long long seq = *px.seq;
+    const int parity = (int)(seq & 1ull);
+    const long long stride = (long long)sp.cap * w + 6;
+    double *dst = px.recv[peer] + ((long long)parity * sp.world + sp.rank) * stride;
+    const int count = sp.cut_hi - sp.cut_lo;
+    for (int i = threadIdx.x; i < count * w; i += blockDim.x) {
+        const int c = i / w, k = i - c * w, node = sp.cut_first + sp.cut_lo + c;
+        dst[i] = k < nx ? q[(long long)node * nx + k] : aux[node];
+    }
+    if (threadIdx.x < 6) dst[(long long)sp.cap * w + threadIdx.x] = slots[threadIdx.x];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release_sys(px.flag[peer] + parity * sp.world + sp.rank, seq);
+}
+
+__global__ void __launch_bounds__(256) k_shard_pull(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, ShardPlan sp,
+                                                    double *__restrict__ q, double *__restrict__ aux, double *__restrict__ slots,
+                                                    PeerXchg px) {
+    if (ctrl->done) return;
+    const int nx = P.L.nx, w = nx + 1;
+    const unsigned long long seq = *px.seq;
+    const int parity = (int)(seq & 1ull);
+    const long long stride = (long long)sp.cap * w + 6;
+    const unsigned long long *flags = px.flag[sp.rank] + parity * sp.world;
+    if (threadIdx.x < sp.world) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys(flags + threadIdx.x) != seq) {
+            if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer is gone -- report instead of hanging the GPU
+                atomicOr(&ctrl->status, 16);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const double *recv = px.recv[sp.rank] + (long long)parity * sp.world * stride;
+    for (int r = 0; r < sp.world; ++r) {
+        if (r == sp.rank) continue;
+        const int lo = sp.cut_bounds[r], count = sp.cut_bounds[r + 1] - lo;
+        const double *msg = recv + r * stride;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count * w; i += gridDim.x * blockDim.x) {
+            const int c = i / w, k = i - c * w, node = sp.cut_first + lo + c;
+            const double v = __ldcg(msg + i);
+            if (k < nx) q[(long long)node * nx + k] = v;
+            else aux[node] = v;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 6) {   // global residual maxima (bit patterns of non-negative doubles)
+        unsigned long long best = 0ull;
+        for (int r = 0; r < sp.world; ++r) {
+            const unsigned long long v = (unsigned long long)__double_as_longlong(__ldcg(recv + r * stride + (long long)sp.cap * w + threadIdx.x));
+            best = v > best ? v : best;
+        }
+        slots[threadIdx.x] = __longlong_as_double((long long)best);
+    }
+}
+
+__global__ void k_shard_seq(const Ctrl *__restrict__ ctrl, unsigned long long *seq) {
+    if (!ctrl->done) *seq = *seq + 1ull;
+}
+
+void launch_shard_push(cudaStream_t st, const Params &P, const Ctrl *ctrl, const ShardPlan &sp, const double *q, const double *aux,
+                       const double *slots, const PeerXchg &px) {
+    k_shard_push<<<sp.world, 256, 0, st>>>(P, ctrl, sp, q, aux, slots, px);
+}
+void launch_shard_pull(cudaStream_t st, const Params &P, Ctrl *ctrl, const ShardPlan &sp, double *q, double *aux, double *slots,
+                       const PeerXchg &px) {
+    k_shard_pull<<<4, 256, 0, st>>>(P, ctrl, sp, q, aux, slots, px);
+    k_shard_seq<<<1, 1, 0, st>>>(ctrl, px.seq);
 }
 
 // ---- NCCL through dlopen ----------------------------------------------------------------------------------------------

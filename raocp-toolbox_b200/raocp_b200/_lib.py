@@ -85,6 +85,8 @@ SYMBOLS = [
     ("rb_use_tree_kernels", C.c_int, [_H, C.c_int32]),
     ("rb_shard_unique_id", C.c_int, [C.c_char_p]),
     ("rb_shard_init", C.c_int, [_H, C.c_char_p]),
+    ("rb_shard_p2p_export", C.c_int, [_H, C.c_char_p]),
+    ("rb_shard_p2p_open", C.c_int, [_H, C.c_char_p]),
     ("rb_shard_info", C.c_int, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("rb_launch_count", C.c_int, [_H, C.POINTER(C.c_int64)]),
     ("rb_cone_project", C.c_int, [C.c_int32, C.c_int32, c_double_p, c_double_p]),

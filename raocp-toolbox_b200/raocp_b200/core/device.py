@@ -305,6 +305,24 @@ class DeviceSolver:
             dist.broadcast(t, src=0)
             unique_id = bytes(t.cpu().tolist())
         self._call("rb_shard_init", C.c_char_p(unique_id))
+        import os
+        if os.environ.get("RAOCP_SHARD_P2P", "1") != "0" and dist.get_world_size() <= 8:
+            self.shard_p2p_init()
+
+    def shard_p2p_init(self):
+        """collective: exchange the CUDA IPC handles of the ranks' receive buffers / flags and map them (rb_shard_p2p_*): from
+        then on the cut-stage exchange is device-initiated over NVLink peer memory and the sharded loop is pipelined + graphed"""
+        import torch
+        import torch.distributed as dist
+        mine = (C.c_char * 128)()
+        self._call("rb_shard_p2p_export", mine)
+        t = torch.tensor(list(mine.raw), dtype=torch.uint8)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+        dist.all_gather(out, t)
+        blob = b"".join(bytes(o.cpu().tolist()) for o in out)
+        self._call("rb_shard_p2p_open", C.c_char_p(blob))
 
     def gather_sharded(self, which=0):
         """assemble the full compact iterates on every rank from the ranks' authoritative parts (torch.distributed)"""
