@@ -29,6 +29,17 @@ namespace rb {
 
 namespace {
 
+// resident CTAs per SM the dual kernels are compiled for (register caps); measured on cfg4 x 4096 (gpurun_out r2p): leaf 3 -> 4:
+// 318 -> 282 us; risk 3 -> 4: 100 -> 146 us (spills); x / u block 2 -> 3: 439 -> 505 us (spills)
+#ifndef RB_BP_LEAF_MINB
+#define RB_BP_LEAF_MINB 4
+#endif
+#ifndef RB_BP_RISK_MINB
+#define RB_BP_RISK_MINB 3
+#endif
+#ifndef RB_BP_XU_MINB
+#define RB_BP_XU_MINB 2
+#endif
 constexpr int kPanel = 32;
 constexpr int kBpWarps = 4;   // nodes per CTA and pass of the node loops
 constexpr int kBpMaxChildren = 4;   // compile-time bound of the risk kernel (2 c + 1 entries of y_i in registers)
@@ -393,7 +404,7 @@ __global__ void k_bp_c2(const __grid_constant__ Params P, double *__restrict__ c
 // this kernel, one runtime loop over the children, ran at 2.7 TB/s with 8 warps per SM waiting on ~10 dependent round trips
 // per node).
 template <int NX, int NU>
-__global__ void __launch_bounds__(kBpWarps * 32, 2) k_bp_dual_xu(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
+__global__ void __launch_bounds__(kBpWarps * 32, RB_BP_XU_MINB) k_bp_dual_xu(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
                                                                 const double *p_old, const double *__restrict__ p_new,
                                                                 const double *__restrict__ d_old, double *__restrict__ d_new,
                                                                 double *__restrict__ slots, double *pbar,   // pbar aliases p_old
@@ -526,7 +537,7 @@ __global__ void __launch_bounds__(kBpWarps * 32, 2) k_bp_dual_xu(const __grid_co
 // risks.py:32-33), d2 (R+), the residual rows of y_i and s_i, and pbar of those rows.  MAXC: compile-time bound on the number of
 // children -- all 3 (2 MAXC + 1) + 3 loads of a node are issued before the first use.
 template <int MAXC>
-__global__ void __launch_bounds__(kBpWarps * 32) k_bp_dual_risk(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
+__global__ void __launch_bounds__(kBpWarps * 32, RB_BP_RISK_MINB) k_bp_dual_risk(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
                                                                const double *p_old, const double *__restrict__ p_new,
                                                                const double *__restrict__ d_old, double *__restrict__ d_new,
                                                                double *__restrict__ slots, double *pbar) {   // pbar aliases p_old
@@ -598,7 +609,7 @@ __global__ void __launch_bounds__(kBpWarps * 32) k_bp_dual_risk(const __grid_con
 }
 
 template <int NX, int NU>
-__global__ void __launch_bounds__(kBpWarps * 32) k_bp_dual_leaf(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
+__global__ void __launch_bounds__(kBpWarps * 32, RB_BP_LEAF_MINB) k_bp_dual_leaf(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
                                                                const double *p_old, const double *__restrict__ p_new,
                                                                const double *__restrict__ d_old, double *__restrict__ d_new,
                                                                double *__restrict__ slots, double *pbar) {   // pbar aliases p_old
