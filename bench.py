@@ -329,6 +329,8 @@ def run_ours(args, rank, world, local_rank):
     t0 = time.perf_counter()
     cuts = tuple(int(v) for v in args.sweep_cuts.split(",")) if args.sweep_cuts else None
     solver = r.core.Solver(problem, batch=batch, dedup=not args.no_dedup, device=local_rank, verbose=False, sweep_cuts=cuts)
+    solver.cache.device_solver.use_batch_panels(not args.no_panels)
+    solver.cache.device_solver.use_launch_overlap(args.overlap)
     solver.cache.device_solver.use_tree_kernels(args.tree_mode)
     solver.cache.device_solver.use_mma_sweeps(0 if args.no_mma else (2 if args.mma_four_warps else 1))
     solver.cache.device_solver.use_pipeline(0 if args.no_pipeline else (3 if args.fwd_split else (4 if args.no_risk_split else 1)))
@@ -670,6 +672,10 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=150.0,
                     help="--impl reference: seconds of stepping the reference may use (at least one iteration is timed)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity_check leg")
+    ap.add_argument("--overlap", action="store_true",
+                    help="ablation: chain the walkers and the fused tree kernel by programmatic dependent launch")
+    ap.add_argument("--no-panels", action="store_true",
+                    help="ablation (batch >= 64): instance-major kernels instead of the batch-innermost panel path")
     ap.add_argument("--tree-mode", type=int, default=2, choices=[0, 1, 2],
                     help="ablation: branching sweep levels with sweeps.cu (0), tree_sweeps.cu per level (1), fused with the top (2)")
     ap.add_argument("--no-mma", action="store_true", help="ablation: chains with one warp per chain instead of chain_mma.cu")

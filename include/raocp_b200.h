@@ -188,6 +188,11 @@ int rb_use_pipeline(rb_solver *s, int32_t enable);
  * chain_nodes) through k_dual_chain; chain_nodes = 0 when the loop is not pipelined or has no chain kernel for (nx, nu) */
 int rb_pipeline_info(const rb_solver *s, int32_t *early_nodes, int32_t *chain_first, int32_t *chain_nodes);
 int rb_use_graphs(rb_solver *s, int32_t enable); /* 1 (default): one CUDA graph per iteration; 0: plain launches */
+/* 1: in the pipelined loop the backward chain walker, the fused tree kernel and the forward chain walker are chained by
+ * programmatic dependent launch -- each starts while the one before it still runs, stages its tables and waits for the data
+ * itself (csrc/chain_mma.cu "launch overlap").  Measured ablation, results identical, not faster on cfg3 (9 586 vs 9 750 it/s):
+ * 0 (default) = plain stream-ordered launches. */
+int rb_use_launch_overlap(rb_solver *s, int32_t enable);
 /* batch >= 64 instances of one tree (instance-parallel mode): 1 (default) = the fused loop runs in the
  * batch-innermost "panel" layout (csrc/batch.cu: the 32 lanes of a warp are 32 instances; iterates are converted at
  * rb_loop_begin / rb_loop_end); 0 = the instance-major kernels of batch == 1, one grid row per instance (ablation). */

@@ -89,6 +89,8 @@ struct rb_solver {
     size_t fuse_smem = 0;
     int fuse_threads = 0;
     int *tree_sync = nullptr;
+    int *overlap_sync = nullptr;   // [2 * batch]: walk_count, tree_done of the launch-overlap protocol (chain_mma.cu)
+    bool allow_overlap = false;   // rb_use_launch_overlap(1): measured ablation (not faster on cfg3: 9 586 vs 9 750 it/s cold)
     TreeLevel tree_top{}, tree_lv[2]{}, shard_tree_lv[2]{};
     size_t tree_smem[3]{};   // dynamic shared memory of the top / level launches   // chain levels on the FP64 tensor cores when the level carries tiles (rb_use_mma_sweeps)
     double *xchg_send = nullptr, *xchg_recv = nullptr;
@@ -359,9 +361,15 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
     };
     const bool tree = s->tree_mode > 0;
     const bool fused = s->tree_mode > 1 && s->fuse_ok && !(s->allow_mma && pl.lv[0].num_tiles > 0);
+    // launch overlap (programmatic dependent launch): backward walker -> fused tree kernel -> forward walker, inside the loop only
+    // (ctrl carries the status word of the bounded waits), one-warp tensor-core walkers on the level right below the tree kernel
+    const bool w4 = s->mma_w4 && chain_mma_w4(L.nx, L.nu);
+    const bool overlap = s->allow_overlap && fused && ctrl && s->overlap_sync && !evs && fwd_split == 0 && pl.num_levels == 2 &&
+                         s->allow_mma && pl.lv[1].num_tiles > 0 && !w4;
+    int *walk_count = overlap ? s->overlap_sync : nullptr, *tree_done = overlap ? s->overlap_sync + L.batch : nullptr;
     auto bwd = [&](int v) {
         if (s->allow_mma && pl.lv[v].num_tiles > 0)
-            launch_chain_mma_bwd(st, s->P, ctrl, pl.lv[v], prim, s->q, s->r, s->mma_w4 && chain_mma_w4(L.nx, L.nu));
+            launch_chain_mma_bwd(st, s->P, ctrl, pl.lv[v], prim, s->q, s->r, w4, walk_count, tree_done);
         else if (tree && s->tree_lv[v].desc)
             launch_tree_bwd(dim3(s->tree_lv[v].num_sub, batch), 32 * s->tree_lv[v].warps, s->tree_smem[1 + v], st, s->P, ctrl,
                             s->tree_lv[v], prim, s->q, s->r);
@@ -375,7 +383,7 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
             if (after_piece) after_piece();
             launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, fwd_split, -1, s->mma_w4 && chain_mma_w4(L.nx, L.nu));
         } else if (s->allow_mma && pl.lv[v].num_tiles > 0)
-            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, 0, -1, s->mma_w4 && chain_mma_w4(L.nx, L.nu));
+            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, 0, -1, w4, tree_done, s->tree_lv[0].num_sub);
         else if (tree && s->tree_lv[v].desc)
             launch_tree_fwd(dim3(s->tree_lv[v].num_sub, batch), 32 * s->tree_lv[v].warps, s->tree_smem[1 + v], st, s->P, ctrl,
                             s->tree_lv[v], prim, s->r);
@@ -386,7 +394,8 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
     for (int v = pl.num_levels - 1; v >= (fused ? 1 : 0); --v) bwd(v);
     if (fused) {
         cudaError_t e = launch_tree_fused((int)batch, s->fuse_threads, s->fuse_smem, st, s->P, ctrl, s->tree_lv[0], s->tree_top,
-                                          prim, s->q, s->r, s->x0, s->tree_sync);
+                                          prim, s->q, s->r, s->x0, s->tree_sync, walk_count, overlap ? pl.lv[1].num_tiles : 0,
+                                          tree_done);
         if (e != cudaSuccess) return fail(s, RB_ERR_CUDA, std::string("fused tree launch: ") + cudaGetErrorString(e));
     } else if (tree && s->tree_top.desc) {
         launch_tree_top(batch, 32 * s->tree_top.warps, s->tree_smem[0], st, s->P, ctrl, s->tree_top, prim, s->q, s->r, s->x0);
@@ -543,6 +552,567 @@ int build_tree_level(rb_solver *s, const std::vector<int> &lo, const std::vector
     return RB_OK;
 }
 
+#define CTRY(x)                       \
+    do {                              \
+        int rc_ = (x);                \
+        if (rc_ != RB_OK) return rc_; \
+    } while (0)
+#define CTRYC(call) RB_CUDA(s, call)
+
+// rb_create, part: the topology the kernels rely on: stages partition the nodes, children are consecutive ranges in node order, class order
+int create_validate(rb_solver *s, const rb_problem *pb) {
+    const int n = pb->n, m = pb->m, nx = pb->nx, nu = pb->nu, nl = n - m;
+    Layout &L = s->P.L;
+    Topo &T = s->P.t;
+    Tabs &M = s->P.m;
+    (void)n; (void)m; (void)nx; (void)nu; (void)nl; (void)L; (void)T; (void)M;
+    // ---- validate the topology the kernels rely on
+    if (s->stage_off[0] != 0 || s->stage_off[pb->num_stages] != n || s->stage_off[pb->num_stages - 1] != m) {
+        return fail(s, RB_ERR_INVALID, "stage_off must partition 0..n with the leaves as the last stage");
+    }
+    {
+        int expect = 1;
+        for (int i = 0; i < m; ++i) {
+            if (s->child_count[i] < 1 || s->child_first[i] != expect) {
+                return fail(s, RB_ERR_INVALID, "children of the nonleaf nodes must be consecutive ranges in node order (renumber the tree " "breadth first)");
+            }
+            for (int j = expect; j < expect + s->child_count[i]; ++j)
+                if (j >= n || s->parent[j] != i) {
+                    return fail(s, RB_ERR_INVALID, "parent[] and child ranges disagree");
+                }
+            expect += s->child_count[i];
+        }
+        if (expect != n) {
+            return fail(s, RB_ERR_INVALID, "child ranges do not cover all nodes");
+        }
+        for (int i = 0; i < m; ++i) {
+            if (s->cls[i] < 0 || s->cls[i] >= s->num_cls) {
+                return fail(s, RB_ERR_INVALID, "cls[] out of range");
+            }
+            for (int j = s->child_first[i]; j < s->child_first[i] + s->child_count[i]; ++j)
+                if (j < m && s->cls[j] <= s->cls[i]) {
+                    return fail(s, RB_ERR_INVALID, "class of a child must be larger than the class of its parent");
+                }
+        }
+    }
+    return RB_OK;
+}
+
+// rb_create, part: compact / padded layout of the iterates, topology and operator tables on the device
+int create_layout_and_tables(rb_solver *s, const rb_problem *pb) {
+    const int n = pb->n, m = pb->m, nx = pb->nx, nu = pb->nu, nl = n - m;
+    Layout &L = s->P.L;
+    Topo &T = s->P.t;
+    Tabs &M = s->P.m;
+    (void)n; (void)m; (void)nx; (void)nu; (void)nl; (void)L; (void)T; (void)M;
+    // ---- layout
+    L.n = n; L.m = m; L.nleaf = nl; L.nx = nx; L.nu = nu; L.nxu = nx + nu;
+    L.num_stages = pb->num_stages; L.batch = pb->batch;
+    L.has_nl_rect = pb->num_nl_rect > 0; L.has_leaf_rect = pb->num_leaf_rect > 0;
+    std::vector<int> yoff(m + 1, 0);
+    for (int i = 0; i < m; ++i) yoff[i + 1] = yoff[i] + 2 * s->child_count[i] + 1;
+    L.ysz = yoff[m];
+    for (int i = 0; i < m; ++i) s->max_children = std::max(s->max_children, s->child_count[i]);
+    s->chain_first = m;   // trailing run of nonleaf nodes with one child: the chain part of the tree (k_dual_chain)
+    while (s->chain_first > 1 && s->child_count[s->chain_first - 1] == 1) --s->chain_first;
+    {
+        int64_t pc = 0, pp = 0;  // compact / padded cursors
+        auto addp = [&](long long &field, int64_t len) {
+            field = pp;
+            s->pseg.push_back({pc, pp, len});
+            pc += len;
+            pp = round16(pp + len);
+        };
+        addp(L.px, (int64_t)n * nx); addp(L.pu, (int64_t)m * nu); addp(L.py, L.ysz); addp(L.ptau, n); addp(L.ps, n);
+        s->np = pc; L.np_pad = pp;
+        pc = 0; pp = 0;
+        auto addd = [&](long long &field, int64_t len) {
+            field = pp;
+            s->dseg.push_back({pc, pp, len});
+            pc += len;
+            pp = round16(pp + len);
+        };
+        addd(L.d1, L.ysz); addd(L.d2, m); addd(L.d3, (int64_t)(n - 1) * nx); addd(L.d4, (int64_t)(n - 1) * nu);
+        addd(L.d5, n - 1); addd(L.d6, n - 1); addd(L.d7, L.has_nl_rect ? (int64_t)m * (nx + nu) : 0);
+        addd(L.d11, (int64_t)nl * nx); addd(L.d12, nl); addd(L.d13, nl); addd(L.d14, L.has_leaf_rect ? (int64_t)nl * nx : 0);
+        s->nd = pc; L.nd_pad = pp;
+    }
+    // ---- topology and tables to the device
+    int *tmp_i = nullptr;
+    double *tmp_d = nullptr;
+    CTRY(upload(s, pb->parent, n, &tmp_i)); T.parent = tmp_i;
+    CTRY(upload(s, pb->child_first, m, &tmp_i)); T.child_first = tmp_i;
+    CTRY(upload(s, pb->child_count, m, &tmp_i)); T.child_count = tmp_i;
+    CTRY(upload(s, yoff.data(), m + 1, &tmp_i)); T.yoff = tmp_i;
+    CTRY(upload(s, pb->dyn_idx, n, &tmp_i)); T.dyn_idx = tmp_i;
+    CTRY(upload(s, pb->cost_idx, n, &tmp_i)); T.cost_idx = tmp_i;
+    CTRY(upload(s, pb->leafcost_idx, nl, &tmp_i)); T.leafcost_idx = tmp_i;
+    CTRY(upload(s, L.has_nl_rect ? pb->nl_rect_idx : nullptr, m, &tmp_i)); T.nl_rect_idx = tmp_i;
+    {   // packed topology records of the chain nodes (k_dual_chain): child, cost row of the child, y offset, rectangle row
+        std::vector<int4> recs(std::max(1, m - s->chain_first));
+        for (int i = s->chain_first; i < m; ++i) {
+            const int j = s->child_first[i];
+            recs[i - s->chain_first] = make_int4(j, s->cost_idx[j], yoff[i], L.has_nl_rect ? pb->nl_rect_idx[i] : 0);
+        }
+        CTRY(upload(s, recs.data(), recs.size(), &s->chain_recs));
+        s->chain_yo0 = yoff[std::min(s->chain_first, m)];
+        s->chain_stride = s->chain_first < m ? s->child_first[s->chain_first] - s->chain_first : -1;
+        for (int i = s->chain_first; i < m; ++i)
+            if (s->child_first[i] - i != s->chain_stride) s->chain_stride = -1;
+    }
+    CTRY(upload(s, L.has_leaf_rect ? pb->leaf_rect_idx : nullptr, nl, &tmp_i)); T.leaf_rect_idx = tmp_i;
+    CTRY(upload(s, pb->cls, m, &tmp_i)); T.cls = tmp_i;
+    CTRY(upload(s, pb->cond_prob, n, &tmp_d)); T.cond_prob = tmp_d;
+    CTRY(upload(s, pb->risk_alpha, m, &tmp_d)); T.risk_alpha = tmp_d;
+    CTRY(upload(s, pb->A, (size_t)pb->num_dyn * nx * nx, &tmp_d)); M.A = tmp_d;
+    CTRY(upload(s, pb->B, (size_t)pb->num_dyn * nx * nu, &tmp_d)); M.B = tmp_d;
+    {
+        const int nxu = nx + nu;
+        std::vector<double> cat((size_t)pb->num_dyn * nx * nxu), catT(cat.size());
+        for (int t = 0; t < pb->num_dyn; ++t)
+            for (int l = 0; l < nx; ++l) {
+                for (int k = 0; k < nx; ++k) {
+                    const double a_lk = pb->A[((size_t)t * nx + l) * nx + k];
+                    cat[((size_t)t * nx + l) * nxu + k] = a_lk;            // row l = [A[l][:], B[l][:]]
+                    catT[((size_t)t * nxu + k) * nx + l] = a_lk;           // row k<nx = A[:][k]
+                }
+                for (int a = 0; a < nu; ++a) {
+                    const double b_la = pb->B[((size_t)t * nx + l) * nu + a];
+                    cat[((size_t)t * nx + l) * nxu + nx + a] = b_la;
+                    catT[((size_t)t * nxu + nx + a) * nx + l] = b_la;      // row nx+a = B[:][a]
+                }
+            }
+        CTRY(upload(s, cat.data(), cat.size(), &tmp_d)); M.ABcat = tmp_d;
+        CTRY(upload(s, catT.data(), catT.size(), &tmp_d)); M.ABcatT = tmp_d;
+        auto sq = transpose_tab(pb->sqrtQ, pb->num_cost, nx, nx);
+        CTRY(upload(s, sq.data(), sq.size(), &tmp_d)); M.sqT = tmp_d;
+        auto sr = transpose_tab(pb->sqrtR, pb->num_cost, nu, nu);
+        CTRY(upload(s, sr.data(), sr.size(), &tmp_d)); M.srT = tmp_d;
+        auto sf = transpose_tab(pb->sqrtQf, pb->num_leafcost, nx, nx);
+        CTRY(upload(s, sf.data(), sf.size(), &tmp_d)); M.sqfT = tmp_d;
+        M.sq_diag = is_diag(pb->sqrtQ, pb->num_cost, nx);
+        M.sr_diag = is_diag(pb->sqrtR, pb->num_cost, nu);
+        M.sqf_diag = is_diag(pb->sqrtQf, pb->num_leafcost, nx);
+        s->diag_costs = M.sq_diag && M.sr_diag && M.sqf_diag;
+        auto diag_of = [](const double *tab, int count, int dim) {
+            std::vector<double> d((size_t)count * dim);
+            for (int t = 0; t < count; ++t)
+                for (int k = 0; k < dim; ++k) d[(size_t)t * dim + k] = tab[((size_t)t * dim + k) * dim + k];
+            return d;
+        };
+        auto dq = diag_of(pb->sqrtQ, pb->num_cost, nx), dr = diag_of(pb->sqrtR, pb->num_cost, nu),
+             df = diag_of(pb->sqrtQf, pb->num_leafcost, nx);
+        CTRY(upload(s, dq.data(), dq.size(), &tmp_d)); M.sq_d = tmp_d;
+        CTRY(upload(s, dr.data(), dr.size(), &tmp_d)); M.sr_d = tmp_d;
+        CTRY(upload(s, df.data(), df.size(), &tmp_d)); M.sqf_d = tmp_d;
+    }
+    CTRY(upload(s, L.has_nl_rect ? pb->nl_lo : nullptr, (size_t)pb->num_nl_rect * (nx + nu), &tmp_d)); M.nl_lo = tmp_d;
+    CTRY(upload(s, L.has_nl_rect ? pb->nl_hi : nullptr, (size_t)pb->num_nl_rect * (nx + nu), &tmp_d)); M.nl_hi = tmp_d;
+    CTRY(upload(s, L.has_leaf_rect ? pb->leaf_lo : nullptr, (size_t)pb->num_leaf_rect * nx, &tmp_d)); M.leaf_lo = tmp_d;
+    CTRY(upload(s, L.has_leaf_rect ? pb->leaf_hi : nullptr, (size_t)pb->num_leaf_rect * nx, &tmp_d)); M.leaf_hi = tmp_d;
+    return RB_OK;
+}
+
+// rb_create, part: class structure of the offline factorisation, iterates and scratch
+int create_classes_and_iterates(rb_solver *s, const rb_problem *pb) {
+    const int n = pb->n, m = pb->m, nx = pb->nx, nu = pb->nu, nl = n - m;
+    Layout &L = s->P.L;
+    Topo &T = s->P.t;
+    Tabs &M = s->P.m;
+    (void)n; (void)m; (void)nx; (void)nu; (void)nl; (void)L; (void)T; (void)M;
+    // ---- class structure for the offline factorisation: representative = first node of the class
+    {
+        std::vector<int> rep(s->num_cls, -1);
+        for (int i = 0; i < m; ++i)
+            if (rep[s->cls[i]] < 0) rep[s->cls[i]] = i;
+        std::vector<int> level(s->num_cls, 0);
+        s->cls_child_ptr.assign(1, 0);
+        for (int c = 0; c < s->num_cls; ++c) {
+            if (rep[c] < 0) {
+                return fail(s, RB_ERR_INVALID, "class without nodes");
+            }
+            const int i = rep[c];
+            for (int j = s->child_first[i]; j < s->child_first[i] + s->child_count[i]; ++j) {
+                s->cls_child_dyn.push_back(s->dyn_idx[j]);
+                s->cls_child_cls.push_back(j < m ? s->cls[j] : -1);
+            }
+            s->cls_child_ptr.push_back((int)s->cls_child_dyn.size());
+        }
+        int max_level = 0;
+        for (int c = s->num_cls - 1; c >= 0; --c) {  // children have larger class ids: already final when visited
+            int lv = 0;
+            for (int k = s->cls_child_ptr[c]; k < s->cls_child_ptr[c + 1]; ++k)
+                if (s->cls_child_cls[k] >= 0) lv = std::max(lv, level[s->cls_child_cls[k]] + 1);
+            level[c] = lv;
+            max_level = std::max(max_level, lv);
+        }
+        s->level_ptr.assign(max_level + 2, 0);
+        for (int c = 0; c < s->num_cls; ++c) ++s->level_ptr[level[c] + 1];
+        for (int l = 0; l <= max_level; ++l) s->level_ptr[l + 1] += s->level_ptr[l];
+        s->level_list.resize(s->num_cls);
+        std::vector<int> cur(s->level_ptr.begin(), s->level_ptr.end() - 1);
+        for (int c = 0; c < s->num_cls; ++c) s->level_list[cur[level[c]]++] = c;
+        CTRY(upload(s, s->cls_child_ptr.data(), s->cls_child_ptr.size(), &s->d_cls_child_ptr));
+        CTRY(upload(s, s->cls_child_dyn.data(), s->cls_child_dyn.size(), &s->d_cls_child_dyn));
+        CTRY(upload(s, s->cls_child_cls.data(), s->cls_child_cls.size(), &s->d_cls_child_cls));
+        CTRY(upload(s, s->level_list.data(), s->level_list.size(), &s->d_level_list));
+    }
+    CTRY(dev_zero(s, (size_t)s->num_cls * nx * nx, &s->Ptab));
+    CTRY(dev_zero(s, (size_t)s->num_cls * nu * nx, &s->Ktab));
+    CTRY(dev_zero(s, (size_t)s->num_cls * (nx + nu) * nu, &s->KRcatT));
+    M.K = s->Ktab; M.KRcatT = s->KRcatT;
+    // ---- iterates and scratch
+    const size_t B = (size_t)L.batch;
+    for (int w = 0; w < 2; ++w) {
+        CTRY(dev_zero(s, B * L.np_pad, &s->prim[w]));
+        CTRY(dev_zero(s, B * L.nd_pad, &s->dual[w]));
+    }
+    CTRY(dev_zero(s, B * n * nx, &s->q));
+    CTRY(dev_zero(s, B * m * nu, &s->r));
+    CTRY(dev_zero(s, B * nx, &s->x0));
+    CTRY(dev_zero(s, 1, &s->ctrl));
+    CTRY(dev_zero(s, B * 6, &s->slots));
+    CTRY(dev_zero(s, B * 6, &s->last));
+    if (B * 6 <= 1024 && L.nx <= 1024 &&
+        cudaHostAlloc((void **)&s->h_last, B * 6 * sizeof(double), cudaHostAllocMapped) == cudaSuccess) {
+        if (cudaHostGetDevicePointer((void **)&s->h_last_dev, s->h_last, 0) != cudaSuccess) {
+            cudaFreeHost(s->h_last);
+            s->h_last = s->h_last_dev = nullptr;
+        }
+    } else {
+        cudaGetLastError();
+        s->h_last = s->h_last_dev = nullptr;
+    }
+    CTRY(dev_zero(s, 1, &s->status));
+    return RB_OK;
+}
+
+// rb_create, part: the sweep plan (cut stages, chain tiles, tree descriptors, fused launch) and the tensor-core fragment tables
+int create_sweep_plan(rb_solver *s, const rb_problem *pb) {
+    const int n = pb->n, m = pb->m, nx = pb->nx, nu = pb->nu, nl = n - m;
+    Layout &L = s->P.L;
+    Topo &T = s->P.t;
+    Tabs &M = s->P.m;
+    (void)n; (void)m; (void)nx; (void)nu; (void)nl; (void)L; (void)T; (void)M;
+    // ---- sweep plan (sweeps.cu): first cut at the first stage with >= 64 nodes; second cut where the tree turns into
+    //      chains (below the stopping time of a Markov tree) if there are >= 200 of them (cfg2, 243 chains: 13 222 vs 12 208 it/s with the chain level), else -- if the tree keeps
+    //      branching -- at the first stage with >= 2048 nodes and >= 8x the first cut
+    {
+        SweepPlan &pl = s->plan;
+        auto width = [&](int t) { return s->stage_off[t + 1] - s->stage_off[t]; };
+        if ((pb->sweep_cut1_min != 0 || pb->sweep_cut2_min != 0) && pb->shard_world > 1) {
+            return fail(s, RB_ERR_INVALID, "sweep_cut*_min must be 0 for a sharded problem");
+        }
+        const int cut1_min = pb->sweep_cut1_min > 0 ? pb->sweep_cut1_min : 64;
+        const int cut2_min = pb->sweep_cut2_min > 0 ? pb->sweep_cut2_min : 200;
+        int c1 = L.num_stages, c2 = L.num_stages;
+        for (int t = 0; t < L.num_stages; ++t)
+            if (width(t) >= cut1_min) {
+                c1 = t;
+                break;
+            }
+        int c_chain = L.num_stages - 1;   // first stage from which every node has at most one child
+        while (c_chain > 0) {
+            bool chains = true;
+            for (int i = s->stage_off[c_chain - 1]; i < s->stage_off[c_chain] && chains; ++i) chains = s->child_count[i] <= 1;
+            if (!chains) break;
+            --c_chain;
+        }
+        if (c_chain > c1 && c_chain < L.num_stages - 1 && L.num_stages - c_chain <= 64 && width(c_chain) >= cut2_min) {
+            c2 = c_chain;
+            // The top is ONE CTA and every level-0 subtree is one CTA; a stage of either costs what its parents cost.
+            // Balance them: the first cut goes where the widest parent stage of the top, width(c - 1), and the widest
+            // parent stage of a subtree, width(c2 - 1) / width(c), are closest (cfg3: stage 3 either way; cfg5, 3 modes:
+            // stage 3 with 27 subtrees of 1 + 3 + 9 nodes instead of stage 4 with a 27-parent stage in the top).
+            if (pb->sweep_cut1_min == 0) {
+                auto cost = [&](int c) { return std::max(width(c - 1), width(c2 - 1) / std::max(1, width(c))); };
+                for (int c = c1 - 1; c >= 1 && width(c) >= 8; --c)
+                    if (cost(c) < cost(c1)) c1 = c;
+            }
+        } else {
+            for (int t = c1 + 1; t < L.num_stages; ++t)
+                if (width(t) >= std::max(2048, cut2_min) && width(t) >= 8 * width(c1)) {
+                    c2 = t;
+                    break;
+                }
+        }
+        pl.t_top = c1;
+        pl.num_levels = c1 >= L.num_stages ? 0 : (c2 >= L.num_stages ? 1 : 2);
+        int *d_so = nullptr;
+        CTRY(upload(s, s->stage_off.data(), s->stage_off.size(), &d_so));
+        pl.stage_off = d_so;
+        const int cuts[3] = {c1, c2, L.num_stages};
+        for (int v = 0; v < pl.num_levels; ++v) {
+            SweepLevel &lv = pl.lv[v];
+            lv.t_lo = cuts[v];
+            lv.depth = (v + 1 < pl.num_levels ? cuts[v + 1] : L.num_stages) - cuts[v];
+            lv.num_sub = width(lv.t_lo);
+            std::vector<int> lo((size_t)lv.num_sub * lv.depth), hi(lo.size());
+            int max_width = 1;
+            for (int c = 0; c < lv.num_sub; ++c) {
+                int a = s->stage_off[lv.t_lo] + c, b = a + 1;
+                for (int d = 0; d < lv.depth; ++d) {
+                    lo[(size_t)c * lv.depth + d] = a;
+                    hi[(size_t)c * lv.depth + d] = b;
+                    max_width = std::max(max_width, b - a);
+                    if (d + 1 < lv.depth) {   // children of [a, b) are one contiguous range of the next stage
+                        const int na = s->child_first[a], nb = s->child_first[b - 1] + s->child_count[b - 1];
+                        a = na;
+                        b = nb;
+                    }
+                }
+            }
+            // widest stage of any subtree, in nodes or in children (rows of the group-shared buffer)
+            int cap = 1;
+            for (int c = 0; c < lv.num_sub; ++c)
+                for (int d = 0; d < lv.depth; ++d) {
+                    const int a = lo[(size_t)c * lv.depth + d], b = hi[(size_t)c * lv.depth + d];
+                    cap = std::max(cap, b - a);
+                    if (a < m) cap = std::max(cap, s->child_first[b - 1] + s->child_count[b - 1] - s->child_first[a]);
+                }
+            lv.stage_cap = max_width == 1 ? 0 : cap;
+            lv.chain = (max_width == 1 && lv.depth <= 64 && lv.t_lo + lv.depth == L.num_stages) ? 1 : 0;
+            lv.warps_per_sub = std::min(16, max_width == 1 ? 1 : cap);
+            lv.subs_per_cta = std::max(1, 8 / lv.warps_per_sub);
+            int *d_lo = nullptr, *d_hi = nullptr;
+            CTRY(upload(s, lo.data(), lo.size(), &d_lo));
+            CTRY(upload(s, hi.data(), hi.size(), &d_hi));
+            lv.lo = d_lo;
+            lv.hi = d_hi;
+            lv.tiles = nullptr;
+            lv.tile_meta = nullptr;
+            lv.num_tiles = 0;
+            if (lv.chain && chain_mma_supported(nx, nu)) {
+                s->chain_lo[v] = lo;
+                CTRY(build_chain_tiles(s, lo, lv.depth, 0, lv.num_sub, &lv.tiles, &lv.num_tiles, &lv.tile_meta));
+            }
+            if (!lv.chain) CTRY(build_tree_level(s, lo, hi, lv.depth, lv.num_sub, false, &s->tree_lv[v], &s->tree_smem[1 + v]));
+        }
+        {   // the top of the tree as one subtree: stages [0, t_top)
+            std::vector<int> lo(pl.t_top), hi(pl.t_top);
+            for (int t = 0; t < pl.t_top; ++t) {
+                lo[t] = s->stage_off[t];
+                hi[t] = s->stage_off[t + 1];
+            }
+            CTRY(build_tree_level(s, lo, hi, pl.t_top, 1, true, &s->tree_top, &s->tree_smem[0]));
+        }
+        size_t tree_need = std::max(s->tree_smem[0], std::max(s->tree_smem[1], s->tree_smem[2]));
+        if (s->tree_top.desc && pl.num_levels > 0 && s->tree_lv[0].desc && s->tree_top.resident == s->tree_lv[0].resident) {
+            // level 0 with the footprint of a two-way pass (tables of both directions, r kept)
+            s->fuse_threads = 32 * std::max(s->tree_top.warps, s->tree_lv[0].warps);
+            s->fuse_smem = std::max(tree_smem_bytes(s->tree_top, nx, nu, s->fuse_threads / 32, true),
+                                    tree_smem_bytes(s->tree_lv[0], nx, nu, s->fuse_threads / 32, true));
+            if (s->fuse_smem <= 200 * 1024) {
+                tree_need = std::max(tree_need, s->fuse_smem);
+                s->fuse_ok = true;
+            }
+        }
+        CTRYC(tree_kernels_set_smem((int)tree_need));
+        if (s->fuse_ok) {
+            s->fuse_ok = tree_fused_fits(nx, nu, s->tree_top.resident != 0, s->fuse_threads, s->fuse_smem,
+                                         (s->tree_lv[0].num_sub + 1) * L.batch);
+            if (s->fuse_ok) CTRY(dev_zero(s, (size_t)2 * L.batch, &s->tree_sync));
+            if (s->fuse_ok) CTRY(dev_zero(s, (size_t)2 * L.batch, &s->overlap_sync));
+        }
+        int top_max = 1;
+        for (int t = 0; t < pl.t_top; ++t) top_max = std::max(top_max, std::max(width(t), t + 1 < L.num_stages ? width(t + 1) : 1));
+        pl.top_cap = top_max;
+        s->top_warps = std::min(32, std::max(1, top_max));
+        const size_t per_warp = (size_t)(2 * (nx + nu) + 32) * sizeof(double);
+        size_t need = per_warp * s->top_warps + (size_t)pl.top_cap * (nx + nu) * sizeof(double);
+        for (int v = 0; v < pl.num_levels; ++v)
+            need = std::max(need, per_warp * pl.lv[v].warps_per_sub * pl.lv[v].subs_per_cta +
+                                      (size_t)pl.lv[v].subs_per_cta * pl.lv[v].stage_cap * (nx + nu) * sizeof(double));
+        if (need > 200 * 1024) {
+            return fail(s, RB_ERR_INVALID, "sweep stage buffers do not fit in shared memory");
+        }
+        s->sweep_smem_max = need;
+        CTRYC(sweep_kernels_set_smem((int)need));
+        // lane-major MMA fragment tables for the tiled chain levels (filled by rb_offline)
+        bool tiled = false;
+        for (int v = 0; v < pl.num_levels; ++v) tiled = tiled || pl.lv[v].num_tiles > 0;
+        if (tiled) {
+            int f_ab, f_abt, f_k, f_kr;
+            chain_mma_frag_counts(nx, nu, &f_ab, &f_abt, &f_k, &f_kr);
+            double *t_ab = nullptr, *t_abt = nullptr, *t_k = nullptr, *t_kr = nullptr;
+            // two images of every table: k-major, then output-block-major (launch_chain_mma_frags)
+            CTRY(dev_zero(s, (size_t)2 * s->num_dyn * f_ab * 32, &t_ab));
+            CTRY(dev_zero(s, (size_t)2 * s->num_dyn * f_abt * 32, &t_abt));
+            CTRY(dev_zero(s, (size_t)2 * s->num_cls * f_k * 32, &t_k));
+            CTRY(dev_zero(s, (size_t)2 * s->num_cls * f_kr * 32, &t_kr));
+            s->P.m.fragAB = t_ab;
+            s->P.m.fragABT = t_abt;
+            s->P.m.fragK = t_k;
+            s->P.m.fragKR = t_kr;
+            s->P.m.fragAB4 = t_ab + (size_t)s->num_dyn * f_ab * 32;
+            s->P.m.fragABT4 = t_abt + (size_t)s->num_dyn * f_abt * 32;
+            s->P.m.fragK4 = t_k + (size_t)s->num_cls * f_k * 32;
+            s->P.m.fragKR4 = t_kr + (size_t)s->num_cls * f_kr * 32;
+            size_t mma_need = 0;
+            for (int v = 0; v < pl.num_levels; ++v)
+                if (pl.lv[v].num_tiles > 0)
+                    mma_need = std::max(mma_need, std::max(chain_mma_smem_bytes(nx, nu, pl.lv[v].depth, true),
+                                                           chain_mma_smem_bytes(nx, nu, pl.lv[v].depth, false)));
+            CTRYC(chain_mma_set_smem((int)mma_need));
+        }
+    }
+    return RB_OK;
+}
+
+// rb_create, part: node tiles of the warp-per-node passes (fused.cu)
+int create_node_tiles(rb_solver *s, const rb_problem *pb) {
+    const int n = pb->n, m = pb->m, nx = pb->nx, nu = pb->nu, nl = n - m;
+    Layout &L = s->P.L;
+    Topo &T = s->P.t;
+    Tabs &M = s->P.m;
+    (void)n; (void)m; (void)nx; (void)nu; (void)nl; (void)L; (void)T; (void)M;
+    // ---- node tiles: runs of consecutive nodes (<= 32 nodes and <= 64 edges; leaves: <= 64 nodes) -----------------
+    {
+        std::vector<int2> tiles;
+        const int kTileNodes = 32, kTileEdges = 64, kTileLeaves = 64;
+        size_t need_p = 0, need_d = 0;
+        auto ev = [](long long c) { return (size_t)(c + 2); };   // chunks are widened to 16-byte boundaries
+        int i = 0;
+        while (i < m) {
+            int j = i, edges = 0;
+            while (j < m && j - i < kTileNodes && (j == i || edges + s->child_count[j] <= kTileEdges)) edges += s->child_count[j++];
+            tiles.push_back(make_int2(i, j));
+            const long long nN = j - i, nE = edges, ny = 2 * nE + nN;
+            need_p = std::max(need_p, ev(nN * nx) + ev(nN * nu) + 2 * ev(ny) + 2 * ev(nE) + ev(nN) + 3 * ev(nE) +
+                                          ev(nE * nx) + ev(nE * nu) + 2 * ev(nE) + ev(nN * (nx + nu)));
+            need_d = std::max(need_d, 2 * ev(nN * nx) + 2 * ev(nN * nu) + 3 * ev(ny) + 2 * ev(nE) + 3 * ev(nN) +
+                                          ev(nE * nx) + ev(nE * nu) + 2 * ev(nE) + ev(nN * (nx + nu)));
+            i = j;
+        }
+        for (i = m; i < n; i += kTileLeaves) {
+            const int j = std::min(n, i + kTileLeaves);
+            tiles.push_back(make_int2(i, j));
+            const long long nN = j - i;
+            need_p = std::max(need_p, 3 * ev(nN * nx));
+            need_d = std::max(need_d, 4 * ev(nN * nx) + 4 * ev(nN));
+        }
+        int2 *d_tiles = nullptr;
+        CTRY(upload(s, tiles.data(), tiles.size(), &d_tiles));
+        s->tiles.tiles = d_tiles;
+        s->tiles.num_tiles = (int)tiles.size();
+        s->tiles.rowlen = (std::max(nx, nu) + 1) & ~1;
+        s->primal_smem = sizeof(double) * (need_p + (size_t)8 * 4 * s->tiles.rowlen);
+        s->dual_smem = sizeof(double) * (need_d + (size_t)8 * kDualRowsHost * s->tiles.rowlen);
+        if (s->dual_smem > 200 * 1024 || s->primal_smem > 200 * 1024) {
+            return fail(s, RB_ERR_INVALID, "tile does not fit in shared memory");
+        }
+        CTRYC(tile_kernels_set_smem(s->primal_smem, s->dual_smem));
+    }
+    s->kernels_per_iter = 0;   // see iter_launches()
+    return RB_OK;
+}
+
+// rb_create, part: subtree sharding: the rank's node lists, restricted sweep levels and exchange buffers
+int create_shard_plan(rb_solver *s, const rb_problem *pb) {
+    const int n = pb->n, m = pb->m, nx = pb->nx, nu = pb->nu, nl = n - m;
+    Layout &L = s->P.L;
+    Topo &T = s->P.t;
+    Tabs &M = s->P.m;
+    (void)n; (void)m; (void)nx; (void)nu; (void)nl; (void)L; (void)T; (void)M;
+    // ---- subtree sharding: rank r owns a contiguous block of the level-0 subtrees, everybody replicates the top
+    if (pb->shard_world > 1) {
+        const SweepPlan &pl = s->plan;
+        const int W = pb->shard_world, R = pb->shard_rank;
+        if (R < 0 || R >= W || L.batch != 1 || pl.num_levels < 1 || pl.lv[0].num_sub < W) {
+            return fail(s, RB_ERR_INVALID, "subtree sharding needs batch == 1 and at least one cut-stage subtree per rank");
+        }
+        const int C = pl.lv[0].num_sub;
+        std::vector<int> bounds(W + 1);
+        for (int r = 0; r <= W; ++r) bounds[r] = (int)((long long)r * C / W);
+        ShardPlan &sp = s->shard;
+        sp.rank = R; sp.world = W;
+        sp.cut_first = s->stage_off[pl.t_top];
+        sp.cut_lo = bounds[R]; sp.cut_hi = bounds[R + 1];
+        sp.cap = 0;
+        for (int r = 0; r < W; ++r) sp.cap = std::max(sp.cap, bounds[r + 1] - bounds[r]);
+        int *d_bounds = nullptr;
+        CTRY(upload(s, bounds.data(), bounds.size(), &d_bounds));
+        sp.cut_bounds = d_bounds;
+        // owned nodes: the descendants of the owned cut nodes, one contiguous range per stage
+        std::vector<int> owned, top, both;
+        for (int i = 0; i < s->stage_off[pl.t_top]; ++i) top.push_back(i);
+        std::vector<std::pair<int, int>> stage_range(L.num_stages, {0, 0});
+        int a = sp.cut_first + sp.cut_lo, b = sp.cut_first + sp.cut_hi;
+        for (int t = pl.t_top; t < L.num_stages; ++t) {
+            stage_range[t] = {a, b};
+            for (int i = a; i < b; ++i) owned.push_back(i);
+            if (t + 1 < L.num_stages) {
+                const int na = s->child_first[a], nb = s->child_first[b - 1] + s->child_count[b - 1];
+                a = na;
+                b = nb;
+            }
+        }
+        both = top;
+        both.insert(both.end(), owned.begin(), owned.end());
+        CTRY(upload(s, owned.data(), owned.size(), &s->owned_nodes));
+        CTRY(upload(s, top.data(), top.size(), &s->top_nodes));
+        CTRY(upload(s, both.data(), both.size(), &s->dual_nodes));
+        s->n_owned = (int)owned.size();
+        s->n_top = (int)top.size();
+        // sweep levels restricted to the owned subtrees (a contiguous block of every level)
+        for (int v = 0; v < pl.num_levels; ++v) {
+            SweepLevel lv = pl.lv[v];
+            const int first = s->stage_off[lv.t_lo];
+            const int sa = stage_range[lv.t_lo].first - first, sb = stage_range[lv.t_lo].second - first;
+            lv.lo += (size_t)sa * lv.depth;
+            lv.hi += (size_t)sa * lv.depth;
+            lv.num_sub = sb - sa;
+            if (lv.num_tiles > 0) {   // tiles of the owned chains only (indices relative to the shifted lo / hi)
+                std::vector<int> sub(s->chain_lo[v].begin() + (size_t)sa * lv.depth, s->chain_lo[v].begin() + (size_t)sb * lv.depth);
+                CTRY(build_chain_tiles(s, sub, lv.depth, 0, lv.num_sub, &lv.tiles, &lv.num_tiles, &lv.tile_meta));
+            }
+            s->shard_lv[v] = lv;
+            s->shard_tree_lv[v] = s->tree_lv[v];
+            if (s->tree_lv[v].desc) {
+                s->shard_tree_lv[v].desc += (size_t)sa * s->tree_lv[v].desc_stride;
+                s->shard_tree_lv[v].num_sub = sb - sa;
+            }
+        }
+        s->xchg_count = (size_t)sp.cap * (nx + 1) + 6;
+        CTRY(dev_zero(s, s->xchg_count, &s->xchg_send));
+        CTRY(dev_zero(s, s->xchg_count * W, &s->xchg_recv));
+        {   // node lists of the pipelined sharded loop: the chain nodes [chain_first, m) go through k_dual_chain (the rank's
+            // columns of every chain stage: OwnMap), everything else the rank owns -- and the replicated top -- through the
+            // general lane pass; the kernel projection takes the nonleaf nodes of either set
+            std::vector<int> own_nl, top_nl, lane;
+            const int cf = s->chain_stride > 0 ? s->chain_first : m;
+            for (int i : top) {
+                if (i < m) top_nl.push_back(i);
+                lane.push_back(i);
+            }
+            for (int i : owned) {
+                if (i < m) own_nl.push_back(i);
+                if (i < cf || i >= m) lane.push_back(i);
+            }
+            CTRY(upload(s, own_nl.data(), own_nl.size(), &s->own_nonleaf));
+            CTRY(upload(s, top_nl.data(), top_nl.size(), &s->top_nonleaf));
+            CTRY(upload(s, lane.data(), lane.size(), &s->own_lane));
+            s->n_own_nonleaf = (int)own_nl.size();
+            s->n_top_nonleaf = (int)top_nl.size();
+            s->n_own_lane = (int)lane.size();
+            if (cf < m) {   // stage of chain_first and the rank's columns there
+                int t = 0;
+                while (s->stage_off[t + 1] <= cf) ++t;
+                const int wdt = s->stage_off[t + 1] - s->stage_off[t];
+                if (s->stage_off[t] == cf && wdt == s->chain_stride && stage_range[t].second > stage_range[t].first) {
+                    s->own_chain = OwnMap{stage_range[t].second - stage_range[t].first, stage_range[t].first - cf, wdt};
+                    s->n_own_chain = (m - cf) / wdt * s->own_chain.w;
+                }
+            }
+        }
+        s->sharded = true;
+    }
+    return RB_OK;
+}
+
+#undef CTRY
+#undef CTRYC
+
 int need_offline(rb_solver *s) {
     if (!s->have_offline) return fail(s, RB_ERR_STATE, "rb_offline() has not been run");
     return RB_OK;
@@ -608,511 +1178,12 @@ int rb_create(const rb_problem *pb, rb_solver **out) {
     s->num_dyn = pb->num_dyn;
     s->num_cost = pb->num_cost;
     s->num_leafcost = pb->num_leafcost;
-    // ---- validate the topology the kernels rely on
-    if (s->stage_off[0] != 0 || s->stage_off[pb->num_stages] != n || s->stage_off[pb->num_stages - 1] != m) {
-        s->err = "stage_off must partition 0..n with the leaves as the last stage";
-        return bail(RB_ERR_INVALID);
-    }
-    {
-        int expect = 1;
-        for (int i = 0; i < m; ++i) {
-            if (s->child_count[i] < 1 || s->child_first[i] != expect) {
-                s->err = "children of the nonleaf nodes must be consecutive ranges in node order (renumber the tree "
-                         "breadth first)";
-                return bail(RB_ERR_INVALID);
-            }
-            for (int j = expect; j < expect + s->child_count[i]; ++j)
-                if (j >= n || s->parent[j] != i) {
-                    s->err = "parent[] and child ranges disagree";
-                    return bail(RB_ERR_INVALID);
-                }
-            expect += s->child_count[i];
-        }
-        if (expect != n) {
-            s->err = "child ranges do not cover all nodes";
-            return bail(RB_ERR_INVALID);
-        }
-        for (int i = 0; i < m; ++i) {
-            if (s->cls[i] < 0 || s->cls[i] >= s->num_cls) {
-                s->err = "cls[] out of range";
-                return bail(RB_ERR_INVALID);
-            }
-            for (int j = s->child_first[i]; j < s->child_first[i] + s->child_count[i]; ++j)
-                if (j < m && s->cls[j] <= s->cls[i]) {
-                    s->err = "class of a child must be larger than the class of its parent";
-                    return bail(RB_ERR_INVALID);
-                }
-        }
-    }
-    // ---- layout
-    Layout &L = s->P.L;
-    L.n = n; L.m = m; L.nleaf = nl; L.nx = nx; L.nu = nu; L.nxu = nx + nu;
-    L.num_stages = pb->num_stages; L.batch = pb->batch;
-    L.has_nl_rect = pb->num_nl_rect > 0; L.has_leaf_rect = pb->num_leaf_rect > 0;
-    std::vector<int> yoff(m + 1, 0);
-    for (int i = 0; i < m; ++i) yoff[i + 1] = yoff[i] + 2 * s->child_count[i] + 1;
-    L.ysz = yoff[m];
-    for (int i = 0; i < m; ++i) s->max_children = std::max(s->max_children, s->child_count[i]);
-    s->chain_first = m;   // trailing run of nonleaf nodes with one child: the chain part of the tree (k_dual_chain)
-    while (s->chain_first > 1 && s->child_count[s->chain_first - 1] == 1) --s->chain_first;
-    {
-        int64_t pc = 0, pp = 0;  // compact / padded cursors
-        auto addp = [&](long long &field, int64_t len) {
-            field = pp;
-            s->pseg.push_back({pc, pp, len});
-            pc += len;
-            pp = round16(pp + len);
-        };
-        addp(L.px, (int64_t)n * nx); addp(L.pu, (int64_t)m * nu); addp(L.py, L.ysz); addp(L.ptau, n); addp(L.ps, n);
-        s->np = pc; L.np_pad = pp;
-        pc = 0; pp = 0;
-        auto addd = [&](long long &field, int64_t len) {
-            field = pp;
-            s->dseg.push_back({pc, pp, len});
-            pc += len;
-            pp = round16(pp + len);
-        };
-        addd(L.d1, L.ysz); addd(L.d2, m); addd(L.d3, (int64_t)(n - 1) * nx); addd(L.d4, (int64_t)(n - 1) * nu);
-        addd(L.d5, n - 1); addd(L.d6, n - 1); addd(L.d7, L.has_nl_rect ? (int64_t)m * (nx + nu) : 0);
-        addd(L.d11, (int64_t)nl * nx); addd(L.d12, nl); addd(L.d13, nl); addd(L.d14, L.has_leaf_rect ? (int64_t)nl * nx : 0);
-        s->nd = pc; L.nd_pad = pp;
-    }
-    // ---- topology and tables to the device
-    Topo &T = s->P.t;
-    int *tmp_i = nullptr;
-    double *tmp_d = nullptr;
-    TRY(upload(s, pb->parent, n, &tmp_i)); T.parent = tmp_i;
-    TRY(upload(s, pb->child_first, m, &tmp_i)); T.child_first = tmp_i;
-    TRY(upload(s, pb->child_count, m, &tmp_i)); T.child_count = tmp_i;
-    TRY(upload(s, yoff.data(), m + 1, &tmp_i)); T.yoff = tmp_i;
-    TRY(upload(s, pb->dyn_idx, n, &tmp_i)); T.dyn_idx = tmp_i;
-    TRY(upload(s, pb->cost_idx, n, &tmp_i)); T.cost_idx = tmp_i;
-    TRY(upload(s, pb->leafcost_idx, nl, &tmp_i)); T.leafcost_idx = tmp_i;
-    TRY(upload(s, L.has_nl_rect ? pb->nl_rect_idx : nullptr, m, &tmp_i)); T.nl_rect_idx = tmp_i;
-    {   // packed topology records of the chain nodes (k_dual_chain): child, cost row of the child, y offset, rectangle row
-        std::vector<int4> recs(std::max(1, m - s->chain_first));
-        for (int i = s->chain_first; i < m; ++i) {
-            const int j = s->child_first[i];
-            recs[i - s->chain_first] = make_int4(j, s->cost_idx[j], yoff[i], L.has_nl_rect ? pb->nl_rect_idx[i] : 0);
-        }
-        TRY(upload(s, recs.data(), recs.size(), &s->chain_recs));
-        s->chain_yo0 = yoff[std::min(s->chain_first, m)];
-        s->chain_stride = s->chain_first < m ? s->child_first[s->chain_first] - s->chain_first : -1;
-        for (int i = s->chain_first; i < m; ++i)
-            if (s->child_first[i] - i != s->chain_stride) s->chain_stride = -1;
-    }
-    TRY(upload(s, L.has_leaf_rect ? pb->leaf_rect_idx : nullptr, nl, &tmp_i)); T.leaf_rect_idx = tmp_i;
-    TRY(upload(s, pb->cls, m, &tmp_i)); T.cls = tmp_i;
-    TRY(upload(s, pb->cond_prob, n, &tmp_d)); T.cond_prob = tmp_d;
-    TRY(upload(s, pb->risk_alpha, m, &tmp_d)); T.risk_alpha = tmp_d;
-    Tabs &M = s->P.m;
-    TRY(upload(s, pb->A, (size_t)pb->num_dyn * nx * nx, &tmp_d)); M.A = tmp_d;
-    TRY(upload(s, pb->B, (size_t)pb->num_dyn * nx * nu, &tmp_d)); M.B = tmp_d;
-    {
-        const int nxu = nx + nu;
-        std::vector<double> cat((size_t)pb->num_dyn * nx * nxu), catT(cat.size());
-        for (int t = 0; t < pb->num_dyn; ++t)
-            for (int l = 0; l < nx; ++l) {
-                for (int k = 0; k < nx; ++k) {
-                    const double a_lk = pb->A[((size_t)t * nx + l) * nx + k];
-                    cat[((size_t)t * nx + l) * nxu + k] = a_lk;            // row l = [A[l][:], B[l][:]]
-                    catT[((size_t)t * nxu + k) * nx + l] = a_lk;           // row k<nx = A[:][k]
-                }
-                for (int a = 0; a < nu; ++a) {
-                    const double b_la = pb->B[((size_t)t * nx + l) * nu + a];
-                    cat[((size_t)t * nx + l) * nxu + nx + a] = b_la;
-                    catT[((size_t)t * nxu + nx + a) * nx + l] = b_la;      // row nx+a = B[:][a]
-                }
-            }
-        TRY(upload(s, cat.data(), cat.size(), &tmp_d)); M.ABcat = tmp_d;
-        TRY(upload(s, catT.data(), catT.size(), &tmp_d)); M.ABcatT = tmp_d;
-        auto sq = transpose_tab(pb->sqrtQ, pb->num_cost, nx, nx);
-        TRY(upload(s, sq.data(), sq.size(), &tmp_d)); M.sqT = tmp_d;
-        auto sr = transpose_tab(pb->sqrtR, pb->num_cost, nu, nu);
-        TRY(upload(s, sr.data(), sr.size(), &tmp_d)); M.srT = tmp_d;
-        auto sf = transpose_tab(pb->sqrtQf, pb->num_leafcost, nx, nx);
-        TRY(upload(s, sf.data(), sf.size(), &tmp_d)); M.sqfT = tmp_d;
-        M.sq_diag = is_diag(pb->sqrtQ, pb->num_cost, nx);
-        M.sr_diag = is_diag(pb->sqrtR, pb->num_cost, nu);
-        M.sqf_diag = is_diag(pb->sqrtQf, pb->num_leafcost, nx);
-        s->diag_costs = M.sq_diag && M.sr_diag && M.sqf_diag;
-        auto diag_of = [](const double *tab, int count, int dim) {
-            std::vector<double> d((size_t)count * dim);
-            for (int t = 0; t < count; ++t)
-                for (int k = 0; k < dim; ++k) d[(size_t)t * dim + k] = tab[((size_t)t * dim + k) * dim + k];
-            return d;
-        };
-        auto dq = diag_of(pb->sqrtQ, pb->num_cost, nx), dr = diag_of(pb->sqrtR, pb->num_cost, nu),
-             df = diag_of(pb->sqrtQf, pb->num_leafcost, nx);
-        TRY(upload(s, dq.data(), dq.size(), &tmp_d)); M.sq_d = tmp_d;
-        TRY(upload(s, dr.data(), dr.size(), &tmp_d)); M.sr_d = tmp_d;
-        TRY(upload(s, df.data(), df.size(), &tmp_d)); M.sqf_d = tmp_d;
-    }
-    TRY(upload(s, L.has_nl_rect ? pb->nl_lo : nullptr, (size_t)pb->num_nl_rect * (nx + nu), &tmp_d)); M.nl_lo = tmp_d;
-    TRY(upload(s, L.has_nl_rect ? pb->nl_hi : nullptr, (size_t)pb->num_nl_rect * (nx + nu), &tmp_d)); M.nl_hi = tmp_d;
-    TRY(upload(s, L.has_leaf_rect ? pb->leaf_lo : nullptr, (size_t)pb->num_leaf_rect * nx, &tmp_d)); M.leaf_lo = tmp_d;
-    TRY(upload(s, L.has_leaf_rect ? pb->leaf_hi : nullptr, (size_t)pb->num_leaf_rect * nx, &tmp_d)); M.leaf_hi = tmp_d;
-    // ---- class structure for the offline factorisation: representative = first node of the class
-    {
-        std::vector<int> rep(s->num_cls, -1);
-        for (int i = 0; i < m; ++i)
-            if (rep[s->cls[i]] < 0) rep[s->cls[i]] = i;
-        std::vector<int> level(s->num_cls, 0);
-        s->cls_child_ptr.assign(1, 0);
-        for (int c = 0; c < s->num_cls; ++c) {
-            if (rep[c] < 0) {
-                s->err = "class without nodes";
-                return bail(RB_ERR_INVALID);
-            }
-            const int i = rep[c];
-            for (int j = s->child_first[i]; j < s->child_first[i] + s->child_count[i]; ++j) {
-                s->cls_child_dyn.push_back(s->dyn_idx[j]);
-                s->cls_child_cls.push_back(j < m ? s->cls[j] : -1);
-            }
-            s->cls_child_ptr.push_back((int)s->cls_child_dyn.size());
-        }
-        int max_level = 0;
-        for (int c = s->num_cls - 1; c >= 0; --c) {  // children have larger class ids: already final when visited
-            int lv = 0;
-            for (int k = s->cls_child_ptr[c]; k < s->cls_child_ptr[c + 1]; ++k)
-                if (s->cls_child_cls[k] >= 0) lv = std::max(lv, level[s->cls_child_cls[k]] + 1);
-            level[c] = lv;
-            max_level = std::max(max_level, lv);
-        }
-        s->level_ptr.assign(max_level + 2, 0);
-        for (int c = 0; c < s->num_cls; ++c) ++s->level_ptr[level[c] + 1];
-        for (int l = 0; l <= max_level; ++l) s->level_ptr[l + 1] += s->level_ptr[l];
-        s->level_list.resize(s->num_cls);
-        std::vector<int> cur(s->level_ptr.begin(), s->level_ptr.end() - 1);
-        for (int c = 0; c < s->num_cls; ++c) s->level_list[cur[level[c]]++] = c;
-        TRY(upload(s, s->cls_child_ptr.data(), s->cls_child_ptr.size(), &s->d_cls_child_ptr));
-        TRY(upload(s, s->cls_child_dyn.data(), s->cls_child_dyn.size(), &s->d_cls_child_dyn));
-        TRY(upload(s, s->cls_child_cls.data(), s->cls_child_cls.size(), &s->d_cls_child_cls));
-        TRY(upload(s, s->level_list.data(), s->level_list.size(), &s->d_level_list));
-    }
-    TRY(dev_zero(s, (size_t)s->num_cls * nx * nx, &s->Ptab));
-    TRY(dev_zero(s, (size_t)s->num_cls * nu * nx, &s->Ktab));
-    TRY(dev_zero(s, (size_t)s->num_cls * (nx + nu) * nu, &s->KRcatT));
-    M.K = s->Ktab; M.KRcatT = s->KRcatT;
-    // ---- iterates and scratch
-    const size_t B = (size_t)L.batch;
-    for (int w = 0; w < 2; ++w) {
-        TRY(dev_zero(s, B * L.np_pad, &s->prim[w]));
-        TRY(dev_zero(s, B * L.nd_pad, &s->dual[w]));
-    }
-    TRY(dev_zero(s, B * n * nx, &s->q));
-    TRY(dev_zero(s, B * m * nu, &s->r));
-    TRY(dev_zero(s, B * nx, &s->x0));
-    TRY(dev_zero(s, 1, &s->ctrl));
-    TRY(dev_zero(s, B * 6, &s->slots));
-    TRY(dev_zero(s, B * 6, &s->last));
-    if (B * 6 <= 1024 && L.nx <= 1024 &&
-        cudaHostAlloc((void **)&s->h_last, B * 6 * sizeof(double), cudaHostAllocMapped) == cudaSuccess) {
-        if (cudaHostGetDevicePointer((void **)&s->h_last_dev, s->h_last, 0) != cudaSuccess) {
-            cudaFreeHost(s->h_last);
-            s->h_last = s->h_last_dev = nullptr;
-        }
-    } else {
-        cudaGetLastError();
-        s->h_last = s->h_last_dev = nullptr;
-    }
-    TRY(dev_zero(s, 1, &s->status));
-    // ---- sweep plan (sweeps.cu): first cut at the first stage with >= 64 nodes; second cut where the tree turns into
-    //      chains (below the stopping time of a Markov tree) if there are >= 200 of them (cfg2, 243 chains: 13 222 vs 12 208 it/s with the chain level), else -- if the tree keeps
-    //      branching -- at the first stage with >= 2048 nodes and >= 8x the first cut
-    {
-        SweepPlan &pl = s->plan;
-        auto width = [&](int t) { return s->stage_off[t + 1] - s->stage_off[t]; };
-        if ((pb->sweep_cut1_min != 0 || pb->sweep_cut2_min != 0) && pb->shard_world > 1) {
-            s->err = "sweep_cut*_min must be 0 for a sharded problem";
-            return bail(RB_ERR_INVALID);
-        }
-        const int cut1_min = pb->sweep_cut1_min > 0 ? pb->sweep_cut1_min : 64;
-        const int cut2_min = pb->sweep_cut2_min > 0 ? pb->sweep_cut2_min : 200;
-        int c1 = L.num_stages, c2 = L.num_stages;
-        for (int t = 0; t < L.num_stages; ++t)
-            if (width(t) >= cut1_min) {
-                c1 = t;
-                break;
-            }
-        int c_chain = L.num_stages - 1;   // first stage from which every node has at most one child
-        while (c_chain > 0) {
-            bool chains = true;
-            for (int i = s->stage_off[c_chain - 1]; i < s->stage_off[c_chain] && chains; ++i) chains = s->child_count[i] <= 1;
-            if (!chains) break;
-            --c_chain;
-        }
-        if (c_chain > c1 && c_chain < L.num_stages - 1 && L.num_stages - c_chain <= 64 && width(c_chain) >= cut2_min) {
-            c2 = c_chain;
-            // The top is ONE CTA and every level-0 subtree is one CTA; a stage of either costs what its parents cost.
-            // Balance them: the first cut goes where the widest parent stage of the top, width(c - 1), and the widest
-            // parent stage of a subtree, width(c2 - 1) / width(c), are closest (cfg3: stage 3 either way; cfg5, 3 modes:
-            // stage 3 with 27 subtrees of 1 + 3 + 9 nodes instead of stage 4 with a 27-parent stage in the top).
-            if (pb->sweep_cut1_min == 0) {
-                auto cost = [&](int c) { return std::max(width(c - 1), width(c2 - 1) / std::max(1, width(c))); };
-                for (int c = c1 - 1; c >= 1 && width(c) >= 8; --c)
-                    if (cost(c) < cost(c1)) c1 = c;
-            }
-        } else {
-            for (int t = c1 + 1; t < L.num_stages; ++t)
-                if (width(t) >= std::max(2048, cut2_min) && width(t) >= 8 * width(c1)) {
-                    c2 = t;
-                    break;
-                }
-        }
-        pl.t_top = c1;
-        pl.num_levels = c1 >= L.num_stages ? 0 : (c2 >= L.num_stages ? 1 : 2);
-        int *d_so = nullptr;
-        TRY(upload(s, s->stage_off.data(), s->stage_off.size(), &d_so));
-        pl.stage_off = d_so;
-        const int cuts[3] = {c1, c2, L.num_stages};
-        for (int v = 0; v < pl.num_levels; ++v) {
-            SweepLevel &lv = pl.lv[v];
-            lv.t_lo = cuts[v];
-            lv.depth = (v + 1 < pl.num_levels ? cuts[v + 1] : L.num_stages) - cuts[v];
-            lv.num_sub = width(lv.t_lo);
-            std::vector<int> lo((size_t)lv.num_sub * lv.depth), hi(lo.size());
-            int max_width = 1;
-            for (int c = 0; c < lv.num_sub; ++c) {
-                int a = s->stage_off[lv.t_lo] + c, b = a + 1;
-                for (int d = 0; d < lv.depth; ++d) {
-                    lo[(size_t)c * lv.depth + d] = a;
-                    hi[(size_t)c * lv.depth + d] = b;
-                    max_width = std::max(max_width, b - a);
-                    if (d + 1 < lv.depth) {   // children of [a, b) are one contiguous range of the next stage
-                        const int na = s->child_first[a], nb = s->child_first[b - 1] + s->child_count[b - 1];
-                        a = na;
-                        b = nb;
-                    }
-                }
-            }
-            // widest stage of any subtree, in nodes or in children (rows of the group-shared buffer)
-            int cap = 1;
-            for (int c = 0; c < lv.num_sub; ++c)
-                for (int d = 0; d < lv.depth; ++d) {
-                    const int a = lo[(size_t)c * lv.depth + d], b = hi[(size_t)c * lv.depth + d];
-                    cap = std::max(cap, b - a);
-                    if (a < m) cap = std::max(cap, s->child_first[b - 1] + s->child_count[b - 1] - s->child_first[a]);
-                }
-            lv.stage_cap = max_width == 1 ? 0 : cap;
-            lv.chain = (max_width == 1 && lv.depth <= 64 && lv.t_lo + lv.depth == L.num_stages) ? 1 : 0;
-            lv.warps_per_sub = std::min(16, max_width == 1 ? 1 : cap);
-            lv.subs_per_cta = std::max(1, 8 / lv.warps_per_sub);
-            int *d_lo = nullptr, *d_hi = nullptr;
-            TRY(upload(s, lo.data(), lo.size(), &d_lo));
-            TRY(upload(s, hi.data(), hi.size(), &d_hi));
-            lv.lo = d_lo;
-            lv.hi = d_hi;
-            lv.tiles = nullptr;
-            lv.tile_meta = nullptr;
-            lv.num_tiles = 0;
-            if (lv.chain && chain_mma_supported(nx, nu)) {
-                s->chain_lo[v] = lo;
-                TRY(build_chain_tiles(s, lo, lv.depth, 0, lv.num_sub, &lv.tiles, &lv.num_tiles, &lv.tile_meta));
-            }
-            if (!lv.chain) TRY(build_tree_level(s, lo, hi, lv.depth, lv.num_sub, false, &s->tree_lv[v], &s->tree_smem[1 + v]));
-        }
-        {   // the top of the tree as one subtree: stages [0, t_top)
-            std::vector<int> lo(pl.t_top), hi(pl.t_top);
-            for (int t = 0; t < pl.t_top; ++t) {
-                lo[t] = s->stage_off[t];
-                hi[t] = s->stage_off[t + 1];
-            }
-            TRY(build_tree_level(s, lo, hi, pl.t_top, 1, true, &s->tree_top, &s->tree_smem[0]));
-        }
-        size_t tree_need = std::max(s->tree_smem[0], std::max(s->tree_smem[1], s->tree_smem[2]));
-        if (s->tree_top.desc && pl.num_levels > 0 && s->tree_lv[0].desc && s->tree_top.resident == s->tree_lv[0].resident) {
-            // level 0 with the footprint of a two-way pass (tables of both directions, r kept)
-            s->fuse_threads = 32 * std::max(s->tree_top.warps, s->tree_lv[0].warps);
-            s->fuse_smem = std::max(tree_smem_bytes(s->tree_top, nx, nu, s->fuse_threads / 32, true),
-                                    tree_smem_bytes(s->tree_lv[0], nx, nu, s->fuse_threads / 32, true));
-            if (s->fuse_smem <= 200 * 1024) {
-                tree_need = std::max(tree_need, s->fuse_smem);
-                s->fuse_ok = true;
-            }
-        }
-        TRYC(tree_kernels_set_smem((int)tree_need));
-        if (s->fuse_ok) {
-            s->fuse_ok = tree_fused_fits(nx, nu, s->tree_top.resident != 0, s->fuse_threads, s->fuse_smem,
-                                         (s->tree_lv[0].num_sub + 1) * L.batch);
-            if (s->fuse_ok) TRY(dev_zero(s, (size_t)2 * L.batch, &s->tree_sync));
-        }
-        int top_max = 1;
-        for (int t = 0; t < pl.t_top; ++t) top_max = std::max(top_max, std::max(width(t), t + 1 < L.num_stages ? width(t + 1) : 1));
-        pl.top_cap = top_max;
-        s->top_warps = std::min(32, std::max(1, top_max));
-        const size_t per_warp = (size_t)(2 * (nx + nu) + 32) * sizeof(double);
-        size_t need = per_warp * s->top_warps + (size_t)pl.top_cap * (nx + nu) * sizeof(double);
-        for (int v = 0; v < pl.num_levels; ++v)
-            need = std::max(need, per_warp * pl.lv[v].warps_per_sub * pl.lv[v].subs_per_cta +
-                                      (size_t)pl.lv[v].subs_per_cta * pl.lv[v].stage_cap * (nx + nu) * sizeof(double));
-        if (need > 200 * 1024) {
-            s->err = "sweep stage buffers do not fit in shared memory";
-            return bail(RB_ERR_INVALID);
-        }
-        s->sweep_smem_max = need;
-        TRYC(sweep_kernels_set_smem((int)need));
-        // lane-major MMA fragment tables for the tiled chain levels (filled by rb_offline)
-        bool tiled = false;
-        for (int v = 0; v < pl.num_levels; ++v) tiled = tiled || pl.lv[v].num_tiles > 0;
-        if (tiled) {
-            int f_ab, f_abt, f_k, f_kr;
-            chain_mma_frag_counts(nx, nu, &f_ab, &f_abt, &f_k, &f_kr);
-            double *t_ab = nullptr, *t_abt = nullptr, *t_k = nullptr, *t_kr = nullptr;
-            // two images of every table: k-major, then output-block-major (launch_chain_mma_frags)
-            TRY(dev_zero(s, (size_t)2 * s->num_dyn * f_ab * 32, &t_ab));
-            TRY(dev_zero(s, (size_t)2 * s->num_dyn * f_abt * 32, &t_abt));
-            TRY(dev_zero(s, (size_t)2 * s->num_cls * f_k * 32, &t_k));
-            TRY(dev_zero(s, (size_t)2 * s->num_cls * f_kr * 32, &t_kr));
-            s->P.m.fragAB = t_ab;
-            s->P.m.fragABT = t_abt;
-            s->P.m.fragK = t_k;
-            s->P.m.fragKR = t_kr;
-            s->P.m.fragAB4 = t_ab + (size_t)s->num_dyn * f_ab * 32;
-            s->P.m.fragABT4 = t_abt + (size_t)s->num_dyn * f_abt * 32;
-            s->P.m.fragK4 = t_k + (size_t)s->num_cls * f_k * 32;
-            s->P.m.fragKR4 = t_kr + (size_t)s->num_cls * f_kr * 32;
-            size_t mma_need = 0;
-            for (int v = 0; v < pl.num_levels; ++v)
-                if (pl.lv[v].num_tiles > 0)
-                    mma_need = std::max(mma_need, std::max(chain_mma_smem_bytes(nx, nu, pl.lv[v].depth, true),
-                                                           chain_mma_smem_bytes(nx, nu, pl.lv[v].depth, false)));
-            TRYC(chain_mma_set_smem((int)mma_need));
-        }
-    }
-    // ---- node tiles: runs of consecutive nodes (<= 32 nodes and <= 64 edges; leaves: <= 64 nodes) -----------------
-    {
-        std::vector<int2> tiles;
-        const int kTileNodes = 32, kTileEdges = 64, kTileLeaves = 64;
-        size_t need_p = 0, need_d = 0;
-        auto ev = [](long long c) { return (size_t)(c + 2); };   // chunks are widened to 16-byte boundaries
-        int i = 0;
-        while (i < m) {
-            int j = i, edges = 0;
-            while (j < m && j - i < kTileNodes && (j == i || edges + s->child_count[j] <= kTileEdges)) edges += s->child_count[j++];
-            tiles.push_back(make_int2(i, j));
-            const long long nN = j - i, nE = edges, ny = 2 * nE + nN;
-            need_p = std::max(need_p, ev(nN * nx) + ev(nN * nu) + 2 * ev(ny) + 2 * ev(nE) + ev(nN) + 3 * ev(nE) +
-                                          ev(nE * nx) + ev(nE * nu) + 2 * ev(nE) + ev(nN * (nx + nu)));
-            need_d = std::max(need_d, 2 * ev(nN * nx) + 2 * ev(nN * nu) + 3 * ev(ny) + 2 * ev(nE) + 3 * ev(nN) +
-                                          ev(nE * nx) + ev(nE * nu) + 2 * ev(nE) + ev(nN * (nx + nu)));
-            i = j;
-        }
-        for (i = m; i < n; i += kTileLeaves) {
-            const int j = std::min(n, i + kTileLeaves);
-            tiles.push_back(make_int2(i, j));
-            const long long nN = j - i;
-            need_p = std::max(need_p, 3 * ev(nN * nx));
-            need_d = std::max(need_d, 4 * ev(nN * nx) + 4 * ev(nN));
-        }
-        int2 *d_tiles = nullptr;
-        TRY(upload(s, tiles.data(), tiles.size(), &d_tiles));
-        s->tiles.tiles = d_tiles;
-        s->tiles.num_tiles = (int)tiles.size();
-        s->tiles.rowlen = (std::max(nx, nu) + 1) & ~1;
-        s->primal_smem = sizeof(double) * (need_p + (size_t)8 * 4 * s->tiles.rowlen);
-        s->dual_smem = sizeof(double) * (need_d + (size_t)8 * kDualRowsHost * s->tiles.rowlen);
-        if (s->dual_smem > 200 * 1024 || s->primal_smem > 200 * 1024) {
-            s->err = "tile does not fit in shared memory";
-            return bail(RB_ERR_INVALID);
-        }
-        TRYC(tile_kernels_set_smem(s->primal_smem, s->dual_smem));
-    }
-    s->kernels_per_iter = 0;   // see iter_launches()
-    // ---- subtree sharding: rank r owns a contiguous block of the level-0 subtrees, everybody replicates the top
-    if (pb->shard_world > 1) {
-        const SweepPlan &pl = s->plan;
-        const int W = pb->shard_world, R = pb->shard_rank;
-        if (R < 0 || R >= W || L.batch != 1 || pl.num_levels < 1 || pl.lv[0].num_sub < W) {
-            s->err = "subtree sharding needs batch == 1 and at least one cut-stage subtree per rank";
-            return bail(RB_ERR_INVALID);
-        }
-        const int C = pl.lv[0].num_sub;
-        std::vector<int> bounds(W + 1);
-        for (int r = 0; r <= W; ++r) bounds[r] = (int)((long long)r * C / W);
-        ShardPlan &sp = s->shard;
-        sp.rank = R; sp.world = W;
-        sp.cut_first = s->stage_off[pl.t_top];
-        sp.cut_lo = bounds[R]; sp.cut_hi = bounds[R + 1];
-        sp.cap = 0;
-        for (int r = 0; r < W; ++r) sp.cap = std::max(sp.cap, bounds[r + 1] - bounds[r]);
-        int *d_bounds = nullptr;
-        TRY(upload(s, bounds.data(), bounds.size(), &d_bounds));
-        sp.cut_bounds = d_bounds;
-        // owned nodes: the descendants of the owned cut nodes, one contiguous range per stage
-        std::vector<int> owned, top, both;
-        for (int i = 0; i < s->stage_off[pl.t_top]; ++i) top.push_back(i);
-        std::vector<std::pair<int, int>> stage_range(L.num_stages, {0, 0});
-        int a = sp.cut_first + sp.cut_lo, b = sp.cut_first + sp.cut_hi;
-        for (int t = pl.t_top; t < L.num_stages; ++t) {
-            stage_range[t] = {a, b};
-            for (int i = a; i < b; ++i) owned.push_back(i);
-            if (t + 1 < L.num_stages) {
-                const int na = s->child_first[a], nb = s->child_first[b - 1] + s->child_count[b - 1];
-                a = na;
-                b = nb;
-            }
-        }
-        both = top;
-        both.insert(both.end(), owned.begin(), owned.end());
-        TRY(upload(s, owned.data(), owned.size(), &s->owned_nodes));
-        TRY(upload(s, top.data(), top.size(), &s->top_nodes));
-        TRY(upload(s, both.data(), both.size(), &s->dual_nodes));
-        s->n_owned = (int)owned.size();
-        s->n_top = (int)top.size();
-        // sweep levels restricted to the owned subtrees (a contiguous block of every level)
-        for (int v = 0; v < pl.num_levels; ++v) {
-            SweepLevel lv = pl.lv[v];
-            const int first = s->stage_off[lv.t_lo];
-            const int sa = stage_range[lv.t_lo].first - first, sb = stage_range[lv.t_lo].second - first;
-            lv.lo += (size_t)sa * lv.depth;
-            lv.hi += (size_t)sa * lv.depth;
-            lv.num_sub = sb - sa;
-            if (lv.num_tiles > 0) {   // tiles of the owned chains only (indices relative to the shifted lo / hi)
-                std::vector<int> sub(s->chain_lo[v].begin() + (size_t)sa * lv.depth, s->chain_lo[v].begin() + (size_t)sb * lv.depth);
-                TRY(build_chain_tiles(s, sub, lv.depth, 0, lv.num_sub, &lv.tiles, &lv.num_tiles, &lv.tile_meta));
-            }
-            s->shard_lv[v] = lv;
-            s->shard_tree_lv[v] = s->tree_lv[v];
-            if (s->tree_lv[v].desc) {
-                s->shard_tree_lv[v].desc += (size_t)sa * s->tree_lv[v].desc_stride;
-                s->shard_tree_lv[v].num_sub = sb - sa;
-            }
-        }
-        s->xchg_count = (size_t)sp.cap * (nx + 1) + 6;
-        TRY(dev_zero(s, s->xchg_count, &s->xchg_send));
-        TRY(dev_zero(s, s->xchg_count * W, &s->xchg_recv));
-        {   // node lists of the pipelined sharded loop: the chain nodes [chain_first, m) go through k_dual_chain (the rank's
-            // columns of every chain stage: OwnMap), everything else the rank owns -- and the replicated top -- through the
-            // general lane pass; the kernel projection takes the nonleaf nodes of either set
-            std::vector<int> own_nl, top_nl, lane;
-            const int cf = s->chain_stride > 0 ? s->chain_first : m;
-            for (int i : top) {
-                if (i < m) top_nl.push_back(i);
-                lane.push_back(i);
-            }
-            for (int i : owned) {
-                if (i < m) own_nl.push_back(i);
-                if (i < cf || i >= m) lane.push_back(i);
-            }
-            TRY(upload(s, own_nl.data(), own_nl.size(), &s->own_nonleaf));
-            TRY(upload(s, top_nl.data(), top_nl.size(), &s->top_nonleaf));
-            TRY(upload(s, lane.data(), lane.size(), &s->own_lane));
-            s->n_own_nonleaf = (int)own_nl.size();
-            s->n_top_nonleaf = (int)top_nl.size();
-            s->n_own_lane = (int)lane.size();
-            if (cf < m) {   // stage of chain_first and the rank's columns there
-                int t = 0;
-                while (s->stage_off[t + 1] <= cf) ++t;
-                const int wdt = s->stage_off[t + 1] - s->stage_off[t];
-                if (s->stage_off[t] == cf && wdt == s->chain_stride && stage_range[t].second > stage_range[t].first) {
-                    s->own_chain = OwnMap{stage_range[t].second - stage_range[t].first, stage_range[t].first - cf, wdt};
-                    s->n_own_chain = (m - cf) / wdt * s->own_chain.w;
-                }
-            }
-        }
-        s->sharded = true;
-    }
+    TRY(create_validate(s, pb));
+    TRY(create_layout_and_tables(s, pb));
+    TRY(create_classes_and_iterates(s, pb));
+    TRY(create_sweep_plan(s, pb));
+    TRY(create_node_tiles(s, pb));
+    TRY(create_shard_plan(s, pb));
     *out = s;
     return RB_OK;
 #undef TRY
@@ -1836,6 +1907,7 @@ int rb_loop_begin(rb_solver *s, double alpha, int32_t max_iters, double tol, int
     hc->hist_capacity = hist_capacity;
     RB_CUDA(s, cudaMemcpyAsync(s->ctrl, hc, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
     RB_CUDA(s, cudaMemsetAsync(s->slots, 0, (size_t)L.batch * 6 * sizeof(double), st));
+    if (s->overlap_sync) RB_CUDA(s, cudaMemsetAsync(s->overlap_sync, 0, (size_t)2 * L.batch * sizeof(int), st));
     // Solver.chock iterates from the OLD iterate (solver.py:29-37); the current one is scratch from here on
     s->collapsed = false;
     s->in_loop = true;
@@ -1905,6 +1977,7 @@ int rb_loop_poll(rb_solver *s, int32_t *iters, int32_t *done, double *last_norms
     if (hc->status) {
         RB_CUDA(s, cudaMemsetAsync(&s->ctrl->status, 0, sizeof(int), s->stream));
         if (hc->status & 16) return fail(s, RB_ERR_CUDA, "subtree sharding: the peer-memory exchange timed out (a rank is gone)");
+        if (hc->status & 32) return fail(s, RB_ERR_CUDA, "launch overlap: a kernel waited ~0.2 s for the kernel in front of it");
         if (hc->status & 1) return fail(s, RB_ERR_NUMERIC, "Rectangle constraint - 'nan' value cannot be constrained");
         return fail(s, RB_ERR_NUMERIC, "non-finite value in the residuals");
     }
@@ -2280,6 +2353,18 @@ int rb_use_mma_sweeps(rb_solver *s, int32_t enable) {
 int rb_use_tree_kernels(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
     s->tree_mode = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
+    for (int i = 0; i < 2; ++i)
+        if (s->graph[i]) {
+            cudaGraphExecDestroy(s->graph[i]);
+            s->graph[i] = nullptr;
+        }
+    return RB_OK;
+}
+
+int rb_use_launch_overlap(rb_solver *s, int32_t enable) {
+    if (!s) return RB_ERR_INVALID;
+    if (s->in_loop) return fail(s, RB_ERR_STATE, "rb_use_launch_overlap() inside a loop");
+    s->allow_overlap = enable != 0;
     for (int i = 0; i < 2; ++i)
         if (s->graph[i]) {
             cudaGraphExecDestroy(s->graph[i]);

@@ -78,6 +78,14 @@ __device__ __forceinline__ void st_state(double *__restrict__ row, int t, const 
         }
     }
 }
+template <int NX, int NU>
+__device__ __forceinline__ void ld_state_cg(const double *row, int t, double (&v)[ChainDims<NX, NU>::QT][2]) {
+    using D = ChainDims<NX, NU>;
+#pragma unroll
+    for (int b = 0; b < D::QT; ++b)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) v[b][j] = 8 * b + 2 * t + j < NX ? __ldcg(row + 8 * b + 2 * t + j) : 0.0;
+}
 // input-sized row (length NU) <-> the slots nx.. of the accumulator layout (block RT0 + i)
 template <int NX, int NU>
 __device__ __forceinline__ void ld_input(const double *__restrict__ row, int t, double (&v)[ChainDims<NX, NU>::RN][2]) {
@@ -272,6 +280,32 @@ __device__ __forceinline__ void mma_rows(const double *w, AF a_of_row, double (&
     }
 }
 
+// ---- launch overlap with the fused tree kernel (programmatic dependent launch) ---------------------------------------------------
+// The backward walker, the fused tree kernel and the forward walker are a chain of three launches whose heads (launch latency,
+// descriptor / metadata / table staging: 3 - 5 us each) do not depend on the kernel before.  With programmatic dependent launch
+// the next kernel starts as soon as every CTA of this one is RUNNING (griddepcontrol.launch_dependents at the top), does its
+// staging next to it and then waits for the data itself: walk_count[instance] counts the tiles whose head q has been stored
+// (the subtree CTAs of the tree kernel wait for all of them), tree_done[instance] the subtree CTAs whose forward pass has
+// written the x of the chain heads (the forward walker waits for all of them).  The tree kernel's top CTA resets walk_count,
+// the next backward walk resets tree_done.  Null pointers = plain stream-ordered launches (no protocol).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// bounded wait (one lane): ~0.2 s, then status bit 32 instead of a hung GPU
+__device__ __forceinline__ void wait_count(const int *counter, int target, const Ctrl *ctrl) {
+    const long long t0 = clock64();
+    while (ld_acquire_gpu(counter) < target) {
+        __nanosleep(64);
+        if (clock64() - t0 > 400000000LL) {
+            atomicOr(const_cast<int *>(&ctrl->status), 32);
+            break;
+        }
+    }
+}
+
 // ---- backward:  r = ubar - B'q_child,  q = A'q_child - xbar - K'r    -------------------------------
 // BIG (nx + nu > 32): the fragments do not fit into registers.  One warp per CTA; the [A | B] fragments of the tile's
 // dynamics row are copied once into shared memory (lane-major, every lane reads only its own words: no barrier), the class
@@ -279,9 +313,12 @@ __device__ __forceinline__ void mma_rows(const double *w, AF a_of_row, double (&
 template <int NX, int NU, bool BIG>
 __global__ void __launch_bounds__(BIG ? 32 : 128) k_chain_mma_bwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
                                                       SweepLevel lv, const double *__restrict__ prim,
-                                                      double *__restrict__ q, double *__restrict__ r) {
+                                                      double *__restrict__ q, double *__restrict__ r, int *walk_count,
+                                                      int *tree_done) {
     using D = ChainDims<NX, NU>;
     extern __shared__ __align__(16) double mma_smem[];
+    pdl_launch_dependents();
+    if (tree_done && blockIdx.x == 0 && threadIdx.x == 0) tree_done[blockIdx.y] = 0;   // nobody waits on it any more (see above)
     const Layout &L = P.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
     const int tile = blockIdx.x * warps + warp;
@@ -392,13 +429,18 @@ __global__ void __launch_bounds__(BIG ? 32 : 128) k_chain_mma_bwd(const __grid_c
         }
         if (d == 0 && tm.valid) st_state<NX, NU>(Q + (long long)node * NX, t, qs);   // only the head's q leaves the chain
     }
+    if (walk_count) {   // publish: every lane's part of the head's q, then one count per tile
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(walk_count + blockIdx.y, 1);
+    }
 }
 
 // ---- forward:  u = K x + R~^-1 r,  x_child = A x + B u -------------------------------------------------------------------
 template <int NX, int NU, bool BIG>
 __global__ void __launch_bounds__(BIG ? 32 : 128) k_chain_mma_fwd(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
                                                       SweepLevel lv, double *__restrict__ prim, const double *__restrict__ r,
-                                                      int d_begin, int d_end) {
+                                                      int d_begin, int d_end, const int *tree_done, int tree_ctas) {
     // steps d_begin <= d < d_end of the walk (d = depth below the head of the chain): a launch starts from the x of depth
     // d_begin, which the level above (d_begin = 0) or the previous launch has written, so the walk can be cut into
     // pieces whose nodes' dual pass runs while the next piece walks on
@@ -441,14 +483,25 @@ __global__ void __launch_bounds__(BIG ? 32 : 128) k_chain_mma_fwd(const __grid_c
         }
         cp_async_commit();
     };
-    prefetch(d_begin);
-    prefetch(d_begin + 1);
     double w4[BIG ? 2 : F4];   // [A ; B]' of the chain's dynamics row, fragment (2 kb + j) * QT + ob
     if constexpr (!BIG) {
         if (lv.depth > 1) ld_frags<F4>(w4, P.m.fragABT, tm.dyns[1], lane);
     }
+    // launched next to the tree kernel (and, transitively, possibly next to the BACKWARD walker, whose r rows the prefetch below
+    // reads): its subtree CTAs count up once the x of the chain heads is written -- and they only get there after every tile of
+    // the backward walk has been counted
+    if (tree_done) {
+        if (lane == 0) wait_count(tree_done + blockIdx.y, tree_ctas, ctrl);
+        __syncwarp();
+    }
+    prefetch(d_begin);
+    prefetch(d_begin + 1);
     double xs[D::QT][2];
-    ld_state<NX, NU, false>(X + (long long)tm.nodes[d_begin * 8 + g] * NX, t, xs);   // written by the level above / the previous piece
+    if (tree_done) {
+        ld_state_cg<NX, NU>(X + (long long)tm.nodes[d_begin * 8 + g] * NX, t, xs);   // past the L1: written while this CTA ran
+    } else {
+        ld_state<NX, NU, false>(X + (long long)tm.nodes[d_begin * 8 + g] * NX, t, xs);   // written by the level above / the previous piece
+    }
 
     for (int d = d_begin; d < d_end && d + 1 < lv.depth && tm.clss[d] >= 0; ++d) {
         prefetch(d + 2);
@@ -959,7 +1012,10 @@ cudaError_t chain_mma_set_smem(int bytes) {
     cudaError_t e = cudaSuccess;
 #define RB_SET(NX, NU, BIG)                                                                                                       \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_bwd<NX, NU, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_fwd<NX, NU, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_fwd<NX, NU, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+    /* largest shared-memory carve-out: a CTA of the fused tree kernel (~158 KB) can then share the SM (launch overlap) */             \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_bwd<NX, NU, BIG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_fwd<NX, NU, BIG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     RB_MMA_DIMS(RB_SET)
 #undef RB_SET
 #define RB_SET(NX, NU)                                                                                                         \
@@ -974,7 +1030,7 @@ cudaError_t chain_mma_set_smem(int bytes) {
 }
 
 void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, const double *prim,
-                          double *q, double *r, bool w4) {
+                          double *q, double *r, bool w4, int *walk_count, int *tree_done) {
 #define RB_GO4(NX, NU)                                                                                                         \
     if (w4 && P.L.nx == NX && P.L.nu == NU) {                                                        \
         k_chain_mma_bwd_w4<NX, NU><<<dim3((lv.num_tiles + 3) / 4, P.L.batch), 4 * kWpt * 32,                                   \
@@ -985,15 +1041,32 @@ void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, co
 #undef RB_GO4
 #define RB_GO(NX, NU, BIG)                                                                                             \
     if (P.L.nx == NX && P.L.nu == NU) {                                                                           \
-        k_chain_mma_bwd<NX, NU, BIG><<<mma_grid(lv, P.L.batch, BIG), BIG ? 32 : 128, chain_mma_smem_bytes(NX, NU, lv.depth, true, false), st>>>(P, ctrl, lv, prim, q, r);     \
+        k_chain_mma_bwd<NX, NU, BIG><<<mma_grid(lv, P.L.batch, BIG), BIG ? 32 : 128, chain_mma_smem_bytes(NX, NU, lv.depth, true, false), st>>>(P, ctrl, lv, prim, q, r, walk_count, tree_done);     \
         return;                                                                                                   \
     }
     RB_MMA_DIMS(RB_GO)
 #undef RB_GO
 }
 
+// pdl: launch with programmatic stream serialization (the kernel may start while the previous one in the stream still runs; it
+// waits for tree_done itself)
+template <typename K, typename... A>
+static void launch_pdl(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t st, A... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 void launch_chain_mma_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, double *prim,
-                          const double *r, int d_begin, int d_end, bool w4) {
+                          const double *r, int d_begin, int d_end, bool w4, const int *tree_done, int tree_ctas) {
     if (d_end < 0) d_end = lv.depth;
 #define RB_GO4(NX, NU)                                                                                                         \
     if (w4 && P.L.nx == NX && P.L.nu == NU) {                                                        \
@@ -1005,7 +1078,11 @@ void launch_chain_mma_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, co
 #undef RB_GO4
 #define RB_GO(NX, NU, BIG)                                                                                             \
     if (P.L.nx == NX && P.L.nu == NU) {                                                                           \
-        k_chain_mma_fwd<NX, NU, BIG><<<mma_grid(lv, P.L.batch, BIG), BIG ? 32 : 128, chain_mma_smem_bytes(NX, NU, lv.depth, false, false), st>>>(P, ctrl, lv, prim, r, d_begin, d_end);        \
+        if (tree_done)                                                                                            \
+            launch_pdl(k_chain_mma_fwd<NX, NU, BIG>, mma_grid(lv, P.L.batch, BIG), BIG ? 32 : 128,                \
+                       chain_mma_smem_bytes(NX, NU, lv.depth, false, false), st, P, ctrl, lv, prim, r, d_begin, d_end, tree_done, tree_ctas); \
+        else                                                                                                      \
+            k_chain_mma_fwd<NX, NU, BIG><<<mma_grid(lv, P.L.batch, BIG), BIG ? 32 : 128, chain_mma_smem_bytes(NX, NU, lv.depth, false, false), st>>>(P, ctrl, lv, prim, r, d_begin, d_end, nullptr, 0);        \
         return;                                                                                                   \
     }
     RB_MMA_DIMS(RB_GO)

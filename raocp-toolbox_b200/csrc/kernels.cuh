@@ -147,7 +147,7 @@ void launch_tree_fwd(dim3 grid, int threads, size_t smem, cudaStream_t st, const
                      double *prim, const double *r);
 cudaError_t launch_tree_fused(int batch, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
                               const TreeLevel &lvs, const TreeLevel &lvt, double *prim, double *q, double *r, const double *x0,
-                              int *sync);
+                              int *sync, int *walk_count = nullptr, int walk_tiles = 0, int *tree_done = nullptr);
 bool tree_fused_fits(int nx, int nu, bool resident, int threads, size_t smem, int ctas);
 void launch_tree_top(int grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl, const TreeLevel &lv,
                      double *prim, double *q, double *r, const double *x0);
@@ -161,11 +161,13 @@ void chain_mma_frag_counts(int nx, int nu, int *f_ab, int *f_abt, int *f_k, int 
 void launch_chain_mma_frags(cudaStream_t st, const Tabs &M, int nx, int nu, int num_dyn, int num_cls, bool dynamics,
                             bool classes);
 // w4: walk a tile with four warps (one output block each) -- only where chain_mma_w4(nx, nu)
+// walk_count / tree_done (null = off): the launch-overlap protocol with the fused tree kernel (chain_mma.cu); one warp per tile only
 void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, const double *prim,
-                          double *q, double *r, bool w4 = false);
+                          double *q, double *r, bool w4 = false, int *walk_count = nullptr, int *tree_done = nullptr);
 // d_begin, d_end: the steps of the walk to run (depth below the chain heads); d_end < 0 = to the leaves
 void launch_chain_mma_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, double *prim,
-                          const double *r, int d_begin = 0, int d_end = -1, bool w4 = false);
+                          const double *r, int d_begin = 0, int d_end = -1, bool w4 = false, const int *tree_done = nullptr,
+                          int tree_ctas = 0);
 
 // ---- batch.cu: many instances of one small tree, batch-innermost ("panel") layout: the lanes of a warp are 32 instances ------
 bool batch_panel_supported(int nx, int nu);

@@ -766,8 +766,14 @@ __device__ __forceinline__ void load_peer_rows(double *dst, const double *src, i
 template <int NX, int NU, bool RES>
 __global__ void __launch_bounds__(512) k_tree_fused(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, TreeLevel lvs,
                                                    TreeLevel lvt, double *__restrict__ prim, double *__restrict__ q,
-                                                   double *__restrict__ r, const double *__restrict__ x0, int *__restrict__ sync) {
+                                                   double *__restrict__ r, const double *__restrict__ x0, int *__restrict__ sync,
+                                                   int *walk_count, int walk_tiles, int *tree_done) {
+    // walk_count / walk_tiles / tree_done (null = off): the launch-overlap protocol with the chain walkers (chain_mma.cu).  The
+    // kernel is then launched while the backward walker still runs: everything except the q of the chain heads is staged, the
+    // subtree CTAs wait for walk_count == walk_tiles before they read it, and count themselves into tree_done once the x of the
+    // chain heads is written (the forward walker, launched the same way behind this kernel, waits for that).
     extern __shared__ __align__(16) double tree_smem[];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 #ifdef RB_TRACE
     long long tr[10];
     int ntr = 0;
@@ -797,7 +803,7 @@ __global__ void __launch_bounds__(512) k_tree_fused(const __grid_constant__ Para
         stage_rows(xb + s.off[d] * nx, X + (long long)s.lo[d] * nx, s.w[d] * nx, vx);
         if (s.cls[s.off[d]] >= 0) stage_rows(ub + s.off[d] * nu, U + (long long)s.lo[d] * nu, s.w[d] * nu, vu);
     }
-    if (!is_top) stage_rows(qa, Q + (long long)s.ext_first * nx, s.ne * nx, vx);   // written by the previous launch
+    if (!is_top && !walk_count) stage_rows(qa, Q + (long long)s.ext_first * nx, s.ne * nx, vx);   // written by the previous launch
     const double *ct = P.m.ABcat, *ctt = P.m.ABcatT, *kt = P.m.K, *krt = P.m.KRcatT;
     if constexpr (RES) {
         double *ctab = cv.take((long long)lv.num_dyn * nx * nxu), *cttab = cv.take((long long)lv.num_dyn * nxu * nx);
@@ -815,6 +821,21 @@ __global__ void __launch_bounds__(512) k_tree_fused(const __grid_constant__ Para
     stage_wait();
     RB_STAMP();
     if (!is_top) {
+        if (walk_count) {   // the backward walker may still be running: wait for all of its tiles, then fetch the heads' q past the L1
+            if (threadIdx.x == 0) {
+                const long long t0 = clock64();
+                while (ld_acquire(walk_count + blockIdx.y) < walk_tiles) {
+                    __nanosleep(64);
+                    if (clock64() - t0 > 400000000LL) {   // ~0.2 s: report (status bit 32) instead of hanging the GPU
+                        atomicOr(const_cast<int *>(&ctrl->status), 32);
+                        break;
+                    }
+                }
+            }
+            __syncthreads();
+            load_peer_rows(qa, Q + (long long)s.ext_first * nx, s.ne * nx);
+            __syncthreads();
+        }
         tree_backward<NX, NU, RES>(L, s, lv, xb, ub, qa, qb, scratch, rbuf, ct, kt, Q, R);
         __threadfence();   // every thread publishes its part of the root's q before the CTA signals
         __syncthreads();
@@ -829,6 +850,11 @@ __global__ void __launch_bounds__(512) k_tree_fused(const __grid_constant__ Para
         load_peer_rows(qa, X + (long long)s.lo[0] * nx, s.w[0] * nx);   // x of the root, from the top CTA
         __syncthreads();
         tree_forward<NX, NU, RES>(L, s, lv, qa, qb, scratch, rbuf, ctt, krt, X, U);
+        if (tree_done) {   // the x of the chain heads below this subtree is written: the forward walker may read it
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(tree_done + blockIdx.y, 1);
+        }
         RB_STAMP();
 #ifdef RB_TRACE
         if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 63) && ctrl && ctrl->iters == 40)
@@ -836,8 +862,10 @@ __global__ void __launch_bounds__(512) k_tree_fused(const __grid_constant__ Para
                    tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4]);
 #endif
     } else {
-        if (threadIdx.x == 0)
+        if (threadIdx.x == 0) {
             while (ld_acquire(counter) < lvs.num_sub) {}
+            if (walk_count) walk_count[blockIdx.y] = 0;   // every subtree CTA is past its wait on the walker's tiles
+        }
         __syncthreads();
         RB_STAMP();
         load_peer_rows(qa, Q + (long long)s.ext_first * nx, s.ne * nx);
@@ -892,7 +920,8 @@ cudaError_t tree_kernels_set_smem(int bytes) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_bwd<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_fwd<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_top<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_fused<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_fused<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_fused<NX, NU, RES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 #define RB_SET(NX, NU) RB_SET1(NX, NU, true) RB_SET1(NX, NU, false)
     RB_TREE_DIMS(RB_SET)
     RB_SET(0, 0)
@@ -944,35 +973,42 @@ void launch_tree_top(int grid, int threads, size_t smem, cudaStream_t st, const 
 }
 
 // cooperative launch: all (num_sub + 1) x batch CTAs must be co-resident (the top CTA spins on the others)
+// walk_count != null: launched with programmatic stream serialization behind the backward chain walker instead (all CTAs of a
+// programmatic dependent become resident together once the walker's CTAs are running: the co-residency the hand-off needs)
 template <typename K>
 static cudaError_t launch_coop(K kernel, dim3 grid, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
                                const TreeLevel &lvs, const TreeLevel &lvt, double *prim, double *q, double *r, const double *x0,
-                               int *sync) {
+                               int *sync, int *walk_count, int walk_tiles, int *tree_done) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = 1;
+    if (walk_count) {
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+    } else {
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+    }
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, P, ctrl, lvs, lvt, prim, q, r, x0, sync);
+    return cudaLaunchKernelEx(&cfg, kernel, P, ctrl, lvs, lvt, prim, q, r, x0, sync, walk_count, walk_tiles, tree_done);
 }
 
 cudaError_t launch_tree_fused(int batch, int threads, size_t smem, cudaStream_t st, const Params &P, const Ctrl *ctrl,
                               const TreeLevel &lvs, const TreeLevel &lvt, double *prim, double *q, double *r, const double *x0,
-                              int *sync) {
+                              int *sync, int *walk_count, int walk_tiles, int *tree_done) {
     const dim3 grid(lvs.num_sub + 1, batch);
 #define RB_GO(NX, NU)                                                                                                       \
     if (P.L.nx == NX && P.L.nu == NU)                                                                                        \
-        return lvs.resident ? launch_coop(k_tree_fused<NX, NU, true>, grid, threads, smem, st, P, ctrl, lvs, lvt, prim, q, r, x0, sync) \
-                            : launch_coop(k_tree_fused<NX, NU, false>, grid, threads, smem, st, P, ctrl, lvs, lvt, prim, q, r, x0, sync);
+        return lvs.resident ? launch_coop(k_tree_fused<NX, NU, true>, grid, threads, smem, st, P, ctrl, lvs, lvt, prim, q, r, x0, sync, walk_count, walk_tiles, tree_done) \
+                            : launch_coop(k_tree_fused<NX, NU, false>, grid, threads, smem, st, P, ctrl, lvs, lvt, prim, q, r, x0, sync, walk_count, walk_tiles, tree_done);
     RB_TREE_DIMS(RB_GO)
 #undef RB_GO
-    return lvs.resident ? launch_coop(k_tree_fused<0, 0, true>, grid, threads, smem, st, P, ctrl, lvs, lvt, prim, q, r, x0, sync)
-                        : launch_coop(k_tree_fused<0, 0, false>, grid, threads, smem, st, P, ctrl, lvs, lvt, prim, q, r, x0, sync);
+    return lvs.resident ? launch_coop(k_tree_fused<0, 0, true>, grid, threads, smem, st, P, ctrl, lvs, lvt, prim, q, r, x0, sync, walk_count, walk_tiles, tree_done)
+                        : launch_coop(k_tree_fused<0, 0, false>, grid, threads, smem, st, P, ctrl, lvs, lvt, prim, q, r, x0, sync, walk_count, walk_tiles, tree_done);
 }
 
 // can the fused launch run?  (co-residency of all CTAs at this block size and shared-memory footprint)

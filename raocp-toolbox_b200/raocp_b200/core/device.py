@@ -217,6 +217,10 @@ class DeviceSolver:
     def use_graphs(self, enable=True):
         self._call("rb_use_graphs", 1 if enable else 0)
 
+    def use_launch_overlap(self, enable=True):
+        """pipelined loop: chain the walkers and the fused tree kernel by programmatic dependent launch (default) or not"""
+        self._call("rb_use_launch_overlap", 1 if enable else 0)
+
     def use_batch_panels(self, enable=True):
         """batch >= 64: fused loop in the batch-innermost panel layout (default) or with the instance-major kernels"""
         self._call("rb_use_batch_panels", 1 if enable else 0)
