@@ -548,6 +548,19 @@ def run_ours(args, rank, world, local_rank):
                  + ("" if args.no_risk_split else "; the risk block d1, d2 of these nodes runs under the sweeps") + ")")
         ktag = f"k_dual_chain<{flat.nx},{flat.nu}>" + ("" if not args.no_risk_split else "+risk")
         traffic, traffic_src = measured_traffic(args.workload, batch, not args.no_dedup, ktag)
+    elif len(cold_parts) == 3 and batch >= 64 and not args.no_panels:
+        # batch-innermost panel path (csrc/batch.cu): the dominant kernel is the x / u block of the nonleaf nodes' dual pass,
+        # k_bp_dual_xu -- x_i, u_i, tau_j of the primal and d7_i, d3_j, d4_j, d5_j, d6_j of the dual, every entry read once and
+        # written once (SURVEY 8d restricted to these entries); it also reads p+ and writes pbar (bytes_moved_model)
+        e_p = flat.m * (flat.nx + flat.nu) + (flat.n - 1)
+        e_d = flat.m * (flat.nx + flat.nu) + (flat.n - 1) * (flat.nx + flat.nu + 2)
+        b_kernel = 16 * batch * (e_p + e_d)
+        b_moved = 8 * batch * (3 * e_p + 2 * e_d)
+        t_kernel = float(cold_parts[0]) * 1e-3
+        kname = (f"k_bp_dual_xu<{flat.nx},{flat.nu}> (batch-innermost layout, lanes = instances): x / u block of the dual pass of all "
+                 f"{flat.m} nonleaf nodes x {batch} instances (L, dual half step, rectangle and second-order-cone projections, "
+                 "residual maxima, pbar of the next iteration)")
+        traffic, traffic_src = measured_traffic(args.workload, batch, not args.no_dedup, f"k_bp_dual_xu<{flat.nx},{flat.nu}>")
     else:
         b_kernel = b_moved = 8 * batch * (2 * flat.np_ + 2 * flat.nd_)
         t_kernel = float(cold_phases[-1]) * 1e-3
@@ -568,7 +581,10 @@ def run_ours(args, rank, world, local_rank):
         "launch_ms_all": {"primal_or_kernel_projection": float(cold_phases[0]),
                           "sweeps_in_launch_order": [float(v) for v in cold_phases[1:-1]],
                           "dual_and_check": float(cold_phases[-1]),
-                          "dual_kernels_branching_chain_leaves": [float(v) for v in cold_parts]},
+                          "dual_kernels_branching_chain_leaves": [float(v) for v in cold_parts],
+                          "note": "panel path (batch >= 64): kernel projection | backward stage launches | fused top + forward stage "
+                                  "launches | dual + check; the three dual kernels are x/u block, risk block, leaves"
+                          if batch >= 64 and not args.no_panels else "see DESIGN.md section 4"},
         "launch_ms_all_warm": {"primal_or_kernel_projection": float(phases[0]),
                                "sweeps_in_launch_order": [float(v) for v in phases[1:-1]],
                                "dual_and_check": float(phases[-1]),
