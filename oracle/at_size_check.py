@@ -35,8 +35,9 @@ def check_against_fixture(flat, g, sfx, k, p, d):
             if seg.size == 0:
                 continue
             amax, l1, l2, tot = stats[s]
-            if amax < 1e-300:
-                assert np.max(np.abs(seg)) == 0.0
+            if amax < 1e-300:   # the reference segment is exactly zero (e.g. the rectangle duals while nothing is active):
+                # ours may carry rounding dust of the Moreau step alpha (w - clip(w)); bound it against the vector's scale
+                assert np.max(np.abs(seg)) <= 1e-9 * max(1e-300, float(np.max(stats[:, 0])))
                 continue
             worst = max(worst, abs(np.max(np.abs(seg)) - amax) / amax, abs(np.sum(np.abs(seg)) - l1) / l1,
                         abs(np.sqrt(np.sum(seg * seg)) - l2) / l2, abs(np.sum(seg) - tot) / l1)

@@ -8,6 +8,6 @@ python - <<PY
 import json
 d=json.load(open("$O/${TAG}_cfg4.json"))
 print("inst-it/s cold", round(d["value"]), "warm", round(d["warm"]["value"]), "e2e", round(d["e2e"]["value"]), "batch-it/s", round(d["value"]/4096,1), "iteration frac", round(d["roofline"]["iteration"]["frac"],3))
-print({k:[round(x*1e3,1) for x in (v if isinstance(v,list) else [v])] for k,v in d["roofline"]["launch_ms_all"].items()})
+print({k:[round(x*1e3,1) for x in (v if isinstance(v,list) else [v])] for k,v in d["roofline"]["launch_ms_all"].items() if k != "note"})
 PY
 tail -2 $O/${TAG}.err

@@ -8,7 +8,7 @@ show() { python - "$1" "$2" <<PY
 import json,sys
 d=json.load(open(sys.argv[1]))
 print(sys.argv[2], "cold", round(d["value"]), "warm", round(d["warm"]["value"]), "e2e", round(d["e2e"]["value"]), "parity", d.get("parity_check",{}).get("pass"))
-print("   ", {k:[round(x*1e3,1) for x in (v if isinstance(v,list) else [v])] for k,v in d["roofline"]["launch_ms_all"].items()})
+print("   ", {k:[round(x*1e3,1) for x in (v if isinstance(v,list) else [v])] for k,v in d["roofline"]["launch_ms_all"].items() if k != "note"})
 PY
 }
 python bench.py --workload $WL --no-cpu --ttt-iters 0 > $O/${TAG}_bench.json 2> $O/${TAG}.err; show $O/${TAG}_bench.json default

@@ -87,6 +87,17 @@ __device__ __forceinline__ PanelPtr panel_view(const double *buf, long long stri
     return PanelPtr{const_cast<double *>(buf) + (long long)panel * stride * kPanel + lane};
 }
 
+// L2 prefetch of `rows` consecutive element rows (256 bytes each) of this warp's panel, starting at element e0: lane l takes
+// the l-th 128-byte line.  The dual kernels hold their bytes in flight in registers (255 of them: 8 warps per SM); prefetching the
+// NEXT node of the warp's loop into L2 while the current one is computed shortens the latency the registers have to cover, at
+// 1 instruction per 32 lines.
+__device__ __forceinline__ void prefetch_rows(const double *panel_base, long long e0, int rows, int lane) {
+#ifndef RB_BP_NO_PREFETCH
+    const char *p = reinterpret_cast<const char *>(panel_base + e0 * kPanel);
+    for (int l = lane; l < 2 * rows; l += 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + (long long)l * 128));
+#endif
+}
+
 // running maxima of |v| as bit patterns: NaN (0x7ff8...) sorts above +inf and sticks (common.cuh atomic_max_nonneg)
 __device__ __forceinline__ void upd(unsigned long long &m, double v) {
     const unsigned long long b = (unsigned long long)__double_as_longlong(fabs(v));
@@ -208,25 +219,48 @@ __device__ __forceinline__ void bp_bwd_node(const Params &P, const PanelPtr &p, 
     double acc[NX + NU];
 #pragma unroll
     for (int k = 0; k < NX + NU; ++k) acc[k] = 0.0;
-    for (int j = c0; j < c0 + cc; ++j) {
-        double qj[NX];
-        if (j >= L.m) {
+    // the node's own rows and the q of its children TWO AT A TIME, all loads issued before the first use (one memory round trip
+    // per pair of children instead of one per child: the wide stages were latency-bound at 2.8 TB/s)
+    double xbar[NX], ubar[NU];
 #pragma unroll
-            for (int l = 0; l < NX; ++l) qj[l] = -p[L.px + (long long)j * NX + l];
-        } else {
+    for (int k = 0; k < NX; ++k) xbar[k] = p[L.px + (long long)node * NX + k];
 #pragma unroll
-            for (int l = 0; l < NX; ++l) qj[l] = CG ? __ldcg(&Q[(long long)j * NX + l]) : Q[(long long)j * NX + l];
+    for (int a = 0; a < NU; ++a) ubar[a] = p[L.pu + (long long)node * NU + a];
+    for (int j0 = c0; j0 < c0 + cc; j0 += 2) {
+        const bool two = j0 + 1 < c0 + cc;
+        const int jb = two ? j0 + 1 : j0;
+        double qa[NX], qb[NX];
+#pragma unroll
+        for (int l = 0; l < NX; ++l) {
+            qa[l] = j0 >= L.m ? -p[L.px + (long long)j0 * NX + l] : (CG ? __ldcg(&Q[(long long)j0 * NX + l]) : Q[(long long)j0 * NX + l]);
+            qb[l] = jb >= L.m ? -p[L.px + (long long)jb * NX + l] : (CG ? __ldcg(&Q[(long long)jb * NX + l]) : Q[(long long)jb * NX + l]);
         }
-        const double *C = P.m.ABcat + (long long)T.dyn_idx[j] * NX * (NX + NU);   // row l = [A[l][:], B[l][:]]
 #pragma unroll
-        for (int l = 0; l < NX; ++l)
+        for (int h = 0; h < 2; ++h) {
+            if (h == 1 && !two) break;
+            const double *qj = h ? qb : qa;
+            const double *C = P.m.ABcat + (long long)T.dyn_idx[h ? jb : j0] * NX * (NX + NU);   // row l = [A[l][:], B[l][:]]
+            if constexpr ((NX + NU) % 2 == 0) {   // rows of an even number of doubles: 16-byte warp-uniform loads
 #pragma unroll
-            for (int k = 0; k < NX + NU; ++k) acc[k] = fma(__ldg(C + l * (NX + NU) + k), qj[l], acc[k]);
+                for (int l = 0; l < NX; ++l)
+#pragma unroll
+                    for (int k = 0; k < NX + NU; k += 2) {
+                        const double2 c = __ldg(reinterpret_cast<const double2 *>(C + l * (NX + NU) + k));
+                        acc[k] = fma(c.x, qj[l], acc[k]);
+                        acc[k + 1] = fma(c.y, qj[l], acc[k + 1]);
+                    }
+            } else {
+#pragma unroll
+                for (int l = 0; l < NX; ++l)
+#pragma unroll
+                    for (int k = 0; k < NX + NU; ++k) acc[k] = fma(__ldg(C + l * (NX + NU) + k), qj[l], acc[k]);
+            }
+        }
     }
     double rv[NU];
 #pragma unroll
     for (int a = 0; a < NU; ++a) {
-        rv[a] = p[L.pu + (long long)node * NU + a] - acc[NX + a];
+        rv[a] = ubar[a] - acc[NX + a];
         R[(long long)node * NU + a] = rv[a];
     }
     const double *K = P.m.K + (long long)T.cls[node] * NU * NX;   // [nu][nx]
@@ -235,7 +269,7 @@ __device__ __forceinline__ void bp_bwd_node(const Params &P, const PanelPtr &p, 
         double kr = 0.0;
 #pragma unroll
         for (int a = 0; a < NU; ++a) kr = fma(__ldg(K + a * NX + k), rv[a], kr);
-        Q[(long long)node * NX + k] = acc[k] - p[L.px + (long long)node * NX + k] - kr;
+        Q[(long long)node * NX + k] = acc[k] - xbar[k] - kr;
     }
 }
 
@@ -274,12 +308,28 @@ __device__ __forceinline__ void bp_fwd_node(const Params &P, const PanelPtr &p, 
     const int c0 = T.child_first[node], cc = T.child_count[node];
     for (int j = c0; j < c0 + cc; ++j) {
         const double *CT = P.m.ABcatT + (long long)T.dyn_idx[j] * (NX + NU) * NX;   // row l < nx: A[:][l]; row nx + a: B[:][a]
+        if constexpr (NX % 2 == 0) {
+            double xj[NX];
 #pragma unroll
-        for (int k = 0; k < NX; ++k) {
-            double x = 0.0;
+            for (int k = 0; k < NX; ++k) xj[k] = 0.0;
 #pragma unroll
-            for (int l = 0; l < NX + NU; ++l) x = fma(__ldg(CT + l * NX + k), v[l], x);
-            p[L.px + (long long)j * NX + k] = x;
+            for (int l = 0; l < NX + NU; ++l)
+#pragma unroll
+                for (int k = 0; k < NX; k += 2) {
+                    const double2 c = __ldg(reinterpret_cast<const double2 *>(CT + l * NX + k));
+                    xj[k] = fma(c.x, v[l], xj[k]);
+                    xj[k + 1] = fma(c.y, v[l], xj[k + 1]);
+                }
+#pragma unroll
+            for (int k = 0; k < NX; ++k) p[L.px + (long long)j * NX + k] = xj[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < NX; ++k) {
+                double x = 0.0;
+#pragma unroll
+                for (int l = 0; l < NX + NU; ++l) x = fma(__ldg(CT + l * NX + k), v[l], x);
+                p[L.px + (long long)j * NX + k] = x;
+            }
         }
     }
 }
@@ -325,6 +375,13 @@ __global__ void __launch_bounds__(kTopWarps * 32) k_bp_top(const __grid_constant
     const PanelPtr p = panel_view(prim, L.np_pad, panel, lane);
     const PanelPtr Q = panel_view(q, (long long)L.n * NX, panel, lane), R = panel_view(r, (long long)L.m * NU, panel, lane);
     const int b = panel * kPanel + lane;
+    {   // xbar / ubar of every node this warp will visit, into L2 now: each stage step is otherwise one cold DRAM round trip
+        const double *pb_ = prim + (long long)panel * L.np_pad * kPanel;
+        for (int node = warp; node < stage_off[t_top]; node += kTopWarps) {
+            prefetch_rows(pb_, L.px + (long long)node * NX, NX, lane);
+            prefetch_rows(pb_, L.pu + (long long)node * NU, NU, lane);
+        }
+    }
     for (int t = t_top - 1; t >= 0; --t) {
         for (int node = stage_off[t] + warp; node < stage_off[t + 1]; node += kTopWarps) bp_bwd_node<NX, NU, true>(P, p, Q, R, node);
         __syncthreads();
@@ -422,8 +479,23 @@ __global__ void __launch_bounds__(kBpWarps * 32, RB_BP_XU_MINB) k_bp_dual_xu(con
 #pragma unroll
     for (int i = 0; i < 6; ++i) mx.m[i] = 0ull;
     int bad = 0;
+    const double *po_b = p_old + (long long)panel * L.np_pad * kPanel, *pn_b = p_new + (long long)panel * L.np_pad * kPanel;
+    const double *do_b = d_old + (long long)panel * L.nd_pad * kPanel;
     for (int node = blockIdx.x * kBpWarps + warp; node < L.m; node += gridDim.x * kBpWarps) {
         const int c0 = T.child_first[node], cc = T.child_count[node];
+        {   // the next node of this warp into L2
+            const int nn = node + gridDim.x * kBpWarps;
+            if (nn < L.m) {
+                prefetch_rows(po_b, L.px + (long long)nn * NX, NX, lane);
+                prefetch_rows(pn_b, L.px + (long long)nn * NX, NX, lane);
+                prefetch_rows(po_b, L.pu + (long long)nn * NU, NU, lane);
+                prefetch_rows(pn_b, L.pu + (long long)nn * NU, NU, lane);
+                if (L.has_nl_rect) prefetch_rows(do_b, L.d7 + (long long)nn * S, S, lane);
+                const int nc0 = T.child_first[nn], ncc = T.child_count[nn];   // children are consecutive: one run of edges
+                prefetch_rows(do_b, L.d3 + (long long)(nc0 - 1) * NX, ncc * NX, lane);
+                prefetch_rows(do_b, L.d4 + (long long)(nc0 - 1) * NU, ncc * NU, lane);
+            }
+        }
         // v = [x; u] old and new; dl = p+ - p, hat = 2 p+ - p
         double vo[S], vn[S];
 #pragma unroll
@@ -441,7 +513,7 @@ __global__ void __launch_bounds__(kBpWarps * 32, RB_BP_XU_MINB) k_bp_dual_xu(con
             for (int k = 0; k < S; ++k) d7o[k] = dO[o7 + k];
 #pragma unroll
             for (int k = 0; k < S; ++k) {
-                const double w = (d7o[k] + alpha * (2.0 * vn[k] - vo[k])) * ia;
+                const double w = __dmul_rn(__fma_rn(alpha, 2.0 * vn[k] - vo[k], d7o[k]), ia);   // one rounding sequence: w - clip(w) is exactly 0 inside the box
                 const double dn = alpha * (w - box_clip(w, __ldg(lo + k), __ldg(hi + k), &bad));
                 dN[o7 + k] = dn;
                 const double dd = d7o[k] - dn;
@@ -625,9 +697,20 @@ __global__ void __launch_bounds__(kBpWarps * 32, RB_BP_LEAF_MINB) k_bp_dual_leaf
 #pragma unroll
     for (int i = 0; i < 6; ++i) mx.m[i] = 0ull;
     int bad = 0;
+    const double *po_b = p_old + (long long)panel * L.np_pad * kPanel, *pn_b = p_new + (long long)panel * L.np_pad * kPanel;
+    const double *do_b = d_old + (long long)panel * L.nd_pad * kPanel;
     for (int node = L.m + blockIdx.x * kBpWarps + warp; node < L.n; node += gridDim.x * kBpWarps) {
         const long long li = node - L.m;
         const int ci = T.leafcost_idx[li];
+        {   // the next leaf of this warp into L2
+            const int nn = node + gridDim.x * kBpWarps;
+            if (nn < L.n) {
+                prefetch_rows(po_b, L.px + (long long)nn * NX, NX, lane);
+                prefetch_rows(pn_b, L.px + (long long)nn * NX, NX, lane);
+                prefetch_rows(do_b, L.d11 + (long long)(nn - L.m) * NX, NX, lane);
+                if (L.has_leaf_rect) prefetch_rows(do_b, L.d14 + (long long)(nn - L.m) * NX, NX, lane);
+            }
+        }
         double xo[NX], xn[NX], w11[NX], f[NX];
         double ss = 0.0;
 #pragma unroll
@@ -656,7 +739,7 @@ __global__ void __launch_bounds__(kBpWarps * 32, RB_BP_LEAF_MINB) k_bp_dual_leaf
             double g1 = f[k] * dd, g2 = f[k] * x2, ld = f[k] * d11n;
             if (L.has_leaf_rect) {   // d14 = x, Rectangle.project
                 const double d14o = dO[L.d14 + li * NX + k];
-                const double w = (d14o + alpha * (2.0 * xn[k] - xo[k])) * ia;
+                const double w = __dmul_rn(__fma_rn(alpha, 2.0 * xn[k] - xo[k], d14o), ia);   // (see the d7 block)
                 const double d14n = alpha * (w - box_clip(w, __ldg(lo + k), __ldg(hi + k), &bad));
                 dN[L.d14 + li * NX + k] = d14n;
                 const double dd4 = d14o - d14n, x24 = dd4 * ia + (xn[k] - xo[k]);
