@@ -332,7 +332,7 @@ def run_ours(args, rank, world, local_rank):
     solver.cache.device_solver.use_batch_panels(not args.no_panels)
     solver.cache.device_solver.use_launch_overlap(args.overlap)
     solver.cache.device_solver.use_tree_kernels(args.tree_mode)
-    solver.cache.device_solver.use_mma_sweeps(0 if args.no_mma else (2 if args.mma_four_warps else 1))
+    solver.cache.device_solver.use_mma_sweeps(0 if args.no_mma else (2 if args.mma_four_warps else (3 if args.mma_one_warp else 1)))
     solver.cache.device_solver.use_pipeline(0 if args.no_pipeline else (3 if args.fwd_split else (4 if args.no_risk_split else 1)))
     dev = solver.cache.device_solver
     dev.synchronize()
@@ -695,6 +695,8 @@ def main():
     ap.add_argument("--tree-mode", type=int, default=2, choices=[0, 1, 2],
                     help="ablation: branching sweep levels with sweeps.cu (0), tree_sweeps.cu per level (1), fused with the top (2)")
     ap.add_argument("--no-mma", action="store_true", help="ablation: chains with one warp per chain instead of chain_mma.cu")
+    ap.add_argument("--mma-one-warp", action="store_true",
+                    help="ablation (wide rows, nx=64 nu=32): one warp per chain tile instead of four")
     ap.add_argument("--mma-four-warps", action="store_true",
                     help="ablation: tensor-core chain walkers with four warps per tile (one output block each)")
     ap.add_argument("--no-risk-split", action="store_true",

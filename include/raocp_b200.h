@@ -218,9 +218,10 @@ int rb_shard_info(const rb_solver *s, int32_t *cut_stage, int32_t *cut_first, in
 /* test hook: 0 = never use the lanes-per-node passes (lane.cu), always the warp-per-node tile kernels */
 int rb_use_lane_kernels(rb_solver *s, int32_t enable);
 /* test hook: 0 = walk chains with one warp per chain (sweeps.cu) instead of eight chains per tile on the FP64 tensor
- * cores (chain_mma.cu); 1 (default) = tensor cores, one warp per tile; 2 = tensor cores, four warps per tile where
- * instantiated (nx = 20, nu = 10; a measured ablation: not faster, see profiles/r2_kernel_evolution.md).  All implement
- * cache.py:259-288. */
+ * cores (chain_mma.cu); 1 (default) = tensor cores: one warp per tile, except wide rows (nx = 64, nu = 32), which are walked
+ * by four warps per tile, one tile per CTA; 2 = additionally four warps per tile for nx = 20, nu = 10 (a measured ablation:
+ * not faster, see profiles/r2_kernel_evolution.md); 3 = one warp per tile everywhere (ablation for the wide rows).  All
+ * implement cache.py:259-288. */
 int rb_use_mma_sweeps(rb_solver *s, int32_t enable);
 /* test hook for the branching levels and the top of the tree: 0 = global-memory stage kernels (sweeps.cu); 1 = the
  * shared-memory-resident subtree kernels (tree_sweeps.cu), one launch per level; 2 (default) = additionally the first

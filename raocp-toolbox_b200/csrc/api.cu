@@ -83,6 +83,7 @@ struct rb_solver {
     SweepLevel shard_lv[2]{};
     std::vector<int> chain_lo[2];   // host copy of lv.lo of chain levels (tile building)
     bool allow_mma = true;
+    bool mma_wide = true;    // wide rows: four warps per tile, one tile per CTA (rb_use_mma_sweeps(3): the one-warp BIG kernels)
     bool mma_w4 = false;     // rb_use_mma_sweeps(2): four warps per chain tile where instantiated (measured ablation, chain_mma.cu)
     int tree_mode = 2;       // 0: sweeps.cu stage kernels; 1: tree_sweeps.cu, one launch per level; 2: + level 0 fused with the top
     bool fuse_ok = false;    // the fused launch is possible (co-residency, same residency mode, one smem footprint)
@@ -265,6 +266,13 @@ void launch_primal(rb_solver *s, cudaStream_t st, int src, int dst, const int *n
     }
 }
 
+// four warps per chain tile: the default where rows are wide (chain_mma_wide: nx = 64, nu = 32; rb_use_mma_sweeps(3) = one warp,
+// ablation), an ablation where four tiles per SM already fill the tensor pipes (chain_mma_w4: rb_use_mma_sweeps(2))
+bool mma_four_warps(const rb_solver *s) {
+    const Layout &L = s->P.L;
+    return (s->mma_w4 && chain_mma_w4(L.nx, L.nu)) || (s->mma_wide && chain_mma_wide(L.nx, L.nu));
+}
+
 bool use_pipe(const rb_solver *s) { return use_lane(s) && s->allow_pipe && !s->sharded; }
 
 // many instances of a small tree: lanes = instances (batch.cu).  Needs diagonal cost square roots; the padding instances of
@@ -363,7 +371,7 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
     const bool fused = s->tree_mode > 1 && s->fuse_ok && !(s->allow_mma && pl.lv[0].num_tiles > 0);
     // launch overlap (programmatic dependent launch): backward walker -> fused tree kernel -> forward walker, inside the loop only
     // (ctrl carries the status word of the bounded waits), one-warp tensor-core walkers on the level right below the tree kernel
-    const bool w4 = s->mma_w4 && chain_mma_w4(L.nx, L.nu);
+    const bool w4 = mma_four_warps(s);
     const bool overlap = s->allow_overlap && fused && ctrl && s->overlap_sync && !evs && fwd_split == 0 && pl.num_levels == 2 &&
                          s->allow_mma && pl.lv[1].num_tiles > 0 && !w4;
     int *walk_count = overlap ? s->overlap_sync : nullptr, *tree_done = overlap ? s->overlap_sync + L.batch : nullptr;
@@ -379,9 +387,9 @@ int launch_sweeps(rb_solver *s, const Ctrl *ctrl, double *prim, cudaStream_t st,
     };
     auto fwd = [&](int v) {
         if (s->allow_mma && pl.lv[v].num_tiles > 0 && fwd_split > 0 && v == pl.num_levels - 1) {
-            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, 0, fwd_split, s->mma_w4 && chain_mma_w4(L.nx, L.nu));
+            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, 0, fwd_split, mma_four_warps(s));
             if (after_piece) after_piece();
-            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, fwd_split, -1, s->mma_w4 && chain_mma_w4(L.nx, L.nu));
+            launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, fwd_split, -1, mma_four_warps(s));
         } else if (s->allow_mma && pl.lv[v].num_tiles > 0)
             launch_chain_mma_fwd(st, s->P, ctrl, pl.lv[v], prim, s->r, 0, -1, w4, tree_done, s->tree_lv[0].num_sub);
         else if (tree && s->tree_lv[v].desc)
@@ -1715,7 +1723,7 @@ int enqueue_iteration_sharded(rb_solver *s, int src, cudaStream_t st) {
     launch_primal(s, st, src, dst, s->owned_nodes, s->n_owned);
     for (int v = pl.num_levels - 1; v >= 0; --v)
         if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
-            launch_chain_mma_bwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->q, s->r, s->mma_w4 && chain_mma_w4(L.nx, L.nu));
+            launch_chain_mma_bwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->q, s->r, mma_four_warps(s));
         else if (s->tree_mode > 0 && s->shard_tree_lv[v].desc)
             launch_tree_bwd(dim3(s->shard_tree_lv[v].num_sub, 1), 32 * s->shard_tree_lv[v].warps, s->tree_smem[1 + v], st, s->P,
                             s->ctrl, s->shard_tree_lv[v], s->prim[dst], s->q, s->r);
@@ -1733,7 +1741,7 @@ int enqueue_iteration_sharded(rb_solver *s, int src, cudaStream_t st) {
                          s->ctrl, pl, s->prim[dst], s->q, s->r, s->x0);
     for (int v = 0; v < pl.num_levels; ++v)
         if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
-            launch_chain_mma_fwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->r, 0, -1, s->mma_w4 && chain_mma_w4(L.nx, L.nu));
+            launch_chain_mma_fwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->r, 0, -1, mma_four_warps(s));
         else if (s->tree_mode > 0 && s->shard_tree_lv[v].desc)
             launch_tree_fwd(dim3(s->shard_tree_lv[v].num_sub, 1), 32 * s->shard_tree_lv[v].warps, s->tree_smem[1 + v], st, s->P,
                             s->ctrl, s->shard_tree_lv[v], s->prim[dst], s->r);
@@ -1757,7 +1765,7 @@ int enqueue_iteration_sharded_pipe(rb_solver *s, int src, cudaStream_t st, bool 
     const SweepPlan &pl = s->plan;
     const Layout &L = s->P.L;
     const int dst = 1 - src;
-    const bool w4 = s->mma_w4 && chain_mma_w4(L.nx, L.nu);
+    const bool w4 = mma_four_warps(s);
     const size_t per_warp = (size_t)(2 * L.nxu + 32) * sizeof(double);
     auto grid = [&](const SweepLevel &lv) { return dim3((lv.num_sub + lv.subs_per_cta - 1) / lv.subs_per_cta, 1); };
     auto threads = [&](const SweepLevel &lv) { return 32 * lv.warps_per_sub * lv.subs_per_cta; };
@@ -2342,6 +2350,7 @@ int rb_use_mma_sweeps(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
     s->allow_mma = enable != 0;
     s->mma_w4 = enable == 2;   // 2: four warps per tile where instantiated (ablation); other non-zero values: one warp per tile
+    s->mma_wide = enable != 3; // 3: wide rows with the one-warp BIG kernels (ablation)
     for (int i = 0; i < 2; ++i)
         if (s->graph[i]) {
             cudaGraphExecDestroy(s->graph[i]);

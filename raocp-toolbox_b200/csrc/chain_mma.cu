@@ -931,6 +931,273 @@ __global__ void __launch_bounds__(4 * kWpt * 32) k_chain_mma_fwd_w4(const __grid
 #endif
 }
 
+
+// ---- wide rows (nx, nu multiples of 32): four warps per tile, ONE tile per CTA ------------------------------------------------------
+// cfg5 (nx = 64, nu = 32) has 92 tiles: with one warp per tile (BIG kernels above) 92 SMs each run ONE tensor pipe out of four,
+// 256 / 288 DMMAs per step back to back (~27 cycles each: 3.5 us per step).  Here the twelve 8-wide slot blocks of a step's
+// products are dealt round robin to four warps -- warp w owns state blocks w, w + 4 and input block w: every warp has the same
+// share (64 / 72 DMMAs) and sits on its own sub-partition, so a tile uses all four tensor pipes of its SM.  Unlike the 20 x 10
+// case (four tiles per SM already fill the pipes; k_chain_mma_*_w4 is an ablation there) this is where splitting a tile pays.
+// The [A | B] / [A ; B]' fragments of a warp's blocks fit in registers (48 words per lane), the class fragments and rows come
+// through a per-warp cp.async ring two steps ahead, q / r / u / x are exchanged through shared memory in the accumulator layout
+// with two block barriers per step.
+template <int NX, int NU>
+struct WideRows {
+    using D = ChainDims<NX, NU>;
+    static_assert(NX % 32 == 0 && NU % 32 == 0, "state and input blocks are dealt four at a time");
+    static constexpr int SB = D::QT / 4, IB = D::RN / 4;                      // state / input blocks per warp
+    static constexpr int K1 = 2 * D::QT, K2 = 2 * D::RN, K34 = 2 * D::NT;     // reduction words of A'q | K'r | K x + R r, A x + B u
+    static constexpr int F1 = K1 * D::NT, F2 = K2 * D::QT, F3 = K34 * D::RN, F4 = K34 * D::QT;
+    static constexpr int LW_B = ring_lane_words(2 * SB + 2 * IB + SB * K2);   // xbar pairs | ubar pairs | K fragments
+    static constexpr int LW_F = ring_lane_words(2 * D::RN + IB * K34);        // r (all input blocks) | [K R~^-1] fragments
+    static constexpr int XW = (D::RN + D::QT) * 64;                           // exchange doubles: r / u blocks, state blocks
+    __host__ __device__ static constexpr size_t smem_bytes(int depth, bool backward) {
+        return (size_t)4 * kStages * 32 * (backward ? LW_B : LW_F) * sizeof(double) + (size_t)XW * sizeof(double) +
+               (size_t)(depth * 10 + 8) * sizeof(int);
+    }
+};
+
+template <int NX, int NU>
+__global__ void __launch_bounds__(128) k_chain_mma_bwd_wide(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
+                                                            SweepLevel lv, const double *__restrict__ prim,
+                                                            double *__restrict__ q, double *__restrict__ r) {
+    using D = ChainDims<NX, NU>;
+    using W = WideRows<NX, NU>;
+    constexpr int SB = W::SB, IB = W::IB, LW = W::LW_B;
+    extern __shared__ __align__(16) double mma_smem[];
+    const Layout &L = P.L;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    if (tile >= lv.num_tiles) return;
+    double *ring = mma_smem + ((size_t)w * kStages * 32 + lane) * LW;
+    double2 *xr = reinterpret_cast<double2 *>(mma_smem + (size_t)4 * kStages * 32 * LW);   // [RN][32]
+    double2 *xq = xr + D::RN * 32;                                                        // [QT][32]
+    TileMeta tm;
+    const bool live = stage_meta(lv, ctrl, tile, 0, lane, reinterpret_cast<int *>(mma_smem + (size_t)4 * kStages * 32 * LW + W::XW), tm);
+    __syncthreads();
+    if (!live) return;
+    const int t = tm.t, g = tm.g;
+    const double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
+    double *Q = q + (long long)blockIdx.y * L.n * NX, *R = r + (long long)blockIdx.y * L.m * NU;
+    auto prefetch = [&](int d) {   // one commit group per step, possibly empty
+        if (d >= 0) {
+            double *dst = ring + (d % kStages) * 32 * LW;
+            const int node = tm.nodes[d * 8 + g], cls = tm.clss[d];
+#pragma unroll
+            for (int i = 0; i < SB; ++i) cp_async<16>(dst + 2 * i, X + (long long)node * NX + 8 * (w + 4 * i) + 2 * t);
+            if (cls >= 0) {
+#pragma unroll
+                for (int i = 0; i < IB; ++i) cp_async<16>(dst + 2 * SB + 2 * i, U + (long long)node * NU + 8 * (w + 4 * i) + 2 * t);
+#pragma unroll
+                for (int i = 0; i < SB; ++i)
+#pragma unroll
+                    for (int k = 0; k < W::K2; k += 2)
+                        cp_async<16>(dst + 2 * SB + 2 * IB + i * W::K2 + k, frag_addr<W::F2>(P.m.fragK4, cls, lane, (w + 4 * i) * W::K2 + k));
+            }
+        }
+        cp_async_commit();
+    };
+    int d = lv.depth - 1;
+    prefetch(d);
+    prefetch(d - 1);
+    // columns of [A | B] for this warp's blocks: state blocks w + 4 i (i < SB), then input blocks RT0 + w + 4 i (i < IB)
+    double w1[SB + IB][W::K1];
+#pragma unroll
+    for (int b = 0; b < SB + IB; ++b) {
+        const int ob = b < SB ? w + 4 * b : D::RT0 + w + 4 * (b - SB);
+#pragma unroll
+        for (int k = 0; k < W::K1; k += 2) {
+            const double2 v = lv.depth > 1 ? __ldg(reinterpret_cast<const double2 *>(frag_addr<W::F1>(P.m.fragAB4, tm.dyns[1], lane, ob * W::K1 + k)))
+                                           : make_double2(0.0, 0.0);
+            w1[b][k] = v.x;
+            w1[b][k + 1] = v.y;
+        }
+    }
+    double qs[D::QT][2];
+#pragma unroll
+    for (int b = 0; b < D::QT; ++b) qs[b][0] = qs[b][1] = 0.0;
+
+    for (; d >= 0; --d) {
+        prefetch(d - 2);
+        cp_async_wait<2>();   // the copies of step d have landed
+        const double *src = ring + (d % kStages) * 32 * LW;
+        const int node = tm.nodes[d * 8 + g];
+        double qp[SB][2];
+        if (tm.clss[d] < 0) {   // leaf: q = -xbar
+#pragma unroll
+            for (int i = 0; i < SB; ++i) {
+                qp[i][0] = -src[2 * i];
+                qp[i][1] = -src[2 * i + 1];
+            }
+        } else {
+            double E[SB + IB][2];
+#pragma unroll
+            for (int b = 0; b < SB + IB; ++b) E[b][0] = E[b][1] = 0.0;
+#pragma unroll
+            for (int k = 0; k < W::K1; ++k)   // SB + IB independent accumulator chains
+#pragma unroll
+                for (int b = 0; b < SB + IB; ++b) dmma(E[b], qs[k >> 1][k & 1], w1[b][k]);
+#pragma unroll
+            for (int i = 0; i < IB; ++i) {   // r = ubar - B'q; -r feeds K'r
+                const double r0 = src[2 * SB + 2 * i] - E[SB + i][0], r1 = src[2 * SB + 2 * i + 1] - E[SB + i][1];
+                if (tm.valid) *reinterpret_cast<double2 *>(R + (long long)node * NU + 8 * (w + 4 * i) + 2 * t) = make_double2(r0, r1);
+                xr[(w + 4 * i) * 32 + lane] = make_double2(-r0, -r1);
+            }
+#pragma unroll
+            for (int i = 0; i < SB; ++i) {
+                qp[i][0] = E[i][0] - src[2 * i];
+                qp[i][1] = E[i][1] - src[2 * i + 1];
+            }
+            __syncthreads();
+            double nr[W::K2];
+#pragma unroll
+            for (int i = 0; i < D::RN; ++i) {
+                const double2 v = xr[i * 32 + lane];
+                nr[2 * i] = v.x;
+                nr[2 * i + 1] = v.y;
+            }
+            const double *w2 = src + 2 * SB + 2 * IB;
+#pragma unroll
+            for (int k = 0; k < W::K2; ++k)   // q = A'q - xbar - K'r: SB independent chains
+#pragma unroll
+                for (int i = 0; i < SB; ++i) dmma(qp[i], nr[k], w2[i * W::K2 + k]);
+        }
+#pragma unroll
+        for (int i = 0; i < SB; ++i) xq[(w + 4 * i) * 32 + lane] = make_double2(qp[i][0], qp[i][1]);
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < D::QT; ++b) {
+            const double2 v = xq[b * 32 + lane];
+            qs[b][0] = v.x;
+            qs[b][1] = v.y;
+        }
+        if (d == 0 && tm.valid) {   // only the head's q leaves the chain
+#pragma unroll
+            for (int i = 0; i < SB; ++i)
+                *reinterpret_cast<double2 *>(Q + (long long)node * NX + 8 * (w + 4 * i) + 2 * t) = make_double2(qp[i][0], qp[i][1]);
+        }
+        __syncthreads();   // xq / xr are rewritten in the next step
+    }
+}
+
+template <int NX, int NU>
+__global__ void __launch_bounds__(128) k_chain_mma_fwd_wide(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl,
+                                                            SweepLevel lv, double *__restrict__ prim, const double *__restrict__ r,
+                                                            int d_begin, int d_end) {
+    using D = ChainDims<NX, NU>;
+    using W = WideRows<NX, NU>;
+    constexpr int SB = W::SB, IB = W::IB, LW = W::LW_F;
+    extern __shared__ __align__(16) double mma_smem[];
+    const Layout &L = P.L;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x;
+    if (tile >= lv.num_tiles) return;
+    double *ring = mma_smem + ((size_t)w * kStages * 32 + lane) * LW;
+    double2 *xu = reinterpret_cast<double2 *>(mma_smem + (size_t)4 * kStages * 32 * LW);   // [RN][32]
+    double2 *xq = xu + D::RN * 32;                                                        // [QT][32]
+    TileMeta tm;
+    const bool live = stage_meta(lv, ctrl, tile, 0, lane, reinterpret_cast<int *>(mma_smem + (size_t)4 * kStages * 32 * LW + W::XW), tm);
+    __syncthreads();
+    if (!live) return;
+    const int t = tm.t, g = tm.g;
+    double *X = prim + (long long)blockIdx.y * L.np_pad + L.px, *U = prim + (long long)blockIdx.y * L.np_pad + L.pu;
+    const double *R = r + (long long)blockIdx.y * L.m * NU;
+    auto prefetch = [&](int d) {
+        if (d < lv.depth) {
+            const int cls = tm.clss[d];
+            if (cls >= 0) {
+                double *dst = ring + (d % kStages) * 32 * LW;
+                const double *row = R + (long long)tm.nodes[d * 8 + g] * NU;
+#pragma unroll
+                for (int i = 0; i < D::RN; ++i) cp_async<16>(dst + 2 * i, row + 8 * i + 2 * t);
+#pragma unroll
+                for (int i = 0; i < IB; ++i)
+#pragma unroll
+                    for (int k = 0; k < W::K34; k += 2)
+                        cp_async<16>(dst + 2 * D::RN + i * W::K34 + k, frag_addr<W::F3>(P.m.fragKR4, cls, lane, (w + 4 * i) * W::K34 + k));
+            }
+        }
+        cp_async_commit();
+    };
+    prefetch(d_begin);
+    prefetch(d_begin + 1);
+    double w4[SB][W::K34];   // columns of [A ; B]' for this warp's state blocks
+#pragma unroll
+    for (int i = 0; i < SB; ++i)
+#pragma unroll
+        for (int k = 0; k < W::K34; k += 2) {
+            const double2 v = lv.depth > 1 ? __ldg(reinterpret_cast<const double2 *>(frag_addr<W::F4>(P.m.fragABT4, tm.dyns[1], lane, (w + 4 * i) * W::K34 + k)))
+                                           : make_double2(0.0, 0.0);
+            w4[i][k] = v.x;
+            w4[i][k + 1] = v.y;
+        }
+    double xs[D::QT][2];
+    ld_state<NX, NU, false>(X + (long long)tm.nodes[d_begin * 8 + g] * NX, t, xs);   // written by the level above / the previous piece
+
+    for (int d = d_begin; d < d_end && d + 1 < lv.depth && tm.clss[d] >= 0; ++d) {
+        prefetch(d + 2);
+        cp_async_wait<2>();
+        const double *src = ring + (d % kStages) * 32 * LW;
+        const int node = tm.nodes[d * 8 + g], child = tm.nodes[(d + 1) * 8 + g];
+        // u = [K R~^-1] [x ; r] on this warp's input blocks; the reduction in two independent halves per block
+        double ua[IB][2], ub[IB][2];
+#pragma unroll
+        for (int i = 0; i < IB; ++i) ua[i][0] = ua[i][1] = ub[i][0] = ub[i][1] = 0.0;
+        const double *w3 = src + 2 * D::RN;
+#pragma unroll
+        for (int kb = 0; kb < D::NT; ++kb)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double v = kb < D::QT ? xs[kb < D::QT ? kb : 0][j] : src[2 * (kb >= D::QT ? kb - D::QT : 0) + j];
+#pragma unroll
+                for (int i = 0; i < IB; ++i) {
+                    if (kb & 1) dmma(ub[i], v, w3[i * W::K34 + 2 * kb + j]);
+                    else dmma(ua[i], v, w3[i * W::K34 + 2 * kb + j]);
+                }
+            }
+#pragma unroll
+        for (int i = 0; i < IB; ++i) {
+            ua[i][0] += ub[i][0];
+            ua[i][1] += ub[i][1];
+            if (tm.valid) *reinterpret_cast<double2 *>(U + (long long)node * NU + 8 * (w + 4 * i) + 2 * t) = make_double2(ua[i][0], ua[i][1]);
+            xu[(w + 4 * i) * 32 + lane] = make_double2(ua[i][0], ua[i][1]);
+        }
+        __syncthreads();
+        double uu[W::K2];
+#pragma unroll
+        for (int i = 0; i < D::RN; ++i) {
+            const double2 v = xu[i * 32 + lane];
+            uu[2 * i] = v.x;
+            uu[2 * i + 1] = v.y;
+        }
+        // x_child = [A B] [x ; u] on this warp's state blocks
+        double xn[SB][2];
+#pragma unroll
+        for (int i = 0; i < SB; ++i) xn[i][0] = xn[i][1] = 0.0;
+#pragma unroll
+        for (int kb = 0; kb < D::NT; ++kb)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const double v = kb < D::QT ? xs[kb < D::QT ? kb : 0][j] : uu[2 * (kb >= D::QT ? kb - D::QT : 0) + j];
+#pragma unroll
+                for (int i = 0; i < SB; ++i) dmma(xn[i], v, w4[i][2 * kb + j]);
+            }
+#pragma unroll
+        for (int i = 0; i < SB; ++i) {
+            if (tm.valid) *reinterpret_cast<double2 *>(X + (long long)child * NX + 8 * (w + 4 * i) + 2 * t) = make_double2(xn[i][0], xn[i][1]);
+            xq[(w + 4 * i) * 32 + lane] = make_double2(xn[i][0], xn[i][1]);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int b = 0; b < D::QT; ++b) {
+            const double2 v = xq[b * 32 + lane];
+            xs[b][0] = v.x;
+            xs[b][1] = v.y;
+        }
+        __syncthreads();   // xq / xu are rewritten in the next step
+    }
+}
+
 }  // namespace
 
 // ---- host side --------------------------------------------------------------------------------------------------------------
@@ -943,6 +1210,16 @@ bool chain_mma_w4(int nx, int nu) {
 #define RB_HAS(NX, NU) \
     if (nx == NX && nu == NU) return true;
     RB_MMA_W4_DIMS(RB_HAS)
+#undef RB_HAS
+    return false;
+}
+
+// (nx, nu) with wide rows walked by four warps per tile, one tile per CTA (k_chain_mma_*_wide): the default for these sizes
+#define RB_MMA_WIDE_DIMS(X) X(64, 32)
+bool chain_mma_wide(int nx, int nu) {
+#define RB_HAS(NX, NU) \
+    if (nx == NX && nu == NU) return true;
+    RB_MMA_WIDE_DIMS(RB_HAS)
 #undef RB_HAS
     return false;
 }
@@ -998,6 +1275,10 @@ static dim3 mma_grid(const SweepLevel &lv, int batch, bool big) {
 }
 // dynamic shared memory of a CTA (4 warps, or 1 if BIG): the cp.async rings (+ the dynamics fragments if BIG) + the tile metadata
 size_t chain_mma_smem_bytes(int nx, int nu, int depth, bool backward, bool w4) {
+#define RB_WIDE(NX, NU) \
+    if (w4 && nx == NX && nu == NU) return WideRows<NX, NU>::smem_bytes(depth, backward);
+    RB_MMA_WIDE_DIMS(RB_WIDE)
+#undef RB_WIDE
 #define RB_W4(NX, NU) \
     if (w4 && nx == NX && nu == NU) return Wide4<NX, NU>::smem_bytes(depth, backward);
     RB_MMA_W4_DIMS(RB_W4)
@@ -1026,11 +1307,26 @@ cudaError_t chain_mma_set_smem(int bytes) {
     }
     RB_MMA_W4_DIMS(RB_SET)
 #undef RB_SET
+#define RB_SET(NX, NU)                                                                                                         \
+    if (e == cudaSuccess) {                                                                                                    \
+        const int need = (int)std::max(WideRows<NX, NU>::smem_bytes(64, true), WideRows<NX, NU>::smem_bytes(64, false));       \
+        e = cudaFuncSetAttribute(k_chain_mma_bwd_wide<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, need);             \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_chain_mma_fwd_wide<NX, NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, need); \
+    }
+    RB_MMA_WIDE_DIMS(RB_SET)
+#undef RB_SET
     return e;
 }
 
 void launch_chain_mma_bwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, const double *prim,
                           double *q, double *r, bool w4, int *walk_count, int *tree_done) {
+#define RB_GOW(NX, NU)                                                                                                         \
+    if (w4 && P.L.nx == NX && P.L.nu == NU) {                                                                                  \
+        k_chain_mma_bwd_wide<NX, NU><<<dim3(lv.num_tiles, P.L.batch), 128, WideRows<NX, NU>::smem_bytes(lv.depth, true), st>>>(P, ctrl, lv, prim, q, r); \
+        return;                                                                                                                \
+    }
+    RB_MMA_WIDE_DIMS(RB_GOW)
+#undef RB_GOW
 #define RB_GO4(NX, NU)                                                                                                         \
     if (w4 && P.L.nx == NX && P.L.nu == NU) {                                                        \
         k_chain_mma_bwd_w4<NX, NU><<<dim3((lv.num_tiles + 3) / 4, P.L.batch), 4 * kWpt * 32,                                   \
@@ -1068,6 +1364,13 @@ static void launch_pdl(K kernel, dim3 grid, int threads, size_t smem, cudaStream
 void launch_chain_mma_fwd(cudaStream_t st, const Params &P, const Ctrl *ctrl, const SweepLevel &lv, double *prim,
                           const double *r, int d_begin, int d_end, bool w4, const int *tree_done, int tree_ctas) {
     if (d_end < 0) d_end = lv.depth;
+#define RB_GOW(NX, NU)                                                                                                         \
+    if (w4 && P.L.nx == NX && P.L.nu == NU) {                                                                                  \
+        k_chain_mma_fwd_wide<NX, NU><<<dim3(lv.num_tiles, P.L.batch), 128, WideRows<NX, NU>::smem_bytes(lv.depth, false), st>>>(P, ctrl, lv, prim, r, d_begin, d_end); \
+        return;                                                                                                                \
+    }
+    RB_MMA_WIDE_DIMS(RB_GOW)
+#undef RB_GOW
 #define RB_GO4(NX, NU)                                                                                                         \
     if (w4 && P.L.nx == NX && P.L.nu == NU) {                                                        \
         k_chain_mma_fwd_w4<NX, NU><<<dim3((lv.num_tiles + 3) / 4, P.L.batch), 4 * kWpt * 32,                                   \

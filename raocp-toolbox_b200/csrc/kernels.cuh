@@ -155,6 +155,7 @@ void launch_tree_top(int grid, int threads, size_t smem, cudaStream_t st, const 
 // ---- chain_mma.cu: chain levels on the FP64 tensor cores, 8 chains per warp ---------------------------------------------------
 bool chain_mma_supported(int nx, int nu);
 bool chain_mma_w4(int nx, int nu);   // four warps per tile are instantiated for these sizes (k_chain_mma_*_w4)
+bool chain_mma_wide(int nx, int nu); // wide rows: four warps per tile, one tile per CTA (k_chain_mma_*_wide), the default there
 size_t chain_mma_smem_bytes(int nx, int nu, int depth, bool backward, bool w4 = false);
 cudaError_t chain_mma_set_smem(int bytes);
 void chain_mma_frag_counts(int nx, int nu, int *f_ab, int *f_abt, int *f_k, int *f_kr);
