@@ -117,6 +117,56 @@ class RAOCP:
         self._leaf_costs[m:] = [cost] * (self._num_nodes - m)
         return self
 
+    # -- per-node data (beyond the reference's builder, SURVEY 8f rank 3: non-Markovian dynamics / node-wise costs and risks).  The
+    #    device path needs nothing new: dynamics, costs and risk levels are tables indexed per node, de-duplicated by identity --
+    def with_nodewise_dynamics(self, dynamics_of_nodes):
+        """one Dynamics per node 1 .. n-1 (entry j-1 -> the edge into node j); shapes must agree"""
+        dyn = list(dynamics_of_nodes)
+        if len(dyn) != self._num_nodes - 1:
+            raise ValueError(f"expected {self._num_nodes - 1} dynamics (nodes 1 .. n-1), got {len(dyn)}")
+        for d in dyn:
+            if d.state_dynamics.shape != dyn[0].state_dynamics.shape or d.control_dynamics.shape != dyn[0].control_dynamics.shape:
+                raise ValueError("node-wise dynamics matrices are different shapes")
+        self._dynamics[1:] = dyn
+        return self
+
+    def with_nodewise_nonleaf_costs(self, costs_of_nodes):
+        """one nonleaf cost per node 1 .. n-1 (indexed by the child, like the Markovian builder)"""
+        costs = list(costs_of_nodes)
+        if len(costs) != self._num_nodes - 1:
+            raise ValueError(f"expected {self._num_nodes - 1} nonleaf costs (nodes 1 .. n-1), got {len(costs)}")
+        for cost in costs:
+            if not cost.node_type.is_nonleaf:
+                raise Exception("Nonleaf cost provided is not nonleaf")
+        self._nonleaf_costs[1:] = costs
+        return self
+
+    def with_nodewise_leaf_costs(self, costs_of_leaves):
+        costs = list(costs_of_leaves)
+        m = self._num_nonleaf_nodes
+        if len(costs) != self._num_nodes - m:
+            raise ValueError(f"expected {self._num_nodes - m} leaf costs, got {len(costs)}")
+        for cost in costs:
+            if not cost.node_type.is_leaf:
+                raise Exception("Leaf cost provided is not leaf")
+        self._leaf_costs[m:] = costs
+        return self
+
+    def with_nodewise_risks(self, risks_of_nonleaf_nodes):
+        """one risk measure per nonleaf node (e.g. AVaR with a node-dependent level)"""
+        risks = list(risks_of_nonleaf_nodes)
+        if len(risks) != self._num_nonleaf_nodes:
+            raise ValueError(f"expected {self._num_nonleaf_nodes} risks, got {len(risks)}")
+        out = []
+        for i, risk in enumerate(risks):
+            if not risk.is_risk:
+                raise Exception("Risk provided is not of risk type")
+            risk_i = copy.copy(risk)
+            risk_i.probs = self._tree.conditional_probabilities_of_children(i)
+            out.append(risk_i)
+        self._risks = out
+        return self
+
     def _check_dynamics_before_constraints(self):
         if self._num_nodes < 2 or self._dynamics[1] is None:
             raise Exception("Constraints provided before dynamics - dynamics must be provided first")
