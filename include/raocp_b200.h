@@ -188,6 +188,9 @@ int rb_use_pipeline(rb_solver *s, int32_t enable);
  * chain_nodes) through k_dual_chain; chain_nodes = 0 when the loop is not pipelined or has no chain kernel for (nx, nu) */
 int rb_pipeline_info(const rb_solver *s, int32_t *early_nodes, int32_t *chain_first, int32_t *chain_nodes);
 int rb_use_graphs(rb_solver *s, int32_t enable); /* 1 (default): one CUDA graph per iteration; 0: plain launches */
+/* 1 (default): every pipelined iteration starts with an L2 prefetch of the read-only operator tables on the side stream
+ * (k_prefetch_ranges); 0: off (ablation). */
+int rb_use_table_prefetch(rb_solver *s, int32_t enable);
 /* 1: in the pipelined loop the backward chain walker, the fused tree kernel and the forward chain walker are chained by
  * programmatic dependent launch -- each starts while the one before it still runs, stages its tables and waits for the data
  * itself (csrc/chain_mma.cu "launch overlap").  Measured ablation, results identical, not faster on cfg3 (9 586 vs 9 750 it/s):

@@ -90,6 +90,11 @@ struct rb_solver {
     size_t fuse_smem = 0;
     int fuse_threads = 0;
     int *tree_sync = nullptr;
+    // read-only operator tables (dynamics, K, R~^-1, tensor-core fragments): prefetched into L2 at the head of every pipelined
+    // iteration by k_prefetch_ranges (ops.cu) -- a few MB that every sweep kernel otherwise fetches through dependent misses
+    std::vector<PrefetchRange> h_tables;
+    PrefetchRange *d_tables = nullptr;
+    bool allow_table_prefetch = true;
     int *overlap_sync = nullptr;   // [2 * batch]: walk_count, tree_done of the launch-overlap protocol (chain_mma.cu)
     bool allow_overlap = false;   // rb_use_launch_overlap(1): measured ablation (not faster on cfg3: 9 586 vs 9 750 it/s cold)
     TreeLevel tree_top{}, tree_lv[2]{}, shard_tree_lv[2]{};
@@ -348,7 +353,9 @@ int iter_launches(const rb_solver *s) {
         return 1 + 2 * (s->P.L.num_stages - 1 - top) + (top > 0 ? 1 : 0) + 3 + 1;
     }
     const int sweeps = 1 + 2 * pl.num_levels - (sweeps_fused(s) ? 2 : 0);
-    if (use_pipe(s)) return 1 + sweeps + pipe_dual_launches(s) + 1 + (s->risk_split && pipe_split(s).cf < s->P.L.m ? 1 : 0);
+    if (use_pipe(s))
+        return 1 + sweeps + pipe_dual_launches(s) + 1 + (s->risk_split && pipe_split(s).cf < s->P.L.m ? 1 : 0) +
+               (s->allow_table_prefetch && !s->h_tables.empty() ? 1 : 0);
     return 1 + sweeps + 1 + 1;
 }
 
@@ -1277,6 +1284,32 @@ int rb_offline(rb_solver *s) {
     }
     int rc = check_status(s);
     if (rc != RB_OK) return rc;
+    if (!s->d_tables) {   // the ranges k_prefetch_ranges walks (all read-only after this point)
+        const Layout &L = s->P.L;
+        const Tabs &M = s->P.m;
+        const size_t nx = L.nx, nu = L.nu, nxu = L.nxu, D = s->num_dyn, C = s->num_cls;
+        auto add = [&](const double *p, size_t doubles) {
+            if (p && doubles) s->h_tables.push_back(PrefetchRange{reinterpret_cast<const char *>(p), (long long)(doubles * sizeof(double))});
+        };
+        add(M.ABcat, D * nx * nxu);
+        add(M.ABcatT, D * nxu * nx);
+        add(M.K, C * nu * nx);
+        add(M.KRcatT, C * nxu * nu);
+        if (M.fragK) {
+            int f_ab, f_abt, f_k, f_kr;
+            chain_mma_frag_counts(L.nx, L.nu, &f_ab, &f_abt, &f_k, &f_kr);
+            add(M.fragAB, 2 * D * f_ab * 32);
+            add(M.fragABT, 2 * D * f_abt * 32);
+            add(M.fragK, 2 * C * f_k * 32);
+            add(M.fragKR, 2 * C * f_kr * 32);
+        }
+        // worth a launch only when the tables are megabytes (cfg5: 5.7 MB, +4 % cold; cfg3: 0.5 MB, -2 %: measured, gpurun_out r2z)
+        long long total = 0;
+        for (const auto &t : s->h_tables) total += t.bytes;
+        if (total < (2ll << 20)) s->h_tables.clear();
+        rc = upload(s, s->h_tables.data(), s->h_tables.size(), &s->d_tables);
+        if (rc != RB_OK) return rc;
+    }
     s->have_offline = true;
     return RB_OK;
 }
@@ -1630,6 +1663,8 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
     if (side0) {
         RB_CUDA(s, cudaEventRecord(ev[0], st));
         RB_CUDA(s, cudaStreamWaitEvent(s0, ev[0], 0));
+        if (s->allow_table_prefetch && s->d_tables && !s->h_tables.empty())
+            k_prefetch_ranges<<<32, 256, 0, s0>>>(s->ctrl, s->d_tables, (int)s->h_tables.size());
         if (have_pbar) launch_kproj(L.batch, s0, s->P, s->ctrl, s->prim[dst], s->h_last_dev ? s->x0 : nullptr, s->prim[src]);
         if (risk_split)
             launch_dual_risk_chain(L.batch, s0, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
@@ -2362,6 +2397,18 @@ int rb_use_mma_sweeps(rb_solver *s, int32_t enable) {
 int rb_use_tree_kernels(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
     s->tree_mode = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
+    for (int i = 0; i < 2; ++i)
+        if (s->graph[i]) {
+            cudaGraphExecDestroy(s->graph[i]);
+            s->graph[i] = nullptr;
+        }
+    return RB_OK;
+}
+
+int rb_use_table_prefetch(rb_solver *s, int32_t enable) {
+    if (!s) return RB_ERR_INVALID;
+    if (s->in_loop) return fail(s, RB_ERR_STATE, "rb_use_table_prefetch() inside a loop");
+    s->allow_table_prefetch = enable != 0;
     for (int i = 0; i < 2; ++i)
         if (s->graph[i]) {
             cudaGraphExecDestroy(s->graph[i]);

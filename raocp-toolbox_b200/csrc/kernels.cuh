@@ -20,6 +20,13 @@ __global__ void k_div_add(double *__restrict__ out, const double *__restrict__ x
                           const double *__restrict__ y, long long count);
 __global__ void k_absmax(const double *__restrict__ x, long long stride, double *__restrict__ slot, int slot_stride,
                          int *__restrict__ status);
+// L2 prefetch of read-only byte ranges (the operator tables), one 128-byte line per thread and step
+struct PrefetchRange {
+    const char *ptr;
+    long long bytes;
+};
+struct Ctrl;
+__global__ void k_prefetch_ranges(const Ctrl *__restrict__ ctrl, const PrefetchRange *__restrict__ ranges, int count);
 __global__ void k_cone(int cone, int dim, const double *__restrict__ in, double *__restrict__ out);
 __global__ void k_box(int dim, const double *__restrict__ in, const double *__restrict__ lo, const double *__restrict__ hi,
                       double *__restrict__ out, int *__restrict__ status);

@@ -304,4 +304,18 @@ __global__ void k_box(int dim, const double *__restrict__ in, const double *__re
     if (bad) atomicOr(status, 1);
 }
 
+// The operator tables of a problem (per-mode dynamics, per-class K and R~^-1, the tensor-core fragment images: 0.2 - 6 MB) are read by
+// every sweep kernel through chains of dependent loads; whenever they have dropped out of L2 (the bench flushes it before every
+// iteration; in a real solve the 100+ MB of iterates of a large tree do it) each of those loads is a DRAM round trip on the critical
+// path.  One small launch at the head of the iteration, on the side stream, pulls them back in.
+__global__ void k_prefetch_ranges(const Ctrl *__restrict__ ctrl, const PrefetchRange *__restrict__ ranges, int count) {
+    if (ctrl && ctrl->done) return;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthreads = (long long)gridDim.x * blockDim.x;
+    for (int r = 0; r < count; ++r) {
+        const char *p = ranges[r].ptr;
+        const long long lines = (ranges[r].bytes + 127) / 128;
+        for (long long i = tid; i < lines; i += nthreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 128));
+    }
+}
+
 }  // namespace rb

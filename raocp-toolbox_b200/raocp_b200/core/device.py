@@ -217,6 +217,10 @@ class DeviceSolver:
     def use_graphs(self, enable=True):
         self._call("rb_use_graphs", 1 if enable else 0)
 
+    def use_table_prefetch(self, enable=True):
+        """pipelined loop: L2 prefetch of the operator tables at the head of every iteration (default on)"""
+        self._call("rb_use_table_prefetch", 1 if enable else 0)
+
     def use_launch_overlap(self, enable=True):
         """pipelined loop: chain the walkers and the fused tree kernel by programmatic dependent launch (default) or not"""
         self._call("rb_use_launch_overlap", 1 if enable else 0)
