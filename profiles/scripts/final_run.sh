@@ -14,8 +14,10 @@ python bench.py --no-cpu --workload cfg2 --ttt-iters 200000 > $O/${TAG}_cfg2.jso
 python bench.py --no-cpu --workload cfg4 --batch 4096 --steps 200 > $O/${TAG}_cfg4.json 2>> $O/${TAG}.err
 python bench.py --no-cpu --workload cfg4 --batch 4096 --steps 50 --no-panels --no-parity > $O/${TAG}_cfg4_instance_major.json 2>> $O/${TAG}.err
 python bench.py --workload cfg5 --steps 1000 > $O/${TAG}_cfg5.json 2>> $O/${TAG}.err
+python bench.py --no-cpu --workload cfg5 --steps 1000 --mma-one-warp --no-parity --ttt-iters 0 > $O/${TAG}_cfg5_one_warp.json 2>> $O/${TAG}.err
 python bench.py --no-cpu --no-dedup --no-parity --ttt-iters 0 > $O/${TAG}_cfg3_nodedup.json 2>> $O/${TAG}.err
 python bench.py --no-cpu --mma-four-warps --no-parity --ttt-iters 0 > $O/${TAG}_cfg3_four_warps.json 2>> $O/${TAG}.err
+python bench.py --no-cpu --overlap --no-parity --ttt-iters 0 > $O/${TAG}_cfg3_launch_overlap.json 2>> $O/${TAG}.err
 python bench.py --no-cpu --batch 8 --steps 500 --no-parity --ttt-iters 0 > $O/${TAG}_b8.json 2>> $O/${TAG}.err
 python profiles/scripts/determinism.py 12 > $O/${TAG}_determinism.log 2>&1; tail -1 $O/${TAG}_determinism.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${TAG}_launches.csv \
@@ -26,4 +28,6 @@ ncu --set full --clock-control none --import-source on -k regex:'k_chain_mma|k_t
     python bench.py --steps 3 --warmup 3 --no-cpu --no-parity --ttt-iters 0 > $O/${TAG}_ncu_c3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'k_bp_dual|k_bp_kproj|k_bp_top' -s 30 -c 6 -f -o $O/${TAG}_cfg4_dual \
     python bench.py --workload cfg4 --batch 4096 --steps 3 --warmup 3 --no-cpu --no-parity --ttt-iters 0 > $O/${TAG}_ncu_c4.log 2>&1
-ls $O/${TAG}_* | head -50
+ncu --set full --clock-control none --import-source on -k regex:'k_chain_mma|k_tree_fused|k_dual_chain' -s 30 -c 4 -f -o $O/${TAG}_cfg5_crit \
+    python bench.py --workload cfg5 --steps 3 --warmup 3 --no-cpu --no-parity --ttt-iters 0 > $O/${TAG}_ncu_c5.log 2>&1
+ls $O/${TAG}_* | head -60

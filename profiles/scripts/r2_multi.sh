@@ -13,4 +13,11 @@ print("strong", {k:(round(v,1) if isinstance(v,float) else v) for k,v in d.get("
 print("replicas", round(d.get("replicas",{}).get("value",0)))
 print(d["config"]["workload"][:200])
 PY
-tail -3 $O/${TAG}_bench${N}.err
+# cfg4: the batch of 4096 initial states split over the GPUs (instance-parallel, no collective)
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --workload cfg4 --batch $((4096 / N)) --steps 100 --warmup 10 --no-cpu --no-parity --ttt-iters 0 > $O/${TAG}_cfg4_${N}.json 2>> $O/${TAG}_bench${N}.err
+python - <<PY
+import json
+d=json.load(open("$O/${TAG}_cfg4_${N}.json"))
+print("cfg4 x 4096 over $N GPUs:", round(d["value"]), "instance-it/s =", round(d["value"]/4096,1), "batch-it/s; per GPU batch", d["config"]["instances_per_gpu"], "ms/step", round(d["ms_per_step"],3))
+PY
+tail -2 $O/${TAG}_bench${N}.err

@@ -1306,7 +1306,7 @@ int rb_offline(rb_solver *s) {
         // worth a launch only when the tables are megabytes (cfg5: 5.7 MB, +4 % cold; cfg3: 0.5 MB, -2 %: measured, gpurun_out r2z)
         long long total = 0;
         for (const auto &t : s->h_tables) total += t.bytes;
-        if (total < (2ll << 20)) s->h_tables.clear();
+        if (total < (2ll << 20) || total > (24ll << 20)) s->h_tables.clear();   // per-node K / R~ (dedup off) is streaming data, not a table
         rc = upload(s, s->h_tables.data(), s->h_tables.size(), &s->d_tables);
         if (rc != RB_OK) return rc;
     }
