@@ -111,6 +111,7 @@ struct rb_solver {
     int n_own_nonleaf = 0, n_top_nonleaf = 0, n_own_lane = 0;
     OwnMap own_chain{0, 0, 0};      // the rank's columns of the chain stages
     int n_own_chain = 0;
+    bool xchg_fused = true;       // peer-memory exchange as ONE launch (k_shard_xchg); RAOCP_SHARD_XCHG=split: push / pull / check
     bool shard_pending = false;   // an executed iteration whose residuals have not been gathered / tested yet
     // pipelined loop (lane passes only): the dual pass of iteration k also writes pbar of iteration k+1 into the old
     // primal buffer, so iteration k+1 has no primal pass -- only the kernel projection, in place, next to the backward
@@ -125,7 +126,7 @@ struct rb_solver {
     int chain_stride = -1;          // > 0: child_first[i] = i + chain_stride on the whole run
     int chain_yo0 = 0;              // offset of y of node chain_first
     cudaStream_t side[2] = {nullptr, nullptr};
-    cudaEvent_t pev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t pev[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     // batch-innermost ("panel") path of the fused loop (batch.cu): buffers allocated on first use; panel_live = the loop's
     // iterates are in the panel buffers (rb_loop_begin converted them, rb_loop_end converts the newest one back)
     bool allow_panel = true;
@@ -1724,7 +1725,12 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
 int shard_exchange(rb_solver *s, int src, cudaStream_t st, double *aux = nullptr) {
     // aux: the per-cut-node scalar that travels with q_j; default d2_j of the old dual (unpipelined loop), else sbar_j of pbar
     if (!aux) aux = s->dual[src] + s->P.L.d2;
-    if (s->p2p) {
+    if (s->p2p && s->P.L.batch == 1 && s->xchg_fused) {   // push, pull and the stopping test in one launch
+        launch_shard_xchg(st, s->P, s->ctrl, s->shard, s->q, aux, s->slots, s->px, s->last, s->h_last_dev, s->shard_pending);
+        s->launches += 1;
+        s->shard_pending = false;
+        return launch_ok(s, "shard exchange");
+    } else if (s->p2p) {
         launch_shard_push(st, s->P, s->ctrl, s->shard, s->q, aux, s->slots, s->px);
         launch_shard_pull(st, s->P, s->ctrl, s->shard, s->q, aux, s->slots, s->px);
         s->launches += 3;
@@ -1831,9 +1837,16 @@ int enqueue_iteration_sharded_pipe(rb_solver *s, int src, cudaStream_t st, bool 
         launch_dual_risk_chain(1, s0, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, cf,
                                s->n_own_chain, s->chain_stride, s->chain_yo0, s->prim[src], s->own_chain);
     RB_CUDA(s, cudaEventRecord(ev[2], s0));
-    if (have_pbar) launch_kproj(1, st, s->P, s->ctrl, s->prim[dst], s->h_last_dev ? s->x0 : nullptr, s->prim[src], s->top_nonleaf,
-                                s->n_top_nonleaf);
-    else launch_primal(s, st, src, dst, s->top_nodes, s->n_top);
+    // the kernel projection of the top touches y, tau, s only (and x_0 of the OLD iterate): it runs next to the top's sweep, which
+    // reads xbar, ubar and writes x, u -- both are needed only by the top's dual pass
+    if (have_pbar) {
+        RB_CUDA(s, cudaStreamWaitEvent(s1, ev[1], 0));
+        launch_kproj(1, s1, s->P, s->ctrl, s->prim[dst], s->h_last_dev ? s->x0 : nullptr, s->prim[src], s->top_nonleaf,
+                     s->n_top_nonleaf);
+        RB_CUDA(s, cudaEventRecord(ev[6], s1));
+    } else {
+        launch_primal(s, st, src, dst, s->top_nodes, s->n_top);
+    }
     launch_tree_top(1, 32 * s->tree_top.warps, s->tree_smem[0], st, s->P, s->ctrl, s->tree_top, s->prim[dst], s->q, s->r, s->x0);
     RB_CUDA(s, cudaEventRecord(ev[3], st));
     RB_CUDA(s, cudaStreamWaitEvent(s1, ev[3], 0));   // the top is final: its dual pass runs next to the forward sweeps
@@ -1849,6 +1862,7 @@ int enqueue_iteration_sharded_pipe(rb_solver *s, int src, cudaStream_t st, bool 
             launch_sweep_sub_fwd(grid(s->shard_lv[v]), threads(s->shard_lv[v]), smem(s->shard_lv[v]), st, s->P, s->ctrl,
                                  s->shard_lv[v], s->prim[dst], s->r);
     RB_CUDA(s, cudaStreamWaitEvent(st, ev[2], 0));   // owned kernel projection (+ risk block) done
+    if (have_pbar) RB_CUDA(s, cudaStreamWaitEvent(st, ev[6], 0));   // sbar of the cut nodes is projected
     RB_CUDA(s, cudaEventRecord(ev[4], st));
     RB_CUDA(s, cudaStreamWaitEvent(s1, ev[4], 0));
     launch_dual_lane(dim3(1, 1), s1, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
@@ -2321,7 +2335,7 @@ int rb_shard_p2p_export(rb_solver *s, char *handles128) {
         rc = dev_zero(s, (size_t)2 * W, &s->p2p_flag);
         if (rc != RB_OK) return rc;
         unsigned long long *seq = nullptr;
-        rc = dev_zero(s, 1, &seq);
+        rc = dev_zero(s, 2, &seq);   // [0] sequence number, [1] arrival counter of k_shard_xchg
         if (rc != RB_OK) return rc;
         const unsigned long long one = 1ull;
         RB_CUDA(s, cudaMemcpy(seq, &one, sizeof(one), cudaMemcpyHostToDevice));
@@ -2357,6 +2371,8 @@ int rb_shard_p2p_open(rb_solver *s, const char *all_handles) {
         s->px.flag[r] = static_cast<unsigned long long *>(pf);
     }
     s->p2p = true;
+    const char *mode = getenv("RAOCP_SHARD_XCHG");   // "split": push / pull / stopping test as separate launches (ablation)
+    s->xchg_fused = !(mode && std::strcmp(mode, "split") == 0);
     return RB_OK;
 }
 

@@ -213,8 +213,10 @@ constexpr int kMaxPeers = 8;
 struct PeerXchg {
     double *recv[kMaxPeers];               // receive buffer of every rank: [2 parities][world][cap * (nx + 1) + 6]
     unsigned long long *flag[kMaxPeers];   // flags of every rank: [2 parities][world]
-    unsigned long long *seq;               // local: number of the next exchange (starts at 1)
+    unsigned long long *seq;               // local: [0] number of the next exchange (starts at 1), [1] CTAs of k_shard_xchg that arrived
 };
+void launch_shard_xchg(cudaStream_t st, const Params &P, Ctrl *ctrl, const ShardPlan &sp, double *q, double *aux, double *slots,
+                       const PeerXchg &px, double *last, double *host_last, bool check);
 void launch_shard_push(cudaStream_t st, const Params &P, const Ctrl *ctrl, const ShardPlan &sp, const double *q, const double *aux,
                        const double *slots, const PeerXchg &px);
 void launch_shard_pull(cudaStream_t st, const Params &P, Ctrl *ctrl, const ShardPlan &sp, double *q, double *aux, double *slots,

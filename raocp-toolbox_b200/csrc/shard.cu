@@ -139,6 +139,88 @@ __global__ void k_shard_seq(const Ctrl *__restrict__ ctrl, unsigned long long *s
     if (!ctrl->done) *seq = *seq + 1ull;
 }
 
+// push, pull and the stopping test of the previous iteration in ONE launch (batch 1; the three-launch form above stays for batches
+// and as the reference the tests compare with).  CTA b pushes this rank's message to rank b and releases its flag there, then waits
+// for rank b's message here and unpacks it; the maxima of the peers are folded into `slots` with atomicMax (own maxima are already
+// there; a message that was packed after a neighbour's maxima had been folded in is still <= the global maximum, so every rank ends
+// with the same six numbers).  The last CTA to arrive runs k_check's body and bumps the sequence number.  Nothing waits before it
+// has pushed, so the CTAs of the W ranks cannot wait on each other in a cycle.
+__global__ void __launch_bounds__(256) k_shard_xchg(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl, ShardPlan sp,
+                                                    double *__restrict__ q, double *__restrict__ aux, double *__restrict__ slots,
+                                                    PeerXchg px, double *__restrict__ last, double *__restrict__ host_last,
+                                                    int do_check) {
+    __shared__ int is_last;
+    if (ctrl->done) return;
+    const int nx = P.L.nx, w = nx + 1, peer = blockIdx.x;
+    const unsigned long long seq = *px.seq;
+    const int parity = (int)(seq & 1ull);
+    const long long stride = (long long)sp.cap * w + 6;
+    if (peer != sp.rank) {
+        double *dst = px.recv[peer] + ((long long)parity * sp.world + sp.rank) * stride;
+        const int count = sp.cut_hi - sp.cut_lo;
+        for (int i = threadIdx.x; i < count * w; i += blockDim.x) {
+            const int c = i / w, k = i - c * w, node = sp.cut_first + sp.cut_lo + c;
+            dst[i] = k < nx ? q[(long long)node * nx + k] : aux[node];
+        }
+        if (threadIdx.x < 6) dst[(long long)sp.cap * w + threadIdx.x] = __ldcg(slots + threadIdx.x);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            st_release_sys(px.flag[peer] + parity * sp.world + sp.rank, seq);
+            const unsigned long long *flag = px.flag[sp.rank] + parity * sp.world + peer;
+            const long long t0 = clock64();
+            while (ld_acquire_sys(flag) != seq) {
+                if (clock64() - t0 > 4000000000LL) {   // ~2 s: a peer is gone -- report instead of hanging the GPU
+                    atomicOr(&ctrl->status, 16);
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+        const double *msg = px.recv[sp.rank] + ((long long)parity * sp.world + peer) * stride;
+        const int lo = sp.cut_bounds[peer], rcount = sp.cut_bounds[peer + 1] - lo;
+        for (int i = threadIdx.x; i < rcount * w; i += blockDim.x) {
+            const int c = i / w, k = i - c * w, node = sp.cut_first + lo + c;
+            const double v = __ldcg(msg + i);
+            if (k < nx) q[(long long)node * nx + k] = v;
+            else aux[node] = v;
+        }
+        if (threadIdx.x < 6)   // bit patterns of non-negative doubles; NaN sorts above +inf and sticks
+            atomicMax(reinterpret_cast<unsigned long long *>(slots) + threadIdx.x,
+                      (unsigned long long)__double_as_longlong(__ldcg(msg + (long long)sp.cap * w + threadIdx.x)));
+    }
+    __threadfence();
+    __syncthreads();
+    unsigned int *arrived = reinterpret_cast<unsigned int *>(px.seq + 1);
+    if (threadIdx.x == 0) is_last = atomicAdd(arrived, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last || threadIdx.x >= 32) return;
+    __threadfence();
+    const int lane = threadIdx.x;
+    const Ctrl c = *ctrl;
+    if (do_check && c.pending) {   // k_check (fused.cu), batch 1
+        const double mine = lane < 6 ? __ldcg(slots + lane) : 0.0;
+        const bool nan = mine != mine, bad = lane < 3 && !(mine <= c.tol);
+        if (lane < 6) {
+            if (c.hist && c.iters < c.hist_capacity) c.hist[(long long)c.iters * 6 + lane] = mine;
+            last[lane] = mine;
+            if (host_last && c.mirror) host_last[lane] = mine;
+            slots[lane] = 0.0;
+        }
+        const bool all_ok = !__any_sync(0xffffffffu, bad), any_nan = __any_sync(0xffffffffu, nan);
+        if (lane == 0) {
+            if (any_nan) ctrl->status |= 2;
+            ctrl->iters = c.iters + 1;
+            ctrl->pending = 0;
+            if (c.iters >= c.max_iters || all_ok) ctrl->done = 1;
+        }
+    }
+    if (lane == 0) {
+        *arrived = 0u;
+        *px.seq = seq + 1ull;
+    }
+}
+
 void launch_shard_push(cudaStream_t st, const Params &P, const Ctrl *ctrl, const ShardPlan &sp, const double *q, const double *aux,
                        const double *slots, const PeerXchg &px) {
     k_shard_push<<<sp.world, 256, 0, st>>>(P, ctrl, sp, q, aux, slots, px);
@@ -147,6 +229,11 @@ void launch_shard_pull(cudaStream_t st, const Params &P, Ctrl *ctrl, const Shard
                        const PeerXchg &px) {
     k_shard_pull<<<4, 256, 0, st>>>(P, ctrl, sp, q, aux, slots, px);
     k_shard_seq<<<1, 1, 0, st>>>(ctrl, px.seq);
+}
+
+void launch_shard_xchg(cudaStream_t st, const Params &P, Ctrl *ctrl, const ShardPlan &sp, double *q, double *aux, double *slots,
+                       const PeerXchg &px, double *last, double *host_last, bool check) {
+    k_shard_xchg<<<sp.world, 256, 0, st>>>(P, ctrl, sp, q, aux, slots, px, last, host_last, check ? 1 : 0);
 }
 
 // ---- NCCL through dlopen ----------------------------------------------------------------------------------------------

@@ -61,8 +61,12 @@ def main():
             orc.alpha = alpha
             for _ in range(iters):
                 orc.iterate()
-        for p2p in ("1", "0"):
+        variants = [("1", "", "peer-memory"), ("0", "", "nccl")]
+        if name == cases[0][0]:   # the three-launch form of the peer-memory exchange (RAOCP_SHARD_XCHG=split), once
+            variants.insert(1, ("1", "split", "peer-memory split"))
+        for p2p, xchg, label in variants:
             os.environ["RAOCP_SHARD_P2P"] = p2p
+            os.environ["RAOCP_SHARD_XCHG"] = xchg
             sharded = r.core.Solver(problem, device=local, verbose=False, shard=(rank, world))
             dev = sharded.cache.device_solver
             dev.shard_init()
@@ -72,7 +76,7 @@ def main():
             xi2, _ = sharded.residual_history
             e1 = max(seg_rel_err(flat, p2, p1, dual=False), seg_rel_err(flat, d2, d1, dual=True))
             er = float(np.max(np.abs(xi2 - xi1) / xi1))
-            line = (f"[rank {rank}] {name} x{world} {'peer-memory' if p2p == '1' else 'nccl'}: cut stage {cut[0]}, after {iters} iterations vs "
+            line = (f"[rank {rank}] {name} x{world} {label}: cut stage {cut[0]}, after {iters} iterations vs "
                     f"single GPU {e1:.2e}, residual history {er:.2e}")
             good = e1 < 1e-10 and er < 1e-9 and sharded.iterations == single.iterations
             if orc is not None:
