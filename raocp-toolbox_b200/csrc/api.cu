@@ -111,6 +111,7 @@ struct rb_solver {
     int n_own_nonleaf = 0, n_top_nonleaf = 0, n_own_lane = 0;
     OwnMap own_chain{0, 0, 0};      // the rank's columns of the chain stages
     int n_own_chain = 0;
+    bool xchg_in_top = true;     // ... and inside the top-of-the-tree kernel (k_tree_top<.., SHARD>) in the pipelined loop
     bool xchg_fused = true;       // peer-memory exchange as ONE launch (k_shard_xchg); RAOCP_SHARD_XCHG=split: push / pull / check
     bool shard_pending = false;   // an executed iteration whose residuals have not been gathered / tested yet
     // pipelined loop (lane passes only): the dual pass of iteration k also writes pbar of iteration k+1 into the old
@@ -787,7 +788,7 @@ int create_classes_and_iterates(rb_solver *s, const rb_problem *pb) {
     CTRY(dev_zero(s, B * m * nu, &s->r));
     CTRY(dev_zero(s, B * nx, &s->x0));
     CTRY(dev_zero(s, 1, &s->ctrl));
-    CTRY(dev_zero(s, B * 6, &s->slots));
+    CTRY(dev_zero(s, B * 6 * 2, &s->slots));   // second half: the other parity of the pipelined sharded loop
     CTRY(dev_zero(s, B * 6, &s->last));
     if (B * 6 <= 1024 && L.nx <= 1024 &&
         cudaHostAlloc((void **)&s->h_last, B * 6 * sizeof(double), cudaHostAllocMapped) == cudaSuccess) {
@@ -1722,26 +1723,28 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
 
 // the gather step of the sharded loop: q_j and d2_j of the cut nodes and the residual maxima of the previous iteration
 // cross NVLink, then the stopping test of the previous iteration runs (identically on every rank)
-int shard_exchange(rb_solver *s, int src, cudaStream_t st, double *aux = nullptr) {
+int shard_exchange(rb_solver *s, int src, cudaStream_t st, double *aux = nullptr, double *sl = nullptr) {
     // aux: the per-cut-node scalar that travels with q_j; default d2_j of the old dual (unpipelined loop), else sbar_j of pbar
+    // sl: the residual maxima that travel (and are tested); default sl, the pipelined loop passes the previous parity
     if (!aux) aux = s->dual[src] + s->P.L.d2;
+    if (!sl) sl = s->slots;
     if (s->p2p && s->P.L.batch == 1 && s->xchg_fused) {   // push, pull and the stopping test in one launch
-        launch_shard_xchg(st, s->P, s->ctrl, s->shard, s->q, aux, s->slots, s->px, s->last, s->h_last_dev, s->shard_pending);
+        launch_shard_xchg(st, s->P, s->ctrl, s->shard, s->q, aux, sl, s->px, s->last, s->h_last_dev, s->shard_pending);
         s->launches += 1;
         s->shard_pending = false;
         return launch_ok(s, "shard exchange");
     } else if (s->p2p) {
-        launch_shard_push(st, s->P, s->ctrl, s->shard, s->q, aux, s->slots, s->px);
-        launch_shard_pull(st, s->P, s->ctrl, s->shard, s->q, aux, s->slots, s->px);
+        launch_shard_push(st, s->P, s->ctrl, s->shard, s->q, aux, sl, s->px);
+        launch_shard_pull(st, s->P, s->ctrl, s->shard, s->q, aux, sl, s->px);
         s->launches += 3;
     } else {
-        k_shard_pack<<<8, 256, 0, st>>>(s->P, s->ctrl, s->shard, s->q, aux, s->slots, s->xchg_send);
+        k_shard_pack<<<8, 256, 0, st>>>(s->P, s->ctrl, s->shard, s->q, aux, sl, s->xchg_send);
         const int rc = nccl_all_gather_f64(s->xchg_send, s->xchg_recv, s->xchg_count, s->nccl_comm, st);
         if (rc != 0) return fail(s, RB_ERR_CUDA, std::string("ncclAllGather: ") + nccl_error(rc));
-        k_shard_unpack<<<8, 256, 0, st>>>(s->P, s->ctrl, s->shard, s->xchg_recv, s->q, aux, s->slots);
+        k_shard_unpack<<<8, 256, 0, st>>>(s->P, s->ctrl, s->shard, s->xchg_recv, s->q, aux, sl);
         s->launches += 2;
     }
-    if (s->shard_pending) launch_check(st, s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
+    if (s->shard_pending) launch_check(st, s->P, s->ctrl, sl, s->last, s->h_last_dev);
     s->shard_pending = false;
     return launch_ok(s, "shard exchange");
 }
@@ -1799,6 +1802,69 @@ int enqueue_iteration_sharded(rb_solver *s, int src, cudaStream_t st) {
 // (+ the stopping test of the previous iteration) -> replicated top (kernel projection, sweep, dual pass) -> owned forward
 // sweeps -> owned dual passes, which leave pbar of the next iteration.  The risk block of the chain nodes adds to the residual
 // maxima of THIS iteration, so it may only start once the exchange has collected those of the previous one.
+// developer aid (RB_SHARD_TIMING=1): CUDA-event stamps on the main stream of the pipelined sharded iteration, plain launches
+// instead of graphs, averages printed per rank when the loop ends
+struct ShardTiming {
+    static constexpr int kRing = 8, kPts = 8;
+    cudaEvent_t ev[kRing][kPts] = {};
+    int used[kRing] = {};
+    const char *label[kPts] = {};
+    double sum[kPts] = {};
+    long long n = 0, it = 0;
+    int slot = 0, pt = 0;
+    bool on = false;
+    void begin() {
+        slot = (int)(it % kRing);
+        if (used[slot] > 1) collect(slot);
+        pt = 0;
+    }
+    void stamp(cudaStream_t st, const char *what) {
+        if (pt >= kPts) return;
+        if (!ev[slot][pt]) cudaEventCreate(&ev[slot][pt]);
+        cudaEventRecord(ev[slot][pt], st);
+        label[pt] = what;
+        ++pt;
+    }
+    void end() {
+        used[slot] = pt;
+        ++it;
+    }
+    void collect(int sl) {
+        cudaEventSynchronize(ev[sl][used[sl] - 1]);
+        if (it > 24) {   // past the warm-up
+            for (int i = 1; i < used[sl]; ++i) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, ev[sl][i - 1], ev[sl][i]);
+                sum[i] += ms * 1e3;
+            }
+            ++n;
+        }
+        used[sl] = 0;
+    }
+    void report(int rank) {
+        for (int sl = 0; sl < kRing; ++sl)
+            if (used[sl] > 1) collect(sl);
+        if (n == 0) return;
+        std::string line = "[shard timing, rank " + std::to_string(rank) + ", " + std::to_string(n) + " iterations] us:";
+        double tot = 0;
+        for (int i = 1; i < kPts && label[i]; ++i) {
+            char buf[96];
+            snprintf(buf, sizeof buf, " %s %.1f |", label[i], sum[i] / n);
+            line += buf;
+            tot += sum[i] / n;
+        }
+        fprintf(stderr, "%s total %.1f\n", line.c_str(), tot);
+        for (auto &v : sum) v = 0;
+        n = 0;
+        it = 0;
+    }
+};
+ShardTiming g_shard_timing;
+bool shard_timing_on() {
+    static const bool on = getenv("RB_SHARD_TIMING") != nullptr;
+    return on;
+}
+
 bool shard_pipe(const rb_solver *s) {
     return s->sharded && s->p2p && use_lane(s) && s->allow_pipe && s->tree_mode > 0 && s->tree_top.desc != nullptr;
 }
@@ -1814,12 +1880,32 @@ int enqueue_iteration_sharded_pipe(rb_solver *s, int src, cudaStream_t st, bool 
         return per_warp * lv.warps_per_sub * lv.subs_per_cta + (size_t)lv.subs_per_cta * lv.stage_cap * L.nxu * sizeof(double);
     };
     cudaStream_t s0 = s->side[0], s1 = s->side[1];
+    // residual maxima, double-buffered by the parity of the iteration: this iteration's dual passes fold into `sw` while the
+    // exchange sends and tests `stt`, the previous iteration's -- so the risk block of the chain nodes need not wait for the exchange
+    double *sw = s->slots + 6 * src, *stt = s->slots + 6 * (1 - src);
     cudaEvent_t *ev = s->pev;
     const int cf = s->n_own_chain > 0 ? s->chain_first : L.m;
+    ShardTiming *tm = shard_timing_on() && have_pbar ? &g_shard_timing : nullptr;
+    if (tm) {   // not while the iteration is being captured into a graph
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) tm = nullptr;
+    }
+    if (tm) {
+        tm->begin();
+        tm->stamp(st, "start");
+    }
+    // the exchange inside the top-of-the-tree kernel (k_tree_top<.., SHARD>): packets instead of buffers + flags, no launch of its own
+    const bool in_top = have_pbar && s->xchg_fused && s->xchg_in_top;
     if (!have_pbar) launch_primal(s, st, src, dst, s->owned_nodes, s->n_owned);   // incl. the kernel projection of the owned nodes
     RB_CUDA(s, cudaEventRecord(ev[0], st));
     RB_CUDA(s, cudaStreamWaitEvent(s0, ev[0], 0));
     if (have_pbar) launch_kproj(1, s0, s->P, s->ctrl, s->prim[dst], nullptr, nullptr, s->own_nonleaf, s->n_own_nonleaf);
+    // the risk block of the owned chain nodes (y, s are final after the owned kernel projection) right behind that projection, under
+    // the backward walker as in the single-GPU loop: the residual maxima are double-buffered, so it need not wait for the exchange
+    const bool risk_early = have_pbar && cf < L.m && s->risk_split;
+    if (risk_early)
+        launch_dual_risk_chain(1, s0, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], sw, cf, s->n_own_chain,
+                               s->chain_stride, s->chain_yo0, s->prim[src], s->own_chain);
     for (int v = pl.num_levels - 1; v >= 0; --v)
         if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
             launch_chain_mma_bwd(st, s->P, s->ctrl, s->shard_lv[v], s->prim[dst], s->q, s->r, w4);
@@ -1829,28 +1915,54 @@ int enqueue_iteration_sharded_pipe(rb_solver *s, int src, cudaStream_t st, bool 
         else
             launch_sweep_sub_bwd(grid(s->shard_lv[v]), threads(s->shard_lv[v]), smem(s->shard_lv[v]), st, s->P, s->ctrl,
                                  s->shard_lv[v], s->prim[dst], s->q, s->r);
-    int rc = shard_exchange(s, src, st, have_pbar ? s->prim[dst] + L.ps : nullptr);
-    if (rc != RB_OK) return rc;
-    RB_CUDA(s, cudaEventRecord(ev[1], st));          // the maxima of the previous iteration are collected and tested
+    if (tm) tm->stamp(st, "chain + tree bwd");
+    if (!in_top) {
+        int rc = shard_exchange(s, src, st, have_pbar ? s->prim[dst] + L.ps : nullptr, stt);
+        if (rc != RB_OK) return rc;
+        if (tm) tm->stamp(st, "exchange");
+    }
+    RB_CUDA(s, cudaEventRecord(ev[1], st));          // (not in_top) the maxima of the previous iteration are collected and tested
     RB_CUDA(s, cudaStreamWaitEvent(s0, ev[1], 0));
-    if (cf < L.m && s->risk_split)
-        launch_dual_risk_chain(1, s0, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, cf,
+    if (!risk_early && cf < L.m && s->risk_split)
+        launch_dual_risk_chain(1, s0, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], sw, cf,
                                s->n_own_chain, s->chain_stride, s->chain_yo0, s->prim[src], s->own_chain);
     RB_CUDA(s, cudaEventRecord(ev[2], s0));
     // the kernel projection of the top touches y, tau, s only (and x_0 of the OLD iterate): it runs next to the top's sweep, which
     // reads xbar, ubar and writes x, u -- both are needed only by the top's dual pass
-    if (have_pbar) {
-        RB_CUDA(s, cudaStreamWaitEvent(s1, ev[1], 0));
+    if (in_top) {   // exchange + stopping test + sweep of the top in one launch; sbar_j of the peers' cut nodes lands in the iterate,
+                    // so the top's kernel projection follows it (next to the forward sweeps)
+        ShardHand sh;
+        sh.sp = s->shard;
+        sh.px = s->px;
+        sh.aux = s->prim[dst] + L.ps;
+        sh.slots = stt;
+        sh.last = s->last;
+        sh.host_last = s->h_last_dev;
+        sh.check = s->shard_pending ? 1 : 0;
+        launch_tree_top_sharded(32 * s->tree_top.warps, s->tree_smem[0], st, s->P, s->ctrl, s->tree_top, s->prim[dst], s->q, s->r,
+                                s->x0, sh);
+        s->shard_pending = false;
+        if (tm) tm->stamp(st, "exchange + top");
+        RB_CUDA(s, cudaEventRecord(ev[3], st));
+        RB_CUDA(s, cudaStreamWaitEvent(s1, ev[3], 0));
         launch_kproj(1, s1, s->P, s->ctrl, s->prim[dst], s->h_last_dev ? s->x0 : nullptr, s->prim[src], s->top_nonleaf,
                      s->n_top_nonleaf);
         RB_CUDA(s, cudaEventRecord(ev[6], s1));
     } else {
-        launch_primal(s, st, src, dst, s->top_nodes, s->n_top);
+        if (have_pbar) {
+            RB_CUDA(s, cudaStreamWaitEvent(s1, ev[1], 0));
+            launch_kproj(1, s1, s->P, s->ctrl, s->prim[dst], s->h_last_dev ? s->x0 : nullptr, s->prim[src], s->top_nonleaf,
+                         s->n_top_nonleaf);
+            RB_CUDA(s, cudaEventRecord(ev[6], s1));
+        } else {
+            launch_primal(s, st, src, dst, s->top_nodes, s->n_top);
+        }
+        launch_tree_top(1, 32 * s->tree_top.warps, s->tree_smem[0], st, s->P, s->ctrl, s->tree_top, s->prim[dst], s->q, s->r, s->x0);
+        if (tm) tm->stamp(st, "top");
+        RB_CUDA(s, cudaEventRecord(ev[3], st));
+        RB_CUDA(s, cudaStreamWaitEvent(s1, ev[3], 0));   // the top is final: its dual pass runs next to the forward sweeps
     }
-    launch_tree_top(1, 32 * s->tree_top.warps, s->tree_smem[0], st, s->P, s->ctrl, s->tree_top, s->prim[dst], s->q, s->r, s->x0);
-    RB_CUDA(s, cudaEventRecord(ev[3], st));
-    RB_CUDA(s, cudaStreamWaitEvent(s1, ev[3], 0));   // the top is final: its dual pass runs next to the forward sweeps
-    launch_dual_lane(dim3(1, 1), s1, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, s->own_lane, 0,
+    launch_dual_lane(dim3(1, 1), s1, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], sw, s->own_lane, 0,
                      s->n_top, s->prim[src], true);
     for (int v = 0; v < pl.num_levels; ++v)
         if (s->allow_mma && s->shard_lv[v].num_tiles > 0)
@@ -1861,17 +1973,23 @@ int enqueue_iteration_sharded_pipe(rb_solver *s, int src, cudaStream_t st, bool 
         else
             launch_sweep_sub_fwd(grid(s->shard_lv[v]), threads(s->shard_lv[v]), smem(s->shard_lv[v]), st, s->P, s->ctrl,
                                  s->shard_lv[v], s->prim[dst], s->r);
+    if (tm) tm->stamp(st, "tree + chain fwd");
     RB_CUDA(s, cudaStreamWaitEvent(st, ev[2], 0));   // owned kernel projection (+ risk block) done
     if (have_pbar) RB_CUDA(s, cudaStreamWaitEvent(st, ev[6], 0));   // sbar of the cut nodes is projected
     RB_CUDA(s, cudaEventRecord(ev[4], st));
     RB_CUDA(s, cudaStreamWaitEvent(s1, ev[4], 0));
-    launch_dual_lane(dim3(1, 1), s1, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
+    launch_dual_lane(dim3(1, 1), s1, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], sw,
                      s->own_lane + s->n_top, 0, s->n_own_lane - s->n_top, s->prim[src]);
     if (cf < L.m)
-        launch_dual_chain(1, st, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, s->chain_recs, cf,
+        launch_dual_chain(1, st, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], sw, s->chain_recs, cf,
                           s->n_own_chain, s->chain_stride, s->chain_yo0, s->prim[src], s->risk_split ? 0 : 1, s->own_chain);
+    if (tm) tm->stamp(st, "dual chain");
     RB_CUDA(s, cudaEventRecord(ev[5], s1));
     RB_CUDA(s, cudaStreamWaitEvent(st, ev[5], 0));
+    if (tm) {
+        tm->stamp(st, "join");
+        tm->end();
+    }
     s->shard_pending = true;
     return launch_ok(s, "pipelined sharded iteration");
 }
@@ -1963,7 +2081,7 @@ int rb_loop_begin(rb_solver *s, double alpha, int32_t max_iters, double tol, int
     hc->hist = hist_capacity > 0 ? s->hist : nullptr;
     hc->hist_capacity = hist_capacity;
     RB_CUDA(s, cudaMemcpyAsync(s->ctrl, hc, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
-    RB_CUDA(s, cudaMemsetAsync(s->slots, 0, (size_t)L.batch * 6 * sizeof(double), st));
+    RB_CUDA(s, cudaMemsetAsync(s->slots, 0, (size_t)L.batch * 6 * 2 * sizeof(double), st));
     if (s->overlap_sync) RB_CUDA(s, cudaMemsetAsync(s->overlap_sync, 0, (size_t)2 * L.batch * sizeof(int), st));
     // Solver.chock iterates from the OLD iterate (solver.py:29-37); the current one is scratch from here on
     s->collapsed = false;
@@ -1984,7 +2102,7 @@ int rb_loop_enqueue(rb_solver *s, int32_t count) {
     for (int k = 0; k < count; ++k) {
         const int src = s->old_i;
         if (s->sharded && shard_pipe(s)) {
-            if (s->use_graphs && s->pbar_ready && s->shard_pending) {
+            if (s->use_graphs && s->pbar_ready && s->shard_pending && !shard_timing_on()) {
                 RB_CUDA(s, cudaGraphLaunch(s->graph[src], s->stream));
             } else {
                 int rc = enqueue_iteration_sharded_pipe(s, src, s->stream, s->pbar_ready);
@@ -2016,7 +2134,7 @@ int rb_loop_poll(rb_solver *s, int32_t *iters, int32_t *done, double *last_norms
     if (!s->in_loop) return fail(s, RB_ERR_STATE, "rb_loop_begin() has not been called");
     const Layout &L = s->P.L;
     if (s->sharded && s->shard_pending) {   // gather and test the residuals of the last enqueued iteration (all ranks)
-        int rcx = shard_exchange(s, s->old_i, s->stream);
+        int rcx = shard_exchange(s, s->old_i, s->stream, nullptr, shard_pipe(s) ? s->slots + 6 * (1 - s->old_i) : nullptr);
         if (rcx != RB_OK) return rcx;
     }
     Ctrl *hc = reinterpret_cast<Ctrl *>(s->h_pinned);
@@ -2048,6 +2166,7 @@ int rb_loop_end(rb_solver *s, double *xi_hist, double *delta_hist, int32_t *iter
     int32_t iters = 0, done = 0;
     int rc = rb_loop_poll(s, &iters, &done, nullptr);
     s->in_loop = false;
+    if (s->sharded && shard_timing_on()) g_shard_timing.report(s->shard.rank);
     if (rc != RB_OK && rc != RB_ERR_NUMERIC) return rc;
     // iterations enqueued after the stopping test fired were no-ops, but the host kept swapping roles while
     // enqueueing: iteration k read buffer (k even ? loop_old0 : 1 - loop_old0) and wrote the other one, so the
@@ -2330,7 +2449,8 @@ int rb_shard_p2p_export(rb_solver *s, char *handles128) {
     RB_CUDA(s, cudaSetDevice(s->device));
     const int W = s->shard.world;
     if (!s->p2p_recv) {
-        int rc = dev_zero(s, (size_t)2 * W * s->xchg_count, &s->p2p_recv);
+        // receive buffers [2][W][xchg_count] doubles, then the packet area [2][W][xchg_count] x 16 bytes (PeerXchg::ll)
+        int rc = dev_zero(s, (size_t)2 * W * s->xchg_count * 3, &s->p2p_recv);
         if (rc != RB_OK) return rc;
         rc = dev_zero(s, (size_t)2 * W, &s->p2p_flag);
         if (rc != RB_OK) return rc;
@@ -2358,6 +2478,7 @@ int rb_shard_p2p_open(rb_solver *s, const char *all_handles) {
         if (r == R) {
             s->px.recv[r] = s->p2p_recv;
             s->px.flag[r] = s->p2p_flag;
+            s->px.ll[r] = reinterpret_cast<uint4 *>(s->p2p_recv + (size_t)2 * W * s->xchg_count);
             continue;
         }
         cudaIpcMemHandle_t h[2];
@@ -2369,10 +2490,14 @@ int rb_shard_p2p_open(rb_solver *s, const char *all_handles) {
         s->p2p_opened[2 * r + 1] = pf;
         s->px.recv[r] = static_cast<double *>(pr);
         s->px.flag[r] = static_cast<unsigned long long *>(pf);
+        s->px.ll[r] = reinterpret_cast<uint4 *>(s->px.recv[r] + (size_t)2 * W * s->xchg_count);
     }
     s->p2p = true;
-    const char *mode = getenv("RAOCP_SHARD_XCHG");   // "split": push / pull / stopping test as separate launches (ablation)
+    // RAOCP_SHARD_XCHG (ablations): "split": push / pull / stopping test as separate launches; "kernel": one exchange launch
+    // (k_shard_xchg) between the level kernels; default: the exchange inside the kernel that sweeps the top of the tree
+    const char *mode = getenv("RAOCP_SHARD_XCHG");
     s->xchg_fused = !(mode && std::strcmp(mode, "split") == 0);
+    s->xchg_in_top = !(mode && (std::strcmp(mode, "split") == 0 || std::strcmp(mode, "kernel") == 0));
     return RB_OK;
 }
 

@@ -214,7 +214,23 @@ struct PeerXchg {
     double *recv[kMaxPeers];               // receive buffer of every rank: [2 parities][world][cap * (nx + 1) + 6]
     unsigned long long *flag[kMaxPeers];   // flags of every rank: [2 parities][world]
     unsigned long long *seq;               // local: [0] number of the next exchange (starts at 1), [1] CTAs of k_shard_xchg that arrived
+    // packet area of every rank, behind its receive buffer: [2 parities][world][cap * (nx + 1) + 6] 16-byte packets
+    // {low word, flag, high word, flag} (flag = low 32 bits of the sequence number): data and flag travel in one store, so the
+    // exchange needs no fence and no separate flag -- one NVLink flight (the "LL" protocol of NCCL, on doubles)
+    uint4 *ll[kMaxPeers];
 };
+// the exchange folded into the top-of-the-tree kernel (k_tree_top<.., SHARD = true>, tree_sweeps.cu): the one CTA that walks the
+// replicated top stores this rank's q_j, aux_j and residual maxima into every peer's packet area, polls the peers' packets straight
+// into its shared-memory row buffer and runs the stopping test, while its tables and rows are still being staged
+struct ShardHand {
+    ShardPlan sp;
+    PeerXchg px;
+    double *aux;                       // per-node scalar that travels with q_j (sbar_j of pbar)
+    double *slots, *last, *host_last;  // residual maxima of the previous iteration / k_check's outputs
+    int check;                         // an iteration is waiting for its stopping test
+};
+void launch_tree_top_sharded(int threads, size_t smem, cudaStream_t st, const Params &P, Ctrl *ctrl, const TreeLevel &lv, double *prim,
+                             double *q, double *r, const double *x0, const ShardHand &sh);
 void launch_shard_xchg(cudaStream_t st, const Params &P, Ctrl *ctrl, const ShardPlan &sp, double *q, double *aux, double *slots,
                        const PeerXchg &px, double *last, double *host_last, bool check);
 void launch_shard_push(cudaStream_t st, const Params &P, const Ctrl *ctrl, const ShardPlan &sp, const double *q, const double *aux,

@@ -695,12 +695,39 @@ __global__ void __launch_bounds__(512) k_tree_fwd(const __grid_constant__ Params
     }
 }
 
-// top of the tree: one CTA per problem instance, backward to the root, x_0 <- initial state (cache.py:282), forward again
-template <int NX, int NU, bool RES>
+// ---- the subtree-sharding exchange as 16-byte packets (kernels.cuh PeerXchg::ll) ---------------------------------------------------
+__device__ __forceinline__ void ll_store(uint4 *p, double v, unsigned flag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"(flag), "r"((unsigned)(b >> 32)),
+                 "r"(flag)
+                 : "memory");
+}
+// spins until both halves of the packet carry `flag`; false after ~2 s (a peer is gone)
+__device__ __forceinline__ bool ll_load(const uint4 *p, unsigned flag, double *out) {
+    unsigned a, fa, b, fb;
+    const long long t0 = clock64();
+    for (;;) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(fa), "=r"(b), "=r"(fb) : "l"(p) : "memory");
+        if (fa == flag && fb == flag) break;
+        if (clock64() - t0 > 4000000000LL) return false;
+    }
+    *out = __longlong_as_double((long long)(((unsigned long long)b << 32) | a));
+    return true;
+}
+
+// top of the tree: one CTA per problem instance, backward to the root, x_0 <- initial state (cache.py:282), forward again.
+// SHARD (subtree sharding, batch 1): the q_j of the cut nodes come from all ranks.  The kernel first stores this rank's rows, aux
+// scalars and residual maxima into every peer's packet area, then -- with its own tables and rows in flight -- polls the peers'
+// packets into the shared-memory row buffer, folds the maxima and runs the stopping test of the previous iteration (k_check's
+// body, fused.cu); if the loop has stopped it returns before the sweep.
+template <int NX, int NU, bool RES, bool SHARD>
 __global__ void __launch_bounds__(512) k_tree_top(const __grid_constant__ Params P, const Ctrl *__restrict__ ctrl, TreeLevel lv,
                                                  double *__restrict__ prim, double *__restrict__ q, double *__restrict__ r,
-                                                 const double *__restrict__ x0) {
+                                                 const double *__restrict__ x0, const __grid_constant__ ShardHand sh) {
     extern __shared__ __align__(16) double tree_smem[];
+    __shared__ double sh_max[SHARD ? kMaxPeers : 1][6];
+    __shared__ int sh_timeout;
+    if (SHARD && threadIdx.x == 0) sh_timeout = 0;   // (the barrier of stage_desc follows)
     const Layout &L = P.L;
     const int nx = NX > 0 ? NX : L.nx, nu = NX > 0 ? NU : L.nu, nxu = nx + nu;
     const bool vx = (nx & 1) == 0, vu = (nu & 1) == 0;
@@ -718,7 +745,34 @@ __global__ void __launch_bounds__(512) k_tree_top(const __grid_constant__ Params
         stage_rows(xb + s.off[d] * nx, X + (long long)s.lo[d] * nx, s.w[d] * nx, vx);
         if (s.cls[s.off[d]] >= 0) stage_rows(ub + s.off[d] * nu, U + (long long)s.lo[d] * nu, s.w[d] * nu, vu);
     }
-    stage_rows(qa, Q + (long long)s.ext_first * nx, s.ne * nx, vx);
+    unsigned long long seq = 0ull;
+    if constexpr (SHARD) {   // this rank's packets leave first
+        const ShardPlan &sp = sh.sp;
+        seq = *sh.px.seq;
+        const int parity = (int)(seq & 1ull), w = nx + 1, count = sp.cut_hi - sp.cut_lo, len = count * w + 6;
+        const long long stride = (long long)sp.cap * w + 6;
+        for (int i = threadIdx.x; i < (sp.world - 1) * len; i += blockDim.x) {
+            int peer = i / len;
+            const int e = i - peer * len;
+            if (peer >= sp.rank) ++peer;
+            double v;
+            long long slot;
+            if (e < count * w) {
+                const int c = e / w, k = e - c * w, node = sp.cut_first + sp.cut_lo + c;
+                v = k < nx ? Q[(long long)node * nx + k] : sh.aux[node];
+                slot = e;
+            } else {
+                v = sh.slots[e - count * w];
+                slot = (long long)sp.cap * w + (e - count * w);
+            }
+            ll_store(sh.px.ll[peer] + ((long long)parity * sp.world + sp.rank) * stride + slot, v, (unsigned)seq);
+        }
+        // own rows of the cut stage
+        for (int i = threadIdx.x; i < count * nx; i += blockDim.x)
+            qa[(long long)sp.cut_lo * nx + i] = Q[(long long)(sp.cut_first + sp.cut_lo) * nx + i];
+    } else {
+        stage_rows(qa, Q + (long long)s.ext_first * nx, s.ne * nx, vx);
+    }
     const double *ct = P.m.ABcat, *ctt = P.m.ABcatT, *kt = P.m.K, *krt = P.m.KRcatT;
     if constexpr (RES) {
         double *ctab = cv.take((long long)lv.num_dyn * nx * nxu), *cttab = cv.take((long long)lv.num_dyn * nxu * nx);
@@ -732,7 +786,75 @@ __global__ void __launch_bounds__(512) k_tree_top(const __grid_constant__ Params
         kt = knode;
         krt = krnode;
     }
-    stage_wait();
+    if constexpr (SHARD) {   // the peers' packets: rows into qa, aux to the iterate (the top's kernel projection reads it), maxima
+        const ShardPlan &sp = sh.sp;
+        Ctrl *cw = const_cast<Ctrl *>(ctrl);
+        const int parity = (int)(seq & 1ull), w = nx + 1;
+        const long long stride = (long long)sp.cap * w + 6;
+        const uint4 *mine = sh.px.ll[sp.rank] + (long long)parity * sp.world * stride;
+        const int per = sp.cap * w + 6;   // packets polled per source (rows beyond the source's count are skipped)
+        for (int i = threadIdx.x; i < (sp.world - 1) * per; i += blockDim.x) {
+            int src = i / per;
+            const int e = i - src * per;
+            if (src >= sp.rank) ++src;
+            const int lo = sp.cut_bounds[src], cnt = sp.cut_bounds[src + 1] - lo;
+            const bool is_max = e >= sp.cap * w;
+            if (!is_max && e >= cnt * w) continue;
+            double v;
+            if (!ll_load(mine + src * stride + e, (unsigned)seq, &v)) {
+                sh_timeout = 1;
+                v = 0.0;
+            }
+            if (is_max) {
+                sh_max[src][e - sp.cap * w] = v;
+            } else {
+                const int c = e / w, k = e - c * w;
+                if (k < nx) qa[(long long)(lo + c) * nx + k] = v;
+                else sh.aux[sp.cut_first + lo + c] = v;
+            }
+        }
+        stage_wait();   // (block barrier inside)
+        if (threadIdx.x < 32) {   // global residual maxima (bit patterns of non-negative doubles), then k_check's body
+            const int lane = threadIdx.x;
+            const Ctrl c = *ctrl;
+            unsigned long long best = lane < 6 ? (unsigned long long)__double_as_longlong(sh.slots[lane]) : 0ull;
+            if (lane < 6)
+                for (int rk = 0; rk < sp.world; ++rk) {
+                    if (rk == sp.rank) continue;
+                    const unsigned long long v = (unsigned long long)__double_as_longlong(sh_max[rk][lane]);
+                    best = v > best ? v : best;
+                }
+            const double val = __longlong_as_double((long long)best);
+            const bool testing = sh.check && c.pending;
+            const bool nan = lane < 6 && val != val, bad = lane < 3 && !(val <= c.tol);
+            if (lane < 6) {
+                if (testing) {
+                    if (c.hist && c.iters < c.hist_capacity) c.hist[(long long)c.iters * 6 + lane] = val;
+                    sh.last[lane] = val;
+                    if (sh.host_last && c.mirror) sh.host_last[lane] = val;
+                    sh.slots[lane] = 0.0;
+                } else {
+                    sh.slots[lane] = val;
+                }
+            }
+            const bool all_ok = !__any_sync(0xffffffffu, bad), any_nan = __any_sync(0xffffffffu, nan);
+            if (lane == 0) {
+                if (sh_timeout) atomicOr(&cw->status, 16);
+                if (testing) {
+                    if (any_nan) cw->status |= 2;
+                    cw->iters = c.iters + 1;
+                    cw->pending = 0;
+                    if (c.iters >= c.max_iters || all_ok) cw->done = 1;
+                }
+                *sh.px.seq = seq + 1ull;
+                sh_timeout = (testing && (c.iters >= c.max_iters || all_ok)) ? 2 : 0;   // 2: the loop has stopped
+            }
+        }
+        __syncthreads();
+        if (sh_timeout == 2) return;
+    } else {
+        stage_wait();
+    }
     tree_backward<NX, NU, RES>(L, s, lv, xb, ub, qa, qb, scratch, rbuf, ct, kt, Q, R);
     // forward: the q ping-pong buffers of the backward pass become the x ping-pong
     __syncthreads();
@@ -919,7 +1041,8 @@ cudaError_t tree_kernels_set_smem(int bytes) {
 #define RB_SET1(NX, NU, RES)                                                                                                  \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_bwd<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_fwd<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_top<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_top<NX, NU, RES, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_top<NX, NU, RES, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_fused<NX, NU, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes); \
     if (e == cudaSuccess) e = cudaFuncSetAttribute(k_tree_fused<NX, NU, RES>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 #define RB_SET(NX, NU) RB_SET1(NX, NU, true) RB_SET1(NX, NU, false)
@@ -962,14 +1085,28 @@ void launch_tree_top(int grid, int threads, size_t smem, cudaStream_t st, const 
                      double *prim, double *q, double *r, const double *x0) {
 #define RB_GO(NX, NU)                                                                    \
     if (P.L.nx == NX && P.L.nu == NU) {                                                  \
-        if (lv.resident) k_tree_top<NX, NU, true><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0);   \
-        else k_tree_top<NX, NU, false><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0);    \
+        if (lv.resident) k_tree_top<NX, NU, true, false><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0, ShardHand{});   \
+        else k_tree_top<NX, NU, false, false><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0, ShardHand{});    \
         return;                                                                          \
     }
     RB_TREE_DIMS(RB_GO)
 #undef RB_GO
-    if (lv.resident) k_tree_top<0, 0, true><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0);
-    else k_tree_top<0, 0, false><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0);
+    if (lv.resident) k_tree_top<0, 0, true, false><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0, ShardHand{});
+    else k_tree_top<0, 0, false, false><<<grid, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0, ShardHand{});
+}
+
+void launch_tree_top_sharded(int threads, size_t smem, cudaStream_t st, const Params &P, Ctrl *ctrl, const TreeLevel &lv, double *prim,
+                             double *q, double *r, const double *x0, const ShardHand &sh) {
+#define RB_GO(NX, NU)                                                                    \
+    if (P.L.nx == NX && P.L.nu == NU) {                                                  \
+        if (lv.resident) k_tree_top<NX, NU, true, true><<<1, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0, sh);   \
+        else k_tree_top<NX, NU, false, true><<<1, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0, sh);    \
+        return;                                                                          \
+    }
+    RB_TREE_DIMS(RB_GO)
+#undef RB_GO
+    if (lv.resident) k_tree_top<0, 0, true, true><<<1, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0, sh);
+    else k_tree_top<0, 0, false, true><<<1, threads, smem, st>>>(P, ctrl, lv, prim, q, r, x0, sh);
 }
 
 // cooperative launch: all (num_sub + 1) x batch CTAs must be co-resident (the top CTA spins on the others)

@@ -7,8 +7,9 @@ Every rank solves the whole problem on its own GPU (single-GPU path) and takes p
   * the assembled sharded iterate against the NumPy oracle (1e-9 per segment, the north-star bar) -- small cases,
   * against the default single-GPU loop (1e-10: same arithmetic, the top of the tree replicated),
   * same residual history (1e-9) and the same stopping iteration at a tolerance,
-for BOTH exchanges: device-initiated over NVLink peer memory (pipelined loop in one CUDA graph, the default) and the NCCL
-all-gather between plain launches (RAOCP_SHARD_P2P=0).  tests/test_gpu_sharding.py runs this file at every world size the box
+for BOTH exchanges: device-initiated over NVLink peer memory (pipelined loop in one CUDA graph; default: the exchange inside the
+fused tree kernel, RAOCP_SHARD_XCHG=kernel / split: its one-launch and three-launch forms) and the NCCL all-gather between plain
+launches (RAOCP_SHARD_P2P=0).  tests/test_gpu_sharding.py runs this file at every world size the box
 offers."""
 import os
 import sys
@@ -62,8 +63,9 @@ def main():
             for _ in range(iters):
                 orc.iterate()
         variants = [("1", "", "peer-memory"), ("0", "", "nccl")]
-        if name == cases[0][0]:   # the three-launch form of the peer-memory exchange (RAOCP_SHARD_XCHG=split), once
-            variants.insert(1, ("1", "split", "peer-memory split"))
+        if name in (cases[0][0], "cfg3"):   # the ablation forms of the peer-memory exchange: one launch between the level kernels
+            variants.insert(1, ("1", "kernel", "peer-memory one-launch"))   # (k_shard_xchg) / push, pull, check as three launches
+            variants.insert(2, ("1", "split", "peer-memory split"))
         for p2p, xchg, label in variants:
             os.environ["RAOCP_SHARD_P2P"] = p2p
             os.environ["RAOCP_SHARD_XCHG"] = xchg
