@@ -454,6 +454,16 @@ def run_ours(args, rank, world, local_rank):
     #      strong: the cfg3 tree itself; weak: a tree ~N times wider (oracle/problems.py wide_spec), so that every GPU owns about
     #      one cfg3 worth of nodes -- the headline at N > 1
     sharded = {}
+
+    def _exchange_form():
+        if os.environ.get("RAOCP_SHARD_P2P", "1") == "0":
+            return "ncclAllGather between plain launches"
+        return {"split": "NVLink peer memory: push / pull / stopping-test kernels inside the CUDA graph",
+                "kernel": "NVLink peer memory: one exchange kernel (buffers + flags) inside the CUDA graph"}.get(
+                    os.environ.get("RAOCP_SHARD_XCHG", ""),
+                    "NVLink peer memory: 16-byte data+flag packets stored and polled by the kernel that sweeps the top of the tree "
+                    "(no exchange launch), inside the CUDA graph")
+
     if dist is not None and batch == 1 and args.workload == "cfg3":
         def sharded_leg(prob, x0_col):
             sh = r.core.Solver(prob, device=local_rank, verbose=False, shard=(rank, world))
@@ -499,8 +509,7 @@ def run_ours(args, rank, world, local_rank):
             fl = sh.cache.flat_problem
             return {"nodes": int(fl.n), "cut_stage": int(sdev.shard_info()[0]), "cut_subtrees": int(sdev.shard_info()[2]),
                     "cold_ms_per_step": cold / K, "warm_ms_per_step": warm / K, "e2e_s_per_step": e2e / K,
-                    "np": int(fl.np_), "nd": int(fl.nd_), "exchange": "peer-memory push / pull kernels inside the CUDA graph"
-                    if os.environ.get("RAOCP_SHARD_P2P", "1") != "0" else "ncclAllGather between plain launches"}
+                    "np": int(fl.np_), "nd": int(fl.nd_), "exchange": _exchange_form()}
         try:
             sharded["strong"] = sharded_leg(problem, spec["x0"][:, :1])
         except Exception as exc:   # e.g. the tree has fewer cut-stage subtrees than ranks
