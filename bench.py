@@ -332,6 +332,7 @@ def run_ours(args, rank, world, local_rank):
     solver.cache.device_solver.use_batch_panels(not args.no_panels)
     solver.cache.device_solver.use_launch_overlap(args.overlap)
     solver.cache.device_solver.use_table_prefetch(not args.no_table_prefetch)
+    solver.cache.device_solver.use_fused_check(args.fused_check)
     solver.cache.device_solver.use_tree_kernels(args.tree_mode)
     solver.cache.device_solver.use_mma_sweeps(0 if args.no_mma else (2 if args.mma_four_warps else (3 if args.mma_one_warp else 1)))
     solver.cache.device_solver.use_pipeline(0 if args.no_pipeline else (3 if args.fwd_split else (4 if args.no_risk_split else 1)))
@@ -698,6 +699,9 @@ def main():
     ap.add_argument("--ref-budget-s", type=float, default=150.0,
                     help="--impl reference: seconds of stepping the reference may use (at least one iteration is timed)")
     ap.add_argument("--no-parity", action="store_true", help="skip the parity_check leg")
+    ap.add_argument("--fused-check", action="store_true",
+                    help="ablation: the stopping test by the last CTA of the dual passes instead of a k_check launch at the end of every "
+                         "iteration (measured slower)")
     ap.add_argument("--no-table-prefetch", action="store_true",
                     help="ablation: no L2 prefetch of the operator tables at the head of the iteration")
     ap.add_argument("--overlap", action="store_true",

@@ -191,6 +191,12 @@ int rb_use_graphs(rb_solver *s, int32_t enable); /* 1 (default): one CUDA graph 
 /* 1 (default): every pipelined iteration starts with an L2 prefetch of the read-only operator tables on the side stream
  * (k_prefetch_ranges); 0: off (ablation). */
 int rb_use_table_prefetch(rb_solver *s, int32_t enable);
+/* 1: in the pipelined single-GPU loop (batch 1) the stopping test of solver.py:137-161 is run by the last CTA of the iteration's
+ * dual-pass kernels to finish (every CTA counts itself in after folding its residual maxima) instead of by a k_check launch at the
+ * end of the iteration.  Same decision, same iteration count, same histories.  Measured ablation: the counted arrival keeps every
+ * CTA of the bandwidth-bound dual pass resident for one more atomic round trip, which costs more than the launch it saves
+ * (cfg3: 9 138 vs 9 525 it/s in one call); 0 (default) = the k_check launch. */
+int rb_use_fused_check(rb_solver *s, int32_t enable);
 /* 1: in the pipelined loop the backward chain walker, the fused tree kernel and the forward chain walker are chained by
  * programmatic dependent launch -- each starts while the one before it still runs, stages its tables and waits for the data
  * itself (csrc/chain_mma.cu "launch overlap").  Measured ablation, results identical, not faster on cfg3 (9 586 vs 9 750 it/s):

@@ -111,6 +111,10 @@ struct rb_solver {
     int n_own_nonleaf = 0, n_top_nonleaf = 0, n_own_lane = 0;
     OwnMap own_chain{0, 0, 0};      // the rank's columns of the chain stages
     int n_own_chain = 0;
+    bool fused_check = false;     // rb_use_fused_check(1): stopping test by the last CTA of the dual passes (measured ablation: slower)
+    bool loop_armed = false;      // the running loop's control block carries arr_expected
+    int arr_expected = 0;         // CTAs of the dual-pass launches of one pipelined iteration (0: not counted yet)
+    int arr_counted = 0;          // ... as counted by the latest unarmed enqueue / capture
     bool xchg_in_top = true;     // ... and inside the top-of-the-tree kernel (k_tree_top<.., SHARD>) in the pipelined loop
     bool xchg_fused = true;       // peer-memory exchange as ONE launch (k_shard_xchg); RAOCP_SHARD_XCHG=split: push / pull / check
     bool shard_pending = false;   // an executed iteration whose residuals have not been gathered / tested yet
@@ -280,6 +284,18 @@ bool mma_four_warps(const rb_solver *s) {
     return (s->mma_w4 && chain_mma_w4(L.nx, L.nu)) || (s->mma_wide && chain_mma_wide(L.nx, L.nu));
 }
 
+// the captured iterations are stale (a kernel-family switch, another stream, another layout): drop them, and with them the CTA
+// count the fused stopping test was armed with
+void drop_graphs(rb_solver *s) {
+    for (int i = 0; i < 2; ++i)
+        if (s->graph[i]) {
+            cudaGraphExecDestroy(s->graph[i]);
+            s->graph[i] = nullptr;
+        }
+    s->arr_expected = 0;
+    s->arr_counted = 0;
+}
+
 bool use_pipe(const rb_solver *s) { return use_lane(s) && s->allow_pipe && !s->sharded; }
 
 // many instances of a small tree: lanes = instances (batch.cu).  Needs diagonal cost square roots; the padding instances of
@@ -356,8 +372,8 @@ int iter_launches(const rb_solver *s) {
     }
     const int sweeps = 1 + 2 * pl.num_levels - (sweeps_fused(s) ? 2 : 0);
     if (use_pipe(s))
-        return 1 + sweeps + pipe_dual_launches(s) + 1 + (s->risk_split && pipe_split(s).cf < s->P.L.m ? 1 : 0) +
-               (s->allow_table_prefetch && !s->h_tables.empty() ? 1 : 0);
+        return 1 + sweeps + pipe_dual_launches(s) + (s->loop_armed ? 0 : 1) + (s->risk_split && pipe_split(s).cf < s->P.L.m ? 1 : 0) +
+               (s->allow_table_prefetch && !s->h_tables.empty() ? 1 : 0);   // (armed loop: no k_check launch)
     return 1 + sweeps + 1 + 1;
 }
 
@@ -1231,11 +1247,7 @@ void rb_destroy(rb_solver *s) {
 int rb_set_stream(rb_solver *s, void *cuda_stream) {
     if (!s) return RB_ERR_INVALID;
     RB_CUDA(s, cudaStreamSynchronize(s->stream));
-    for (int i = 0; i < 2; ++i)
-        if (s->graph[i]) {
-            cudaGraphExecDestroy(s->graph[i]);
-            s->graph[i] = nullptr;
-        }
+    drop_graphs(s);
     if (cuda_stream) {
         if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
         s->stream = (cudaStream_t)cuda_stream;
@@ -1637,6 +1649,12 @@ int enqueue_iteration_panel(rb_solver *s, int src, cudaStream_t st, bool have_pb
     return launch_ok(s, "panel iteration");
 }
 
+// the stopping test rides on the last CTA of the dual passes (batch 1, pipelined single-GPU loop on the lane kernels) once the
+// number of those CTAs is known (counted by the first enqueue / capture) and the running loop's control block carries it
+bool fused_check_on(const rb_solver *s) {
+    return s->fused_check && s->loop_armed && s->arr_expected > 0 && s->P.L.batch == 1 && !s->sharded && !s->panel_live && use_pipe(s);
+}
+
 int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_pbar) {
     const Layout &L = s->P.L;
     const int dst = 1 - src;
@@ -1653,9 +1671,13 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
     const dim3 nb(1, L.batch);
     cudaStream_t s0 = s->side[0], s1 = s->side[1];
     cudaEvent_t *ev = s->pev;
+    // stopping test by the last CTA of the dual passes instead of a launch of its own (lane.cu iteration_arrive): the CTAs of this
+    // iteration's dual-pass launches are counted here and must add up to what the control block expects
+    const bool arrive = have_pbar && fused_check_on(s);
+    int ctas = 0;
     auto dual_lane = [&](cudaStream_t q, int first, int count, bool narrow = false) {
-        launch_dual_lane(nb, q, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, nullptr, first,
-                         count, s->prim[src], narrow);
+        ctas += launch_dual_lane(nb, q, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots, nullptr,
+                                 first, count, s->prim[src], narrow, arrive);
     };
     // side stream 0, under the backward sweeps: the kernel projection in place (or, in the first iteration of a loop, after
     // the stand-alone primal pass on the main stream), then the risk block of the chain nodes' dual pass, which needs y, s only
@@ -1669,8 +1691,9 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
             k_prefetch_ranges<<<32, 256, 0, s0>>>(s->ctrl, s->d_tables, (int)s->h_tables.size());
         if (have_pbar) launch_kproj(L.batch, s0, s->P, s->ctrl, s->prim[dst], s->h_last_dev ? s->x0 : nullptr, s->prim[src]);
         if (risk_split)
-            launch_dual_risk_chain(L.batch, s0, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
-                                   ps.cf, L.m - ps.cf, s->chain_stride, s->chain_yo0, s->prim[src]);
+            ctas += launch_dual_risk_chain(L.batch, s0, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst],
+                                           s->slots, ps.cf, L.m - ps.cf, s->chain_stride, s->chain_yo0, s->prim[src],
+                                           OwnMap{0, 0, 0}, arrive);
         RB_CUDA(s, cudaEventRecord(ev[1], s0));
     }
     bool early_done = false;
@@ -1684,9 +1707,9 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
         early_done = true;
     };
     auto dual_chain = [&](cudaStream_t q, int first, int count) {
-        launch_dual_chain(L.batch, q, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
-                          s->chain_recs + (first - ps.cf), first, count, s->chain_stride, s->chain_yo0 + 3 * (first - ps.cf),
-                          s->prim[src], risk_split ? 0 : 1);
+        ctas += launch_dual_chain(L.batch, q, s->P, s->ctrl, s->prim[src], s->prim[dst], s->dual[src], s->dual[dst], s->slots,
+                                  s->chain_recs + (first - ps.cf), first, count, s->chain_stride,
+                                  s->chain_yo0 + 3 * (first - ps.cf), s->prim[src], risk_split ? 0 : 1, OwnMap{0, 0, 0}, arrive);
     };
     bool piece_done = false;
     auto after_piece = [&]() {   // the first piece of the forward chain walk is done: its nodes' dual pass starts
@@ -1717,7 +1740,14 @@ int enqueue_iteration_kernels(rb_solver *s, int src, cudaStream_t st, bool have_
         RB_CUDA(s, cudaEventRecord(ev[4], s1));
         RB_CUDA(s, cudaStreamWaitEvent(st, ev[4], 0));
     }
-    launch_check(st, s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
+    if (arrive) {
+        if (ctas != s->arr_expected)
+            return fail(s, RB_ERR_STATE, "pipelined iteration: the dual passes launched " + std::to_string(ctas) + " CTAs, the control "
+                        "block expects " + std::to_string(s->arr_expected));
+    } else {
+        launch_check(st, s->P, s->ctrl, s->slots, s->last, s->h_last_dev);
+        if (have_pbar) s->arr_counted = ctas;   // what an armed loop will expect (rb_loop_begin / build_graphs)
+    }
     return launch_ok(s, "pipelined iteration");
 }
 
@@ -1997,6 +2027,25 @@ int enqueue_iteration_sharded_pipe(rb_solver *s, int src, cudaStream_t st, bool 
 // capture one iteration per buffer parity into a CUDA graph (the kernel arguments never change afterwards: step size
 // and stopping parameters live in the device control block)
 int build_graphs(rb_solver *s) {
+    // the stopping test by the last CTA of the dual passes needs their CTA count before the iteration is captured: one throw-away
+    // capture counts them (enqueue_iteration_kernels, unarmed), the real captures then carry the `arrive` arguments
+    const bool want_arrive = s->fused_check && s->P.L.batch == 1 && !s->sharded && !s->panel_live && use_pipe(s);
+    if (want_arrive && s->arr_expected == 0 && !s->graph[0] && !s->graph[1]) {
+        cudaStream_t cap = nullptr;
+        RB_CUDA(s, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+        RB_CUDA(s, cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal));
+        s->loop_armed = false;
+        s->arr_counted = 0;
+        const int rc = enqueue_iteration_kernels(s, 0, cap, true);
+        cudaGraph_t g = nullptr;
+        const cudaError_t e = cudaStreamEndCapture(cap, &g);
+        cudaStreamDestroy(cap);
+        if (g) cudaGraphDestroy(g);
+        if (rc != RB_OK) return rc;
+        if (e != cudaSuccess) return fail(s, RB_ERR_CUDA, std::string("graph capture (counting pass): ") + cudaGetErrorString(e));
+        s->arr_expected = s->arr_counted;
+    }
+    s->loop_armed = want_arrive && s->arr_expected > 0;   // (rb_loop_begin sets it again, the same way, for the loop itself)
     for (int src = 0; src < 2; ++src) {
         if (s->graph[src]) continue;
         cudaStream_t cap = nullptr;
@@ -2032,11 +2081,7 @@ int rb_loop_begin(rb_solver *s, double alpha, int32_t max_iters, double tol, int
     cudaStream_t st = s->stream;
     const bool panel = use_panel(s);
     if (panel != s->panel_live)   // the graphs were captured for the other layout
-        for (int i = 0; i < 2; ++i)
-            if (s->graph[i]) {
-                cudaGraphExecDestroy(s->graph[i]);
-                s->graph[i] = nullptr;
-            }
+        drop_graphs(s);
     s->panel_live = panel;
     if (panel && !s->pq) {
         for (int w = 0; w < 2; ++w) {
@@ -2080,6 +2125,11 @@ int rb_loop_begin(rb_solver *s, double alpha, int32_t max_iters, double tol, int
     hc->alpha = alpha;
     hc->hist = hist_capacity > 0 ? s->hist : nullptr;
     hc->hist_capacity = hist_capacity;
+    if (s->arr_expected == 0 && s->arr_counted > 0) s->arr_expected = s->arr_counted;   // counted by an earlier loop's plain launches
+    s->loop_armed = s->fused_check && s->arr_expected > 0 && L.batch == 1 && !s->sharded && !s->panel_live && use_pipe(s);
+    hc->arr_expected = s->loop_armed ? s->arr_expected : 0;
+    hc->last = s->last;
+    hc->host_last = s->h_last_dev;
     RB_CUDA(s, cudaMemcpyAsync(s->ctrl, hc, sizeof(Ctrl), cudaMemcpyHostToDevice, st));
     RB_CUDA(s, cudaMemsetAsync(s->slots, 0, (size_t)L.batch * 6 * 2 * sizeof(double), st));
     if (s->overlap_sync) RB_CUDA(s, cudaMemsetAsync(s->overlap_sync, 0, (size_t)2 * L.batch * sizeof(int), st));
@@ -2395,11 +2445,7 @@ int rb_use_pipeline(rb_solver *s, int32_t enable) {
     s->allow_pipe = enable != 0;
     s->risk_split = enable != 4;       // 4: pipelined, the risk block inside the chain dual pass (ablation)
     s->pipe_fwd_split = enable == 3;   // 3: additionally the forward chain walk in two pieces (measured slower: kept as an ablation)
-    for (int i = 0; i < 2; ++i)
-        if (s->graph[i]) {
-            cudaGraphExecDestroy(s->graph[i]);
-            s->graph[i] = nullptr;
-        }
+    drop_graphs(s);
     return RB_OK;
 }
 
@@ -2408,11 +2454,7 @@ int rb_force_dense_costs(rb_solver *s, int32_t enable) {
     // test hook: run the general (dense matrix) cost path even when sqrtQ, sqrtR, sqrtQf are all diagonal
     const Tabs &M = s->P.m;
     s->diag_costs = !enable && M.sq_diag && M.sr_diag && M.sqf_diag;
-    for (int i = 0; i < 2; ++i)
-        if (s->graph[i]) {
-            cudaGraphExecDestroy(s->graph[i]);
-            s->graph[i] = nullptr;
-        }
+    drop_graphs(s);
     return RB_OK;
 }
 
@@ -2514,11 +2556,7 @@ int rb_shard_info(const rb_solver *s, int32_t *cut_stage, int32_t *cut_first, in
 int rb_use_lane_kernels(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
     s->allow_lane = enable != 0;
-    for (int i = 0; i < 2; ++i)
-        if (s->graph[i]) {
-            cudaGraphExecDestroy(s->graph[i]);
-            s->graph[i] = nullptr;
-        }
+    drop_graphs(s);
     return RB_OK;
 }
 
@@ -2527,22 +2565,14 @@ int rb_use_mma_sweeps(rb_solver *s, int32_t enable) {
     s->allow_mma = enable != 0;
     s->mma_w4 = enable == 2;   // 2: four warps per tile where instantiated (ablation); other non-zero values: one warp per tile
     s->mma_wide = enable != 3; // 3: wide rows with the one-warp BIG kernels (ablation)
-    for (int i = 0; i < 2; ++i)
-        if (s->graph[i]) {
-            cudaGraphExecDestroy(s->graph[i]);
-            s->graph[i] = nullptr;
-        }
+    drop_graphs(s);
     return RB_OK;
 }
 
 int rb_use_tree_kernels(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
     s->tree_mode = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
-    for (int i = 0; i < 2; ++i)
-        if (s->graph[i]) {
-            cudaGraphExecDestroy(s->graph[i]);
-            s->graph[i] = nullptr;
-        }
+    drop_graphs(s);
     return RB_OK;
 }
 
@@ -2550,11 +2580,7 @@ int rb_use_table_prefetch(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
     if (s->in_loop) return fail(s, RB_ERR_STATE, "rb_use_table_prefetch() inside a loop");
     s->allow_table_prefetch = enable != 0;
-    for (int i = 0; i < 2; ++i)
-        if (s->graph[i]) {
-            cudaGraphExecDestroy(s->graph[i]);
-            s->graph[i] = nullptr;
-        }
+    drop_graphs(s);
     return RB_OK;
 }
 
@@ -2562,11 +2588,7 @@ int rb_use_launch_overlap(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
     if (s->in_loop) return fail(s, RB_ERR_STATE, "rb_use_launch_overlap() inside a loop");
     s->allow_overlap = enable != 0;
-    for (int i = 0; i < 2; ++i)
-        if (s->graph[i]) {
-            cudaGraphExecDestroy(s->graph[i]);
-            s->graph[i] = nullptr;
-        }
+    drop_graphs(s);
     return RB_OK;
 }
 
@@ -2574,6 +2596,14 @@ int rb_use_batch_panels(rb_solver *s, int32_t enable) {
     if (!s) return RB_ERR_INVALID;
     if (s->in_loop) return fail(s, RB_ERR_STATE, "rb_use_batch_panels() inside a loop");
     s->allow_panel = enable != 0;
+    return RB_OK;
+}
+
+int rb_use_fused_check(rb_solver *s, int32_t enable) {
+    if (!s) return RB_ERR_INVALID;
+    if (s->in_loop) return fail(s, RB_ERR_STATE, "rb_use_fused_check() inside a loop");
+    s->fused_check = enable != 0;
+    drop_graphs(s);
     return RB_OK;
 }
 

@@ -46,6 +46,10 @@ struct Ctrl {
     int mirror;      // k_check also writes the norms to mapped host memory (switched on by the first rb_step of a loop: the
     int pad;         // posted write to system memory costs the kernel ~1 us, which a loop that never reads them need not pay)
     int chk_fail, chk_nan, chk_arrived;   // scratch of k_check_wide (many CTAs): some instance above tol / NaN seen / CTAs done
+    // stopping test without a launch of its own (batch 1, pipelined loop): every CTA of the dual-pass kernels counts itself in after
+    // its maxima are folded into `slots`; the one that completes arr_expected runs k_check's body (lane.cu iteration_arrive)
+    int arr_count, arr_expected;
+    double *last, *host_last;             // k_check's outputs, for that CTA
 };
 // tiles of consecutive nodes for the node-parallel passes (fused.cu): tiles[t] = (first node, one past the last);
 // a tile is either all nonleaf or all leaf nodes
@@ -81,22 +85,23 @@ void launch_primal_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, cons
 // first: node of lane group 0 when node_list is null.  pbar (may be null) = the p_old buffer: the pass also leaves
 // there the half step pbar = p+ - alpha L* d+ of the NEXT iteration (then the next iteration needs no primal pass, only
 // the kernel projection k_kproj_node in place)
-void launch_dual_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old,
-                      const double *p_new, const double *d_old, double *d_new, double *slots, const int *node_list,
-                      int first, int count, double *pbar, bool narrow = false);
+// (the three dual-pass launchers return the number of CTAs launched; arrive: those CTAs count themselves into Ctrl::arr_count)
+int launch_dual_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old,
+                     const double *p_new, const double *d_old, double *d_new, double *slots, const int *node_list,
+                     int first, int count, double *pbar, bool narrow = false, bool arrive = false);
 // narrow: keep the default lanes per node for a small launch (fewest CTAs: it runs next to a latency-critical kernel)
 // the same pass specialised for a run of nonleaf nodes with ONE child each (the chain part of the tree)
 bool dual_chain_supported(int nx, int nu);
 // recs[i]: packed topology of node first + i = (child, cost-table row of the child, offset of y_i, rectangle row);
 // stride > 0: the child of node i is i + stride for the whole run; yo0 = offset of y_first
-void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
-                       const double *d_old, double *d_new, double *slots, const int4 *recs, int first, int count,
-                       int stride, int yo0, double *pbar, int with_risk = 1, OwnMap own = OwnMap{0, 0, 0});
+int launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
+                      const double *d_old, double *d_new, double *slots, const int4 *recs, int first, int count,
+                      int stride, int yo0, double *pbar, int with_risk = 1, OwnMap own = OwnMap{0, 0, 0}, bool arrive = false);
 // the risk block (d1, d2, ybar, sbar, y / s residual rows) of the same run of nodes on its own: needs y, s only, runs
 // under the sweeps; the chain pass is then launched with with_risk = 0
-void launch_dual_risk_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
-                            const double *d_old, double *d_new, double *slots, int first, int count, int stride, int yo0,
-                            double *pbar, OwnMap own = OwnMap{0, 0, 0});
+int launch_dual_risk_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
+                           const double *d_old, double *d_new, double *slots, int first, int count, int stride, int yo0,
+                           double *pbar, OwnMap own = OwnMap{0, 0, 0}, bool arrive = false);
 // x0 / p_old (may be null): also copy the initial state x0 [batch][nx] into x_0 of the OLD iterate (what
 // cache_initial_state does, cache.py:79-82) -- rb_step then uploads x0 once
 void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim, const double *x0 = nullptr,

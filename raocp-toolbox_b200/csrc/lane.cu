@@ -239,12 +239,48 @@ __global__ void __launch_bounds__(kLaneThreads, 3) k_primal_lane(const __grid_co
 }
 
 // ====================================================================================================================
+// The stopping test without a launch of its own (batch 1): called by ALL threads of a CTA at the end of a dual-pass kernel.  The
+// CTA's atomics on `slots` / the status word are ordered before its count; the CTA that completes Ctrl::arr_expected -- the last
+// one of the last dual-pass kernel of the iteration, whichever stream that is on -- runs k_check's body (fused.cu; solver.py:137-161)
+// with one warp.  Saves the k_check launch and its dependency edge at the end of every iteration -- and costs every CTA of the
+// dual passes one atomic round trip of residency at its tail (the count needs its return value, the maxima are fire-and-forget
+// reductions): measured slower on cfg3 (9 138 vs 9 525 it/s), so it is an ablation behind rb_use_fused_check(1).
+__device__ __noinline__ void iteration_arrive(Ctrl *ctrl, double *slots) {   // (out of line: the callers are register-bound)
+    __shared__ int is_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        is_last = atomicAdd(&ctrl->arr_count, 1) == ctrl->arr_expected - 1;
+    }
+    __syncthreads();
+    if (!is_last || threadIdx.x >= 32) return;
+    __threadfence();
+    const int lane = threadIdx.x;
+    const Ctrl c = *ctrl;   // (iters, tol, max_iters, hist, last: not written by any kernel of this iteration)
+    const double mine = lane < 6 ? __ldcg(slots + lane) : 0.0;
+    const bool nan = mine != mine, bad = lane < 3 && !(mine <= c.tol);
+    if (lane < 6) {
+        if (c.hist && c.iters < c.hist_capacity) c.hist[(long long)c.iters * 6 + lane] = mine;
+        c.last[lane] = mine;
+        if (c.host_last && c.mirror) c.host_last[lane] = mine;
+        slots[lane] = 0.0;
+    }
+    const bool all_ok = !__any_sync(0xffffffffu, bad), any_nan = __any_sync(0xffffffffu, nan);
+    if (lane == 0) {
+        if (any_nan) atomicOr(&ctrl->status, 2);   // a NaN maximum: some iterate entry is not finite
+        ctrl->iters = c.iters + 1;
+        ctrl->pending = 0;
+        ctrl->arr_count = 0;
+        if (c.iters >= c.max_iters || all_ok) ctrl->done = 1;
+    }
+}
+
 template <int kOct, int MINB, int BT = kLaneThreads>
 __global__ void __launch_bounds__(BT, MINB) k_dual_lane(const __grid_constant__ Params P, Ctrl *__restrict__ ctrl,
                                                            const double *__restrict__ p_old, const double *__restrict__ p_new,
                                                            const double *__restrict__ d_old, double *__restrict__ d_new,
                                                            double *__restrict__ slots, const int *__restrict__ node_list,
-                                                           int first, int count, double *pbar) {
+                                                           int first, int count, double *pbar, int arrive) {
     // pbar (may be null): the buffer of p_old; when given, the pass also leaves there pbar = p+ - alpha L* d+, the
     // half step of the NEXT iteration (solver.py:27-39), from the d+ it has in registers.  Every entry of p_old is
     // read and overwritten by the same lane (s_i: all lanes of the group read it, so it is written after the block
@@ -625,6 +661,7 @@ __global__ void __launch_bounds__(BT, MINB) k_dual_lane(const __grid_constant__ 
     if (tid == 0 && blockflags) atomicOr(&ctrl->status, blockflags);
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) ctrl->pending = 1;
     if (Pb && sbar_set && g == 0) Pb[L.ps + node] = sbar;
+    if (arrive) iteration_arrive(ctrl, slots);
 }
 
 // ====================================================================================================================
@@ -646,7 +683,10 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
                  const double *__restrict__ p_new, const double *__restrict__ d_old, double *__restrict__ d_new,
                  double *__restrict__ slots, const int4 *__restrict__ recs, int first, int count, int stride, int yo0,
                  double *pbar, int with_risk, OwnMap own) {
-    // with_risk = 0: the risk block (d1, d2, ybar, sbar) of these nodes has been done by k_dual_risk_chain
+    // with_risk bit 0 clear: the risk block (d1, d2, ybar, sbar) of these nodes has been done by k_dual_risk_chain; bit 1: the CTAs
+    // count themselves into Ctrl::arr_count (iteration_arrive) -- a bit of an existing argument, the kernel is register-bound
+    const int arrive = with_risk & 2;
+    with_risk &= 1;
     constexpr int HX = NX / 2, K = (NX + NU) / 2, R = (K + G - 1) / G, NXU = NX + NU;
     const Layout &L = P.L;
     const Topo &T = P.t;
@@ -865,6 +905,7 @@ __global__ void __launch_bounds__(kChainDualThreads, MINB)
         atomicMax(reinterpret_cast<unsigned long long *>(slots + (long long)blockIdx.y * 6 + tid), mval);
     }
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) ctrl->pending = 1;
+    if (arrive) iteration_arrive(ctrl, slots);
 }
 
 // ====================================================================================================================
@@ -878,7 +919,7 @@ __global__ void __launch_bounds__(1024) k_dual_risk_chain(const __grid_constant_
                                                            const double *__restrict__ p_old, const double *__restrict__ p_new,
                                                            const double *__restrict__ d_old, double *__restrict__ d_new,
                                                            double *__restrict__ slots, int first, int count, int stride,
-                                                           int yo0, double *pbar, OwnMap own) {
+                                                           int yo0, double *pbar, OwnMap own, int arrive) {
     if (ctrl->done) return;
     const double alpha = ctrl->alpha, inv_alpha = 1.0 / alpha;
     const Layout &L = P.L;
@@ -946,6 +987,7 @@ __global__ void __launch_bounds__(1024) k_dual_risk_chain(const __grid_constant_
         atomicMax(reinterpret_cast<unsigned long long *>(slots + (long long)blockIdx.y * 6 + tid), mval);
     }
     if (tid == 0 && blockIdx.x == 0 && blockIdx.y == 0) ctrl->pending = 1;
+    if (arrive) iteration_arrive(ctrl, slots);
 }
 
 // ====================================================================================================================
@@ -1003,10 +1045,11 @@ void launch_primal_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, cons
     else k_primal_lane<8><<<grid, kLaneThreads, 0, st>>>(P, ctrl, p_old, d_old, p_new, node_list, count);
 }
 
-void launch_dual_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old,
-                      const double *p_new, const double *d_old, double *d_new, double *slots, const int *node_list,
-                      int first, int count, double *pbar, bool narrow) {
-    if (count <= 0) return;
+int launch_dual_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old,
+                     const double *p_new, const double *d_old, double *d_new, double *slots, const int *node_list,
+                     int first, int count, double *pbar, bool narrow, bool arrive) {
+    if (count <= 0) return 0;
+    const int arr = arrive ? 1 : 0;
     const int G = lane_group_width(P.L.nx);
     const dim3 grid((count * G + kLaneThreads - 1) / kLaneThreads, nodes_batch.y);
     // A launch over a few thousand nodes (the branching top of the tree, the leaves) is a handful of warps per SM, each
@@ -1019,22 +1062,25 @@ void launch_dual_lane(dim3 nodes_batch, cudaStream_t st, const Params &P, Ctrl *
     static const int early_g = getenv("RB_EARLY_G") ? atoi(getenv("RB_EARLY_G")) : 0;   // ablation knob
     if (narrow && early_g == 85 && G == 4) {   // 8 lanes per node, 512-thread CTAs: the same few SMs, shorter warps
         const dim3 grid_w((count * 8 + 511) / 512, nodes_batch.y);
-        k_dual_lane<8, 1, 512><<<grid_w, 512, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, node_list, first, count, pbar);
-        return;
+        k_dual_lane<8, 1, 512><<<grid_w, 512, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, node_list, first, count, pbar, arr);
+        return (int)(grid_w.x * grid_w.y);
     }
     if (narrow) Gs = early_g == 8 || early_g == 16 ? early_g : G;
     else if (force_g == 4) Gs = G;
     else if (force_g == 8 && Gs == 16) Gs = 8;
     const dim3 grid_s((count * Gs + kLaneThreads - 1) / kLaneThreads, nodes_batch.y);
     const bool roomy = (long long)grid_s.x * grid_s.y <= 2 * 148;
-#define RB_GO(G_, B_, GRID_) \
-    k_dual_lane<G_, B_><<<GRID_, kLaneThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, node_list, first, count, pbar)
-    if (roomy && Gs == 16) RB_GO(16, 2, grid_s);
-    else if (roomy && Gs == 8) RB_GO(8, 2, grid_s);
-    else if (G == 4 && roomy) RB_GO(4, 2, grid);
-    else if (G == 4) RB_GO(4, 3, grid);
-    else if (roomy) RB_GO(8, 2, grid);
-    else RB_GO(8, 3, grid);
+#define RB_GO(G_, B_, GRID_)                                                                                                      \
+    {                                                                                                                             \
+        k_dual_lane<G_, B_><<<GRID_, kLaneThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, node_list, first, count, pbar, arr); \
+        return (int)(GRID_.x * GRID_.y);                                                                                          \
+    }
+    if (roomy && Gs == 16) RB_GO(16, 2, grid_s)
+    else if (roomy && Gs == 8) RB_GO(8, 2, grid_s)
+    else if (G == 4 && roomy) RB_GO(4, 2, grid)
+    else if (G == 4) RB_GO(4, 3, grid)
+    else if (roomy) RB_GO(8, 2, grid)
+    else RB_GO(8, 3, grid)
 #undef RB_GO
 }
 
@@ -1049,10 +1095,11 @@ bool dual_chain_supported(int nx, int nu) {
     return false;
 }
 
-void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
-                       const double *d_old, double *d_new, double *slots, const int4 *recs, int first, int count,
-                       int stride, int yo0, double *pbar, int with_risk, OwnMap own) {
-    if (count <= 0) return;
+int launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
+                      const double *d_old, double *d_new, double *slots, const int4 *recs, int first, int count,
+                      int stride, int yo0, double *pbar, int with_risk, OwnMap own, bool arrive) {
+    if (count <= 0) return 0;
+    with_risk = (with_risk ? 1 : 0) | (arrive ? 2 : 0);   // bit 1: the CTAs count themselves in (iteration_arrive)
     // resident CTAs per SM the kernel is compiled for: 3 (168 registers, no spills) or 4 (128 registers, ~40 words
     // spilled to L1); RB_CHAIN_DUAL_MINB overrides for ablation runs
     static const int minb = [] {
@@ -1070,7 +1117,7 @@ void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, 
             k_dual_chain<NX, NU, G, 4><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, stride, yo0, pbar, with_risk, own); \
         else                                                                                                         \
             k_dual_chain<NX, NU, G, 3><<<grid, kChainDualThreads, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, recs, first, count, stride, yo0, pbar, with_risk, own); \
-        return;                                                                                                      \
+        return (int)(grid.x * grid.y);                                                                               \
     }
 #define RB_GO(NX, NU, G)                                                                                             \
     if (P.L.nx == NX && P.L.nu == NU) {                                                                              \
@@ -1079,14 +1126,17 @@ void launch_dual_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, 
     }
     RB_CHAIN_DUAL_DIMS(RB_GO)
 #undef RB_GO
+    return 0;
 }
 
-void launch_dual_risk_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
-                            const double *d_old, double *d_new, double *slots, int first, int count, int stride, int yo0,
-                            double *pbar, OwnMap own) {
-    if (count <= 0) return;
+int launch_dual_risk_chain(int batch, cudaStream_t st, const Params &P, Ctrl *ctrl, const double *p_old, const double *p_new,
+                           const double *d_old, double *d_new, double *slots, int first, int count, int stride, int yo0,
+                           double *pbar, OwnMap own, bool arrive) {
+    if (count <= 0) return 0;
     const int ctas = std::max(1, std::min((count + 1023) / 1024, std::max(1, 16 / batch)));
-    k_dual_risk_chain<<<dim3(ctas, batch), 1024, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, first, count, stride, yo0, pbar, own);
+    k_dual_risk_chain<<<dim3(ctas, batch), 1024, 0, st>>>(P, ctrl, p_old, p_new, d_old, d_new, slots, first, count, stride, yo0, pbar, own,
+                                                          arrive ? 1 : 0);
+    return ctas * batch;
 }
 
 void launch_kproj(int batch, cudaStream_t st, const Params &P, const Ctrl *ctrl, double *prim, const double *x0, double *p_old,

@@ -79,6 +79,7 @@ SYMBOLS = [
     ("rb_use_batch_panels", C.c_int, [_H, C.c_int32]),
     ("rb_use_launch_overlap", C.c_int, [_H, C.c_int32]),
     ("rb_use_table_prefetch", C.c_int, [_H, C.c_int32]),
+    ("rb_use_fused_check", C.c_int, [_H, C.c_int32]),
     ("rb_use_pipeline", C.c_int, [_H, C.c_int32]),
     ("rb_pipeline_info", C.c_int, [_H, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     ("rb_force_dense_costs", C.c_int, [_H, C.c_int32]),

@@ -221,6 +221,10 @@ class DeviceSolver:
         """pipelined loop: L2 prefetch of the operator tables at the head of every iteration (default on)"""
         self._call("rb_use_table_prefetch", 1 if enable else 0)
 
+    def use_fused_check(self, enable=True):
+        """pipelined loop, batch 1: stopping test by the last CTA of the dual passes (measured ablation) or by a k_check launch (default)"""
+        self._call("rb_use_fused_check", 1 if enable else 0)
+
     def use_launch_overlap(self, enable=True):
         """pipelined loop: chain the walkers and the fused tree kernel by programmatic dependent launch (default) or not"""
         self._call("rb_use_launch_overlap", 1 if enable else 0)

@@ -25,7 +25,8 @@ CASES = [
 ]
 
 
-MODES = ["mma", "mma_launch_overlap", "mma_four_warps", "mma_one_warp_wide_rows", "warp_per_chain", "tree_per_level", "global_stage_kernels"]
+MODES = ["mma", "mma_fused_check", "mma_launch_overlap", "mma_four_warps", "mma_one_warp_wide_rows", "warp_per_chain", "tree_per_level",
+         "global_stage_kernels"]
 
 
 def _pair(name, cuts, mode, batch=1):
@@ -36,7 +37,8 @@ def _pair(name, cuts, mode, batch=1):
     problem = problems.build(s, r.core)
     solver = r.core.Solver(problem, verbose=False, sweep_cuts=cuts, batch=batch)
     # chain_mma.cu (one warp per tile; four where instantiated: nx=20, nu=10) vs the sweeps.cu chain walker
-    solver.cache.device_solver.use_mma_sweeps({"mma": 1, "mma_launch_overlap": 1, "mma_four_warps": 2, "mma_one_warp_wide_rows": 3}.get(mode, 0))
+    solver.cache.device_solver.use_mma_sweeps({"mma": 1, "mma_fused_check": 1, "mma_launch_overlap": 1, "mma_four_warps": 2, "mma_one_warp_wide_rows": 3}.get(mode, 0))
+    solver.cache.device_solver.use_fused_check(mode == "mma_fused_check")   # stopping test by the last CTA of the dual passes (ablation)
     solver.cache.device_solver.use_launch_overlap(mode == "mma_launch_overlap")   # programmatic dependent launch (ablation)
     # tree_sweeps.cu fused with the top (default) / one launch per level, or the sweeps.cu stage kernels
     solver.cache.device_solver.use_tree_kernels({"global_stage_kernels": 0, "tree_per_level": 1}.get(mode, 2))
