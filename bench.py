@@ -474,6 +474,7 @@ def run_ours(args, rank, world, local_rank):
             sdev.set_stream(stream.cuda_stream)
             a = sh.compute_step_size()
             sdev.set_initial_state(x0_col.reshape(-1))
+            barrier()   # the first exchange waits at most ~2 s for a peer: all ranks enter the loop together
             with torch.cuda.stream(stream):
                 sdev.loop_begin(a, 1 << 30, -1.0, 0)
                 sdev.loop_enqueue(W)

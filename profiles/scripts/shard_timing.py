@@ -24,6 +24,7 @@ problem = problems.build(spec, r.core)
 solver = r.core.Solver(problem, device=local, verbose=False, shard=(rank, world))
 solver.cache.device_solver.shard_init()
 alpha = solver.compute_step_size()
+dist.barrier()
 for _ in range(2):
     solver.chock(spec["x0"][:, :1], max_iters=400, tol=0.0, alpha=alpha)
 dist.barrier()

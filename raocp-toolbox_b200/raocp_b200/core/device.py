@@ -196,7 +196,16 @@ class DeviceSolver:
         self._call("rb_residuals", float(alpha), _lib.dptr(norms), _lib.dptr(vec) if vectors else None)
         return norms, vec
 
+    def _shard_rendezvous(self):
+        """sharded solve with the peer-memory exchange: the device waits ~2 s for a peer's packets before it reports the peer as gone,
+        so the ranks enter a loop together (torch.distributed barrier; a no-op for single-GPU solvers)"""
+        if getattr(self, "_p2p_ready", False):
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                dist.barrier()
+
     def iterate(self, alpha, max_iters, tol, history=True):
+        self._shard_rendezvous()
         cap = max_iters + 1
         xi = np.zeros((cap, self.batch, 3)) if history else None
         delta = np.zeros((cap, self.batch, 3)) if history else None
@@ -209,6 +218,7 @@ class DeviceSolver:
         return status.value, iters.value, xi, delta
 
     def iterate_fixed(self, alpha, iters):
+        self._shard_rendezvous()
         norms = np.empty((self.batch, 6))
         self._call("rb_iterate_fixed", float(alpha), int(iters), _lib.dptr(norms))
         return norms
@@ -264,6 +274,7 @@ class DeviceSolver:
         self._call("rb_use_tree_kernels", int(mode))
 
     def loop_begin(self, alpha, max_iters, tol=-1.0, hist_capacity=0):
+        self._shard_rendezvous()
         self._call("rb_loop_begin", float(alpha), int(max_iters), float(tol), int(hist_capacity))
 
     def loop_enqueue(self, count=1):
@@ -335,6 +346,7 @@ class DeviceSolver:
         dist.all_gather(out, t)
         blob = b"".join(bytes(o.cpu().tolist()) for o in out)
         self._call("rb_shard_p2p_open", C.c_char_p(blob))
+        self._p2p_ready = True
 
     def gather_sharded(self, which=0):
         """assemble the full compact iterates on every rank from the ranks' authoritative parts (torch.distributed)"""
