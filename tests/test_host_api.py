@@ -114,6 +114,18 @@ def test_builder_and_component_shapes():
         r.core.Rectangle(r.core.Leaf(), np.ones((2, 1)), -np.ones((2, 1)))
 
 
+# ---- the roofline's algorithmic bytes (VERDICT r1's recomputation) --------------------------------------------------
+def test_algorithmic_bytes_match_survey():
+    """bench.py's numerator: 8 B x 2 x (Np + Nd) per instance and iteration, plus the per-node operators when they are not shared"""
+    import bench
+    f3 = FlatProblem(problems.build(problems.spec("cfg3"), r.core))
+    assert (f3.n, f3.np_, f3.nd_) == (62805, 2153117, 4186056)
+    assert bench.algorithmic_bytes(f3, 1, True) == 8 * 2 * (2153117 + 4186056) == 101426768          # 101.4 MB
+    assert bench.algorithmic_bytes(f3, 1, False) == 101426768 + 8 * f3.m * (2 * 10 * 20 + 10 * 10)   # 336.3 MB, per-node K, K, R~
+    f4 = FlatProblem(problems.build(problems.spec("cfg4"), r.core))
+    assert bench.algorithmic_bytes(f4, 4096, True) == 3116302336                                      # 3 116 MB per batch iteration
+
+
 # ---- flattening ------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name,np_,nd_", [("cfg1", 214, 381), ("cfg2", 30120, 58040)])
 def test_flatten_sizes_match_survey(name, np_, nd_):
