@@ -215,3 +215,54 @@ def test_step_with_a_new_initial_state_mid_loop(pipe):
     dev.loop_end()
     assert seg_rel_err(flat, dev.get_primal(0)[0], oracle.flat_primal(oracle.p), dual=False) < 1e-9
     assert seg_rel_err(flat, dev.get_dual(0)[0], oracle.flat_dual(oracle.d), dual=True) < 1e-9
+
+
+@pytest.mark.parametrize("graphs", [True, False])
+@pytest.mark.parametrize("name", ["cfg1", "chain2010"])
+def test_fused_check_stops_like_the_check_launch(name, graphs):
+    """rb_use_fused_check(1): the stopping test of solver.py:156-161 run by the last CTA of the dual passes -- same stopping
+    iteration, same status, same residual history and iterates as with the k_check launch, with a tolerance, with the iteration cap,
+    across a second chock() (warm start) and through rb_step"""
+    import raocp_b200 as r
+    import torch
+    from oracle import problems
+    s = problems.spec(name)
+    problem = problems.build(s, r.core)
+    x0 = s["x0"][:, :1]
+    out = {}
+    for fused in (False, True):
+        solver = r.core.Solver(problem, verbose=False)
+        dev = solver.cache.device_solver
+        dev.use_fused_check(fused)
+        dev.use_graphs(graphs)
+        alpha = solver.compute_step_size()
+        st_cap = solver.chock(x0, max_iters=40, tol=0.0, alpha=alpha)            # the cap fires: M + 1 iterations
+        hist_cap = solver.residual_history[0].copy()
+        n_cap = solver.iterations
+        st_warm = solver.chock(x0, max_iters=9, tol=0.0, alpha=alpha)            # warm start from iterate 41
+        hist_warm = solver.residual_history[0].copy()
+        # a tolerance first met inside the recorded window, fresh solver
+        tol = float(np.sort(hist_cap.max(axis=1))[1]) * (1 + 1e-9)
+        fresh = r.core.Solver(problem, verbose=False)
+        fresh.cache.device_solver.use_fused_check(fused)
+        fresh.cache.device_solver.use_graphs(graphs)
+        st_tol = fresh.chock(x0, max_iters=400, tol=tol, alpha=alpha)
+        n_tol = fresh.iterations
+        # rb_step: norms of every step on the host
+        dev.loop_begin(alpha, 1 << 30, -1.0, 0)
+        xh = torch.from_numpy(np.ascontiguousarray(x0.reshape(1, -1))).pin_memory()
+        nh = torch.zeros(1, 6, dtype=torch.float64).pin_memory()
+        steps = []
+        for _ in range(5):
+            dev.step(xh.data_ptr(), nh.data_ptr())
+            steps.append(nh.numpy().copy())
+        dev.loop_end()
+        out[fused] = (st_cap, n_cap, hist_cap, st_warm, hist_warm, st_tol, n_tol, fresh.residual_history[0].copy(),
+                      dev.get_primal(0)[0], dev.get_dual(0)[0], np.array(steps))
+    a, b = out[False], out[True]
+    assert (a[0], a[1]) == (b[0], b[1]) == (1, 41)
+    assert np.array_equal(a[2], b[2])
+    assert a[3] == b[3] == 1 and a[4].shape[0] == 10 and np.array_equal(a[4], b[4])
+    assert (a[5], a[6]) == (b[5], b[6]) and a[5] == 0 and 1 < a[6] <= 41
+    assert np.array_equal(a[7], b[7]) and np.array_equal(a[8], b[8]) and np.array_equal(a[9], b[9])
+    assert np.array_equal(a[10], b[10]) and np.all(a[10] > 0)
