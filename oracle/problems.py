@@ -64,18 +64,20 @@ def spec(name, seed=0, batch=1):
                 x_lim=5.0, u_lim=1.0, x0=x0, rectangles=True)
 
 
-def wide_spec(n_gpus, seed=0):
+def wide_spec(n_gpus, seed=0, horizon=20, tau=None):
     """cfg3 made ~n_gpus times WIDER (the weak-scaling tree of the subtree-sharded bench): same nx = 20, nu = 10, horizon 20,
     AVaR(0.5), rectangles.  n_gpus = 2: eight modes in two blocks of four (block-diagonal transition matrix, so every node
     still has four children but the root has eight) -> 8 192 chains; 4: four modes with stopping time 7 -> 16 384 chains;
-    8: both -> 32 768 chains.  At most 8 children per node (the limit of the lanes-per-node passes)."""
+    8: both -> 32 768 chains.  At most 8 children per node (the limit of the lanes-per-node passes).
+    horizon / tau: smaller siblings of the same shape for oracle checks (tests/test_gpu_sweeps.py)."""
     if n_gpus == 1:
         return spec("cfg3", seed=seed)
     blocks = 2 if n_gpus in (2, 8) else 1
-    tau = 7 if n_gpus in (4, 8) else 6
+    if tau is None:
+        tau = 7 if n_gpus in (4, 8) else 6
     if n_gpus not in (2, 4, 8):
         raise ValueError("wide_spec: n_gpus must be 1, 2, 4 or 8")
-    modes, nx, nu, horizon = 4 * blocks, 20, 10, 20
+    modes, nx, nu = 4 * blocks, 20, 10
     rng = np.random.default_rng(seed + 1000 * n_gpus)
     p = np.zeros((modes, modes))
     for b in range(blocks):

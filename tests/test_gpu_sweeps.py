@@ -266,3 +266,31 @@ def test_fused_check_stops_like_the_check_launch(name, graphs):
     assert (a[5], a[6]) == (b[5], b[6]) and a[5] == 0 and 1 < a[6] <= 41
     assert np.array_equal(a[7], b[7]) and np.array_equal(a[8], b[8]) and np.array_equal(a[9], b[9])
     assert np.array_equal(a[10], b[10]) and np.all(a[10] > 0)
+
+
+@pytest.mark.parametrize("n_gpus,horizon,tau", [(2, 8, 4), (8, 7, 5)])
+def test_widened_tree_sibling_matches_oracle(n_gpus, horizon, tau):
+    """small siblings of the trees `bench.py --gpus N` shards (oracle/problems.py wide_spec: block-diagonal transition matrix, so the
+    root has eight children and every other node four): default kernels, 30 iterations, 1e-9 from the oracle"""
+    import raocp_b200 as r
+    from oracle import problems
+    from oracle.cp_flat_oracle import FlatOracle
+    s = problems.wide_spec(n_gpus, horizon=horizon, tau=tau)
+    problem = problems.build(s, r.core)
+    x0 = s["x0"][:, :1]
+    oracle = FlatOracle(problem)
+    alpha = oracle.step_size()
+    solver = r.core.Solver(problem, verbose=False)
+    flat, dev = solver.cache.flat_problem, solver.cache.device_solver
+    assert int(np.max(flat.child_count)) == 8 and int(flat.child_count[1]) == 4
+    assert abs(solver.compute_step_size() - alpha) <= 1e-11 * alpha
+    assert solver.chock(x0, max_iters=29, tol=0.0, alpha=alpha) == 1 and solver.iterations == 30
+    oracle.cache_initial_state(x0)
+    oracle.alpha = alpha
+    for _ in range(30):
+        xi, delta = oracle.iterate()
+    assert seg_rel_err(flat, dev.get_primal(0)[0], oracle.flat_primal(oracle.p), dual=False) < 1e-9
+    assert seg_rel_err(flat, dev.get_dual(0)[0], oracle.flat_dual(oracle.d), dual=True) < 1e-9
+    got = np.concatenate((solver.residual_history[0][-1], solver.residual_history[1][-1]))
+    want = np.concatenate((np.array(xi), np.array(delta)))
+    assert np.max(np.abs(got - want) / want) < 1e-6
